@@ -1,0 +1,144 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules
+(imported from /root/reference through oracle/ref_shim.py) on seeded synthetic
+inputs and the seeded weights of oracle/synth.py.
+
+Run in the authoring container only:  python -m oracle.make_golden
+The reference cannot travel to the GPU box, so the outputs are committed as
+fixtures; weights/inputs are regenerated from seeds on both sides.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+def golden_distmaps():
+    from core.model.ops import DistMaps
+    cases = {}
+    img = torch.zeros(3, 3, 40, 56)
+    specs = [("int_p4", 4, False, torch.int64), ("f32_p4", 4, False, torch.float32),
+             ("frac_p5", 5, True, torch.float32), ("frac_p24", 24, True, torch.float32)]
+    for tag, p, frac, dt in specs:
+        pts = synth.click_points(3, p, 40, 56, seed=10 + p, frac=frac)
+        pts[2, p:] = -1  # one image with no negative click at all
+        pts[1, 0] = torch.tensor([-1.0, 7.0, 0.0])  # one negative coord only -> still VALID (ops.py:40)
+        pts = pts.to(dt)
+        for disks in (True, False):
+            out = DistMaps(norm_radius=5, spatial_scale=1.0, cpu_mode=False, use_disks=disks)(img, pts.clone())
+            cases[f"{tag}_{'disk' if disks else 'tanh'}"] = out
+            cases[f"{tag}_points"] = pts
+    # Cython BFS path (demo-only, a3): integer clicks, both modes
+    try:
+        pts = synth.click_points(2, 3, 24, 32, seed=5).float()
+        for disks in (True, False):
+            out = DistMaps(norm_radius=5, spatial_scale=1.0, cpu_mode=True, use_disks=disks)(
+                torch.zeros(2, 3, 24, 32), pts.clone())
+            cases[f"bfs_{'disk' if disks else 'tanh'}"] = out
+        cases["bfs_points"] = pts
+    except Exception as e:  # pyximport build problem: record, do not fail the rest
+        print("cython path unavailable:", e)
+    save("distmaps", **cases)
+
+
+def golden_loftup():
+    from core.model.upsamplers.loftup.layers import ChannelNorm
+    from core.model.upsamplers.loftup.loftup import LoftUp, UpsamplerwithChannelNorm
+    sd = synth.loftup_state_dict(384, seed=0)
+    cn = synth.channelnorm_state_dict(384, seed=1)
+    up, chn = LoftUp(384, lr_pe_type="sine"), ChannelNorm(384)
+    up.load_state_dict(sd, strict=True)
+    chn.load_state_dict(cn, strict=True)
+    model = UpsamplerwithChannelNorm(up, chn).eval()
+    img = (synth.image_batch(2, 28, 42, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 384, 2, 3, seed=2)
+    with torch.no_grad():
+        out = model(lr, img)
+        q = up.first_conv(up.fourier_feat(img))
+        ff = up.fourier_feat(img)
+    save("loftup_28x42", out=out, first_conv=q[:, :, ::3, ::3], fourier=ff[:, :, ::3, ::3])
+
+
+def golden_lift():
+    from core.model.upsamplers.LiFT import LiFT
+    sd = synth.lift_state_dict(384, seed=0)
+    m = LiFT(384, 14)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    img = (synth.image_batch(2, 56, 84, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 384, 4, 6, seed=2)
+    with torch.no_grad():
+        out = m(img, lr)
+    save("lift_56x84", out=out)
+
+
+def golden_head():
+    from core.model.heads.conv_heads import ConvSegHead
+    from core.model.featurizers.utils.patch_embed import PatchEmbed
+    sd = synth.convhead_state_dict(384, 2, 1, seed=0)
+    m = ConvSegHead(384, 2, 1)
+    m.load_state_dict(sd, strict=True)
+    x = synth.lr_features(2, 384, 20, 28, seed=4)
+    with torch.no_grad():
+        out = m(x)
+    pe_sd = synth.patch_embed_state_dict(384, 14, 3, seed=0)
+    pe = PatchEmbed((28, 42), (14, 14), 3, 384)
+    pe.load_state_dict(pe_sd, strict=True)
+    maps = synth.image_batch(2, 28, 42, seed=6)
+    with torch.no_grad():
+        emb = pe(maps)
+    save("head_20x28", out=out, patch_embed=emb)
+
+
+def golden_vit():
+    from core.model.featurizers.DINOv2 import vit_small
+    sd = synth.vit_state_dict(384, depth=12, seed=0)
+    m = vit_small(patch_size=14, img_size=518, init_values=1.0, block_chunks=0)
+    missing = m.load_state_dict(sd, strict=True)
+    m.eval()
+    img = (synth.image_batch(2, 56, 84, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 384, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():  # DINOv2Featurizer.forward 'before_backbone' (DINOv2.py:518-546)
+        x = m.patch_embed(img)
+        x = x + emb
+        x = torch.cat((m.cls_token.expand(2, -1, -1), x), dim=1)
+        x = x + m.interpolate_pos_encoding(x, 56, 84)
+        for blk in m.blocks:
+            x = blk(x)
+        f = m.norm(x)[:, 1:]
+        f = f.reshape(-1, 4, 6, 384).permute(0, 3, 1, 2)
+    save("vit_56x84", out=f)
+
+
+def golden_jbu_shape():
+    """The only anchor the reference holds for JBU is the shape contract of
+    JBUFeatUp.py:36-45; record it (parity unpinned, see oracle/jbu.py)."""
+    save("jbu_contract", source_shape=np.array([1, 384, 14, 14]), guidance_shape=np.array([1, 3, 224, 224]),
+         out_shape=np.array([1, 384, 224, 224]))
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "reference tree not mounted"
+    ref_shim.install()
+    torch.set_num_threads(os.cpu_count())
+    golden_distmaps()
+    golden_loftup()
+    golden_lift()
+    golden_head()
+    golden_vit()
+    golden_jbu_shape()
