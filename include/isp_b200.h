@@ -1,0 +1,113 @@
+/* libisp_b200 -- C ABI of the B200-native (sm_100a) hot path of iSegProbe.
+ *
+ * Drop-in boundary: the reference is pure Python, so the
+ * "FFI" a maintainer binds is ctypes from the reference's plugin classes
+ * (UPSAMPLER_REGISTRY / HEAD_REGISTRY entries, DistMaps).  Every entry point
+ * below names the reference function it replaces.  Conventions:
+ *   - plain device pointers + sizes, no torch types; the caller owns all memory;
+ *   - nothing allocates, synchronises or keeps global state (apart from a
+ *     process-wide TMA-encode function pointer resolved once);
+ *   - work is enqueued on `stream` (a cudaStream_t) and is stream-ordered;
+ *   - returns ISP_OK or a negative code; isp_last_error() gives the text;
+ *   - there is NO CPU fallback: without a sm_100 device the launch fails.
+ * Layouts: "NHWC" = channels innermost.  Unless said otherwise tensors are dense.
+ */
+#ifndef ISP_B200_H
+#define ISP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* isp_stream_t; /* cudaStream_t */
+
+#define ISP_OK 0
+#define ISP_ERR_BAD_SHAPE (-1)
+#define ISP_ERR_MISALIGNED (-2)
+#define ISP_ERR_CUDA (-3)
+#define ISP_ERR_UNSUPPORTED (-4)
+#define ISP_ERR_WORKSPACE (-5)
+
+#define ISP_ABI_VERSION 1
+
+int isp_version(void);
+const char* isp_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long isp_launch_count(void);
+
+/* ---- click-map encoding -------------------------------------------------
+ * Replaces DistMaps.get_coord_features, torch path
+ * (core/model/ops.py:35-77): points [B,2P,3] float32 (row, col, order) ->
+ * out [B,2,H,W] float32.  use_disks: 1.0 where min squared distance <=
+ * (norm_radius*spatial_scale)^2 else 0.0; otherwise tanh(2*sqrt(d2)) with
+ * coordinates divided by norm_radius*spatial_scale.  Bit-exact (disks). */
+int isp_distmaps_fwd(const float* points, float* out, int B, int P, int H, int W,
+                     float norm_radius, float spatial_scale, int use_disks, isp_stream_t stream);
+
+/* Replaces the Cython `get_dist_maps` (core/utils/cython/_get_dist_maps.pyx:18-64)
+ * as dispatched by DistMaps cpu_mode (ops.py:21-34): click coordinates are
+ * ROUNDED, validity tests the row only, output is the squared distance
+ * divided by norm_delimeter^2 (1e6 where no click), [B,2,H,W]. */
+int isp_distmaps_rounded_sqdist_fwd(const float* points, float* out, int B, int P, int H, int W,
+                                    float norm_delimeter, isp_stream_t stream);
+
+/* Fuses prepare_input + get_coord_features (core/model/iseg_base_model.py:91-110,
+ * BatchImageNormalize ops.py:96-105): image [B,Cin,H,W] (Cin = 3, or 4 with the
+ * previous mask as channel 3) -> norm_image [B,3,H,W] and coord [B,Cc,H,W] with
+ * Cc = 2 (+1 leading prev-mask channel when Cin == 4). */
+int isp_prepare_input_fwd(const float* image, const float* points, float* norm_image, float* coord,
+                          int B, int Cin, int P, int H, int W, const float* mean3, const float* std3,
+                          float norm_radius, float spatial_scale, int use_disks, isp_stream_t stream);
+
+/* ---- layout / dtype movers ---------------------------------------------- */
+/* [B,C,H,W] f32 (arbitrary element strides) -> dense NHWC f32 or bf16 */
+int isp_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W,
+                         long long sb, long long sc, long long sh, long long sw, isp_stream_t stream);
+int isp_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int B, int C, int H, int W, int Cpad,
+                          long long sb, long long sc, long long sh, long long sw, isp_stream_t stream);
+/* bilinear, align_corners=True, NHWC f32 -> NHWC f32 (iseg_probe_model.py:120-129,
+ * basic_upsamplers.py:26-33).  out_bf16 != 0 writes bf16 with Cpad channels. */
+int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int Hout, int Wout,
+                         int out_bf16, int Cpad, isp_stream_t stream);
+
+/* ---- FeatUp JBU stack (external to the reference tree: JBUFeatUp.py:30-32) --- */
+/* F.adaptive_avg_pool2d(guidance, (OH,OW)): NCHW f32 [B,3,H,W] -> NHWC4 f32 [B,OH,OW,4] (4th = 0) */
+int isp_jbu_pool_guidance(const float* guidance, float* out, int B, int H, int W, int OH, int OW,
+                          long long sb, long long sc, long long sh, long long sw, isp_stream_t stream);
+/* range_proj: Conv1x1(3->32) -> GELU -> Conv1x1(32->32).  g NHWC4 -> proj [B,H,W,32].
+ * w0 [32,3], b0 [32], w1 [32,32], b1 [32] (row-major, out-channel first). */
+int isp_jbu_range_proj(const float* g, float* proj, long long npix, const float* w0, const float* b0,
+                       const float* w1, const float* b1, isp_stream_t stream);
+/* combined kernel of JBULearnedRange.forward: softmax_49(temp*<proj nbr, proj>) * spatial,
+ * renormalised, + 0.1*fixup([k,g]).  filters out [B,H,W,49].
+ * fw0 [49,52], fb0 [49], fw1 [49,49], fb1 [49]; temp = clamp(exp(range_temp),1e-4,1e4). */
+int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W,
+                    float temp, float sigma_spatial, const float* fw0, const float* fb0,
+                    const float* fw1, const float* fb1, isp_stream_t stream);
+/* bicubic x2 (align_corners=False, A=-0.75) followed by reflect pad 3:
+ * src NHWC [B,h,w,C] -> out NHWC [B,2h+6,2w+6,C] */
+int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,
+                                 isp_stream_t stream);
+/* AdaptiveConv.forward: out[b,y,x,c] = sum_{i,j<7} in[b,y+i,x+j,c] * filt[b,y,x,i*7+j].
+ * NHWC fast path: in [B,H+6,W+6,C], out [B,H,W,C], C % 64 == 0. */
+int isp_adaptive_conv_fwd(const float* in_padded, const float* filters, float* out,
+                          int B, int H, int W, int C, isp_stream_t stream);
+/* same op, FeatUp's own layout (NCHW in [B,C,H+6,W+6], out [B,C,H,W]); any C */
+int isp_adaptive_conv_fwd_nchw(const float* in_padded, const float* filters, float* out,
+                               int B, int H, int W, int C, isp_stream_t stream);
+/* AdaptiveConv.backward wrt the padded input (NHWC): gi [B,H+6,W+6,C] */
+int isp_adaptive_conv_grad_input(const float* grad_out, const float* filters, float* grad_in,
+                                 int B, int H, int W, int C, isp_stream_t stream);
+
+/* ---- SIMT fp32 GEMM (bring-up / cross-check of the tensor-core path) -----
+ * C[M,N] = A[M,K] * W[N,K]^T + bias[N]; optional residual: C = alpha*C + resid */
+int isp_gemm_f32_simt(const float* A, const float* W, const float* bias, const float* resid, float alpha,
+                      float* C, long long M, int N, int K, isp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISP_B200_H */

@@ -1,0 +1,59 @@
+// Shared helpers for libisp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/isp_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libisp_b200 targets sm_100a only (no multi-arch dispatch)"
+#endif
+
+namespace isp {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ISP_REQUIRE(cond, code, ...)          \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::isp::set_error(__VA_ARGS__);          \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+#define ISP_CHECK_LAUNCH(name)                                              \
+  do {                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) {                                               \
+      ::isp::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return ISP_ERR_CUDA;                                                  \
+    }                                                                       \
+    ::isp::count_launch(1);                                                 \
+  } while (0)
+
+#define ISP_CUDA(call)                                                      \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) {                                               \
+      ::isp::set_error("%s failed: %s", #call, cudaGetErrorString(e__));    \
+      return ISP_ERR_CUDA;                                                  \
+    }                                                                       \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline cudaStream_t as_stream(isp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// exact (erf) GELU, as torch.nn.GELU() default
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' padding (no edge repeat)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+}  // namespace isp

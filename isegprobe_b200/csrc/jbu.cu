@@ -1,0 +1,333 @@
+// FeatUp JBU stage pieces around AdaptiveConv (a12 of SURVEY.md section 8a),
+// all fp32, channels-last.  Algorithm: upstream featup/upsamplers.py
+// (JBULearnedRange.forward / JBUStack.upsample), restated in oracle/jbu.py.
+//
+//   guidance --adaptive_avg_pool--> g[B,GH,GW,4]
+//   g --range_proj (3->32->32)-----> proj[B,GH,GW,32]
+//   proj,g --49-tap range softmax * spatial, renorm, +0.1*fixup MLP--> filters[B,GH,GW,49]
+//   source[B,h,w,C] --bicubic x2 + reflect pad 3--> hr_pad[B,GH+6,GW+6,C]
+//   (hr_pad, filters) --adaptive_conv.cu--> out[B,GH,GW,C]
+#include "common.cuh"
+
+namespace isp {
+
+// ---------------------------------------------------------------------------
+// adaptive_avg_pool2d of the 3-channel guidance image, NCHW (strided) -> NHWC4.
+// ATen window: [floor(o*I/O), ceil((o+1)*I/O)); sum rows-then-cols in fp32, divide by count.
+__global__ void __launch_bounds__(256) pool_guidance_kernel(const float* __restrict__ gd, float4* __restrict__ out,
+                                                            int B, int H, int W, int OH, int OW, long long sb,
+                                                            long long sc, long long sh, long long sw) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * OH * OW;
+  if (idx >= total) return;
+  const int ox = (int)(idx % OW);
+  const int oy = (int)((idx / OW) % OH);
+  const int b = (int)(idx / ((long long)OW * OH));
+  const int y0 = (int)(((long long)oy * H) / OH), y1 = (int)((((long long)oy + 1) * H + OH - 1) / OH);
+  const int x0 = (int)(((long long)ox * W) / OW), x1 = (int)((((long long)ox + 1) * W + OW - 1) / OW);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < 3; ++c) {
+    const float* p = gd + b * sb + c * sc;
+    float s = 0.f;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) s += p[y * sh + x * sw];
+    acc[c] = s / (float)((y1 - y0) * (x1 - x0));
+  }
+  out[idx] = make_float4(acc[0], acc[1], acc[2], 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// range_proj: per-pixel MLP 3 -> 32 (GELU) -> 32.  One thread per pixel; weights in smem.
+__global__ void __launch_bounds__(128) range_proj_kernel(const float4* __restrict__ g, float4* __restrict__ proj,
+                                                         long long npix, const float* __restrict__ w0,
+                                                         const float* __restrict__ b0, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1) {
+  __shared__ float s_w0[32 * 3], s_b0[32], s_w1t[32 * 32], s_b1[32];  // s_w1t[k][o]
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) s_w0[i] = w0[i];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) { s_b0[i] = b0[i]; s_b1[i] = b1[i]; }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_w1t[(i % 32) * 32 + i / 32] = w1[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix) return;
+  const float4 gv = g[idx];
+  float o[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) o[j] = s_b1[j];
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    float h = s_b0[k];
+    h = fmaf(s_w0[k * 3 + 0], gv.x, h);
+    h = fmaf(s_w0[k * 3 + 1], gv.y, h);
+    h = fmaf(s_w0[k * 3 + 2], gv.z, h);
+    h = gelu_erf(h);
+    const float4* wr = reinterpret_cast<const float4*>(&s_w1t[k * 32]);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 w = wr[j4];
+      o[j4 * 4 + 0] = fmaf(w.x, h, o[j4 * 4 + 0]);
+      o[j4 * 4 + 1] = fmaf(w.y, h, o[j4 * 4 + 1]);
+      o[j4 * 4 + 2] = fmaf(w.z, h, o[j4 * 4 + 2]);
+      o[j4 * 4 + 3] = fmaf(w.w, h, o[j4 * 4 + 3]);
+    }
+  }
+  float4* dst = proj + idx * 8;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+}
+
+// ---------------------------------------------------------------------------
+// Combined 7x7 kernel per pixel.  One thread per pixel (linear over B*H*W so a
+// block's 128 pixels own one contiguous 128*49-float slab of `filters`).
+//   phase 1 (registers): 49 range logits = temp * <proj[nbr], proj[centre]>, softmax,
+//            * spatial Gaussian, renormalise -> k[49]
+//   phase 2 (outer-product MLP): vector in smem [c][tid] (stride 129: conflict-free both
+//            for the per-thread column walk and for the transposed final copy), weights
+//            broadcast from smem as float4, 49 register accumulators.
+constexpr int kFT = 128;        // threads / pixels per block
+constexpr int kVS = kFT + 1;    // smem row stride of the per-thread vectors
+constexpr int kWP = 52;         // padded weight row (49 -> 52 floats = 13 float4)
+
+struct FilterSmem {
+  float v[52 * kVS];            // input vector [k(49), g(3)] then hidden, then output
+  float w0t[52 * kWP];          // fixup_proj.0 transposed: [c][r]
+  float w1t[49 * kWP];          // fixup_proj.3 transposed: [c][r]
+  float b0[kWP], b1[kWP];
+  float spatial[kWP];
+};
+
+__global__ void __launch_bounds__(kFT) jbu_filters_kernel(const float* __restrict__ proj, const float4* __restrict__ g,
+                                                          float* __restrict__ filters, int B, int H, int W, float temp,
+                                                          float inv2s2, const float* __restrict__ fw0,
+                                                          const float* __restrict__ fb0, const float* __restrict__ fw1,
+                                                          const float* __restrict__ fb1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FilterSmem& S = *reinterpret_cast<FilterSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 52 * kWP; i += kFT) {
+    const int c = i / kWP, r = i % kWP;
+    S.w0t[i] = (r < 49) ? fw0[r * 52 + c] : 0.f;
+  }
+  for (int i = tid; i < 49 * kWP; i += kFT) {
+    const int c = i / kWP, r = i % kWP;
+    S.w1t[i] = (r < 49) ? fw1[r * 49 + c] : 0.f;
+  }
+  for (int i = tid; i < kWP; i += kFT) {
+    S.b0[i] = (i < 49) ? fb0[i] : 0.f;
+    S.b1[i] = (i < 49) ? fb1[i] : 0.f;
+    float sp = 0.f;
+    if (i < 49) {  // linspace(-1,1,7): -1 + k/3
+      const float dy = -1.f + (float)(i / 7) * (1.f / 3.f), dx = -1.f + (float)(i % 7) * (1.f / 3.f);
+      sp = expf(-(dy * dy + dx * dx) * inv2s2);
+    }
+    S.spatial[i] = sp;
+  }
+  __syncthreads();
+
+  const long long npix = (long long)B * H * W;
+  const long long pix0 = (long long)blockIdx.x * kFT;
+  const long long pix = pix0 + tid;
+  const bool live = pix < npix;
+  if (live) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const long long img = pix / ((long long)W * H);
+    const float4* pc = reinterpret_cast<const float4*>(proj + pix * 32);
+    float4 ctr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ctr[q] = pc[q];
+    float k[49];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int yy = reflect_idx(y + i - 3, H);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int xx = reflect_idx(x + j - 3, W);
+        const float4* pn = reinterpret_cast<const float4*>(proj + ((img * H + yy) * W + xx) * 32);
+        float d = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 n = __ldg(pn + q);
+          d = fmaf(n.x, ctr[q].x, d);
+          d = fmaf(n.y, ctr[q].y, d);
+          d = fmaf(n.z, ctr[q].z, d);
+          d = fmaf(n.w, ctr[q].w, d);
+        }
+        d *= temp;
+        k[i * 7 + j] = d;
+        mx = fmaxf(mx, d);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
+    const float inv = 1.f / sum;
+    float sum2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) { k[t] = (k[t] * inv) * S.spatial[t]; sum2 += k[t]; }
+    sum2 = fmaxf(sum2, 1e-7f);
+#pragma unroll
+    for (int t = 0; t < 49; ++t) S.v[t * kVS + tid] = k[t] / sum2;
+    const float4 gv = g[pix];
+    S.v[49 * kVS + tid] = gv.x;
+    S.v[50 * kVS + tid] = gv.y;
+    S.v[51 * kVS + tid] = gv.z;
+  }
+  // layer 0: h = GELU(W0 [k;g] + b0)   (each thread only touches its own column of S.v)
+  float acc[kWP];
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < kWP; ++r) acc[r] = S.b0[r];
+    for (int c = 0; c < 52; ++c) {
+      const float vc = S.v[c * kVS + tid];
+      const float4* wr = reinterpret_cast<const float4*>(&S.w0t[c * kWP]);
+#pragma unroll
+      for (int q = 0; q < 13; ++q) {
+        const float4 w = wr[q];
+        acc[q * 4 + 0] = fmaf(w.x, vc, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(w.y, vc, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(w.z, vc, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(w.w, vc, acc[q * 4 + 3]);
+      }
+    }
+    float kk[49];  // keep k to add the fixup onto; re-read before overwriting with the hidden vector
+#pragma unroll
+    for (int t = 0; t < 49; ++t) kk[t] = S.v[t * kVS + tid];
+#pragma unroll
+    for (int r = 0; r < 49; ++r) S.v[r * kVS + tid] = gelu_erf(acc[r]);
+    // layer 1: o = W1 h + b1 ; out = k + 0.1 * o
+#pragma unroll
+    for (int r = 0; r < kWP; ++r) acc[r] = S.b1[r];
+    for (int c = 0; c < 49; ++c) {
+      const float vc = S.v[c * kVS + tid];
+      const float4* wr = reinterpret_cast<const float4*>(&S.w1t[c * kWP]);
+#pragma unroll
+      for (int q = 0; q < 13; ++q) {
+        const float4 w = wr[q];
+        acc[q * 4 + 0] = fmaf(w.x, vc, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(w.y, vc, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(w.z, vc, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(w.w, vc, acc[q * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 49; ++t) S.v[t * kVS + tid] = fmaf(0.1f, acc[t], kk[t]);
+  }
+  __syncthreads();
+  // coalesced copy-out: element e of the block's slab = (pixel e/49, tap e%49)
+  const long long nlive = min((long long)kFT, npix - pix0);
+  float* dst = filters + pix0 * 49;
+  for (int e = tid; e < nlive * 49; e += kFT) dst[e] = S.v[(e % 49) * kVS + (e / 49)];
+}
+
+// ---------------------------------------------------------------------------
+// bicubic x2 (align_corners=False, A=-0.75, border clamp) + reflect pad 3, NHWC.
+// thread = (padded pixel, 4 channels).  ATen: src = (dst+0.5)*0.5-0.5, taps floor-1..floor+2.
+__device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
+  const float A = -0.75f;
+  float x = t + 1.f;
+  w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+  x = t;
+  w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  x = 1.f - t;
+  w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  x = 2.f - t;
+  w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) bicubic2x_pad_kernel(const float* __restrict__ src, float* __restrict__ out,
+                                                            int B, int h, int w, int C) {
+  const int GH = 2 * h, GW = 2 * w, PH = GH + 6, PW = GW + 6, C4 = C / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * PH * PW * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const long long p = idx / C4;
+  const int px = (int)(p % PW), py = (int)((p / PW) % PH), b = (int)(p / ((long long)PW * PH));
+  const int oy = reflect_idx(py - 3, GH), ox = reflect_idx(px - 3, GW);
+  const float sy = ((float)oy + 0.5f) * 0.5f - 0.5f, sx = ((float)ox + 0.5f) * 0.5f - 0.5f;
+  const float fy = floorf(sy), fx = floorf(sx);
+  float wy[4], wx[4];
+  cubic_coeffs(sy - fy, wy);
+  cubic_coeffs(sx - fx, wx);
+  const int iy = (int)fy, ix = (int)fx;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (long long)b * h * w * C4 + c4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(iy - 1 + i, 0), h - 1);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xx = min(max(ix - 1 + j, 0), w - 1);
+      const float4 v = __ldg(s4 + ((long long)yy * w + xx) * C4);
+      r.x = fmaf(v.x, wx[j], r.x);
+      r.y = fmaf(v.y, wx[j], r.y);
+      r.z = fmaf(v.z, wx[j], r.z);
+      r.w = fmaf(v.w, wx[j], r.w);
+    }
+    acc.x = fmaf(r.x, wy[i], acc.x);
+    acc.y = fmaf(r.y, wy[i], acc.y);
+    acc.z = fmaf(r.z, wy[i], acc.z);
+    acc.w = fmaf(r.w, wy[i], acc.w);
+  }
+  reinterpret_cast<float4*>(out)[idx] = acc;
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int isp_jbu_pool_guidance(const float* guidance, float* out, int B, int H, int W, int OH, int OW,
+                                     long long sb, long long sc, long long sh, long long sw, isp_stream_t stream) {
+  ISP_REQUIRE(guidance && out, ISP_ERR_BAD_SHAPE, "jbu_pool_guidance: null pointer");
+  ISP_REQUIRE(B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, ISP_ERR_BAD_SHAPE, "jbu_pool_guidance: bad shape");
+  ISP_REQUIRE(aligned16(out), ISP_ERR_MISALIGNED, "jbu_pool_guidance: out must be 16-byte aligned");
+  const long long total = (long long)B * OH * OW;
+  pool_guidance_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(guidance, reinterpret_cast<float4*>(out), B, H,
+                                                                       W, OH, OW, sb, sc, sh, sw);
+  ISP_CHECK_LAUNCH("pool_guidance_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_jbu_range_proj(const float* g, float* proj, long long npix, const float* w0, const float* b0,
+                                  const float* w1, const float* b1, isp_stream_t stream) {
+  ISP_REQUIRE(g && proj && w0 && b0 && w1 && b1, ISP_ERR_BAD_SHAPE, "jbu_range_proj: null pointer");
+  ISP_REQUIRE(npix > 0, ISP_ERR_BAD_SHAPE, "jbu_range_proj: npix=%lld", npix);
+  ISP_REQUIRE(aligned16(g) && aligned16(proj), ISP_ERR_MISALIGNED, "jbu_range_proj: pointers must be 16-byte aligned");
+  range_proj_kernel<<<cdiv(npix, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g),
+                                                                    reinterpret_cast<float4*>(proj), npix, w0, b0, w1, b1);
+  ISP_CHECK_LAUNCH("range_proj_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
+                               float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
+                               const float* fb1, isp_stream_t stream) {
+  ISP_REQUIRE(proj && g && filters && fw0 && fb0 && fw1 && fb1, ISP_ERR_BAD_SHAPE, "jbu_filters: null pointer");
+  ISP_REQUIRE(B > 0 && H >= 4 && W >= 4, ISP_ERR_BAD_SHAPE, "jbu_filters: need H,W >= 4 (reflect pad 3), got %dx%d", H, W);
+  ISP_REQUIRE(aligned16(proj) && aligned16(g), ISP_ERR_MISALIGNED, "jbu_filters: pointers must be 16-byte aligned");
+  static bool attr_set = false;
+  const int smem = (int)sizeof(FilterSmem);
+  if (!attr_set) {
+    ISP_CUDA(cudaFuncSetAttribute(jbu_filters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long long npix = (long long)B * H * W;
+  const float inv2s2 = 1.f / (2.f * sigma_spatial * sigma_spatial);
+  jbu_filters_kernel<<<cdiv(npix, kFT), kFT, smem, as_stream(stream)>>>(proj, reinterpret_cast<const float4*>(g),
+                                                                       filters, B, H, W, temp, inv2s2, fw0, fb0, fw1, fb1);
+  ISP_CHECK_LAUNCH("jbu_filters_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,
+                                            isp_stream_t stream) {
+  ISP_REQUIRE(src && out, ISP_ERR_BAD_SHAPE, "jbu_bicubic2x_reflectpad: null pointer");
+  ISP_REQUIRE(B > 0 && h >= 2 && w >= 2 && C > 0 && C % 4 == 0, ISP_ERR_BAD_SHAPE,
+              "jbu_bicubic2x_reflectpad: need h,w >= 2 and C %% 4 == 0 (h=%d w=%d C=%d)", h, w, C);
+  ISP_REQUIRE(aligned16(src) && aligned16(out), ISP_ERR_MISALIGNED, "jbu_bicubic2x_reflectpad: 16-byte alignment");
+  const long long total = (long long)B * (2 * h + 6) * (2 * w + 6) * (C / 4);
+  bicubic2x_pad_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, out, B, h, w, C);
+  ISP_CHECK_LAUNCH("bicubic2x_pad_kernel");
+  return ISP_OK;
+}

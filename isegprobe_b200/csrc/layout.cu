@@ -1,0 +1,168 @@
+// Layout / dtype movers and the align_corners=True bilinear resize (a14/a16 of
+// core/model/iseg_probe_model.py:120-129, iseg_base_model.py:75-80).
+#include "common.cuh"
+
+namespace isp {
+
+// [B,C,H,W] (element strides sb,sc,sh,sw) -> dense [B,H*W,Cpad]; 32x32 smem transpose
+template <typename OutT>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, OutT* __restrict__ out, int C,
+                                                           int H, int W, int Cpad, long long sb, long long sc,
+                                                           long long sh, long long sw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int HW = H * W;
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) v = in[b * sb + c * sc + (p / W) * sh + (p % W) * sw];
+    tile[k][tx] = v;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int p = p0 + k, c = c0 + tx;
+    if (p < HW && c < Cpad) {
+      const float v = tile[tx][k];
+      if constexpr (sizeof(OutT) == 2) out[((size_t)b * HW + p) * Cpad + c] = __float2bfloat16(v);
+      else out[((size_t)b * HW + p) * Cpad + c] = v;
+    }
+  }
+}
+
+// bilinear, align_corners=True (ATen upsample_bilinear2d): NHWC f32 -> NHWC f32|bf16
+template <typename OutT>
+__global__ void __launch_bounds__(256) bilinear_ac_kernel(const float* __restrict__ in, OutT* __restrict__ out, int B,
+                                                          int C, int Hin, int Win, int Hout, int Wout, int Cpad,
+                                                          float sy, float sx) {
+  const int C4 = Cpad / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Hout * Wout * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const long long p = idx / C4;
+  const int ox = (int)(p % Wout), oy = (int)((p / Wout) % Hout), b = (int)(p / ((long long)Wout * Hout));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < C) {
+    const float fy = sy * (float)oy, fx = sx * (float)ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float4* s = reinterpret_cast<const float4*>(in) + (size_t)b * Hin * Win * (C / 4) + c4;
+    const int Ci4 = C / 4;
+    const float4 v00 = __ldg(s + ((size_t)y0 * Win + x0) * Ci4), v01 = __ldg(s + ((size_t)y0 * Win + x1) * Ci4);
+    const float4 v10 = __ldg(s + ((size_t)y1 * Win + x0) * Ci4), v11 = __ldg(s + ((size_t)y1 * Win + x1) * Ci4);
+    r.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+    r.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+    r.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+    r.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  }
+  if constexpr (sizeof(OutT) == 2) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(r.x, r.y), c = __floats2bfloat162_rn(r.z, r.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&a);
+    u.y = *reinterpret_cast<unsigned*>(&c);
+    reinterpret_cast<uint2*>(out)[idx] = u;
+  } else {
+    reinterpret_cast<float4*>(out)[idx] = r;
+  }
+}
+
+// C[M,N] = alpha * (A[M,K] W[N,K]^T + bias) + resid   -- fp32 SIMT, 64x64x16 tiles, 4x4 per thread
+__global__ void __launch_bounds__(256) gemm_f32_simt_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ resid, float alpha,
+                                                            float* __restrict__ Cm, long long M, int N, int K) {
+  __shared__ float As[16][65], Ws[16][65];
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      As[k][r] = (m0 + r < M && k0 + k < K) ? A[(m0 + r) * K + k0 + k] : 0.f;
+      Ws[k][r] = (n0 + r < N && k0 + k < K) ? Wt[(size_t)(n0 + r) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      v *= alpha;
+      if (resid) v += resid[m * N + n];
+      Cm[m * N + n] = v;
+    }
+  }
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int isp_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, long long sb, long long sc,
+                                    long long sh, long long sw, isp_stream_t stream) {
+  ISP_REQUIRE(in && out && B > 0 && C > 0 && H > 0 && W > 0, ISP_ERR_BAD_SHAPE, "nchw_to_nhwc_f32: bad arguments");
+  ISP_REQUIRE(B <= 65535 && cdiv(C, 32) <= 65535, ISP_ERR_UNSUPPORTED, "nchw_to_nhwc_f32: grid too large");
+  dim3 grid(cdiv((long long)H * W, 32), cdiv(C, 32), B);
+  nchw_to_nhwc_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, out, C, H, W, C, sb, sc, sh, sw);
+  ISP_CHECK_LAUNCH("nchw_to_nhwc_kernel<float>");
+  return ISP_OK;
+}
+
+extern "C" int isp_nchw_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, int Cpad, long long sb,
+                                     long long sc, long long sh, long long sw, isp_stream_t stream) {
+  ISP_REQUIRE(in && out && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, ISP_ERR_BAD_SHAPE,
+              "nchw_to_nhwc_bf16: bad arguments");
+  ISP_REQUIRE(B <= 65535 && cdiv(Cpad, 32) <= 65535, ISP_ERR_UNSUPPORTED, "nchw_to_nhwc_bf16: grid too large");
+  dim3 grid(cdiv((long long)H * W, 32), cdiv(Cpad, 32), B);
+  nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), C,
+                                                                         H, W, Cpad, sb, sc, sh, sw);
+  ISP_CHECK_LAUNCH("nchw_to_nhwc_kernel<bf16>");
+  return ISP_OK;
+}
+
+extern "C" int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int Hout, int Wout,
+                                    int out_bf16, int Cpad, isp_stream_t stream) {
+  ISP_REQUIRE(in && out && B > 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, ISP_ERR_BAD_SHAPE,
+              "bilinear_ac_nhwc: bad arguments");
+  ISP_REQUIRE(C % 4 == 0 && Cpad % 4 == 0 && Cpad >= C, ISP_ERR_UNSUPPORTED, "bilinear_ac_nhwc: C, Cpad %% 4 == 0");
+  ISP_REQUIRE(aligned16(in) && aligned16(out), ISP_ERR_MISALIGNED, "bilinear_ac_nhwc: 16-byte alignment");
+  const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  const long long total = (long long)B * Hout * Wout * (Cpad / 4);
+  if (out_bf16)
+    bilinear_ac_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
+        in, reinterpret_cast<__nv_bfloat16*>(out), B, C, Hin, Win, Hout, Wout, Cpad, sy, sx);
+  else
+    bilinear_ac_kernel<float><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), B, C,
+                                                                               Hin, Win, Hout, Wout, Cpad, sy, sx);
+  ISP_CHECK_LAUNCH("bilinear_ac_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_gemm_f32_simt(const float* A, const float* W, const float* bias, const float* resid, float alpha,
+                                 float* C, long long M, int N, int K, isp_stream_t stream) {
+  ISP_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, ISP_ERR_BAD_SHAPE, "gemm_f32_simt: bad arguments");
+  dim3 grid(cdiv(M, 64), cdiv(N, 64));
+  ISP_REQUIRE(grid.y <= 65535, ISP_ERR_UNSUPPORTED, "gemm_f32_simt: N too large");
+  gemm_f32_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, W, bias, resid, alpha, C, M, N, K);
+  ISP_CHECK_LAUNCH("gemm_f32_simt_kernel");
+  return ISP_OK;
+}

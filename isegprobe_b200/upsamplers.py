@@ -1,0 +1,179 @@
+"""Feature upsamplers -- the reference's plugin API
+(core/model/upsamplers/__init__.py:6-33): `forward(source, guidance) -> hr_feats`,
+same registry keys, same constructor kwargs as models/*.py pass them.
+
+Everything internal is channels-last: a module returns a tensor whose logical
+shape is the reference's [B, C, H', W'] and whose memory is NHWC (a
+`.permute(0, 3, 1, 2)` view), so the next stage (resize, head) reads it without a
+transpose.  Compute is libisp_b200 only; there is no fallback.
+"""
+import math
+from abc import ABC, abstractmethod
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class BaseUpsampler(nn.Module, ABC):
+    """core/model/upsamplers/__init__.py:6-11"""
+
+    @abstractmethod
+    def forward(self, source, guidance):
+        pass
+
+
+def to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] float32 CUDA tensor (any strides) -> dense [B,H,W,C].  Free when the
+    tensor already is channels-last (the reference's ViT adapters return permuted
+    [B,h,w,C] views, DINOv2.py:545)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, C, dtype=torch.float32, device=x.device)
+    sb, sc, sh, sw = x.stride()
+    _lib.call("isp_nchw_to_nhwc_f32", _lib.dptr(x), _lib.dptr(out), B, C, H, W, sb, sc, sh, sw, _lib.stream_ptr())
+    return out
+
+
+def bilinear_align_corners_nhwc(x_nhwc: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(mode='bilinear', align_corners=True) on a dense NHWC fp32 tensor."""
+    B, H, W, C = x_nhwc.shape
+    out = torch.empty(B, size[0], size[1], C, dtype=torch.float32, device=x_nhwc.device)
+    _lib.call("isp_bilinear_ac_nhwc", _lib.dptr(x_nhwc), _lib.dptr(out), B, C, H, W, size[0], size[1], 0, C,
+              _lib.stream_ptr())
+    return out
+
+
+class IdentityUpsampler(BaseUpsampler):
+    def forward(self, source, guidance):
+        return source
+
+
+class NearestUpsampler(BaseUpsampler):
+    def forward(self, source, guidance):
+        return F.interpolate(source, guidance.shape[2:], mode="nearest")
+
+
+class BilinearUpsampler(BaseUpsampler):
+    """basic_upsamplers.py:26-33 on the library's own resize kernel."""
+
+    def forward(self, source, guidance):
+        out = bilinear_align_corners_nhwc(to_nhwc_f32(source), tuple(guidance.shape[2:]))
+        return out.permute(0, 3, 1, 2)
+
+
+class BicubicUpsampler(BaseUpsampler):
+    def forward(self, source, guidance):
+        return F.interpolate(source, guidance.shape[2:], mode="bicubic")
+
+
+# --------------------------------------------------------------------------- JBU
+_JBU_FEAT_DIM = {"dinov2": 384, "dino16": 384, "vit": 384, "maskclip": 512, "clip": 512, "resnet50": 2048}
+
+
+class _JBULearnedRange(nn.Module):
+    """Parameter container with upstream FeatUp's names/shapes (featup/upsamplers.py
+    JBULearnedRange: guidance_dim=3, key_dim=32, radius=3)."""
+
+    def __init__(self):
+        super().__init__()
+        self.range_temp = nn.Parameter(torch.tensor(0.0))
+        self.range_proj = nn.Sequential(nn.Conv2d(3, 32, 1), nn.GELU(), nn.Dropout2d(0.1), nn.Conv2d(32, 32, 1))
+        self.fixup_proj = nn.Sequential(nn.Conv2d(52, 49, 1), nn.GELU(), nn.Dropout2d(0.1), nn.Conv2d(49, 49, 1))
+        self.sigma_spatial = nn.Parameter(torch.tensor(1.0))
+
+
+class _JBUStack(nn.Module):
+    def __init__(self, feat_dim):
+        super().__init__()
+        self.up1, self.up2, self.up3, self.up4 = (_JBULearnedRange() for _ in range(4))
+        self.fixup_proj = nn.Sequential(nn.Dropout2d(0.2), nn.Conv2d(feat_dim, feat_dim, kernel_size=1))
+
+
+class JBUFeatUpUpsampler(BaseUpsampler):
+    """FeatUp's learned JBU stack (x16), same constructor as the reference wrapper
+    (core/model/upsamplers/JBUFeatUp.py:9-32).  The reference pulls weights and code
+    from torch.hub (network); here the stack is built locally with upstream's
+    parameter layout (so a FeatUp `upsampler` state dict loads with
+    `self.upsampler.load_state_dict`) and random-initialised otherwise.
+    `weights` (extension): path to such a state dict."""
+
+    def __init__(self, backbone_type: str = None, use_norm: bool = True, weights: str = None) -> None:
+        super().__init__()
+        self.backbone_type = backbone_type
+        self.use_norm = use_norm
+        assert self.backbone_type in _JBU_FEAT_DIM, f"Invalid model type: {self.backbone_type}"
+        self.feat_dim = _JBU_FEAT_DIM[self.backbone_type]
+        self.upsampler = _JBUStack(self.feat_dim)
+        if weights is not None:
+            self.upsampler.load_state_dict(torch.load(weights, map_location="cpu"))
+
+    @staticmethod
+    def _flat(p):
+        return p.detach().reshape(p.shape[0], -1).float().contiguous()
+
+    def _scalar(self, p: torch.Tensor) -> float:
+        """Host value of a 0-d parameter, cached per parameter version (avoids a
+        device sync on every forward of the frozen stack)."""
+        cache = self.__dict__.setdefault("_scalar_cache", {})
+        key = id(p)
+        hit = cache.get(key)
+        if hit is None or hit[0] != p._version or hit[1] != p.data_ptr():
+            hit = (p._version, p.data_ptr(), float(p.detach()))
+            cache[key] = hit
+        return hit[2]
+
+    def _stage(self, up: _JBULearnedRange, src: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        B, h, w, C = src.shape
+        GH, GW = 2 * h, 2 * w
+        dev, st = src.device, _lib.stream_ptr()
+        g = torch.empty(B, GH, GW, 4, dtype=torch.float32, device=dev)
+        sb, sc, sh, sw = guidance.stride()
+        _lib.call("isp_jbu_pool_guidance", _lib.dptr(guidance), _lib.dptr(g), B, guidance.shape[2], guidance.shape[3],
+                  GH, GW, sb, sc, sh, sw, st)
+        proj = torch.empty(B, GH, GW, 32, dtype=torch.float32, device=dev)
+        rp, fp = up.range_proj, up.fixup_proj
+        w0, b0, w1, b1 = self._flat(rp[0].weight), rp[0].bias.detach().float(), self._flat(rp[3].weight), rp[3].bias.detach().float()
+        _lib.call("isp_jbu_range_proj", _lib.dptr(g), _lib.dptr(proj), B * GH * GW, _lib.dptr(w0), _lib.dptr(b0),
+                  _lib.dptr(w1), _lib.dptr(b1), st)
+        filt = torch.empty(B, GH, GW, 49, dtype=torch.float32, device=dev)
+        temp = min(max(math.exp(self._scalar(up.range_temp)), 1e-4), 1e4)
+        f0, fb0, f1, fb1 = self._flat(fp[0].weight), fp[0].bias.detach().float(), self._flat(fp[3].weight), fp[3].bias.detach().float()
+        _lib.call("isp_jbu_filters", _lib.dptr(proj), _lib.dptr(g), _lib.dptr(filt), B, GH, GW, float(temp),
+                  self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), st)
+        hr = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
+        _lib.call("isp_jbu_bicubic2x_reflectpad", _lib.dptr(src), _lib.dptr(hr), B, h, w, C, st)
+        out = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
+        _lib.call("isp_adaptive_conv_fwd", _lib.dptr(hr), _lib.dptr(filt), _lib.dptr(out), B, GH, GW, C, st)
+        return out
+
+    def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        if self.training and torch.is_grad_enabled() and source.requires_grad:
+            raise NotImplementedError("JBUFeatUpUpsampler: activation backward is not implemented yet")
+        x = to_nhwc_f32(source.detach())
+        guidance = guidance.detach().float()
+        for up in (self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4):
+            x = self._stage(up, x, guidance)
+        B, H, W, C = x.shape
+        conv = self.upsampler.fixup_proj[1]
+        out = torch.empty_like(x)
+        wf, bf = self._flat(conv.weight), conv.bias.detach().float()
+        # fixup_proj(x) * 0.1 + x  (JBUStack.forward)
+        _lib.call("isp_gemm_f32_simt", _lib.dptr(x), _lib.dptr(wf), _lib.dptr(bf), _lib.dptr(x), 0.1, _lib.dptr(out),
+                  B * H * W, C, C, _lib.stream_ptr())
+        return out.permute(0, 3, 1, 2)
+
+
+UPSAMPLER_REGISTRY = {
+    "identity": IdentityUpsampler,
+    "nearest": NearestUpsampler,
+    "bilinear": BilinearUpsampler,
+    "bicubic": BicubicUpsampler,
+    "jbu_featup": JBUFeatUpUpsampler,
+}

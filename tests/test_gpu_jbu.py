@@ -1,0 +1,155 @@
+"""GPU parity: FeatUp JBU stack pieces and the AdaptiveConv kernels vs the oracle
+(oracle/jbu.py; parity UNPINNED upstream, see its header).  fp32 mode: <= 1e-3 max
+relative error (north_star)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import jbu as ojbu
+from oracle import synth
+from tests.gpu_util import DEV, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def isp():
+    import isegprobe_b200
+    return isegprobe_b200
+
+
+def _call(name, *a):
+    from isegprobe_b200 import _lib
+    _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 32, 64), (1, 19, 37, 128), (2, 64, 64, 384), (1, 8, 16, 512)])
+def test_adaptive_conv_nhwc(isp, B, H, W, C):
+    g = torch.Generator().manual_seed(B * H + C)
+    x = torch.randn(B, C, H + 6, W + 6, generator=g)
+    f = torch.randn(B, H, W, 7, 7, generator=g) * 0.2
+    want = ojbu.adaptive_conv(x, f)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty(B, H, W, C, device=DEV)
+    _call("isp_adaptive_conv_fwd", xin, f.reshape(B, H, W, 49).contiguous().to(DEV), out, B, H, W, C)
+    assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+    # FeatUp-layout kernel must agree as well (independent implementation)
+    out2 = torch.empty(B, C, H, W, device=DEV)
+    _call("isp_adaptive_conv_fwd_nchw", x.to(DEV), f.reshape(B, H, W, 49).contiguous().to(DEV), out2, B, H, W, C)
+    assert relerr(out2, want) < 1e-5
+
+
+def test_adaptive_conv_properties_full_size(isp):
+    """Size-independent properties at BASELINE size (512x512x384): a centre-delta
+    filter is the identity; linearity in the input."""
+    B, H, W, C = 1, 512, 512, 384
+    x = torch.randn(B, H + 6, W + 6, C, device=DEV)
+    f = torch.zeros(B, H, W, 49, device=DEV)
+    f[..., 24] = 1
+    out = torch.empty(B, H, W, C, device=DEV)
+    _call("isp_adaptive_conv_fwd", x, f, out, B, H, W, C)
+    assert torch.equal(out, x[:, 3:-3, 3:-3])
+    f = torch.rand(B, H, W, 49, device=DEV)
+    y = torch.randn_like(x)
+    o1, o2, o3 = (torch.empty(B, H, W, C, device=DEV) for _ in range(3))
+    _call("isp_adaptive_conv_fwd", x, f, o1, B, H, W, C)
+    _call("isp_adaptive_conv_fwd", y, f, o2, B, H, W, C)
+    _call("isp_adaptive_conv_fwd", x + 2 * y, f, o3, B, H, W, C)
+    assert relerr(o3, o1 + 2 * o2) < 1e-5
+
+
+def test_adaptive_conv_grad_input(isp):
+    B, H, W, C = 2, 11, 13, 64
+    g = torch.Generator().manual_seed(7)
+    go = torch.randn(B, C, H, W, generator=g)
+    f = torch.randn(B, H, W, 7, 7, generator=g)
+    want = ojbu.adaptive_conv_grad_input(go, f)
+    gi = torch.empty(B, H + 6, W + 6, C, device=DEV)
+    _call("isp_adaptive_conv_grad_input", go.permute(0, 2, 3, 1).contiguous().to(DEV),
+          f.reshape(B, H, W, 49).contiguous().to(DEV), gi, B, H, W, C)
+    assert relerr(gi.permute(0, 3, 1, 2), want) < 1e-5
+
+
+@pytest.mark.parametrize("H,W,OH,OW", [(448, 448, 64, 64), (448, 448, 128, 128), (448, 448, 512, 512), (50, 70, 16, 24)])
+def test_pool_guidance(isp, H, W, OH, OW):
+    gd = synth.image_batch(2, H, W, seed=1)
+    out = torch.empty(2, OH, OW, 4, device=DEV)
+    d = gd.to(DEV)
+    _call("isp_jbu_pool_guidance", d, out, 2, H, W, OH, OW, *d.stride())
+    want = F.adaptive_avg_pool2d(gd, (OH, OW)).permute(0, 2, 3, 1)
+    assert relerr(out[..., :3], want) < 1e-6 and float(out[..., 3].abs().max()) == 0
+
+
+def test_bicubic_reflectpad(isp):
+    src = synth.lr_features(2, 64, 9, 12, seed=2)
+    out = torch.empty(2, 24, 30, 64, device=DEV)
+    _call("isp_jbu_bicubic2x_reflectpad", src.permute(0, 2, 3, 1).contiguous().to(DEV), out, 2, 9, 12, 64)
+    want = F.pad(F.interpolate(src, size=(18, 24), mode="bicubic", align_corners=False), [3] * 4, mode="reflect")
+    assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+
+
+def test_filters_and_range_proj(isp):
+    sd = ojbu.init_state_dict(8, seed=3)
+    sd["up2.range_temp"] = torch.tensor(0.7)
+    sd["up2.sigma_spatial"] = torch.tensor(0.8)
+    g = F.adaptive_avg_pool2d((synth.image_batch(2, 60, 44, seed=1) - 0.45) / 0.225, (30, 22))
+    want = ojbu.combined_kernel(sd, "up2", g).reshape(2, 30, 22, 49)
+    g4 = torch.cat([g, torch.zeros(2, 1, 30, 22)], 1).permute(0, 2, 3, 1).contiguous().to(DEV)
+    proj = torch.empty(2, 30, 22, 32, device=DEV)
+    p = "up2"
+    w = {k: sd[f"{p}.{k}"].reshape(sd[f"{p}.{k}"].shape[0], -1).contiguous().to(DEV) if sd[f"{p}.{k}"].dim() > 1
+         else sd[f"{p}.{k}"].to(DEV) for k in ("range_proj.0.weight", "range_proj.0.bias", "range_proj.3.weight",
+                                                "range_proj.3.bias", "fixup_proj.0.weight", "fixup_proj.0.bias",
+                                                "fixup_proj.3.weight", "fixup_proj.3.bias")}
+    _call("isp_jbu_range_proj", g4, proj, 2 * 30 * 22, w["range_proj.0.weight"], w["range_proj.0.bias"],
+          w["range_proj.3.weight"], w["range_proj.3.bias"])
+    pw = F.conv2d(F.gelu(F.conv2d(g, sd[p + ".range_proj.0.weight"], sd[p + ".range_proj.0.bias"])),
+                  sd[p + ".range_proj.3.weight"], sd[p + ".range_proj.3.bias"])
+    assert relerr(proj.permute(0, 3, 1, 2), pw) < 1e-5
+    filt = torch.empty(2, 30, 22, 49, device=DEV)
+    import math
+    _call("isp_jbu_filters", proj, g4, filt, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
+          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"])
+    assert relerr(filt, want) < 1e-4
+
+
+@pytest.mark.parametrize("B,h,w,H,W", [(2, 4, 4, 64, 64), (1, 6, 9, 96, 144), (1, 8, 8, 112, 112)])
+def test_jbu_stack_module(isp, B, h, w, H, W):
+    sd = ojbu.init_state_dict(384, seed=0)
+    up = isp.JBUFeatUpUpsampler("dinov2").to(DEV).eval()
+    up.upsampler.load_state_dict(sd)
+    src = synth.lr_features(B, 384, h, w, seed=2)
+    gd = (synth.image_batch(B, H, W, seed=1) - 0.45) / 0.225
+    with torch.no_grad():
+        out = up(source=src.to(DEV), guidance=gd.to(DEV))
+        want = ojbu.jbu_stack_forward(sd, src, gd)
+    assert tuple(out.shape) == (B, 384, 16 * h, 16 * w)
+    assert relerr(out, want) < TOL
+
+
+def test_jbu_reference_shape_contract(isp):
+    """JBUFeatUp.py:36-45: [1,384,14,14] + [1,3,224,224] -> [1,384,224,224]."""
+    up = isp.JBUFeatUpUpsampler(backbone_type="dinov2").to(DEV).eval()
+    out = up(torch.rand(1, 384, 14, 14, device=DEV), torch.rand(1, 3, 224, 224, device=DEV))
+    assert tuple(out.shape) == (1, 384, 224, 224) and bool(torch.isfinite(out).all())
+    with pytest.raises(AssertionError):
+        isp.JBUFeatUpUpsampler(backbone_type="nope")
+
+
+def test_layout_bilinear_gemm(isp):
+    x = synth.lr_features(2, 96, 10, 14, seed=5)
+    xin = x.to(DEV)
+    nhwc = torch.empty(2, 10, 14, 96, device=DEV)
+    _call("isp_nchw_to_nhwc_f32", xin, nhwc, 2, 96, 10, 14, *xin.stride())
+    assert torch.equal(nhwc.cpu(), x.permute(0, 2, 3, 1))
+    from isegprobe_b200.upsamplers import bilinear_align_corners_nhwc
+    out = bilinear_align_corners_nhwc(nhwc, (23, 31))
+    want = F.interpolate(x, size=(23, 31), mode="bilinear", align_corners=True)
+    assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+    g = torch.Generator().manual_seed(1)
+    A, Wt, b = torch.randn(300, 70, generator=g), torch.randn(50, 70, generator=g), torch.randn(50, generator=g)
+    R = torch.randn(300, 50, generator=g)
+    C = torch.empty(300, 50, device=DEV)
+    _call("isp_gemm_f32_simt", A.to(DEV), Wt.to(DEV), b.to(DEV), R.to(DEV), 0.1, C, 300, 50, 70)
+    assert relerr(C, 0.1 * (A @ Wt.T + b) + R) < 1e-5
