@@ -107,6 +107,27 @@ int isp_adaptive_conv_grad_input(const float* grad_out, const float* filters, fl
 int isp_gemm_f32_simt(const float* A, const float* W, const float* bias, const float* resid, float alpha,
                       float* C, long long M, int N, int K, isp_stream_t stream);
 
+/* ---- tcgen05 tensor-core GEMM (TMA -> smem ring -> tcgen05.mma -> TMEM -> epilogue) ----
+ * D[M,N] = alpha * act(A[M,K] * W[N,K]^T + bias[N]) + resid[M,N]
+ * A, W bf16 row-major (K contiguous; lda, ldw in elements, multiples of 8); D bf16 or f32
+ * with row stride ldd >= N (columns N..ldd-1 of a written 8-column group are zeroed);
+ * resid bf16 or f32 with row stride ldr, or NULL; act: 0 none, 1 ReLU, 2 GELU(erf), 3 QuickGELU.
+ * Replaces the cuBLAS fp32 GEMMs under nn.Linear / Conv2d(1x1) in LoftUp
+ * (loftup/layers.py:161-202, loftup/loftup.py:67-70) and the ViT blocks
+ * (featurizers/dinov2/layers/attention.py:54-71, mlp.py:34-40). */
+int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
+                     long long ldd, int out_bf16, long long M, int N, int K, isp_stream_t stream);
+
+/* Implicit-GEMM 3x3 convolution, stride 1, padding 1, on the same core:
+ * X NHWC bf16 [Nimg,H,W,ldx] (Cin real channels), Wp bf16 [Cout][9][Cin_pad] with
+ * Cin_pad = ceil(Cin/64)*64 (tap-major, zero padded), Y NHWC [Nimg,H,W,ldy] bf16|f32,
+ * Y = act(conv(X) + bias).  Padding comes from TMA out-of-bounds zero fill.
+ * Replaces cuDNN under LoftUp.first_conv (loftup/loftup.py:55-65, BatchNorm folded by the
+ * caller) and ConvSegHead.convs (heads/conv_heads.py:58-66). */
+int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
+                        int Nimg, int H, int W, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,8 @@ SIGNATURES = {
     "isp_adaptive_conv_fwd_nchw": [_P, _P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_grad_input": [_P, _P, _P, _I, _I, _I, _I, _S],
     "isp_gemm_f32_simt": [_P, _P, _P, _P, _F, _P, _LL, _I, _I, _S],
+    "isp_gemm_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _F, _I, _P, _LL, _I, _LL, _I, _I, _S],
+    "isp_conv3x3_bf16_tc": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S],
 }
 
 _lib = None

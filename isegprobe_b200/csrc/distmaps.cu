@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128) prepare_input_kernel(
 using namespace isp;
 
 static int check_distmaps(const void* points, const void* out, int B, int P, int H, int W) {
-  ISP_REQUIRE(points && out, ISP_ERR_BAD_SHAPE, "distmaps: null pointer");
+  ISP_REQUIRE((points || P == 0) && out, ISP_ERR_BAD_SHAPE, "distmaps: null pointer");
   ISP_REQUIRE(B > 0 && H > 0 && W > 0 && P >= 0, ISP_ERR_BAD_SHAPE, "distmaps: bad shape B=%d P=%d H=%d W=%d", B, P, H, W);
   ISP_REQUIRE(P <= kMaxClicks, ISP_ERR_UNSUPPORTED, "distmaps: P=%d exceeds %d clicks per polarity", P, kMaxClicks);
   ISP_REQUIRE(B <= 65535, ISP_ERR_UNSUPPORTED, "distmaps: B=%d exceeds grid.z", B);

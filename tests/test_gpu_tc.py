@@ -1,0 +1,65 @@
+"""GPU parity: tcgen05 GEMM and implicit-GEMM 3x3 conv vs a plain torch fp32 reference of
+the same op on the same bf16-rounded operands (tolerance: bf16 output rounding + fp32
+accumulation order, 1e-2 relative to max; cosine >= 0.9999)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import DEV, cosine, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tc():
+    from isegprobe_b200 import tc
+    return tc
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 128), (1000, 404, 404), (4096, 384, 1536),
+                                   (333, 1152, 384), (70000, 384, 404), (128, 16, 8)])
+def test_gemm_plain(tc, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    Ap, Wp = tc.pack_linear_weight(A).to(DEV), tc.pack_linear_weight(W).to(DEV)
+    out = tc.gemm(Ap, Wp, out_dtype=torch.float32, N=N, K=K)
+    want = A.float() @ W.float().T
+    assert out.shape == (M, N)
+    assert relerr(out, want) < 1e-4, relerr(out, want)
+
+
+def test_gemm_epilogue(tc):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 777, 404, 384
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    for act, fn in (("relu", torch.relu), ("gelu", F.gelu), (None, lambda x: x)):
+        out = tc.gemm(A.to(DEV), W.to(DEV), bias=b.to(DEV), resid=R.to(DEV), alpha=0.5, act=act,
+                      out_dtype=torch.float32)
+        want = 0.5 * fn(A.float() @ W.float().T + b) + R
+        assert relerr(out, want) < 1e-4, act
+    # bf16 output with padded leading dimension, bf16 residual
+    Rb = R.to(torch.bfloat16)
+    out = tc.gemm(A.to(DEV), W.to(DEV), bias=b.to(DEV), resid=Rb.to(DEV), act=None, out_dtype=torch.bfloat16, ldd=416)
+    want = A.float() @ W.float().T + b + Rb.float()
+    assert out.shape == (M, 416) and float(out[:, 404:].abs().max()) == 0
+    assert relerr(out[:, :404].float(), want) < 1e-2 and cosine(out[:, :404].float(), want) > 0.9999
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (2, 16, 32, 128, 96), (1, 14, 18, 203, 404),
+                                            (1, 32, 64, 384, 384), (2, 9, 11, 404, 404)])
+def test_conv3x3(tc, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g)
+    ldx = tc.round_up(Cin, 8)
+    xn = torch.full((B, H, W, ldx), float("nan"), dtype=torch.bfloat16)  # pad channels are poison: must be ignored
+    xn[..., :Cin] = x.permute(0, 2, 3, 1)
+    y = tc.conv3x3(xn.to(DEV), tc.pack_conv3x3_weight(w).to(DEV), b.to(DEV), Cin, Cout, act="relu",
+                   out_dtype=torch.float32)
+    want = torch.relu(F.conv2d(x.float(), w.float(), b, padding=1)).permute(0, 2, 3, 1)
+    assert relerr(y[..., :Cout], want) < 1e-4, relerr(y[..., :Cout], want)
