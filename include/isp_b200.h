@@ -128,6 +128,63 @@ int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw,
 int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
                         int Nimg, int H, int W, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream);
 
+/* Flash-style attention on tcgen05: out = softmax(Q K^T) V, scores never leave the SM.
+ * Q bf16 [B*rows_per_img, ldq] (pre-scaled by 1/sqrt(d)), head h at column h*q_head_stride;
+ * K bf16 [B, heads, ceil128(nkeys), DKC] and Vt bf16 [B, heads, DV, ceil128(nkeys)], zero
+ * padded (see isp_repack_heads); out bf16 [B*rows_per_img, ldo], head h writes DV columns at
+ * h*o_head_stride.  variant 0: head_dim <= 64 (DKC = DV = 64); variant 1: head_dim <= 112
+ * (DKC = 128, DV = 112).  Replaces nn.MultiheadAttention in LoftUp's CrossAttentionLayer
+ * (loftup/layers.py:186-202) and Attention.forward of the ViT (dinov2/layers/attention.py:54-71). */
+int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                          void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                          int heads, int nkeys, int variant, isp_stream_t stream);
+
+/* LayerNorm over the last dim of a row-major matrix (f32 or bf16 in/out, biased variance):
+ * nn.LayerNorm in loftup/layers.py:26-35,161-202,222-228 and the channel LayerNorm :38-58.
+ * Output columns C..ldo-1 are zero-filled. */
+int isp_layernorm_rows(const void* in, int in_bf16, long long ldi, void* out, int out_bf16, long long ldo,
+                       const float* gamma, const float* beta, long long M, int C, float eps, isp_stream_t stream);
+
+/* MinMaxScaler statistics (loftup/layers.py:66-71): per-channel min/max of a 3-channel image
+ * over batch and space -> mm6 (device int[6], order-preserving encoding consumed by
+ * isp_loftup_fourier_chnorm).  sb/sc: batch/channel strides in elements; H*W must be dense. */
+int isp_minmax_per_channel(const float* img, int* mm6, int B, int H, int W, long long sb, long long sc,
+                           isp_stream_t stream);
+
+/* LoftUp query producer: MinMaxScaler -> ImplicitFeaturizer(colour, 20 freqs, learned bias) ->
+ * ChannelNorm(203) (loftup/layers.py:61-158, loftup/loftup.py:50-56) -> bf16 NHWC [B,H,W,ldo].
+ * gridr[H], gridc[W], freqs20[20]: the host's torch.linspace / torch.exp tables;
+ * bias_sin/bias_cos[100]: biases[0/1].flatten(); gamma/beta[203]. */
+int isp_loftup_fourier_chnorm(const float* img, long long sb, long long sc, long long sh, long long sw,
+                              const int* mm6, const float* gridr, const float* gridc, const float* freqs20,
+                              const float* bias_sin, const float* bias_cos, const float* gamma,
+                              const float* beta, void* out_bf16, int B, int H, int W, int ldo, float eps,
+                              isp_stream_t stream);
+
+/* LoftUp key/value source: optional ChannelNorm(C) of the LR features (loftup.py:141-149)
+ * concatenated with the 20-channel sine PE of the LR grid (loftup.py:113-118):
+ * lr [B,C,h,w] f32 (strided) -> out f32 [B*h*w, C+20].  cn_w/cn_b may be NULL. */
+int isp_loftup_lr_prepare(const float* lr, long long sb, long long sc, long long sh, long long sw,
+                          const float* cn_w, const float* cn_b, const float* gridr, const float* gridc,
+                          const float* freqs5, const float* bias_sin, const float* bias_cos, float* out,
+                          int B, int C, int h, int w, float eps, isp_stream_t stream);
+
+/* Split heads out of a [B*T, ld] projection (columns col0 + head*head_dim + d) into the
+ * attention kernel's operand layouts: transpose == 0 -> [B, heads, Tpad, D] (keys),
+ * transpose == 1 -> [B, heads, D, Tpad] (values, transposed); bf16, zero padded. */
+int isp_repack_heads(const void* src, int src_bf16, long long ld, int col0, int head_dim, void* dst_bf16,
+                     int B, int T, int Tpad, int heads, int D, int transpose, isp_stream_t stream);
+
+/* ViT patch embedding front half: [B,Cin,H,W] f32 -> bf16 [B*(H/P)*(W/P), ldo], column order
+ * c*P*P + i*P + j (Conv2d(k=s=P) weight flattening; dinov2/layers/patch_embed.py:25-100,
+ * featurizers/utils/patch_embed.py:36-42). */
+int isp_vit_patchify(const float* img, long long sb, long long sc, long long sh, long long sw, void* out_bf16,
+                     int B, int Cin, int H, int W, int P, int ldo, isp_stream_t stream);
+
+/* ViT token assembly (DINOv2.py:518-529): out[b,0]=cls+pos[0]; out[b,1+n]=patch[b,n]+extra[b,n]+pos[1+n] */
+int isp_vit_assemble_tokens(const float* patch, const float* extra, const float* cls, const float* pos,
+                            float* out, int B, int N, int C, isp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,14 @@ SIGNATURES = {
     "isp_gemm_f32_simt": [_P, _P, _P, _P, _F, _P, _LL, _I, _I, _S],
     "isp_gemm_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _F, _I, _P, _LL, _I, _LL, _I, _I, _S],
     "isp_conv3x3_bf16_tc": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S],
+    "isp_attention_bf16_tc": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _S],
+    "isp_layernorm_rows": [_P, _I, _LL, _P, _I, _LL, _P, _P, _LL, _I, _F, _S],
+    "isp_minmax_per_channel": [_P, _P, _I, _I, _I, _LL, _LL, _S],
+    "isp_loftup_fourier_chnorm": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _S],
+    "isp_loftup_lr_prepare": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _S],
+    "isp_repack_heads": [_P, _I, _LL, _I, _I, _P, _I, _I, _I, _I, _I, _I, _S],
+    "isp_vit_patchify": [_P, _LL, _LL, _LL, _LL, _P, _I, _I, _I, _I, _I, _I, _S],
+    "isp_vit_assemble_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _S],
 }
 
 _lib = None

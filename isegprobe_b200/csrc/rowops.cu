@@ -1,0 +1,346 @@
+// Row-wise / elementwise producers and consumers around the tensor-core kernels:
+// LayerNorm over channels, LoftUp's Fourier-feature + ChannelNorm producer, batch-global
+// min/max, low-res key/value preparation, attention operand repacking, ViT patchify.
+// All bandwidth-bound; one warp per row with 128-bit accesses where the layout allows.
+#include "common.cuh"
+
+namespace isp {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float ld_any(const void* p, long long i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, long long i, float v, int is_bf16) {
+  if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm over the last dim of a row-major matrix (nn.LayerNorm / loftup layers.py:26-58):
+// y = (x - mean) / sqrt(biased_var + eps) * gamma + beta.  One warp per row, C <= 1024.
+// Columns C..ldo-1 of the output row are zero-filled (K padding for the next GEMM).
+constexpr int kLnMaxPerLane = 32;
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const void* __restrict__ in, int in_bf16, long long ldi,
+                                                             void* __restrict__ out, int out_bf16, long long ldo,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long M, int C,
+                                                             float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float x[kLnMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    x[i] = (c < C) ? ld_any(in, row * ldi + c, in_bf16) : 0.f;
+    s += x[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    const float d = (c < C) ? x[i] - mean : 0.f;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) st_any(out, row * ldo + c, (x[i] - mean) * rstd * gamma[c] + beta[c], out_bf16);
+    else if (c < ldo) st_any(out, row * ldo + c, 0.f, out_bf16);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-channel min / max of a [B,3,H,W] image over batch + space (MinMaxScaler,
+// loftup/layers.py:66-71).  mm[0..2] = min, mm[3..5] = max; order-preserving int atomics.
+__device__ __forceinline__ int float_ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int* mm) {
+  if (threadIdx.x < 3) mm[threadIdx.x] = float_ord(INFINITY);
+  else if (threadIdx.x < 6) mm[threadIdx.x] = float_ord(-INFINITY);
+}
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ img, int* __restrict__ mm, int B,
+                                                     long long HW, long long sb, long long sc) {
+  const int c = blockIdx.y;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int b = 0; b < B; ++b) {
+    const float* p = img + b * sb + c * sc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+      const float v = p[i];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[c], float_ord(mn));
+    atomicMax(&mm[3 + c], float_ord(mx));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LoftUp query producer: MinMaxScaler -> ImplicitFeaturizer(color, 20 freqs, learned bias)
+// -> ChannelNorm(203)  (loftup/layers.py:61-158, loftup/loftup.py:50-56), one warp per pixel,
+// output bf16 NHWC [B,H,W,ldo] (203 real channels, rest zero).  fp32 throughout; the
+// argument u*f + b is formed with explicit mul/add (no FMA contraction) and accurate
+// sinf/cosf because |u*f| reaches 2.2e4.  gridr/gridc/freqs are the host's
+// torch.linspace / torch.exp values so the reference's CPU rounding is reproduced exactly.
+__global__ void __launch_bounds__(256) fourier_chnorm_kernel(
+    const float* __restrict__ img, long long sb, long long sc, long long sh, long long sw, const int* __restrict__ mm,
+    const float* __restrict__ gridr, const float* __restrict__ gridc, const float* __restrict__ freqs,
+    const float* __restrict__ bias_sin, const float* __restrict__ bias_cos, const float* __restrict__ gamma,
+    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int B, int H, int W, int ldo, float eps) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * H * W;
+  if (pix >= total) return;
+  const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float u[5];
+  u[0] = gridr[h];
+  u[1] = gridc[w];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float mn = ord_float(mm[c]), mx = ord_float(mm[3 + c]);
+    const float sc_ = fmaxf(__fsub_rn(mx, mn), 1e-4f);
+    const float x = img[b * sb + c * sc + h * sh + w * sw];
+    u[2 + c] = __fsub_rn(__fdiv_rn(__fsub_rn(x, mn), sc_), 0.5f);
+  }
+  float val[7];  // channels lane, lane+32, ..., lane+192
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int c = lane + i * 32;
+    float v = 0.f;
+    if (c < 200) {
+      const int cc = c < 100 ? c : c - 100;
+      const int f = cc / 5, d = cc - f * 5;
+      float ud = u[0];
+      ud = d == 1 ? u[1] : ud; ud = d == 2 ? u[2] : ud; ud = d == 3 ? u[3] : ud; ud = d == 4 ? u[4] : ud;
+      const float arg = __fadd_rn(__fmul_rn(ud, freqs[f]), c < 100 ? bias_sin[cc] : bias_cos[cc]);
+      v = c < 100 ? sinf(arg) : cosf(arg);
+    } else if (c < 203) {
+      v = c == 200 ? u[2] : (c == 201 ? u[3] : u[4]);
+    }
+    val[i] = v;
+    s += v;
+  }
+  const float mean = warp_sum(s) / 203.f;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int c = lane + i * 32;
+    const float d = c < 203 ? val[i] - mean : 0.f;
+    var += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(var) / 203.f + eps);
+  __nv_bfloat16* o = out + pix * ldo;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int c = lane + i * 32;
+    if (c < 203) o[c] = __float2bfloat16((val[i] - mean) * rstd * gamma[c] + beta[c]);
+    else if (c < ldo) o[c] = __float2bfloat16(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LoftUp key/value source: ChannelNorm(C) on the LR features (wrapper, loftup.py:141-149),
+// then cat with the 20-channel sine PE of the LR grid (loftup.py:115-118) -> fp32 [B*h*w, C+20].
+// One warp per LR pixel; lr is [B,C,h,w] with arbitrary strides.
+__global__ void __launch_bounds__(256) lr_prepare_kernel(const float* __restrict__ lr, long long sb, long long sc,
+                                                         long long sh, long long sw, const float* __restrict__ cn_w,
+                                                         const float* __restrict__ cn_b, int use_cn,
+                                                         const float* __restrict__ gridr, const float* __restrict__ gridc,
+                                                         const float* __restrict__ freqs5,
+                                                         const float* __restrict__ bias_sin,
+                                                         const float* __restrict__ bias_cos, float* __restrict__ out,
+                                                         int B, int C, int h, int w, float eps) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)B * h * w) return;
+  const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((long long)w * h));
+  const float* p = lr + b * sb + y * sh + x * sw;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += p[c * sc];
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = p[c * sc] - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+  float* o = out + pix * (C + 20);
+  for (int c = lane; c < C; c += 32) {
+    const float val = p[c * sc];
+    o[c] = use_cn ? (val - mean) * rstd * cn_w[c] + cn_b[c] : val;
+  }
+  if (lane < 20) {  // channel f*2+d: sin (0..9) then cos (10..19)
+    const int cc = lane < 10 ? lane : lane - 10;
+    const int f = cc >> 1, d = cc & 1;
+    const float arg = __fadd_rn(__fmul_rn(d ? gridc[x] : gridr[y], freqs5[f]), lane < 10 ? bias_sin[cc] : bias_cos[cc]);
+    o[C + lane] = lane < 10 ? sinf(arg) : cosf(arg);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Attention operand repack.  src: [B*T, ld] (f32|bf16) holding per-head slices at column
+// col0 + head*hd.  Writes K-style [B, heads, Tpad, DKC] (row = token, zero padded) when
+// transpose == 0, or V^T-style [B, heads, DV, Tpad] when transpose == 1 (bf16).
+__global__ void __launch_bounds__(256) repack_heads_kernel(const void* __restrict__ src, int src_bf16, long long ld,
+                                                           int col0, int hd, __nv_bfloat16* __restrict__ dst, int B,
+                                                           int T, int Tpad, int heads, int D, int transpose) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * heads * Tpad * D;
+  if (idx >= total) return;
+  int t, d;
+  long long bh;
+  if (!transpose) { d = (int)(idx % D); t = (int)((idx / D) % Tpad); bh = idx / ((long long)D * Tpad); }
+  else { t = (int)(idx % Tpad); d = (int)((idx / Tpad) % D); bh = idx / ((long long)D * Tpad); }
+  const int hh = (int)(bh % heads), b = (int)(bh / heads);
+  float v = 0.f;
+  if (t < T && d < hd) v = ld_any(src, ((long long)b * T + t) * ld + col0 + hh * hd + d, src_bf16);
+  dst[idx] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------
+// ViT patchify: [B,Cin,H,W] f32 (strided) -> bf16 [B*nh*nw, ldo], column = c*p*p + i*p + j
+// (the flattening order of Conv2d(k=s=p) weights), zero padded to ldo.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, long long sb, long long sc,
+                                                       long long sh, long long sw, __nv_bfloat16* __restrict__ out,
+                                                       int B, int Cin, int H, int W, int P, int ldo) {
+  const int nh = H / P, nw = W / P, K = Cin * P * P;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * nh * nw * ldo;
+  if (idx >= total) return;
+  const int k = (int)(idx % ldo);
+  const long long tok = idx / ldo;
+  float v = 0.f;
+  if (k < K) {
+    const int j = k % P, i = (k / P) % P, c = k / (P * P);
+    const int px = (int)(tok % nw), py = (int)((tok / nw) % nh), b = (int)(tok / ((long long)nw * nh));
+    v = img[b * sb + c * sc + (py * P + i) * sh + (px * P + j) * sw];
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+// ViT token assembly: x[b,0,:] = cls + pos[0]; x[b,1+n,:] = patch[b,n,:] (+ extra[b,n,:]) + pos[1+n]
+// (DINOv2.py:518-529).  fp32 out [B, T, C].
+__global__ void __launch_bounds__(256) vit_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ extra,
+                                                         const float* __restrict__ cls, const float* __restrict__ pos,
+                                                         float* __restrict__ out, int B, int N, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * (N + 1) * C;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int t = (int)((idx / C) % (N + 1));
+  const int b = (int)(idx / ((long long)C * (N + 1)));
+  float v;
+  if (t == 0) v = cls[c];
+  else {
+    const long long src = ((long long)b * N + (t - 1)) * C + c;
+    v = patch[src] + (extra ? extra[src] : 0.f);
+  }
+  out[idx] = v + pos[(long long)t * C + c];
+}
+
+}  // namespace isp
+
+using namespace isp;
+
+extern "C" int isp_layernorm_rows(const void* in, int in_bf16, long long ldi, void* out, int out_bf16, long long ldo,
+                                  const float* gamma, const float* beta, long long M, int C, float eps,
+                                  isp_stream_t stream) {
+  ISP_REQUIRE(in && out && gamma && beta, ISP_ERR_BAD_SHAPE, "layernorm_rows: null pointer");
+  ISP_REQUIRE(M > 0 && C > 0 && C <= 32 * kLnMaxPerLane && ldi >= C && ldo >= C && ldo <= 32 * kLnMaxPerLane,
+              ISP_ERR_BAD_SHAPE, "layernorm_rows: bad shape M=%lld C=%d ldi=%lld ldo=%lld", M, C, ldi, ldo);
+  layernorm_rows_kernel<<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(in, in_bf16, ldi, out, out_bf16, ldo, gamma, beta, M,
+                                                                 C, eps);
+  ISP_CHECK_LAUNCH("layernorm_rows_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_minmax_per_channel(const float* img, int* mm6, int B, int H, int W, long long sb, long long sc,
+                                      isp_stream_t stream) {
+  ISP_REQUIRE(img && mm6 && B > 0 && H > 0 && W > 0, ISP_ERR_BAD_SHAPE, "minmax_per_channel: bad arguments");
+  minmax_init_kernel<<<1, 32, 0, as_stream(stream)>>>(mm6);
+  ISP_CHECK_LAUNCH("minmax_init_kernel");
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)min((long long)296, (HW + 255) / 256), 3);
+  minmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, mm6, B, HW, sb, sc);
+  ISP_CHECK_LAUNCH("minmax_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_loftup_fourier_chnorm(const float* img, long long sb, long long sc, long long sh, long long sw,
+                                         const int* mm6, const float* gridr, const float* gridc, const float* freqs20,
+                                         const float* bias_sin, const float* bias_cos, const float* gamma,
+                                         const float* beta, void* out_bf16, int B, int H, int W, int ldo, float eps,
+                                         isp_stream_t stream) {
+  ISP_REQUIRE(img && mm6 && gridr && gridc && freqs20 && bias_sin && bias_cos && gamma && beta && out_bf16,
+              ISP_ERR_BAD_SHAPE, "loftup_fourier_chnorm: null pointer");
+  ISP_REQUIRE(B > 0 && H > 0 && W > 0 && ldo >= 203 && ldo <= 224, ISP_ERR_BAD_SHAPE,
+              "loftup_fourier_chnorm: bad shape (ldo must be in [203,224])");
+  const long long total = (long long)B * H * W;
+  fourier_chnorm_kernel<<<cdiv(total, 8), 256, 0, as_stream(stream)>>>(
+      img, sb, sc, sh, sw, mm6, gridr, gridc, freqs20, bias_sin, bias_cos, gamma, beta,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), B, H, W, ldo, eps);
+  ISP_CHECK_LAUNCH("fourier_chnorm_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_loftup_lr_prepare(const float* lr, long long sb, long long sc, long long sh, long long sw,
+                                     const float* cn_w, const float* cn_b, const float* gridr, const float* gridc,
+                                     const float* freqs5, const float* bias_sin, const float* bias_cos, float* out,
+                                     int B, int C, int h, int w, float eps, isp_stream_t stream) {
+  ISP_REQUIRE(lr && gridr && gridc && freqs5 && bias_sin && bias_cos && out, ISP_ERR_BAD_SHAPE,
+              "loftup_lr_prepare: null pointer");
+  ISP_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, ISP_ERR_BAD_SHAPE, "loftup_lr_prepare: bad shape");
+  const long long total = (long long)B * h * w;
+  lr_prepare_kernel<<<cdiv(total, 8), 256, 0, as_stream(stream)>>>(lr, sb, sc, sh, sw, cn_w, cn_b, cn_w != nullptr, gridr,
+                                                                 gridc, freqs5, bias_sin, bias_cos, out, B, C, h, w, eps);
+  ISP_CHECK_LAUNCH("lr_prepare_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_repack_heads(const void* src, int src_bf16, long long ld, int col0, int head_dim, void* dst_bf16,
+                                int B, int T, int Tpad, int heads, int D, int transpose, isp_stream_t stream) {
+  ISP_REQUIRE(src && dst_bf16, ISP_ERR_BAD_SHAPE, "repack_heads: null pointer");
+  ISP_REQUIRE(B > 0 && T > 0 && Tpad >= T && heads > 0 && D >= head_dim && head_dim > 0, ISP_ERR_BAD_SHAPE,
+              "repack_heads: bad shape");
+  const long long total = (long long)B * heads * Tpad * D;
+  repack_heads_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, src_bf16, ld, col0, head_dim,
+                                                                     reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, T,
+                                                                     Tpad, heads, D, transpose);
+  ISP_CHECK_LAUNCH("repack_heads_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_vit_patchify(const float* img, long long sb, long long sc, long long sh, long long sw, void* out_bf16,
+                                int B, int Cin, int H, int W, int P, int ldo, isp_stream_t stream) {
+  ISP_REQUIRE(img && out_bf16, ISP_ERR_BAD_SHAPE, "vit_patchify: null pointer");
+  ISP_REQUIRE(B > 0 && Cin > 0 && P > 0 && H >= P && W >= P && ldo >= Cin * P * P, ISP_ERR_BAD_SHAPE,
+              "vit_patchify: bad shape");
+  const long long total = (long long)B * (H / P) * (W / P) * ldo;
+  patchify_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(img, sb, sc, sh, sw,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, H, W,
+                                                                 P, ldo);
+  ISP_CHECK_LAUNCH("patchify_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_vit_assemble_tokens(const float* patch, const float* extra, const float* cls, const float* pos,
+                                       float* out, int B, int N, int C, isp_stream_t stream) {
+  ISP_REQUIRE(patch && cls && pos && out && B > 0 && N > 0 && C > 0, ISP_ERR_BAD_SHAPE, "vit_assemble_tokens: bad arguments");
+  const long long total = (long long)B * (N + 1) * C;
+  vit_tokens_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(patch, extra, cls, pos, out, B, N, C);
+  ISP_CHECK_LAUNCH("vit_tokens_kernel");
+  return ISP_OK;
+}

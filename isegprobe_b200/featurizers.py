@@ -1,0 +1,218 @@
+"""Frozen ViT backbone and the trainable click-map patch embedding on libisp_b200.
+
+`DINOv2Featurizer` mirrors the reference adapter (core/model/featurizers/DINOv2.py:468-546):
+same constructor, `forward(x, additional_features)`, `[B, C, h, w]` output, click-embedding
+injection before the blocks.  The reference hub-loads `dinov2_vits14` (network); here the
+ViT-S/14 is built locally with the hub/vendored parameter names (`model.blocks.{i}...`,
+SURVEY Appendix A.5) so that checkpoint loads with `load_state_dict`, random-init otherwise.
+
+Per block (dinov2/layers/block.py:92-117): LN -> QKV GEMM -> tcgen05 flash attention ->
+proj GEMM (+LayerScale, +residual) -> LN -> fc1 GEMM + GELU -> fc2 GEMM (+LayerScale, +residual).
+LayerScale and the 1/sqrt(d) query scale are folded into the packed weights.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, tc
+
+
+def _call(name, *a):
+    _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
+
+
+def _ln(x, w, b, C, eps, out_dtype, ldo=None):
+    ldo = C if ldo is None else ldo
+    out = torch.empty(x.shape[0], ldo, dtype=out_dtype, device=x.device)
+    _call("isp_layernorm_rows", x, int(x.dtype == torch.bfloat16), x.stride(0), out, int(out_dtype == torch.bfloat16),
+          ldo, w, b, x.shape[0], C, float(eps))
+    return out
+
+
+class PatchEmbed(nn.Module):
+    """Click-map embedding Conv2d(in_chans -> D, k = s = patch) -> [B, N, D]
+    (core/model/featurizers/utils/patch_embed.py:12-42); same ctor and parameter names."""
+
+    def __init__(self, img_size=(224, 224), patch_size=(16, 16), in_chans=3, embed_dim=768, norm_layer=None,
+                 flatten=True):
+        super().__init__()
+        self.in_chans, self.img_size, self.patch_size = in_chans, img_size, patch_size
+        self.grid_size = (img_size[0] // patch_size[0], img_size[1] // patch_size[1])
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.flatten = flatten
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
+        self._packed = None
+
+    def _pack(self, dev):
+        key = (str(dev), self.proj.weight._version, self.proj.bias._version)
+        if self._packed is None or self._packed[0] != key:
+            w = self.proj.weight.detach().float().reshape(self.proj.weight.shape[0], -1)
+            self._packed = (key, tc.pack_linear_weight(w).to(dev), self.proj.bias.detach().float().to(dev))
+        return self._packed[1], self._packed[2]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and self.proj.weight.requires_grad and self.training:
+            raise NotImplementedError("PatchEmbed: weight gradient is not implemented yet")
+        x = x.detach().float()
+        B, Cin, H, W = x.shape
+        p = self.patch_size[0]
+        K = Cin * p * p
+        Wp, b = self._pack(x.device)
+        N = (H // p) * (W // p)
+        cols = torch.empty(B * N, Wp.shape[1], dtype=torch.bfloat16, device=x.device)
+        _call("isp_vit_patchify", x, *x.stride(), cols, B, Cin, H, W, p, Wp.shape[1])
+        y = tc.gemm(cols, Wp, bias=b, out_dtype=torch.float32, K=K)
+        y = y.view(B, N, -1)
+        if not self.flatten:
+            y = y.transpose(1, 2).reshape(B, -1, H // p, W // p)
+        return self.norm(y)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio=4):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = nn.Module()
+        self.attn.qkv = nn.Linear(dim, 3 * dim)
+        self.attn.proj = nn.Linear(dim, dim)
+        self.ls1 = nn.Module()
+        self.ls1.gamma = nn.Parameter(torch.ones(dim))
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = nn.Module()
+        self.mlp.fc1 = nn.Linear(dim, mlp_ratio * dim)
+        self.mlp.fc2 = nn.Linear(mlp_ratio * dim, dim)
+        self.ls2 = nn.Module()
+        self.ls2.gamma = nn.Parameter(torch.ones(dim))
+
+
+class _ViT(nn.Module):
+    """Parameter container with DinoVisionTransformer's names (DINOv2.py:53-160)."""
+
+    def __init__(self, dim=384, depth=12, heads=6, patch=14, img_size=518):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.patch_size = dim, heads, patch
+        n = (img_size // patch) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, dim))
+        self.mask_token = nn.Parameter(torch.zeros(1, dim))
+        self.patch_embed = nn.Module()
+        self.patch_embed.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+        self.blocks = nn.ModuleList([_Block(dim, heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.normal_(self.cls_token, std=1e-6)
+
+
+class DINOv2Featurizer(nn.Module):
+    def __init__(self, arch: str = "dinov2_vits14", feats_injection_mode: str = "no_injection") -> None:
+        super().__init__()
+        self.arch, self.feats_injection_mode = arch, feats_injection_mode
+        if arch != "dinov2_vits14":
+            raise NotImplementedError(f"Only 'dinov2_vits14' is supported, got {arch}")
+        if feats_injection_mode not in ("no_injection", "before_backbone", "after_backbone"):
+            raise NameError(f"Unknown feats_injection_mode: {feats_injection_mode}")
+        self.model = _ViT()
+        self.patch_size = self.model.patch_size
+        self._packed = None
+        self._pos_cache = {}
+
+    def _version(self):
+        return sum(p._version for p in self.parameters())
+
+    def _pack(self, dev):
+        key = (str(dev), self._version())
+        if self._packed is not None and self._packed["key"] == key:
+            return self._packed
+        m = self.model
+        C, nh = m.embed_dim, m.num_heads
+        f32 = lambda t: t.detach().float().contiguous().to(dev)
+        P = {"key": key}
+        P["Wpe"] = tc.pack_linear_weight(m.patch_embed.proj.weight.detach().float().reshape(C, -1)).to(dev)
+        P["bpe"] = f32(m.patch_embed.proj.bias)
+        P["cls"] = f32(m.cls_token.reshape(-1))
+        blocks = []
+        sc = (C // nh) ** -0.5
+        for blk in m.blocks:
+            Wqkv, bqkv = blk.attn.qkv.weight.detach().float().clone(), blk.attn.qkv.bias.detach().float().clone()
+            Wqkv[:C] *= sc  # attention.py:66: q * scale
+            bqkv[:C] *= sc
+            g1, g2 = blk.ls1.gamma.detach().float(), blk.ls2.gamma.detach().float()
+            blocks.append({
+                "n1w": f32(blk.norm1.weight), "n1b": f32(blk.norm1.bias),
+                "Wqkv": tc.pack_linear_weight(Wqkv).to(dev), "bqkv": f32(bqkv),
+                "Wproj": tc.pack_linear_weight(blk.attn.proj.weight.detach().float() * g1[:, None]).to(dev),
+                "bproj": f32(blk.attn.proj.bias.detach().float() * g1),
+                "n2w": f32(blk.norm2.weight), "n2b": f32(blk.norm2.bias),
+                "W1": tc.pack_linear_weight(blk.mlp.fc1.weight).to(dev), "b1": f32(blk.mlp.fc1.bias),
+                "W2": tc.pack_linear_weight(blk.mlp.fc2.weight.detach().float() * g2[:, None]).to(dev),
+                "b2": f32(blk.mlp.fc2.bias.detach().float() * g2),
+            })
+        P["blocks"] = blocks
+        P["nw"], P["nb"] = f32(m.norm.weight), f32(m.norm.bias)
+        self._packed = P
+        self._pos_cache = {}
+        return P
+
+    def _pos(self, H, W, dev):
+        """interpolate_pos_encoding (DINOv2.py:199-230): bicubic resize of the patch position
+        table with the +0.1 scale-factor quirk.  Parameter preprocessing, cached per size."""
+        key = (H, W, str(dev), self.model.pos_embed._version)
+        if key not in self._pos_cache:
+            pe = self.model.pos_embed.detach().float().cpu()
+            N = pe.shape[1] - 1
+            p = self.patch_size
+            if (H // p) * (W // p) == N and H == W:
+                out = pe
+            else:
+                w0, h0 = H // p + 0.1, W // p + 0.1  # reference passes (input_h, input_w) as (w, h)
+                s = int(math.sqrt(N))
+                pp = F.interpolate(pe[:, 1:].reshape(1, s, s, -1).permute(0, 3, 1, 2),
+                                   scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+                out = torch.cat([pe[:, :1], pp.permute(0, 2, 3, 1).reshape(1, -1, pe.shape[-1])], 1)
+            self._pos_cache[key] = out.reshape(-1, pe.shape[-1]).contiguous().to(dev)
+        return self._pos_cache[key]
+
+    def forward(self, x, additional_features=None):
+        x = x.detach().float()
+        dev = x.device
+        B, _, H, W = x.shape
+        p = self.patch_size
+        h, w = H // p, W // p
+        m = self.model
+        C, nh = m.embed_dim, m.num_heads
+        P = self._pack(dev)
+        inject = additional_features is not None and self.feats_injection_mode != "no_injection"
+        extra = None
+        if inject and self.feats_injection_mode == "before_backbone":
+            extra = additional_features.detach().float().contiguous()
+            assert tuple(extra.shape) == (B, h * w, C), f"x.shape: {(B, h * w, C)}, additional_features.shape: {tuple(extra.shape)}"
+        N, T = h * w, h * w + 1
+        cols = torch.empty(B * N, P["Wpe"].shape[1], dtype=torch.bfloat16, device=dev)
+        _call("isp_vit_patchify", x, *x.stride(), cols, B, 3, H, W, p, P["Wpe"].shape[1])
+        patch = tc.gemm(cols, P["Wpe"], bias=P["bpe"], out_dtype=torch.float32, K=3 * p * p)
+        xs = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+        _call("isp_vit_assemble_tokens", patch, extra, P["cls"], self._pos(H, W, dev), xs, B, N, C)
+        Tp = tc.round_up(T, 128)
+        hd = C // nh
+        bf = torch.bfloat16
+        for L in P["blocks"]:
+            hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-6, bf)
+            qkv = tc.gemm(hn, L["Wqkv"], bias=L["bqkv"], out_dtype=bf)
+            Kp = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
+            Vt = torch.empty(B, nh, 64, Tp, dtype=bf, device=dev)
+            _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Kp, B, T, Tp, nh, 64, 0)
+            _call("isp_repack_heads", qkv, 1, 3 * C, 2 * C, hd, Vt, B, T, Tp, nh, 64, 1)
+            O = torch.empty(B * T, C, dtype=bf, device=dev)
+            _call("isp_attention_bf16_tc", qkv, 3 * C, hd, Kp, Vt, O, C, hd, B, T, nh, T, 0)
+            xs = tc.gemm(O, L["Wproj"], bias=L["bproj"], resid=xs, out_dtype=torch.float32)
+            hn = _ln(xs, L["n2w"], L["n2b"], C, 1e-6, bf)
+            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu", out_dtype=bf)
+            xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
+        xn = _ln(xs, P["nw"], P["nb"], C, 1e-6, torch.float32)
+        feats = xn.view(B, T, C)[:, 1:]
+        if inject and self.feats_injection_mode == "after_backbone":
+            feats = feats + additional_features.to(feats.dtype)
+        return feats.reshape(B, h, w, C).permute(0, 3, 1, 2)

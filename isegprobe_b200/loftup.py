@@ -1,0 +1,264 @@
+"""LoftUp upsampler on the tcgen05 kernels -- same plugin surface as the reference
+`LoftUpUpsampler(upsampler_path, n_dim, lr_pe_type, lr_size)`
+(core/model/upsamplers/LoftUp.py:10-24) and the same state-dict layout as
+`UpsamplerwithChannelNorm(LoftUp(dim), ChannelNorm(dim))`
+(core/model/upsamplers/loftup/loftup.py:16-98,141-177), so reference checkpoints load.
+
+Pipeline (bf16 tensors, fp32 accumulation / statistics), all in libisp_b200:
+  image --minmax, Fourier features, ChannelNorm(203)--> bf16 NHWC
+        --conv3x3+BN+ReLU x2 (implicit GEMM, BN folded)--> queries x [B*HW, 404]
+  LR    --ChannelNorm, sine PE--> kv [B*hw, 404] --LN, K/V projections, head repack-->
+  2 x { x += out_proj(attention(q_proj(LN x), K, V)) ; x += W2 gelu(W1 LN x) }
+  LN --conv1x1 404->384--> channel LayerNorm(1e-6) --> [B,384,H,W] fp32 (NHWC memory)
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, tc
+from .upsamplers import BaseUpsampler
+
+
+# ------------------------------------------------------------------ parameter containers
+class _ChannelNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+
+class _Biases(nn.Module):
+    def __init__(self, dm, n_freqs):
+        super().__init__()
+        self.biases = nn.Parameter(torch.randn(2, dm, n_freqs))
+
+
+class _LN2d(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class _CrossAttention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.norm_q = nn.LayerNorm(dim)
+        self.norm_kv = nn.LayerNorm(dim)
+        self.attention = nn.MultiheadAttention(embed_dim=dim, num_heads=heads)  # parameter holder only
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.0),
+                                 nn.Linear(hidden, dim), nn.Dropout(0.0))
+
+
+class _CATransformer(nn.Module):
+    def __init__(self, dim, depth, heads, mlp_dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.layers = nn.ModuleList([nn.ModuleList([_CrossAttention(dim, heads), _FeedForward(dim, mlp_dim)])
+                                     for _ in range(depth)])
+
+
+class _LoftUpParams(nn.Module):
+    """Same keys/shapes as reference LoftUp(dim, lr_pe_type='sine').state_dict()."""
+
+    def __init__(self, dim, n_freqs=20, heads=4, depth=2):
+        super().__init__()
+        D = dim + 20
+        start = 5 * n_freqs * 2 + 3
+        self.lr_pe = _Biases(2, 5)
+        self.fourier_feat = nn.Sequential(nn.Identity(), _Biases(5, n_freqs))
+        self.first_conv = nn.Sequential(_ChannelNorm(start), nn.Conv2d(start, D, 3, padding=1), nn.BatchNorm2d(D),
+                                        nn.ReLU(inplace=True), nn.Conv2d(D, D, 3, padding=1), nn.BatchNorm2d(D),
+                                        nn.ReLU(inplace=True))
+        self.final_conv = nn.Sequential(nn.Conv2d(D, dim, 1), _LN2d(dim))
+        self.ca_transformer = _CATransformer(D, depth, heads, dim)
+
+
+class _UpsamplerWithChannelNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.upsampler = _LoftUpParams(dim)
+        self.channelnorm = _ChannelNorm(dim)
+
+
+def _call(name, *a):
+    _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
+
+
+class LoftUpUpsampler(BaseUpsampler):
+    """`upsampler_path=None` (extension) keeps the random initialisation -- the reference
+    always torch.load()s (loftup.py:155), benchmarks here use random-init weights."""
+
+    HEADS = 4
+    chunk_images = 4  # images per internal pass (bounds the [B*HW, 416] intermediates)
+
+    def __init__(self, upsampler_path: str = None, n_dim: int = 384, lr_pe_type: str = "sine", lr_size: int = 16):
+        super().__init__()
+        if lr_pe_type != "sine":
+            raise NotImplementedError("only lr_pe_type='sine' is implemented (no shipped config uses 'learnable')")
+        self.n_dim = n_dim
+        self.upsampler = _UpsamplerWithChannelNorm(n_dim)
+        if upsampler_path is not None:
+            self.load_reference_checkpoint(torch.load(upsampler_path, map_location="cpu")["state_dict"])
+        for p in self.parameters():
+            p.requires_grad = False
+        self._packed = None
+
+    def load_reference_checkpoint(self, ckpt):
+        """Key remap of load_loftup_checkpoint (loftup.py:152-177)."""
+        cn = {k.replace("model.1.", ""): v for k, v in ckpt.items() if "model.1" in k}
+        up = {k.replace("upsampler.", "", 1): v for k, v in ckpt.items() if k.startswith("upsampler")}
+        self.upsampler.upsampler.load_state_dict(up)
+        self.upsampler.channelnorm.load_state_dict(cn)
+        self._packed = None
+
+    # ---------------------------------------------------------------- weight packing
+    def _version(self):
+        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+
+    def _pack(self, dev):
+        key = (str(dev), self._version())
+        if self._packed is not None and self._packed["key"] == key:
+            return self._packed
+        up = self.upsampler.upsampler
+        D = self.n_dim + 20
+        hd = D // self.HEADS
+        f32 = lambda t: t.detach().float().contiguous().to(dev)
+        P = {"key": key, "D": D, "hd": hd}
+
+        def fold_bn(conv, bn):
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            w = conv.weight.detach().float() * s[:, None, None, None]
+            b = (conv.bias.detach().float() - bn.running_mean.float()) * s + bn.bias.detach().float()
+            return tc.pack_conv3x3_weight(w).to(dev), f32(b)
+
+        fc = up.first_conv
+        P["cn203_w"], P["cn203_b"] = f32(fc[0].norm.weight), f32(fc[0].norm.bias)
+        P["conv1_w"], P["conv1_b"] = fold_bn(fc[1], fc[2])
+        P["conv2_w"], P["conv2_b"] = fold_bn(fc[4], fc[5])
+        fb = up.fourier_feat[1].biases.detach().float()
+        P["fb_sin"], P["fb_cos"] = f32(fb[0].flatten()), f32(fb[1].flatten())
+        lb = up.lr_pe.biases.detach().float()
+        P["lb_sin"], P["lb_cos"] = f32(lb[0].flatten()), f32(lb[1].flatten())
+        # reference computes these tables with torch on the host dtype/device of the image; we pin the
+        # CPU values (the oracle's) so results do not depend on the GPU's expf rounding
+        P["freqs20"] = f32(torch.exp(torch.linspace(-2, 10, 20)))
+        P["freqs5"] = f32(torch.exp(torch.linspace(-2, 10, 5)))
+        cn = self.upsampler.channelnorm.norm
+        P["cn_w"], P["cn_b"] = f32(cn.weight), f32(cn.bias)
+        layers = []
+        for ca, ff in up.ca_transformer.layers:
+            Wi, bi = ca.attention.in_proj_weight.detach().float(), ca.attention.in_proj_bias.detach().float()
+            sc = 1.0 / math.sqrt(hd)
+            Wo = ca.attention.out_proj.weight.detach().float()
+            Wo_p = torch.zeros(D, self.HEADS * 112)
+            Wq_p, bq_p = torch.zeros(self.HEADS * 112, D), torch.zeros(self.HEADS * 112)
+            for h in range(self.HEADS):  # Q and the attention output are head-padded to 112 columns
+                Wo_p[:, h * 112:h * 112 + hd] = Wo[:, h * hd:(h + 1) * hd]
+                Wq_p[h * 112:h * 112 + hd] = Wi[h * hd:(h + 1) * hd] * sc
+                bq_p[h * 112:h * 112 + hd] = bi[h * hd:(h + 1) * hd] * sc
+            layers.append({
+                "nq_w": f32(ca.norm_q.weight), "nq_b": f32(ca.norm_q.bias),
+                "nkv_w": f32(ca.norm_kv.weight), "nkv_b": f32(ca.norm_kv.bias),
+                "Wq": tc.pack_linear_weight(Wq_p).to(dev), "bq": f32(bq_p),
+                "Wk": tc.pack_linear_weight(Wi[D:2 * D]).to(dev), "bk": f32(bi[D:2 * D]),
+                "Wv": tc.pack_linear_weight(Wi[2 * D:]).to(dev), "bv": f32(bi[2 * D:]),
+                "Wo": tc.pack_linear_weight(Wo_p).to(dev), "bo": f32(ca.attention.out_proj.bias),
+                "nf_w": f32(ff.net[0].weight), "nf_b": f32(ff.net[0].bias),
+                "W1": tc.pack_linear_weight(ff.net[1].weight).to(dev), "b1": f32(ff.net[1].bias),
+                "W2": tc.pack_linear_weight(ff.net[4].weight).to(dev), "b2": f32(ff.net[4].bias),
+            })
+        P["layers"] = layers
+        P["n_w"], P["n_b"] = f32(up.ca_transformer.norm.weight), f32(up.ca_transformer.norm.bias)
+        P["Wf"] = tc.pack_linear_weight(up.final_conv[0].weight.detach().float().reshape(self.n_dim, D)).to(dev)
+        P["bf"] = f32(up.final_conv[0].bias)
+        P["lnf_w"], P["lnf_b"] = f32(up.final_conv[1].weight), f32(up.final_conv[1].bias)
+        P["grids"] = {}
+        self._packed = P
+        return P
+
+    @staticmethod
+    def _grid(P, n, dev):
+        g = P["grids"].get(n)
+        if g is None:
+            g = torch.linspace(-1, 1, n).to(dev)
+            P["grids"][n] = g
+        return g
+
+    @staticmethod
+    def _ln(x, w, b, C, eps, out_dtype, ldo):
+        out = torch.empty(x.shape[0], ldo, dtype=out_dtype, device=x.device)
+        _call("isp_layernorm_rows", x, int(x.dtype == torch.bfloat16), x.stride(0), out,
+              int(out_dtype == torch.bfloat16), ldo, w, b, x.shape[0], C, float(eps))
+        return out
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and source.requires_grad:
+            raise NotImplementedError("LoftUpUpsampler: activation backward is not implemented yet")
+        dev = guidance.device
+        P = self._pack(dev)
+        D, hd, C = P["D"], P["hd"], self.n_dim
+        img = guidance.detach().float()
+        src = source.detach().float()
+        B, _, H, W = img.shape
+        h, w = src.shape[2], src.shape[3]
+        if not (img.stride(3) == 1 and img.stride(2) == W):
+            img = img.contiguous()
+        # batch-global min/max is computed once, then images go through in chunks
+        mm = torch.empty(6, dtype=torch.int32, device=dev)
+        _call("isp_minmax_per_channel", img, mm, B, H, W, img.stride(0), img.stride(1))
+        out = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+        for b0 in range(0, B, self.chunk_images):
+            b1 = min(B, b0 + self.chunk_images)
+            self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w)
+        return out.permute(0, 3, 1, 2)
+
+    def _forward_chunk(self, P, img, src, mm, out, H, W, h, w):
+        dev = img.device
+        D, hd, C, nh = P["D"], P["hd"], self.n_dim, self.HEADS
+        B = img.shape[0]
+        M, T = B * H * W, h * w
+        Dp = tc.round_up(D, 16)  # row stride of the token matrices (404 -> 416)
+        bf = torch.bfloat16
+        ff = torch.empty(B, H, W, 208, dtype=bf, device=dev)
+        _call("isp_loftup_fourier_chnorm", img, *img.stride(), mm, self._grid(P, H, dev), self._grid(P, W, dev),
+              P["freqs20"], P["fb_sin"], P["fb_cos"], P["cn203_w"], P["cn203_b"], ff, B, H, W, 208, 1e-5)
+        x = tc.conv3x3(ff, P["conv1_w"], P["conv1_b"], 203, D, act="relu", ldy=Dp)
+        del ff
+        x = tc.conv3x3(x, P["conv2_w"], P["conv2_b"], D, D, act="relu", ldy=Dp).view(M, Dp)
+        kv = torch.empty(B * T, D, dtype=torch.float32, device=dev)
+        _call("isp_loftup_lr_prepare", src, *src.stride(), P["cn_w"], P["cn_b"], self._grid(P, h, dev),
+              self._grid(P, w, dev), P["freqs5"], P["lb_sin"], P["lb_cos"], kv, B, C, h, w, 1e-5)
+        Tp = tc.round_up(T, 128)
+        for L in P["layers"]:
+            kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, tc.round_up(D, 8))
+            Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
+            Vl = tc.gemm(kvn, L["Wv"], bias=L["bv"], out_dtype=torch.float32, N=D, K=D)
+            Kp = torch.empty(B, nh, Tp, 128, dtype=bf, device=dev)
+            Vt = torch.empty(B, nh, 112, Tp, dtype=bf, device=dev)
+            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, Tp, nh, 128, 0)
+            _call("isp_repack_heads", Vl, 0, D, 0, hd, Vt, B, T, Tp, nh, 112, 1)
+            qn = self._ln(x, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
+            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * 112, K=D)
+            del qn
+            O = torch.empty(M, nh * 112, dtype=bf, device=dev)
+            _call("isp_attention_bf16_tc", Q, nh * 112, 112, Kp, Vt, O, nh * 112, 112, B, H * W, nh, T, 1)
+            del Q
+            x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * 112, ldd=Dp)
+            del O
+            hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
+            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu", out_dtype=bf, N=C, K=D)
+            del hn
+            x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp)
+            del h1
+        xn = self._ln(x, P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
+        del x
+        y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
+        del xn
+        _call("isp_layernorm_rows", y, 0, C, out.view(M, C), 0, C, P["lnf_w"], P["lnf_b"], M, C, 1e-6)
