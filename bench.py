@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (driver contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W [--workload jbu|loftup] [--impl reference]
+
+A step = one pass of  click maps -> click embedding -> DINOv2 ViT-S/14 -> upsampler (-> 448^2)
+over one batch of synthetic 448x448 images with random-init weights.
+  jbu    : BASELINE.json configs[1]  (FeatUp JBU stack / AdaptiveConv, batch 16 per GPU)  [default]
+  loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)
+Multi-GPU: one process per GPU (torchrun), images sharded across ranks, no data-path
+collective (weak scaling); time = max over ranks of the CUDA-event time of the K steps.
+`--impl reference` times the CPU oracle port of the same path on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "jbu": {"batch": 16, "upsampler": "jbu_featup", "params": {"backbone_type": "dinov2", "use_norm": True},
+            "name": "DINOv2 ViT-S/14 + FeatUp JBU stack (AdaptiveConv, 32->448 px) forward, batch 16 at 448x448"},
+    "loftup": {"batch": 32, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 384},
+               "name": "DINOv2 ViT-S/14 + LoftUp cross-attention upsampler to 448x448, bf16, batch 32"},
+}
+H = W = 448
+P_CLICKS = 24
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synth_inputs(batch, seed):
+    from oracle import synth  # input generator only (seeded tensors), shared with the tests
+    img = torch.cat([synth.image_batch(batch, H, W, seed=seed),
+                     (synth.image_batch(batch, H, W, seed=seed + 77)[:, :1] > 0.7).float()], 1)
+    pts = synth.click_points(batch, P_CLICKS, H, W, seed=seed + 5)
+    return img, pts
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_step(wl, batch, seed=1):
+    """One pass of the same path with the CPU oracle (torch fp32, all host threads)."""
+    from oracle import distmaps as odm, head as ohead, jbu as ojbu, loftup as oloft, synth, vit as ovit
+    torch.manual_seed(0)
+    img, pts = synth_inputs(batch, seed)
+    vsd = synth.vit_state_dict(384, 12, seed=0)
+    psd = synth.patch_embed_state_dict(384, 14, 3, seed=0)
+    if wl == "jbu":
+        usd = ojbu.init_state_dict(384, seed=0)
+    else:
+        usd, cn = synth.loftup_state_dict(384, seed=0), synth.channelnorm_state_dict(384, seed=1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        nimg = ohead.normalize_image(img[:, :3])
+        maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
+        emb = ohead.patch_embed_forward(psd, torch.cat([img[:, 3:], maps], 1))
+        lr = ovit.dinov2_forward(vsd, nimg, emb)
+        if wl == "jbu":
+            hr = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
+        else:
+            hr = oloft.loftup_forward(usd, lr, nimg, cn["norm.weight"], cn["norm.bias"])
+        chk = float(hr.mean())
+    return time.perf_counter() - t0, chk
+
+
+def run_reference(args):
+    """Reference arm: the CPU port of the reference path (oracle/) on the host cores.  The
+    reference itself cannot run on this box (no omegaconf/mmcv/timm, hub downloads); see DESIGN.md."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    wl = args.workload
+    sample_b = 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_step(wl, sample_b)
+    ts = [cpu_port_step(wl, sample_b)[0] for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = sample_b / t
+    line = {"impl": "reference", "metric": "images/sec @448^2 DINOv2-S/14 + upsampler forward", "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOADS[wl]["name"], "batch_per_step": sample_b},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{sample_b} image per step of the same workload, torch CPU fp32 oracle"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="jbu")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import isegprobe_b200 as isp
+    from isegprobe_b200 import _lib, upsamplers
+
+    wl = WORKLOADS[args.workload]
+    B = wl["batch"]
+    torch.manual_seed(0)
+    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=False).to(dev).eval()
+    img_h, pts_h = synth_inputs(B, seed=1 + rank)
+    img_h, pts_h = img_h.pin_memory(), pts_h.pin_memory()
+    img_d, pts_d = img_h.to(dev), pts_h.to(dev)
+
+    def step_device():
+        with torch.no_grad():
+            return pipe.features(img_d, pts_d)
+
+    def step_e2e():
+        with torch.no_grad():
+            out = pipe.features(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True))
+            return out.mean(dim=(1, 2, 3)).cpu()  # per-image checksum read back each step
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    upsamplers.KERNEL_TIMERS.clear()
+    upsamplers.KERNEL_TIMING = True
+    l0 = _lib.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = _lib.launch_count() - l0
+    upsamplers.KERNEL_TIMING = False
+    torch.cuda.synchronize()
+    ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk, pk_kind = peaks()
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    C = 384
+    roofline = None
+    if args.workload == "jbu" and ktimes.get("adaptive_conv_512"):
+        t = sum(ktimes["adaptive_conv_512"]) / len(ktimes["adaptive_conv_512"])
+        alg = 4.0 * B * (C * 518 * 518 + 49 * 512 * 512 + C * 512 * 512)  # padded input + filters + output, fp32
+        ach = alg / (t * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("adaptive_conv_512_bytes_per_image")
+            traffic = traffic * B if traffic else None
+        roofline = {"kernel": "adaptive_conv_nhwc_kernel (JBU stage 512)", "bound": "hbm", "achieved": ach,
+                    "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} hbm copy", "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": traffic, "ms_per_launch": t, "algorithmic_bytes_per_launch": alg}
+    elif args.workload == "loftup" and ktimes.get("loftup_attention"):
+        t = sum(ktimes["loftup_attention"]) / len(ktimes["loftup_attention"])
+        imgs = ktimes.get("_loftup_attention_images", [pipe.upsampler.chunk_images])[0]
+        flops = 2.0 * 2 * 4 * 200704 * 1024 * 101 * pipe.upsampler.chunk_images  # QK^T + PV, un-padded head dim
+        ach = flops / (t * 1e-3) / 1e12
+        roofline = {"kernel": "attention_kernel<2,7,112> (LoftUp cross-attention, per layer call)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["bf16_tflops_sustained"], "peak_kind": f"{pk_kind} cuBLAS bf16 sustained",
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "ms_per_launch": t,
+                    "algorithmic_flops_per_launch": flops}
+    line = {
+        "metric": "images/sec @448^2 DINOv2-S/14 + upsampler forward", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (JBU SIMT kernels) + bf16 tcgen05 (ViT, 1x1 conv)" if args.workload == "jbu" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": B * world, "image": "448x448",
+                   "clicks_per_polarity": P_CLICKS, "weights": "random init (seed 0)",
+                   "l2": "no explicit flush: every step streams > 10 GB of intermediates (>> 126 MB L2)",
+                   "parallelism": f"dp{world} (images sharded, no data-path collective)"},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4) * world,
+                "d2h_bytes_per_step": 4 * B * world, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary() if sampler else None,
+        "roofline": roofline,
+        "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count())
+        t, _ = cpu_port_step(args.workload, 1)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "1 image of the same workload (one step at batch 1), torch CPU fp32 oracle"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

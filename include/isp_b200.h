@@ -175,6 +175,27 @@ int isp_loftup_lr_prepare(const float* lr, long long sb, long long sc, long long
 int isp_repack_heads(const void* src, int src_bf16, long long ld, int col0, int head_dim, void* dst_bf16,
                      int B, int T, int Tpad, int heads, int D, int transpose, isp_stream_t stream);
 
+/* ---- LiFT helpers (core/model/upsamplers/LiFT.py:47-122) ------------------------------
+ * conv3x3 stride 2 pad 1, Cout = 32, Cin <= 32, + bias (BatchNorm folded by the caller) + ReLU:
+ * in f32 with element strides (sb,sc,sh,sw) -> out NHWC f32 [B,ceil(Hi/2),ceil(Wi/2),32];
+ * w [32][Cin][3][3].  LiFT.image_convs_1 / image_convs_2 (LiFT.py:69-90). */
+int isp_conv3x3_s2_c32(const float* in, long long sb, long long sc, long long sh, long long sw,
+                       const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
+                       isp_stream_t stream);
+/* F.adaptive_max_pool2d on NHWC f32 (LiFT.py:110) */
+int isp_adaptive_maxpool_nhwc(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                              isp_stream_t stream);
+/* dst[b,y,x,c] (strides db,dh,dw; channel stride 1) = src[b,c,y,x] (strides sb,sc,sh,sw), f32|bf16
+ * either side: channel concat (LiFT.py:42,117), pixel shuffle of the k=2,s=2 transposed conv. */
+int isp_copy_channels(const void* src, int src_bf16, long long sb, long long sc, long long sh, long long sw,
+                      void* dst, int dst_bf16, long long db, long long dh, long long dw, int B, int C, int H,
+                      int W, isp_stream_t stream);
+
+/* IS-head classifier Conv2d(C -> K, 1x1) on an NHWC activation (heads/base_head.py:16,
+ * conv_heads.py:72): out[m,k] = sum_c x[m,c]*w[k,c] + b[k]; x f32|bf16 [M,ld], K <= 8, out f32 [M,K]. */
+int isp_rowdot(const void* x, int x_bf16, long long ld, const float* w, const float* b, float* out,
+               long long M, int C, int K, isp_stream_t stream);
+
 /* ViT patch embedding front half: [B,Cin,H,W] f32 -> bf16 [B*(H/P)*(W/P), ldo], column order
  * c*P*P + i*P + j (Conv2d(k=s=P) weight flattening; dinov2/layers/patch_embed.py:25-100,
  * featurizers/utils/patch_embed.py:36-42). */

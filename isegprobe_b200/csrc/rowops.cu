@@ -251,6 +251,32 @@ __global__ void __launch_bounds__(256) vit_tokens_kernel(const float* __restrict
   out[idx] = v + pos[(long long)t * C + c];
 }
 
+// ---------------------------------------------------------------------------
+// Classifier of the IS head: Conv2d(C -> K, 1x1) on an NHWC activation
+// (heads/base_head.py:16, conv_heads.py:72): out[m, k] = sum_c x[m, c] * w[k, c] + b[k].
+// One warp per pixel, K <= 8 classes; output [M, K] fp32 (== NCHW when K == 1).
+__global__ void __launch_bounds__(256) rowdot_kernel(const void* __restrict__ x, int x_bf16, long long ld,
+                                                     const float* __restrict__ w, const float* __restrict__ b,
+                                                     float* __restrict__ out, long long M, int C, int K) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = lane; c < C; c += 32) {
+    const float v = ld_any(x, row * ld + c, x_bf16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < K) acc[k] = fmaf(v, w[k * C + c], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < K) {
+      const float s = warp_sum(acc[k]);
+      if (lane == 0) out[row * K + k] = s + (b ? b[k] : 0.f);
+    }
+  }
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -342,5 +368,14 @@ extern "C" int isp_vit_assemble_tokens(const float* patch, const float* extra, c
   const long long total = (long long)B * (N + 1) * C;
   vit_tokens_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(patch, extra, cls, pos, out, B, N, C);
   ISP_CHECK_LAUNCH("vit_tokens_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_rowdot(const void* x, int x_bf16, long long ld, const float* w, const float* b, float* out,
+                          long long M, int C, int K, isp_stream_t stream) {
+  ISP_REQUIRE(x && w && out, ISP_ERR_BAD_SHAPE, "rowdot: null pointer");
+  ISP_REQUIRE(M > 0 && C > 0 && K > 0 && K <= 8 && ld >= C, ISP_ERR_BAD_SHAPE, "rowdot: bad shape (K <= 8)");
+  rowdot_kernel<<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(x, x_bf16, ld, w, b, out, M, C, K);
+  ISP_CHECK_LAUNCH("rowdot_kernel");
   return ISP_OK;
 }

@@ -1,0 +1,144 @@
+"""LiFT x2 conv upsampler -- same plugin surface as the reference
+`LiFTUpsampler(lift_path, n_dim=384, patch=14)` (core/model/upsamplers/LiFT.py:139-146) and the
+same state-dict layout as `LiFT(n_dim, patch)` (LiFT.py:47-90), eval-mode BatchNorm folded.
+
+  image --conv3x3 s2 (3->32) --conv3x3 s2 (32->32)--> adaptive max-pool to (2h,2w) = imgs_1
+  imgs_1 --conv3x3 s2 (32->32)--> imgs_2 ; cat[source, imgs_2] (C+32)
+        --ConvTranspose2d k2 s2 (one GEMM to 4*(C+32)/2 columns + pixel shuffle)--> cat with imgs_1
+        --conv3x3+BN+ReLU x2 (tcgen05 implicit GEMM)--> conv1x1 --> [B,C,2h,2w]
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, tc
+from .upsamplers import BaseUpsampler
+
+
+def _call(name, *a):
+    _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
+
+
+class _DoubleConv(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout),
+                                         nn.ReLU(inplace=True), nn.Conv2d(cout, cout, 3, padding=1, bias=False),
+                                         nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(cin, cin // 2, kernel_size=2, stride=2)
+        self.conv_1 = _DoubleConv(cin // 2 + 32, cout // 2)
+
+
+class _LiFTParams(nn.Module):
+    """Keys/shapes of reference LiFT(in_channels, patch_size).state_dict()."""
+
+    def __init__(self, C, patch):
+        super().__init__()
+        if patch not in (8, 14, 16):
+            raise ValueError("ERROR: patch size %i not currently supported" % patch)  # LiFT.py:83-85
+        self.up1 = _Up(C + 32, C)
+        self.outc = nn.Conv2d(C // 2, C, kernel_size=1)
+        self.image_convs_1 = nn.Sequential(nn.Conv2d(3, 32, 3, padding=1, stride=2), nn.BatchNorm2d(32),
+                                           nn.ReLU(inplace=True), nn.Conv2d(32, 32, 3, padding=1, stride=2),
+                                           nn.BatchNorm2d(32), nn.ReLU(inplace=True))
+        self.image_convs_2 = nn.Sequential(nn.Conv2d(32, 32, 3, padding=1, stride=2), nn.BatchNorm2d(32),
+                                           nn.ReLU(inplace=True))
+
+
+def _fold(conv, bn):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    w = conv.weight.detach().float() * s[:, None, None, None]
+    b0 = conv.bias.detach().float() if conv.bias is not None else torch.zeros_like(s)
+    return w, (b0 - bn.running_mean.float()) * s + bn.bias.detach().float()
+
+
+class LiFTUpsampler(BaseUpsampler):
+    """`lift_path=None` (extension) keeps the random initialisation (reference always loads)."""
+
+    def __init__(self, lift_path: str = None, n_dim: int = 384, patch: int = 14):
+        super().__init__()
+        self.n_dim = n_dim
+        self.lift = _LiFTParams(n_dim, patch)
+        if lift_path is not None:
+            sd = torch.load(lift_path, map_location="cpu")
+            sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}  # LiFT.py:129-132
+            self.lift.load_state_dict(sd)
+        self._packed = None
+
+    def _version(self):
+        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+
+    def _pack(self, dev):
+        key = (str(dev), self._version())
+        if self._packed is not None and self._packed["key"] == key:
+            return self._packed
+        L, C = self.lift, self.n_dim
+        f32 = lambda t: t.detach().float().contiguous().to(dev)
+        P = {"key": key}
+        for name, conv, bn in (("ic1a", L.image_convs_1[0], L.image_convs_1[1]),
+                               ("ic1b", L.image_convs_1[3], L.image_convs_1[4]),
+                               ("ic2", L.image_convs_2[0], L.image_convs_2[1])):
+            w, b = _fold(conv, bn)
+            P[name] = (f32(w), f32(b))
+        up = L.up1.up  # weight [Cin, Cout, 2, 2]
+        Cin, Co = up.weight.shape[0], up.weight.shape[1]
+        wt = up.weight.detach().float().permute(2, 3, 1, 0).reshape(4 * Co, Cin)  # row (dy*2+dx)*Co + co
+        P["up_w"] = tc.pack_linear_weight(wt).to(dev)
+        P["up_b"] = f32(up.bias.detach().float().repeat(4))
+        dc = L.up1.conv_1.double_conv
+        w, b = _fold(dc[0], dc[1])
+        P["dc1"] = (tc.pack_conv3x3_weight(w).to(dev), f32(b))
+        w, b = _fold(dc[3], dc[4])
+        P["dc2"] = (tc.pack_conv3x3_weight(w).to(dev), f32(b))
+        P["out_w"] = tc.pack_linear_weight(L.outc.weight.detach().float().reshape(C, C // 2)).to(dev)
+        P["out_b"] = f32(L.outc.bias)
+        self._packed = P
+        return P
+
+    def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and source.requires_grad:
+            raise NotImplementedError("LiFTUpsampler: activation backward is not implemented yet")
+        dev = guidance.device
+        P = self._pack(dev)
+        img, src = guidance.detach().float(), source.detach().float()
+        B, _, H, W = img.shape
+        C, h, w = src.shape[1], src.shape[2], src.shape[3]
+        bf = torch.bfloat16
+        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        a = torch.empty(B, H1, W1, 32, device=dev)
+        _call("isp_conv3x3_s2_c32", img, *img.stride(), P["ic1a"][0], P["ic1a"][1], a, B, 3, H, W)
+        H2, W2 = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
+        i1 = torch.empty(B, H2, W2, 32, device=dev)
+        _call("isp_conv3x3_s2_c32", a, H1 * W1 * 32, 1, W1 * 32, 32, P["ic1b"][0], P["ic1b"][1], i1, B, 32, H1, W1)
+        GH, GW = 2 * h, 2 * w
+        i1p = torch.empty(B, GH, GW, 32, device=dev)
+        _call("isp_adaptive_maxpool_nhwc", i1, i1p, B, 32, H2, W2, GH, GW)
+        i2 = torch.empty(B, h, w, 32, device=dev)
+        _call("isp_conv3x3_s2_c32", i1p, GH * GW * 32, 1, GW * 32, 32, P["ic2"][0], P["ic2"][1], i2, B, 32, GH, GW)
+        # cat[source, imgs_2] -> bf16 [B*h*w, C+32]
+        Cc = C + 32
+        cat1 = torch.empty(B, h, w, Cc, dtype=bf, device=dev)
+        _call("isp_copy_channels", src, 0, *src.stride(), cat1, 1, h * w * Cc, w * Cc, Cc, B, C, h, w)
+        _call("isp_copy_channels", i2, 0, h * w * 32, 1, w * 32, 32, cat1[..., C:], 1, h * w * Cc, w * Cc, Cc, B, 32, h, w)
+        Co = Cc // 2
+        up = tc.gemm(cat1.view(B * h * w, Cc), P["up_w"], bias=P["up_b"], out_dtype=bf, N=4 * Co, K=Cc)
+        # pixel shuffle into cat[up, imgs_1] -> bf16 [B,2h,2w,Co+32]
+        C2 = Co + 32
+        cat2 = torch.empty(B, GH, GW, C2, dtype=bf, device=dev)
+        for dy in range(2):
+            for dx in range(2):
+                s = up[:, (dy * 2 + dx) * Co:]
+                d = cat2[:, dy::2, dx::2]
+                _call("isp_copy_channels", s, 1, h * w * 4 * Co, 1, w * 4 * Co, 4 * Co, d, 1, GH * GW * C2,
+                      2 * GW * C2, 2 * C2, B, Co, h, w)
+        _call("isp_copy_channels", i1p, 0, GH * GW * 32, 1, GW * 32, 32, cat2[..., Co:], 1, GH * GW * C2, GW * C2, C2,
+              B, 32, GH, GW)
+        Ch = C // 2
+        x = tc.conv3x3(cat2, P["dc1"][0], P["dc1"][1], C2, Ch, act="relu", ldy=tc.round_up(Ch, 8))
+        x = tc.conv3x3(x, P["dc2"][0], P["dc2"][1], Ch, Ch, act="relu", ldy=tc.round_up(Ch, 8))
+        out = tc.gemm(x.view(B * GH * GW, -1), P["out_w"], bias=P["out_b"], out_dtype=torch.float32, N=C, K=Ch)
+        return out.view(B, GH, GW, C).permute(0, 3, 1, 2)

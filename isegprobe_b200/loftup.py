@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, tc
-from .upsamplers import BaseUpsampler
+from .upsamplers import BaseUpsampler, timed_kernel
 
 
 # ------------------------------------------------------------------ parameter containers
@@ -248,7 +248,8 @@ class LoftUpUpsampler(BaseUpsampler):
             Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * 112, K=D)
             del qn
             O = torch.empty(M, nh * 112, dtype=bf, device=dev)
-            _call("isp_attention_bf16_tc", Q, nh * 112, 112, Kp, Vt, O, nh * 112, 112, B, H * W, nh, T, 1)
+            with timed_kernel("loftup_attention"):
+                _call("isp_attention_bf16_tc", Q, nh * 112, 112, Kp, Vt, O, nh * 112, 112, B, H * W, nh, T, 1)
             del Q
             x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * 112, ldd=Dp)
             del O

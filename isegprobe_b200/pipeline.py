@@ -1,0 +1,84 @@
+"""Model assembly of the hot path, mirroring iSegBaseModel.forward
+(core/model/iseg_base_model.py:67-110) and iSegProbeModel.backbone_forward
+(core/model/iseg_probe_model.py:110-134) with this package's modules, plus the
+registry hook that drops them into the reference's ModelBuilder
+(core/utils/model_builder.py:59-95).
+
+The reference's own `iSegProbeModel` keeps working unchanged once `install_into_reference()`
+has swapped the registry entries; `ISegPipeline` is the same call sequence for users (and
+bench.py) that do not have the reference's Python dependencies (omegaconf, mmcv, timm)."""
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .featurizers import DINOv2Featurizer, PatchEmbed
+from .heads import HEAD_REGISTRY
+from .upsamplers import UPSAMPLER_REGISTRY, bilinear_align_corners_nhwc, to_nhwc_f32
+
+FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "patch_embedding": PatchEmbed}
+
+
+def install_into_reference() -> None:
+    """Swap the reference's registry entries for the B200-native modules (same keys), so
+    `ModelBuilder.load_upsampler/load_head` construct ours.  Call after importing the
+    reference's `core.model` package and before building a model."""
+    import core.model.heads as ref_heads
+    import core.model.upsamplers as ref_up
+
+    ref_up.UPSAMPLER_REGISTRY.update(UPSAMPLER_REGISTRY)
+    ref_heads.HEAD_REGISTRY.update(HEAD_REGISTRY)
+    try:
+        import core.model.ops as ref_ops
+        ref_ops.DistMaps = ops.DistMaps
+    except ImportError:
+        pass
+
+
+class ISegPipeline(nn.Module):
+    """image [B,3|4,H,W] in [0,1] + points [B,2P,3] -> {"instances": [B,1,H,W] logits}.
+
+    Constructor keys follow models/sbd/dinov2/patch-embed_*.py: upsampler/head `type` strings
+    and `params` dicts, `use_disks`, `norm_radius`, `with_prev_mask`."""
+
+    def __init__(self, upsampler_type: str = "loftup", upsampler_params: Optional[dict] = None,
+                 head_type: str = "convhead", head_params: Optional[dict] = None, backbone_dim: int = 384,
+                 patch: int = 14, use_disks: bool = True, norm_radius: int = 5, with_prev_mask: bool = True,
+                 with_head: bool = True):
+        super().__init__()
+        if upsampler_type not in UPSAMPLER_REGISTRY:
+            raise ValueError(f"Unknown upsampler type: {upsampler_type}")  # model_builder.py:64-65
+        self.use_disks, self.norm_radius, self.with_prev_mask = use_disks, norm_radius, with_prev_mask
+        self.upsampler_type = upsampler_type
+        self.backbone = DINOv2Featurizer("dinov2_vits14", "before_backbone")
+        self.embed_coords = PatchEmbed((448, 448), (patch, patch), 3 if with_prev_mask else 2, backbone_dim)
+        self.upsampler = UPSAMPLER_REGISTRY[upsampler_type](**(upsampler_params or {}))
+        self.head = None
+        if with_head:
+            if head_type not in HEAD_REGISTRY:
+                raise ValueError(f"Unknown head type: {head_type}")  # model_builder.py:81-82
+            self.head = HEAD_REGISTRY[head_type](**(head_params or {"in_channels": backbone_dim, "num_layers": 2,
+                                                                    "num_classes": 1}))
+        for m in (self.backbone, self.upsampler):  # frozen, as ModelBuilder(freeze=True)
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def features(self, image: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+        """Up to the upsampler output, resized to the image size: [B,C,H,W] (NHWC memory)."""
+        norm_img, coord = ops.prepare_input(image, points, self.norm_radius, 1.0, self.use_disks)
+        emb = self.embed_coords(coord)
+        lr = self.backbone(norm_img, emb)
+        hr = self.upsampler(source=lr, guidance=norm_img)
+        if self.upsampler_type != "identity" and tuple(hr.shape[2:]) != tuple(norm_img.shape[2:]):
+            hr = bilinear_align_corners_nhwc(to_nhwc_f32(hr), tuple(norm_img.shape[2:])).permute(0, 3, 1, 2)
+        return hr
+
+    def forward(self, image: torch.Tensor, points: torch.Tensor) -> Dict:
+        hr = self.features(image, points)
+        if self.head is None:
+            return {"features": hr, "instances": None, "instances_aux": None}
+        logits = self.head(hr)
+        if tuple(logits.shape[2:]) != tuple(image.shape[2:]):
+            logits = bilinear_align_corners_nhwc(to_nhwc_f32(logits), tuple(image.shape[2:])).permute(0, 3, 1, 2)
+        return {"instances": logits, "instances_aux": None}

@@ -17,6 +17,29 @@ import torch.nn.functional as F
 from . import _lib
 
 
+KERNEL_TIMING = False  # bench.py: record CUDA events around the dominant kernels (roofline)
+KERNEL_TIMERS = {}
+
+
+class timed_kernel:
+    """with timed_kernel("name"): <launch>   -- CUDA events on the launching (current) stream."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_TIMING:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMING:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            KERNEL_TIMERS.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
 class BaseUpsampler(nn.Module, ABC):
     """core/model/upsamplers/__init__.py:6-11"""
 
@@ -150,7 +173,8 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         hr = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
         _lib.call("isp_jbu_bicubic2x_reflectpad", _lib.dptr(src), _lib.dptr(hr), B, h, w, C, st)
         out = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
-        _lib.call("isp_adaptive_conv_fwd", _lib.dptr(hr), _lib.dptr(filt), _lib.dptr(out), B, GH, GW, C, st)
+        with timed_kernel(f"adaptive_conv_{GH}"):
+            _lib.call("isp_adaptive_conv_fwd", _lib.dptr(hr), _lib.dptr(filt), _lib.dptr(out), B, GH, GW, C, st)
         return out
 
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,153 @@
+"""GPU parity: IS head, ViT backbone, LiFT and the assembled pipeline vs the oracle and the
+reference's golden vectors (bf16 tensor-core path: cosine >= 0.999)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distmaps as odm
+from oracle import head as ohead
+from oracle import lift as olift
+from oracle import loftup as oloft
+from oracle import synth
+from oracle import vit as ovit
+from tests.gpu_util import DEV, cosine, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def isp():
+    import isegprobe_b200
+    return isegprobe_b200
+
+
+def test_head_golden_and_oracle(isp, golden):
+    sd = synth.convhead_state_dict(384, 2, 1, seed=0)
+    head = isp.ConvSegHead(384, 2, 1)
+    head.load_state_dict(sd, strict=True)  # reference checkpoint key layout
+    head = head.to(DEV).eval()
+    x = synth.lr_features(2, 384, 20, 28, seed=4)
+    with torch.no_grad():
+        out = head(x.to(DEV))
+    want = torch.from_numpy(golden("head_20x28")["out"])
+    assert tuple(out.shape) == (2, 1, 20, 28)
+    assert cosine(out, want) > 0.9995 and relerr(out, want) < 3e-2
+    # channels-last input (what our upsamplers return) must give the same result
+    with torch.no_grad():
+        out2 = head(x.to(DEV).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    assert torch.equal(out, out2)
+    # 1x1 variants
+    for cls, fn in ((isp.SimpleClassifierHead, None), (isp.SimpleConvSegHead, None)):
+        h = cls(384, 1) if cls is isp.SimpleClassifierHead else cls(384, 2, 1)
+        h = h.to(DEV).eval()
+        with torch.no_grad():
+            o = h(x.to(DEV))
+            f = x
+            if cls is isp.SimpleConvSegHead:
+                for m in h.convs:
+                    f = torch.relu(torch.nn.functional.conv2d(f, m.conv.weight.cpu(), m.conv.bias.cpu()))
+            w = torch.nn.functional.conv2d(f, h.classifier.weight.cpu(), h.classifier.bias.cpu())
+        assert cosine(o, w) > 0.9995
+
+
+def test_patch_embed_golden(isp, golden):
+    pe = isp.PatchEmbed((28, 42), (14, 14), 3, 384)
+    pe.load_state_dict(synth.patch_embed_state_dict(384, 14, 3, seed=0), strict=True)
+    pe = pe.to(DEV).eval()
+    with torch.no_grad():
+        emb = pe(synth.image_batch(2, 28, 42, seed=6).to(DEV))
+    want = torch.from_numpy(golden("head_20x28")["patch_embed"])
+    assert tuple(emb.shape) == (2, 6, 384) and cosine(emb, want) > 0.9999 and relerr(emb, want) < 2e-2
+
+
+def test_vit_golden_and_oracle(isp, golden):
+    sd = synth.vit_state_dict(384, depth=12, seed=0)
+    f = isp.DINOv2Featurizer("dinov2_vits14", "before_backbone")
+    f.model.load_state_dict(sd, strict=True)  # hub / vendored key layout
+    f = f.to(DEV).eval()
+    img = (synth.image_batch(2, 56, 84, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 384, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():
+        out = f(img.to(DEV), emb.to(DEV))
+    want = torch.from_numpy(golden("vit_56x84")["out"])
+    assert tuple(out.shape) == (2, 384, 4, 6)
+    assert cosine(out, want) > 0.999, cosine(out, want)
+    # square 1025-token case against the oracle, no injection
+    img = (synth.image_batch(1, 448, 448, seed=3) - 0.45) / 0.225
+    f2 = isp.DINOv2Featurizer("dinov2_vits14", "no_injection")
+    f2.model.load_state_dict(sd, strict=True)
+    f2 = f2.to(DEV).eval()
+    with torch.no_grad():
+        out = f2(img.to(DEV))
+        want = ovit.dinov2_forward(sd, img, None)
+    assert tuple(out.shape) == (1, 384, 32, 32) and cosine(out, want) > 0.999, cosine(out, want)
+
+
+def test_lift_golden(isp, golden):
+    m = isp.LiFTUpsampler(None, 384, 14)
+    m.lift.load_state_dict(synth.lift_state_dict(384, seed=0), strict=True)
+    m = m.to(DEV).eval()
+    img = (synth.image_batch(2, 56, 84, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 384, 4, 6, seed=2)
+    with torch.no_grad():
+        out = m(source=lr.to(DEV), guidance=img.to(DEV))
+    want = torch.from_numpy(golden("lift_56x84")["out"])
+    assert tuple(out.shape) == (2, 384, 8, 12)
+    assert cosine(out, want) > 0.999 and relerr(out, want) < 5e-2, (cosine(out, want), relerr(out, want))
+
+
+@pytest.mark.parametrize("up_type,params", [("lift", {"lift_path": None, "n_dim": 384, "patch": 14}),
+                                            ("jbu_featup", {"backbone_type": "dinov2", "use_norm": True}),
+                                            ("loftup", {"upsampler_path": None, "n_dim": 384}),
+                                            ("bilinear", {})])
+def test_pipeline_masks_vs_oracle(isp, up_type, params):
+    """End to end: image + clicks -> logits; >= 99.9 % mask agreement with the oracle chain
+    away from the decision boundary (north_star: per-click masks >= 99.9 % pixel agreement)."""
+    from oracle import jbu as ojbu
+    torch.manual_seed(0)
+    H = W = 112
+    pipe = isp.ISegPipeline(up_type, params).to(DEV).eval()
+    pipe.embed_coords = isp.PatchEmbed((H, W), (14, 14), 3, 384).to(DEV)
+    vsd = synth.vit_state_dict(384, depth=12, seed=0)
+    pipe.backbone.model.load_state_dict(vsd)
+    hsd = synth.convhead_state_dict(384, 2, 1, seed=0)
+    pipe.head.load_state_dict(hsd)
+    psd = synth.patch_embed_state_dict(384, 14, 3, seed=0)
+    pipe.embed_coords.load_state_dict(psd)
+    image = torch.cat([synth.image_batch(2, H, W, seed=1), (synth.image_batch(2, H, W, seed=8)[:, :1] > 0.5).float()], 1)
+    pts = synth.click_points(2, 3, H, W, seed=3)
+    if up_type == "lift":
+        usd = synth.lift_state_dict(384, seed=0)
+        pipe.upsampler.lift.load_state_dict(usd)
+    elif up_type == "jbu_featup":
+        usd = ojbu.init_state_dict(384, seed=0)
+        pipe.upsampler.upsampler.load_state_dict(usd)
+    elif up_type == "loftup":
+        usd, cn = synth.loftup_state_dict(384, seed=0), synth.channelnorm_state_dict(384, seed=1)
+        pipe.upsampler.upsampler.upsampler.load_state_dict(usd)
+        pipe.upsampler.upsampler.channelnorm.load_state_dict(cn)
+    with torch.no_grad():
+        logits = pipe(image.to(DEV), pts.to(DEV))["instances"].cpu()
+        # oracle chain (iseg_base_model.py:67-110, iseg_probe_model.py:110-134)
+        nimg = ohead.normalize_image(image[:, :3])
+        maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
+        coord = torch.cat([image[:, 3:], maps], 1)
+        emb = ohead.patch_embed_forward(psd, coord)
+        lr = ovit.dinov2_forward(vsd, nimg, emb)
+        if up_type == "lift":
+            hr = olift.lift_forward(usd, lr, nimg)
+        elif up_type == "jbu_featup":
+            hr = ojbu.jbu_stack_forward(usd, lr, nimg)
+        elif up_type == "loftup":
+            hr = oloft.loftup_forward(usd, lr, nimg, cn["norm.weight"], cn["norm.bias"])
+        else:
+            hr = lr
+        if tuple(hr.shape[2:]) != (H, W):
+            hr = ohead.bilinear_align_corners(hr, (H, W))
+        want = ohead.convhead_forward(hsd, hr)
+    assert tuple(logits.shape) == (2, 1, H, W)
+    assert cosine(logits, want) > 0.998, cosine(logits, want)
+    margin = 0.05 * want.abs().max()
+    decided = want.abs() > margin
+    agree = ((logits > 0) == (want > 0))[decided].float().mean()
+    assert float(agree) >= 0.999, float(agree)
