@@ -40,6 +40,12 @@ struct Params {
   int ldo, o_head_stride;      // column offset between heads in out
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz); inputs are <= 8
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DK_CHUNKS, int DK_STEPS, int DV>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -182,27 +188,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t pk[64];  // P row as packed bf16 pairs
         float mj = -INFINITY;
         const int kbase = j * BKEY;
-        // pass 1: row max of this block (log2 units).  S is read from TMEM twice (max, then
-        // exp) instead of being held in 128 registers; TMEM reads are cheap.
+        // pass 1: row max of this block.  S is read from TMEM twice (max, then exp) instead of
+        // being held in 128 registers; TMEM reads are cheap.  Only the last key block can hold
+        // padded keys, so the masked variant is a block-uniform slow path.
+        const bool tail = kbase + BKEY > p.nkeys;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           tc::tmem_ld32(ts + c * 32, v);
           tc::tmem_ld_wait();
+          if (!tail) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (kbase + c * 32 + e < p.nkeys) mj = fmaxf(mj, __uint_as_float(v[e]));
+            for (int e = 0; e < 32; ++e) mj = fmaxf(mj, __uint_as_float(v[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (kbase + c * 32 + e < p.nkeys) mj = fmaxf(mj, __uint_as_float(v[e]));
+          }
         }
         mj *= kLog2e;
         // lazy max update: only move the reference when the row max grew by more than 2^8
         float scale = 1.f;
         bool need = false;
         if (mj > m_ref + kRescaleThresh) {
-          scale = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - mj);
+          scale = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - mj);
           m_ref = mj;
           need = (j > 0);
         }
-        float rs = 0.f;
+        float rs0 = 0.f, rs1 = 0.f;
+        const float neg_m = -m_ref;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
@@ -210,16 +224,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc::tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const int key = kbase + c * 32 + e;
-            float p0 = exp2f(fmaf(__uint_as_float(v[e]), kLog2e, -m_ref));
-            float p1 = exp2f(fmaf(__uint_as_float(v[e + 1]), kLog2e, -m_ref));
-            if (key >= p.nkeys) p0 = 0.f;
-            if (key + 1 >= p.nkeys) p1 = 0.f;
-            rs += p0 + p1;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), kLog2e, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), kLog2e, neg_m));
+            if (tail) {
+              const int key = kbase + c * 32 + e;
+              if (key >= p.nkeys) p0 = 0.f;
+              if (key + 1 >= p.nkeys) p1 = 0.f;
+            }
+            rs0 += p0;
+            rs1 += p1;
             __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
             pk[c * 16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&bb);
           }
         }
+        const float rs = rs0 + rs1;
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_empty[s_it & 1]);  // S(j) consumed; QK(j+2) may overwrite it

@@ -1,12 +1,15 @@
 // tcgen05 GEMM / implicit-GEMM 3x3 convolution core (sm_100a).
 //
-//   D[M,N] = epilogue( A[M,K] * W[N,K]^T )          bf16 operands, fp32 accumulate in TMEM
+//   D[M,N] = alpha * act( A[M,K] * W[N,K]^T + bias ) + resid     bf16 operands, fp32 accumulate (TMEM)
 //
 // One persistent CTA per SM, warp-specialised:
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1   : MMA issuer     (one elected lane: tcgen05.mma 128 x BN x 16, tcgen05.commit)
-//   warps 2-5: epilogue       (tcgen05.ld TMEM->registers, bias/activation/residual, global store)
-// TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2-5: epilogue       each warp owns 32 rows: tcgen05.ld -> bias/act -> (+ residual chunk it
+//                             TMA-loaded itself) -> 128B-swizzled smem chunk -> TMA store.
+//                             All global traffic of the epilogue is bulk/coalesced; OOB rows and
+//                             columns are clipped by TMA, so there is no per-element masking.
+// TMEM holds two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // GEMM mode   : A is a row-major [M, K] bf16 matrix (2D tensor map).
 // CONV3x3 mode: A is an NHWC bf16 activation [Nimg, H, W, Cin]; a tile is TH x TW output
@@ -32,19 +35,25 @@ tmap_encode_fn get_tmap_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const char* what) {
+int make_tmap(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what, bool swizzle128) {
   tmap_encode_fn enc = get_tmap_encode();
   ISP_REQUIRE(enc, ISP_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable (no CUDA driver?)", what);
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];  // stride of dim i+1
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ISP_REQUIRE(r == CUDA_SUCCESS, ISP_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   return ISP_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const char* what) {
+  return make_tmap(out, 2, base, rank, dims, strides_bytes, box, what, true);
 }
 
 namespace gemm {
@@ -53,26 +62,26 @@ constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024;  // also forces one CTA per SM (TMEM: 512 columns each)
+constexpr int kEpiBytesPerWarp = 4 * 4096;  // 2 output + 2 residual staging chunks of 32 rows x 128 B
+constexpr int kEpiBytes = 4 * kEpiBytesPerWarp;
+constexpr int kMainBudget = 160 * 1024;
+constexpr int kSmemBytes = kMainBudget + kEpiBytes;  // 224 KB: also forces one CTA per SM (TMEM: 512 columns)
 
 struct Params {
-  // problem
   long long M;        // rows (GEMM) or Nimg*H*W (conv)
   int N, K;           // K = padded reduction length actually looped (multiple of 64)
   int BN;             // tile width, multiple of 16, <= 256
   int stages;
   // conv mode (TW == 0 -> plain GEMM)
-  int TW, TH, H, W, cin_chunks;  // cin_chunks = Cin_pad / 64
+  int TW, TH, H, W, cin_chunks;
   long long tiles_m, tiles_n;
-  int tiles_w, tiles_h;          // conv: tiles per image row / column
+  int tiles_w, tiles_h;
   // epilogue
-  const float* bias;   // [N] or null
-  const void* resid;   // [M, ldr] or null
-  int resid_bf16, ldr;
-  float alpha;         // out = alpha * act(acc + bias) + resid
-  int act;             // 0 none, 1 relu, 2 gelu(erf), 3 quick-gelu
-  void* D;
-  int ldd, out_bf16;
+  const float* bias;  // [N] or null
+  int has_resid;      // residual has the dtype and addressing of D
+  float alpha;        // out = alpha * act(acc + bias) + resid
+  int act;            // 0 none, 1 relu, 2 gelu(erf), 3 quick-gelu
+  int out_bf16;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -83,9 +92,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct TileCoord {
-  long long m0;     // first output row of the tile (GEMM) / unused (conv)
+  long long m0;
   int n0;
-  int img, h0, w0;  // conv
+  int img, h0, w0;
 };
 
 __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
@@ -104,23 +113,161 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
   return c;
 }
 
+// One epilogue warp, one tile.  CW = columns per 128-byte chunk (64 bf16 / 32 f32).
+// res_seq / st_seq count this warp's residual loads / output stores since kernel start; they pick
+// the staging buffer (seq & 1) and, for the residual mbarriers, the phase parity ((seq >> 1) & 1).
+template <bool OUT_BF16>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmD, const CUtensorMap* tmR,
+                                              const CUtensorMap* tmDt, const CUtensorMap* tmRt, const TileCoord& tc_, uint32_t t_addr, uint8_t* stage, uint64_t* res_bar,
+                                              uint32_t& res_seq, uint32_t& st_seq, int q, int lane) {
+  constexpr int CW = OUT_BF16 ? 64 : 32;
+  uint8_t* out_buf = stage;             // [2][4096]
+  uint8_t* res_buf = stage + 2 * 4096;  // [2][4096]
+  const int nchunks = (p.BN + CW - 1) / CW;
+  // where this warp's 32 rows live in the output tensor
+  int c1, c2 = 0, c3 = 0;
+  if (p.TW) {
+    const int bw = p.TW < 32 ? p.TW : 32;
+    const int pix = q * 32;
+    c1 = tc_.w0 + (p.TW >= 32 ? pix % p.TW : 0);
+    c2 = tc_.h0 + (p.TW >= 32 ? pix / p.TW : q * (32 / bw));
+    c3 = tc_.img;
+  } else {
+    c1 = (int)tc_.m0 + q * 32;
+  }
+  // The last chunk of a tile may be narrower than CW (BN % CW columns).  It goes through a second,
+  // un-swizzled tensor map with a box of exactly that width, so it never touches the next tile.
+  constexpr int ESZ = OUT_BF16 ? 2 : 4;
+  const int tail_cols = p.BN % CW;
+  auto load_res = [&](int chunk, uint32_t seq) {  // lane 0 only
+    uint64_t* bar = &res_bar[seq & 1];
+    const bool tl_ = tail_cols && chunk == nchunks - 1;
+    tc::mbar_arrive_expect_tx(bar, tl_ ? 32 * tail_cols * ESZ : 4096);
+    const CUtensorMap* m = tl_ ? tmRt : tmR;
+    if (p.TW) tc::tma_load_4d(res_buf + (seq & 1) * 4096, m, bar, tc_.n0 + chunk * CW, c1, c2, c3);
+    else tc::tma_load_2d(res_buf + (seq & 1) * 4096, m, bar, tc_.n0 + chunk * CW, c1);
+  };
+  if (p.has_resid && lane == 0) load_res(0, res_seq);
+  const int r7 = lane & 7;
+  for (int c = 0; c < nchunks; ++c) {
+    const int col0 = c * CW;                 // column inside the tile
+    const int ncols = min(CW, p.BN - col0);  // multiple of 16
+    const bool is_tail = ncols < CW;
+    const int row_bytes = ncols * ESZ;       // dense row pitch of a tail chunk
+    uint32_t vr[CW];
+#pragma unroll
+    for (int g = 0; g < CW / 16; ++g) {
+      if (g * 16 < ncols) {
+        tc::tmem_ld16(t_addr + col0 + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&vr[g * 16]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) vr[g * 16 + e] = 0u;
+      }
+    }
+    tc::tmem_ld_wait();
+    float v[CW];
+    // bias / activation / scale (columns >= N produce exact zeros: they are K-padding for the next GEMM)
+#pragma unroll
+    for (int e4 = 0; e4 < CW; e4 += 4) {
+      const int n = tc_.n0 + col0 + e4;
+      float b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.bias) {
+        if (n + 3 < p.N) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < p.N) b[e] = __ldg(p.bias + n + e);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        v[e4 + e] = (n + e < p.N) ? apply_act(__uint_as_float(vr[e4 + e]) + b[e], p.act) * p.alpha : 0.f;
+    }
+    if (p.has_resid) {
+      if (lane == 0 && c + 1 < nchunks) load_res(c + 1, res_seq + 1);
+      tc::mbar_wait(&res_bar[res_seq & 1], (res_seq >> 1) & 1);
+      const uint8_t* rb = res_buf + (res_seq & 1) * 4096 + lane * (is_tail ? row_bytes : 128);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (u * 16 >= row_bytes) break;
+        const uint4 w = *reinterpret_cast<const uint4*>(rb + (is_tail ? (u << 4) : ((u ^ r7) << 4)));
+        if constexpr (OUT_BF16) {
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = tc_.n0 + col0 + u * 8 + 2 * i;
+            if (n < p.N) v[u * 8 + 2 * i] += __uint_as_float(ww[i] << 16);
+            if (n + 1 < p.N) v[u * 8 + 2 * i + 1] += __uint_as_float(ww[i] & 0xffff0000u);
+          }
+        } else {
+          const int n = tc_.n0 + col0 + u * 4;
+          if (n < p.N) v[u * 4] += __uint_as_float(w.x);
+          if (n + 1 < p.N) v[u * 4 + 1] += __uint_as_float(w.y);
+          if (n + 2 < p.N) v[u * 4 + 2] += __uint_as_float(w.z);
+          if (n + 3 < p.N) v[u * 4 + 3] += __uint_as_float(w.w);
+        }
+      }
+      ++res_seq;
+      __syncwarp();  // everyone has consumed this residual buffer before lane 0 re-arms it (two chunks later)
+    }
+    // stage the chunk (32 rows x 128 B, 16-byte units XOR-swizzled like TMA's SWIZZLE_128B) and store it
+    if (lane == 0) tc::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+    __syncwarp();
+    uint8_t* ob = out_buf + (st_seq & 1) * 4096 + lane * (is_tail ? row_bytes : 128);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u * 16 >= row_bytes) break;
+      uint4 w;
+      if constexpr (OUT_BF16) {
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[u * 8 + 0], v[u * 8 + 1]);
+        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[u * 8 + 2], v[u * 8 + 3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[u * 8 + 4], v[u * 8 + 5]);
+        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[u * 8 + 6], v[u * 8 + 7]);
+        w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
+                       *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
+      } else {
+        w = make_uint4(__float_as_uint(v[u * 4 + 0]), __float_as_uint(v[u * 4 + 1]), __float_as_uint(v[u * 4 + 2]),
+                       __float_as_uint(v[u * 4 + 3]));
+      }
+      *reinterpret_cast<uint4*>(ob + (is_tail ? (u << 4) : ((u ^ r7) << 4))) = w;
+    }
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const CUtensorMap* m = is_tail ? tmDt : tmD;
+      if (p.TW) tc::tma_store_4d(m, out_buf + (st_seq & 1) * 4096, tc_.n0 + col0, c1, c2, c3);
+      else tc::tma_store_2d(m, out_buf + (st_seq & 1) * 4096, tc_.n0 + col0, c1);
+      tc::tma_store_commit();
+    }
+    ++st_seq;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmDt, const __grid_constant__ CUtensorMap tmRt, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2],
+      res_bar[4][2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
-  // dynamic smem base is 1024-aligned by declaration; keep tiles 1024-aligned (b_bytes % 1024 == 0 since BN % 8 == 0)
   const long long ntiles = p.tiles_m * p.tiles_n;
   const int kblocks = p.K / BK;
+  uint8_t* epi_smem = smem + kMainBudget;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tmD);
+    if (p.has_resid) tc::prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
+    for (int w = 0; w < 4; ++w) { tc::mbar_init(&res_bar[w][0], 1); tc::mbar_init(&res_bar[w][1], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -173,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step inside the 128B swizzle row
             tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          tc::umma_commit(&empty_bar[s]);                       // smem slot free when these MMAs retire
+          tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
           if (kb == kblocks - 1) tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
@@ -181,89 +328,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------- epilogue (warps 2..5)
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row_in_tile = q * 32 + lane;
-    uint32_t tl = 0;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32 rows of the tile
+    uint8_t* stage = epi_smem + q * kEpiBytesPerWarp;
+    uint32_t tl = 0, res_seq = 0, st_seq = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       const TileCoord tc_ = tile_coord(p, t);
-      long long row;
-      bool row_ok;
-      if (p.TW) {
-        const int hh = tc_.h0 + row_in_tile / p.TW, ww = tc_.w0 + row_in_tile % p.TW;
-        row_ok = hh < p.H && ww < p.W;
-        row = ((long long)tc_.img * p.H + hh) * p.W + ww;
-      } else {
-        row = tc_.m0 + row_in_tile;
-        row_ok = row < p.M;
-      }
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v[32];
-        const int ncol = min(32, p.BN - c0);  // 32 or 16 (BN % 16 == 0)
-        if (ncol == 32) {
-          tc::tmem_ld32(t_addr + c0, v);
-        } else {
-          uint32_t h[16];
-          tc::tmem_ld16(t_addr + c0, h);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = h[i];
-        }
-        tc::tmem_ld_wait();
-        if (row_ok) {
-          const int nbase = tc_.n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j >= ncol || nbase + j >= p.ldd) break;
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int n = nbase + j + e;
-              float x = __uint_as_float(v[j + e]);
-              if (n < p.N) {
-                if (p.bias) x += __ldg(p.bias + n);
-                x = apply_act(x, p.act) * p.alpha;
-                if (p.resid) {
-                  x += p.resid_bf16
-                           ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[row * p.ldr + n])
-                           : reinterpret_cast<const float*>(p.resid)[row * p.ldr + n];
-                }
-              } else {
-                x = 0.f;
-              }
-              o[e] = x;
-            }
-            const int nvalid = min(8, p.ldd - (nbase + j));  // columns up to ldd are ours to write (pad = 0)
-            if (p.out_bf16) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + nbase + j;
-              if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                uint4 u;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(o[4], o[5]), b3 = __floats2bfloat162_rn(o[6], o[7]);
-                u.x = *reinterpret_cast<uint32_t*>(&b0); u.y = *reinterpret_cast<uint32_t*>(&b1);
-                u.z = *reinterpret_cast<uint32_t*>(&b2); u.w = *reinterpret_cast<uint32_t*>(&b3);
-                *reinterpret_cast<uint4*>(dst) = u;
-              } else {
-                for (int e = 0; e < nvalid; ++e) dst[e] = __float2bfloat16(o[e]);
-              }
-            } else {
-              float* dst = reinterpret_cast<float*>(p.D) + row * p.ldd + nbase + j;
-              if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              } else {
-                for (int e = 0; e < nvalid; ++e) dst[e] = o[e];
-              }
-            }
-          }
-        }
-      }
+      if (p.out_bf16) epilogue_tile<true>(p, &tmD, &tmR, &tmDt, &tmRt, tc_, t_addr, stage, res_bar[q], res_seq, st_seq, q, lane);
+      else epilogue_tile<false>(p, &tmD, &tmR, &tmDt, &tmRt, tc_, t_addr, stage, res_bar[q], res_seq, st_seq, q, lane);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA retires
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -281,7 +361,8 @@ static int pick_bn(int N) {
   return 256;
 }
 
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmR,
+                  const CUtensorMap& tmDt, const CUtensorMap& tmRt, Params& p, cudaStream_t stream) {
   static int num_sms = 0;
   static bool attr_set = false;
   if (!num_sms) {
@@ -290,16 +371,16 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, cud
     ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    ISP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  p.stages = kSmemBudget / stage_bytes;
+  p.stages = kMainBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   const long long ntiles = p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBudget, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmR, tmDt, tmRt, p);
   ISP_CHECK_LAUNCH("gemm_tc_kernel");
   return ISP_OK;
 }
@@ -317,9 +398,19 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   ISP_REQUIRE(lda >= K && ldw >= K && ldd >= N, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: leading dimensions too small");
   ISP_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, ISP_ERR_MISALIGNED,
               "gemm_bf16_tc: lda/ldw must be multiples of 8 elements (TMA 16-byte strides), got %lld/%lld", lda, ldw);
+  const int esz = out_bf16 ? 2 : 4;
+  ISP_REQUIRE((ldd * esz) % 16 == 0 && aligned16(D), ISP_ERR_MISALIGNED,
+              "gemm_bf16_tc: D rows must be 16-byte aligned (ldd=%lld)", ldd);
   ISP_REQUIRE(aligned16(A) && aligned16(W), ISP_ERR_MISALIGNED, "gemm_bf16_tc: A/W must be 16-byte aligned");
   ISP_REQUIRE(act >= 0 && act <= 3, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: unknown activation %d", act);
+  ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "gemm_bf16_tc: bias must be 16-byte aligned");
   ISP_REQUIRE(M < (1ll << 31), ISP_ERR_UNSUPPORTED, "gemm_bf16_tc: M too large for TMA coordinates");
+  if (resid) {
+    ISP_REQUIRE((resid_bf16 != 0) == (out_bf16 != 0), ISP_ERR_UNSUPPORTED,
+                "gemm_bf16_tc: residual must have the output dtype");
+    ISP_REQUIRE(ldr >= N && (ldr * esz) % 16 == 0 && aligned16(resid), ISP_ERR_MISALIGNED,
+                "gemm_bf16_tc: residual rows must be 16-byte aligned (ldr=%lld)", ldr);
+  }
   gemm::Params p = {};
   p.M = M; p.N = N;
   p.K = (K + gemm::BK - 1) / gemm::BK * gemm::BK;  // TMA zero-fills the K tail (global dim = K)
@@ -327,9 +418,8 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   p.TW = 0;
   p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
-  p.bias = bias; p.resid = resid; p.resid_bf16 = resid_bf16; p.ldr = (int)ldr; p.alpha = alpha; p.act = act;
-  p.D = D; p.ldd = (int)ldd; p.out_bf16 = out_bf16;
-  CUtensorMap tmA, tmB;
+  p.bias = bias; p.has_resid = resid != nullptr; p.alpha = alpha; p.act = act; p.out_bf16 = out_bf16;
+  CUtensorMap tmA, tmB, tmD, tmR;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)lda * 2};
     const uint32_t box[2] = {gemm::BK, gemm::BM};
@@ -340,7 +430,24 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
     const uint32_t box[2] = {gemm::BK, (uint32_t)p.BN};
     if (int e = make_tmap_bf16(&tmB, W, 2, dims, str, box, "gemm_bf16_tc(W)")) return e;
   }
-  return gemm::launch(tmA, tmB, p, as_stream(stream));
+  const uint32_t cw = out_bf16 ? 64 : 32;
+  const uint32_t tailw = (uint32_t)p.BN % cw;  // narrower last chunk of every tile (0 = none)
+  CUtensorMap tmDt, tmRt;
+  {
+    const uint64_t dims[2] = {(uint64_t)ldd, (uint64_t)M}, str[2] = {(uint64_t)esz, (uint64_t)ldd * esz};
+    const uint32_t box[2] = {cw, 32}, boxt[2] = {tailw ? tailw : cw, 32};
+    if (int e = make_tmap(&tmD, esz, D, 2, dims, str, box, "gemm_bf16_tc(D)", true)) return e;
+    if (int e = make_tmap(&tmDt, esz, D, 2, dims, str, boxt, "gemm_bf16_tc(D tail)", false)) return e;
+  }
+  tmR = tmD;
+  tmRt = tmDt;
+  if (resid) {
+    const uint64_t dims[2] = {(uint64_t)ldr, (uint64_t)M}, str[2] = {(uint64_t)esz, (uint64_t)ldr * esz};
+    const uint32_t box[2] = {cw, 32}, boxt[2] = {tailw ? tailw : cw, 32};
+    if (int e = make_tmap(&tmR, esz, resid, 2, dims, str, box, "gemm_bf16_tc(resid)", true)) return e;
+    if (int e = make_tmap(&tmRt, esz, resid, 2, dims, str, boxt, "gemm_bf16_tc(resid tail)", false)) return e;
+  }
+  return gemm::launch(tmA, tmB, tmD, tmR, tmDt, tmRt, p, as_stream(stream));
 }
 
 extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
@@ -349,10 +456,13 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   ISP_REQUIRE(Nimg > 0 && H > 0 && Wd > 0 && Cout > 0 && Cin > 0, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: bad shape");
   ISP_REQUIRE(ldx >= Cin && ldx % 8 == 0, ISP_ERR_MISALIGNED,
               "conv3x3_bf16_tc: channel stride must be >= Cin and a multiple of 8 (got %d)", ldx);
-  ISP_REQUIRE(ldy >= Cout, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: ldy < Cout");
+  const int esz = out_bf16 ? 2 : 4;
+  ISP_REQUIRE(ldy >= Cout && (ldy * esz) % 16 == 0 && aligned16(Y), ISP_ERR_MISALIGNED,
+              "conv3x3_bf16_tc: output pixels must be 16-byte aligned (ldy=%d)", ldy);
   const int Cin_pad = (Cin + 63) / 64 * 64;  // weights are packed [Cout][9][Cin_pad]; TMA zero-fills c >= Cin
   ISP_REQUIRE(aligned16(X) && aligned16(Wp), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: X/W must be 16-byte aligned");
   ISP_REQUIRE(act >= 0 && act <= 3, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: unknown activation %d", act);
+  ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: bias must be 16-byte aligned");
   gemm::Params p = {};
   p.M = (long long)Nimg * H * Wd; p.N = Cout; p.K = 9 * Cin_pad;
   p.BN = gemm::pick_bn(Cout);
@@ -365,9 +475,8 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   p.tiles_w = (Wd + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
-  p.bias = bias; p.resid = nullptr; p.alpha = 1.f; p.act = act;
-  p.D = Y; p.ldd = ldy; p.out_bf16 = out_bf16;
-  CUtensorMap tmA, tmB;
+  p.bias = bias; p.has_resid = 0; p.alpha = 1.f; p.act = act; p.out_bf16 = out_bf16;
+  CUtensorMap tmA, tmB, tmD, tmDt;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
     const uint64_t str[4] = {2, (uint64_t)ldx * 2, (uint64_t)Wd * ldx * 2, (uint64_t)H * Wd * ldx * 2};
@@ -379,5 +488,14 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
     const uint32_t box[2] = {gemm::BK, (uint32_t)p.BN};
     if (int e = make_tmap_bf16(&tmB, Wp, 2, dims, str, box, "conv3x3_bf16_tc(W)")) return e;
   }
-  return gemm::launch(tmA, tmB, p, as_stream(stream));
+  {
+    const uint32_t bw = TW < 32 ? TW : 32;
+    const uint64_t dims[4] = {(uint64_t)ldy, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
+    const uint64_t str[4] = {(uint64_t)esz, (uint64_t)ldy * esz, (uint64_t)Wd * ldy * esz, (uint64_t)H * Wd * ldy * esz};
+    const uint32_t cw = out_bf16 ? 64u : 32u, tailw = (uint32_t)p.BN % cw;
+    const uint32_t box[4] = {cw, bw, 32 / bw, 1}, boxt[4] = {tailw ? tailw : cw, bw, 32 / bw, 1};
+    if (int e = make_tmap(&tmD, esz, Y, 4, dims, str, box, "conv3x3_bf16_tc(Y)", true)) return e;
+    if (int e = make_tmap(&tmDt, esz, Y, 4, dims, str, boxt, "conv3x3_bf16_tc(Y tail)", false)) return e;
+  }
+  return gemm::launch(tmA, tmB, tmD, tmD, tmDt, tmDt, p, as_stream(stream));
 }

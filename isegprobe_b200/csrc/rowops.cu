@@ -57,6 +57,91 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const void* __restr
   }
 }
 
+// Vectorised variant: each lane owns V groups of 8 consecutive columns (128-bit loads/stores for
+// bf16, 2 x 128-bit for f32); needs 16-byte aligned rows.  This is the one the hot path uses.
+template <bool IN_BF16>
+__device__ __forceinline__ void ld8(const void* p, long long idx, float (&v)[8]) {
+  if constexpr (IN_BF16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+template <bool OUT_BF16>
+__device__ __forceinline__ void st8(void* p, long long idx, const float (&v)[8]) {
+  if constexpr (OUT_BF16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <bool IN_BF16, bool OUT_BF16, int V>
+__global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const void* __restrict__ in, long long ldi,
+                                                                 void* __restrict__ out, long long ldo,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, long long M, int C,
+                                                                 float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float x[V][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c0 = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[i][e] = 0.f;
+    if (c0 < C && c0 + 8 <= ldi) ld8<IN_BF16>(in, row * ldi + c0, x[i]);
+    else if (c0 < C)
+      for (int e = 0; e < 8 && c0 + e < C; ++e) x[i][e] = ld_any(in, row * ldi + c0 + e, IN_BF16);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (c0 + e >= C) x[i][e] = 0.f;
+      s += x[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c0 = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = (c0 + e < C) ? x[i][e] - mean : 0.f;
+      v += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c0 = (lane + 32 * i) * 8;
+    if (c0 >= ldo) continue;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      y[e] = (c < C) ? (x[i][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+    }
+    st8<OUT_BF16>(out, row * ldo + c0, y);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Per-channel min / max of a [B,3,H,W] image over batch + space (MinMaxScaler,
 // loftup/layers.py:66-71).  mm[0..2] = min, mm[3..5] = max; order-preserving int atomics.
@@ -287,6 +372,26 @@ extern "C" int isp_layernorm_rows(const void* in, int in_bf16, long long ldi, vo
   ISP_REQUIRE(in && out && gamma && beta, ISP_ERR_BAD_SHAPE, "layernorm_rows: null pointer");
   ISP_REQUIRE(M > 0 && C > 0 && C <= 32 * kLnMaxPerLane && ldi >= C && ldo >= C && ldo <= 32 * kLnMaxPerLane,
               ISP_ERR_BAD_SHAPE, "layernorm_rows: bad shape M=%lld C=%d ldi=%lld ldo=%lld", M, C, ldi, ldo);
+  if (ldi % 8 == 0 && ldo % 8 == 0 && aligned16(in) && aligned16(out) && ldo <= 1024) {
+    const int nvec = (int)((ldo + 7) / 8);
+    const int V = (nvec + 31) / 32;  // 8-element vectors per lane
+    dim3 grid(cdiv(M, 8));
+#define ISP_LN_LAUNCH(IB, OB, VV)                                                                        \
+  layernorm_rows_vec_kernel<IB, OB, VV><<<grid, 256, 0, as_stream(stream)>>>(in, ldi, out, ldo, gamma, beta, M, C, eps)
+#define ISP_LN_V(IB, OB)                                                           \
+  do {                                                                             \
+    if (V == 1) ISP_LN_LAUNCH(IB, OB, 1); else if (V == 2) ISP_LN_LAUNCH(IB, OB, 2); \
+    else if (V == 3) ISP_LN_LAUNCH(IB, OB, 3); else ISP_LN_LAUNCH(IB, OB, 4);       \
+  } while (0)
+    if (in_bf16 && out_bf16) ISP_LN_V(true, true);
+    else if (in_bf16) ISP_LN_V(true, false);
+    else if (out_bf16) ISP_LN_V(false, true);
+    else ISP_LN_V(false, false);
+#undef ISP_LN_V
+#undef ISP_LN_LAUNCH
+    ISP_CHECK_LAUNCH("layernorm_rows_vec_kernel");
+    return ISP_OK;
+  }
   layernorm_rows_kernel<<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(in, in_bf16, ldi, out, out_bf16, ldo, gamma, beta, M,
                                                                  C, eps);
   ISP_CHECK_LAUNCH("layernorm_rows_kernel");

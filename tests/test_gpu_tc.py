@@ -42,9 +42,11 @@ def test_gemm_epilogue(tc):
         want = 0.5 * fn(A.float() @ W.float().T + b) + R
         assert relerr(out, want) < 1e-4, act
     # bf16 output with padded leading dimension, bf16 residual
-    Rb = R.to(torch.bfloat16)
-    out = tc.gemm(A.to(DEV), W.to(DEV), bias=b.to(DEV), resid=Rb.to(DEV), act=None, out_dtype=torch.bfloat16, ldd=416)
-    want = A.float() @ W.float().T + b + Rb.float()
+    Rb = torch.zeros(M, 416, dtype=torch.bfloat16)  # residual rows must be 16-byte aligned (TMA)
+    Rb[:, :N] = R.to(torch.bfloat16)
+    out = tc.gemm(A.to(DEV), W.to(DEV), bias=b.to(DEV), resid=Rb.to(DEV), act=None, out_dtype=torch.bfloat16, ldd=416,
+                  N=N)
+    want = A.float() @ W.float().T + b + Rb[:, :N].float()
     assert out.shape == (M, 416) and float(out[:, 404:].abs().max()) == 0
     assert relerr(out[:, :404].float(), want) < 1e-2 and cosine(out[:, :404].float(), want) > 0.9999
 
