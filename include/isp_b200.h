@@ -84,17 +84,27 @@ int isp_jbu_range_proj(const float* g, float* proj, long long npix, const float*
 /* combined kernel of JBULearnedRange.forward: softmax_49(temp*<proj nbr, proj>) * spatial,
  * renormalised, + 0.1*fixup([k,g]).  filters out [B,H,W,49].
  * fw0 [49,52], fb0 [49], fw1 [49,49], fb1 [49]; temp = clamp(exp(range_temp),1e-4,1e4). */
+/* out_ld selects the filter layout: 49 = dense [B,H,W,49]; 56 = row-padded [B,H,W,7,8] (8th tap of
+ * each filter row is 0), which isp_adaptive_conv_fwd fetches with one TMA box per tile. */
 int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W,
                     float temp, float sigma_spatial, const float* fw0, const float* fb0,
-                    const float* fw1, const float* fb1, isp_stream_t stream);
+                    const float* fw1, const float* fb1, int out_ld, isp_stream_t stream);
+/* first-generation kernel (neighbour projections read from global memory), dense [.,49] output; A/B runs */
+int isp_jbu_filters_v1(const float* proj, const float* g, float* filters, int B, int H, int W,
+                       float temp, float sigma_spatial, const float* fw0, const float* fb0,
+                       const float* fw1, const float* fb1, isp_stream_t stream);
 /* bicubic x2 (align_corners=False, A=-0.75) followed by reflect pad 3:
  * src NHWC [B,h,w,C] -> out NHWC [B,2h+6,2w+6,C] */
 int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,
                                  isp_stream_t stream);
 /* AdaptiveConv.forward: out[b,y,x,c] = sum_{i,j<7} in[b,y+i,x+j,c] * filt[b,y,x,i*7+j].
- * NHWC fast path: in [B,H+6,W+6,C], out [B,H,W,C], C % 64 == 0. */
+ * NHWC fast path: in [B,H+6,W+6,C], out [B,H,W,C], C % 64 == 0.  filt_ld: 49 = dense filters
+ * [B,H,W,49] (FeatUp's layout), 56 = row-padded [B,H,W,7,8] (see isp_jbu_filters). */
 int isp_adaptive_conv_fwd(const float* in_padded, const float* filters, float* out,
-                          int B, int H, int W, int C, isp_stream_t stream);
+                          int B, int H, int W, int C, int filt_ld, isp_stream_t stream);
+/* first-generation NHWC kernel (cp.async fill, per-pixel 7x7 register window), kept for A/B runs */
+int isp_adaptive_conv_fwd_v1(const float* in_padded, const float* filters, float* out,
+                             int B, int H, int W, int C, isp_stream_t stream);
 /* same op, FeatUp's own layout (NCHW in [B,C,H+6,W+6], out [B,C,H,W]); any C */
 int isp_adaptive_conv_fwd_nchw(const float* in_padded, const float* filters, float* out,
                                int B, int H, int W, int C, isp_stream_t stream);

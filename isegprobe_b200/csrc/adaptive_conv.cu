@@ -170,9 +170,9 @@ static int ac_check(const void* a, const void* f, const void* o, int B, int H, i
   return ISP_OK;
 }
 
-extern "C" int isp_adaptive_conv_fwd(const float* in_padded, const float* filters, float* out, int B, int H, int W,
+extern "C" int isp_adaptive_conv_fwd_v1(const float* in_padded, const float* filters, float* out, int B, int H, int W,
                                      int C, isp_stream_t stream) {
-  if (int e = ac_check(in_padded, filters, out, B, H, W, C, "adaptive_conv_fwd")) return e;
+  if (int e = ac_check(in_padded, filters, out, B, H, W, C, "adaptive_conv_fwd_v1")) return e;
   ISP_REQUIRE(C % AC_CG == 0, ISP_ERR_UNSUPPORTED, "adaptive_conv_fwd: NHWC path needs C %% 64 == 0 (C=%d)", C);
   ISP_REQUIRE(aligned16(in_padded) && aligned16(out), ISP_ERR_MISALIGNED, "adaptive_conv_fwd: 16-byte alignment");
   static bool attr_set = false;

@@ -59,11 +59,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 namespace gemm {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter (they split the chunks)
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kEpiBytesPerWarp = 4 * 4096;  // 2 output + 2 residual staging chunks of 32 rows x 128 B
-constexpr int kEpiBytes = 4 * kEpiBytesPerWarp;
+constexpr int kEpiBytesPerWarp = 2 * 4096;         // two output staging chunks of 32 rows x 128 B
+constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 constexpr int kMainBudget = 160 * 1024;
 constexpr int kSmemBytes = kMainBudget + kEpiBytes;  // 224 KB: also forces one CTA per SM (TMEM: 512 columns)
 
@@ -77,17 +78,32 @@ struct Params {
   long long tiles_m, tiles_n;
   int tiles_w, tiles_h;
   // epilogue
-  const float* bias;  // [N] or null
-  int has_resid;      // residual has the dtype and addressing of D
-  float alpha;        // out = alpha * act(acc + bias) + resid
-  int act;            // 0 none, 1 relu, 2 gelu(erf), 3 quick-gelu
+  const float* bias;   // [N] or null
+  const void* resid;   // [M, ldr] in the dtype of D, or null (GEMM mode only)
+  long long ldr;
+  float alpha;         // out = alpha * act(acc + bias) + resid
+  int act;             // 0 none, 1 relu, 2 gelu(erf), 3 quick-gelu
   int out_bf16;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return gelu_erf(v);
-  if (act == 3) return v / (1.f + __expf(-1.702f * v));
+// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): 1 RCP + 1 EX2 + 7 FMA instead of erff's ~25
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-ax * ax * 1.4426950408889634f);
+  const float r = fmaf(-poly * t, e, 1.f);
+  return copysignf(r, x);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if constexpr (ACT == 1) return fmaxf(v, 0.f);
+  if constexpr (ACT == 2) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752440f));
+  if constexpr (ACT == 3) return v / (1.f + __expf(-1.702f * v));
   return v;
 }
 
@@ -113,19 +129,19 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
   return c;
 }
 
-// One epilogue warp, one tile.  CW = columns per 128-byte chunk (64 bf16 / 32 f32).
-// res_seq / st_seq count this warp's residual loads / output stores since kernel start; they pick
-// the staging buffer (seq & 1) and, for the residual mbarriers, the phase parity ((seq >> 1) & 1).
-template <bool OUT_BF16>
-__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmD, const CUtensorMap* tmR,
-                                              const CUtensorMap* tmDt, const CUtensorMap* tmRt, const TileCoord& tc_, uint32_t t_addr, uint8_t* stage, uint64_t* res_bar,
-                                              uint32_t& res_seq, uint32_t& st_seq, int q, int lane) {
+// One epilogue warp, its share of one tile.  CW = columns per 128-byte chunk (64 bf16 / 32 f32).
+// The two warps of a lane quarter take alternate chunks.  Per chunk: prefetch the residual slice
+// with coalesced 16-byte loads (8 lanes = one 128-byte row segment), tcgen05.ld the accumulator,
+// bias/activation in registers, stage into 128B-swizzled smem, add the residual there
+// (row-coalesced pass), TMA-store the chunk.  st_seq counts this warp's stores (staging buffer).
+template <bool OUT_BF16, int ACT>
+__device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmD, const CUtensorMap* tmDt,
+                                              const TileCoord& tc_, uint32_t t_addr, uint8_t* stage, uint32_t& st_seq,
+                                              int q, int half, int lane) {
   constexpr int CW = OUT_BF16 ? 64 : 32;
-  uint8_t* out_buf = stage;             // [2][4096]
-  uint8_t* res_buf = stage + 2 * 4096;  // [2][4096]
+  constexpr int ESZ = OUT_BF16 ? 2 : 4;
   const int nchunks = (p.BN + CW - 1) / CW;
-  // where this warp's 32 rows live in the output tensor
-  int c1, c2 = 0, c3 = 0;
+  int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
   if (p.TW) {
     const int bw = p.TW < 32 ? p.TW : 32;
     const int pix = q * 32;
@@ -135,110 +151,128 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
   } else {
     c1 = (int)tc_.m0 + q * 32;
   }
-  // The last chunk of a tile may be narrower than CW (BN % CW columns).  It goes through a second,
-  // un-swizzled tensor map with a box of exactly that width, so it never touches the next tile.
-  constexpr int ESZ = OUT_BF16 ? 2 : 4;
-  const int tail_cols = p.BN % CW;
-  auto load_res = [&](int chunk, uint32_t seq) {  // lane 0 only
-    uint64_t* bar = &res_bar[seq & 1];
-    const bool tl_ = tail_cols && chunk == nchunks - 1;
-    tc::mbar_arrive_expect_tx(bar, tl_ ? 32 * tail_cols * ESZ : 4096);
-    const CUtensorMap* m = tl_ ? tmRt : tmR;
-    if (p.TW) tc::tma_load_4d(res_buf + (seq & 1) * 4096, m, bar, tc_.n0 + chunk * CW, c1, c2, c3);
-    else tc::tma_load_2d(res_buf + (seq & 1) * 4096, m, bar, tc_.n0 + chunk * CW, c1);
-  };
-  if (p.has_resid && lane == 0) load_res(0, res_seq);
   const int r7 = lane & 7;
-  for (int c = 0; c < nchunks; ++c) {
+  const int sub_r = lane >> 3, sub_u = lane & 7;  // residual pass: lane -> (row within group of 4, 16-byte unit)
+  for (int c = half; c < nchunks; c += 2) {
     const int col0 = c * CW;                 // column inside the tile
     const int ncols = min(CW, p.BN - col0);  // multiple of 16
     const bool is_tail = ncols < CW;
     const int row_bytes = ncols * ESZ;       // dense row pitch of a tail chunk
-    uint32_t vr[CW];
+    const int nglob = tc_.n0 + col0;         // first global column of the chunk
+    const bool full = nglob + ncols <= p.N;  // no column masking needed
+    // ---- residual prefetch (registers), coalesced: 8 lanes cover one row's 128-byte slice
+    uint4 rres[8];
+    const int units = row_bytes >> 4;
+    if (p.resid) {
 #pragma unroll
-    for (int g = 0; g < CW / 16; ++g) {
-      if (g * 16 < ncols) {
-        tc::tmem_ld16(t_addr + col0 + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&vr[g * 16]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) vr[g * 16 + e] = 0u;
+      for (int it = 0; it < 8; ++it) {
+        const long long grow = tc_.m0 + q * 32 + it * 4 + sub_r;
+        rres[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (grow < p.M && sub_u < units && nglob + sub_u * (16 / ESZ) < p.ldr)
+          rres[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid) +
+                                                          (grow * p.ldr + nglob) * ESZ + sub_u * 16));
       }
     }
-    tc::tmem_ld_wait();
-    float v[CW];
-    // bias / activation / scale (columns >= N produce exact zeros: they are K-padding for the next GEMM)
-#pragma unroll
-    for (int e4 = 0; e4 < CW; e4 += 4) {
-      const int n = tc_.n0 + col0 + e4;
-      float b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.bias) {
-        if (n + 3 < p.N) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < p.N) b[e] = __ldg(p.bias + n + e);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        v[e4 + e] = (n + e < p.N) ? apply_act(__uint_as_float(vr[e4 + e]) + b[e], p.act) * p.alpha : 0.f;
-    }
-    if (p.has_resid) {
-      if (lane == 0 && c + 1 < nchunks) load_res(c + 1, res_seq + 1);
-      tc::mbar_wait(&res_bar[res_seq & 1], (res_seq >> 1) & 1);
-      const uint8_t* rb = res_buf + (res_seq & 1) * 4096 + lane * (is_tail ? row_bytes : 128);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (u * 16 >= row_bytes) break;
-        const uint4 w = *reinterpret_cast<const uint4*>(rb + (is_tail ? (u << 4) : ((u ^ r7) << 4)));
-        if constexpr (OUT_BF16) {
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = tc_.n0 + col0 + u * 8 + 2 * i;
-            if (n < p.N) v[u * 8 + 2 * i] += __uint_as_float(ww[i] << 16);
-            if (n + 1 < p.N) v[u * 8 + 2 * i + 1] += __uint_as_float(ww[i] & 0xffff0000u);
-          }
-        } else {
-          const int n = tc_.n0 + col0 + u * 4;
-          if (n < p.N) v[u * 4] += __uint_as_float(w.x);
-          if (n + 1 < p.N) v[u * 4 + 1] += __uint_as_float(w.y);
-          if (n + 2 < p.N) v[u * 4 + 2] += __uint_as_float(w.z);
-          if (n + 3 < p.N) v[u * 4 + 3] += __uint_as_float(w.w);
-        }
-      }
-      ++res_seq;
-      __syncwarp();  // everyone has consumed this residual buffer before lane 0 re-arms it (two chunks later)
-    }
-    // stage the chunk (32 rows x 128 B, 16-byte units XOR-swizzled like TMA's SWIZZLE_128B) and store it
+    // ---- staging buffer of this chunk (32 rows x 128 B, 16-byte units XOR-swizzled like TMA's
+    //      SWIZZLE_128B; tail chunks dense and un-swizzled)
     if (lane == 0) tc::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
     __syncwarp();
-    uint8_t* ob = out_buf + (st_seq & 1) * 4096 + lane * (is_tail ? row_bytes : 128);
+    uint8_t* obuf = stage + (st_seq & 1) * 4096;
+    uint8_t* ob = obuf + lane * (is_tail ? row_bytes : 128);
+    // ---- accumulator -> registers -> bias / activation / scale -> staging, 32 columns at a time
+    //      (columns >= N give exact zeros: they are K-padding for the next GEMM)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (u * 16 >= row_bytes) break;
-      uint4 w;
-      if constexpr (OUT_BF16) {
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[u * 8 + 0], v[u * 8 + 1]);
-        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[u * 8 + 2], v[u * 8 + 3]);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[u * 8 + 4], v[u * 8 + 5]);
-        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[u * 8 + 6], v[u * 8 + 7]);
-        w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
-                       *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
-      } else {
-        w = make_uint4(__float_as_uint(v[u * 4 + 0]), __float_as_uint(v[u * 4 + 1]), __float_as_uint(v[u * 4 + 2]),
-                       __float_as_uint(v[u * 4 + 3]));
+    for (int sb = 0; sb < CW / 32; ++sb) {
+      const int scol = sb * 32;
+      if (scol >= ncols) break;
+      uint32_t vr[32];
+      if (scol + 32 <= ncols) {
+        tc::tmem_ld32(t_addr + col0 + scol, vr);
+      } else {  // 16 live columns
+        tc::tmem_ld16(t_addr + col0 + scol, *reinterpret_cast<uint32_t(*)[16]>(&vr[0]));
+#pragma unroll
+        for (int e = 16; e < 32; ++e) vr[e] = 0u;
       }
-      *reinterpret_cast<uint4*>(ob + (is_tail ? (u << 4) : ((u ^ r7) << 4))) = w;
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int e4 = 0; e4 < 32; e4 += 4) {
+        const int n = nglob + scol + e4;
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias) {
+          if (n + 3 < p.N) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) b[e] = __ldg(p.bias + n + e);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = act_fn<ACT>(__uint_as_float(vr[e4 + e]) + b[e]) * p.alpha;
+          vr[e4 + e] = __float_as_uint((full || n + e < p.N) ? x : 0.f);
+        }
+      }
+      constexpr int UPS = OUT_BF16 ? 4 : 8;  // 16-byte units produced per 32-column sub-block
+#pragma unroll
+      for (int uu = 0; uu < UPS; ++uu) {
+        const int u = sb * UPS + uu;
+        if (u * 16 >= row_bytes) break;
+        uint4 w;
+        if constexpr (OUT_BF16) {
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 0]), __uint_as_float(vr[uu * 8 + 1]));
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 2]), __uint_as_float(vr[uu * 8 + 3]));
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 4]), __uint_as_float(vr[uu * 8 + 5]));
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 6]), __uint_as_float(vr[uu * 8 + 7]));
+          w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
+                         *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
+        } else {
+          w = make_uint4(vr[uu * 4 + 0], vr[uu * 4 + 1], vr[uu * 4 + 2], vr[uu * 4 + 3]);
+        }
+        *reinterpret_cast<uint4*>(ob + (is_tail ? (u << 4) : ((u ^ r7) << 4))) = w;
+      }
+    }
+    // ---- residual: row-coalesced read-modify-write of the staged chunk
+    if (p.resid) {
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (sub_u >= units) continue;
+        const int r = it * 4 + sub_r;
+        uint8_t* sp = obuf + (is_tail ? r * row_bytes + (sub_u << 4) : r * 128 + ((sub_u ^ (r & 7)) << 4));
+        uint4 o = *reinterpret_cast<uint4*>(sp);
+        const uint4 rr = rres[it];
+        const int nb = nglob + sub_u * (16 / ESZ);
+        if constexpr (OUT_BF16) {
+          uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+          const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float lo = __uint_as_float(ow[i] << 16), hi = __uint_as_float(ow[i] & 0xffff0000u);
+            if (full || nb + 2 * i < p.N) lo += __uint_as_float(rw[i] << 16);
+            if (full || nb + 2 * i + 1 < p.N) hi += __uint_as_float(rw[i] & 0xffff0000u);
+            __nv_bfloat162 bb = __floats2bfloat162_rn(lo, hi);
+            ow[i] = *reinterpret_cast<uint32_t*>(&bb);
+          }
+          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else {
+          float f[4] = {__uint_as_float(o.x), __uint_as_float(o.y), __uint_as_float(o.z), __uint_as_float(o.w)};
+          const float g[4] = {__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (full || nb + i < p.N) f[i] += g[i];
+          o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+        }
+        *reinterpret_cast<uint4*>(sp) = o;
+      }
     }
     tc::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
       const CUtensorMap* m = is_tail ? tmDt : tmD;
-      if (p.TW) tc::tma_store_4d(m, out_buf + (st_seq & 1) * 4096, tc_.n0 + col0, c1, c2, c3);
-      else tc::tma_store_2d(m, out_buf + (st_seq & 1) * 4096, tc_.n0 + col0, c1);
+      if (p.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
+      else tc::tma_store_2d(m, obuf, nglob, c1);
       tc::tma_store_commit();
     }
     ++st_seq;
@@ -247,11 +281,9 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmDt, const __grid_constant__ CUtensorMap tmRt, const Params p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDt, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2],
-      res_bar[4][2];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,10 +296,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
     tc::prefetch_tmap(&tmD);
-    if (p.has_resid) tc::prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], 4); }
-    for (int w = 0; w < 4; ++w) { tc::mbar_init(&res_bar[w][0], 1); tc::mbar_init(&res_bar[w][1], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -327,18 +357,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------- epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access == its 32 rows of the tile
-    uint8_t* stage = epi_smem + q * kEpiBytesPerWarp;
-    uint32_t tl = 0, res_seq = 0, st_seq = 0;
+    // ------------------------------------------------------------- epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int q = warp & 3;      // TMEM lane quarter this warp may access == its 32 rows of the tile
+    const int half = ew >> 2;    // which of the two warps sharing that quarter (takes chunks half, half+2, ...)
+    uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
+    uint32_t tl = 0, st_seq = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       const TileCoord tc_ = tile_coord(p, t);
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-      if (p.out_bf16) epilogue_tile<true>(p, &tmD, &tmR, &tmDt, &tmRt, tc_, t_addr, stage, res_bar[q], res_seq, st_seq, q, lane);
-      else epilogue_tile<false>(p, &tmD, &tmR, &tmDt, &tmRt, tc_, t_addr, stage, res_bar[q], res_seq, st_seq, q, lane);
+#define ISP_EPI(OB, A) epilogue_tile<OB, A>(p, &tmD, &tmDt, tc_, t_addr, stage, st_seq, q, half, lane)
+      if (p.out_bf16) {
+        if (p.act == 0) ISP_EPI(true, 0); else if (p.act == 1) ISP_EPI(true, 1);
+        else if (p.act == 2) ISP_EPI(true, 2); else ISP_EPI(true, 3);
+      } else {
+        if (p.act == 0) ISP_EPI(false, 0); else if (p.act == 1) ISP_EPI(false, 1);
+        else if (p.act == 2) ISP_EPI(false, 2); else ISP_EPI(false, 3);
+      }
+#undef ISP_EPI
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
@@ -361,8 +400,8 @@ static int pick_bn(int N) {
   return 256;
 }
 
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmR,
-                  const CUtensorMap& tmDt, const CUtensorMap& tmRt, Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmDt,
+                  Params& p, cudaStream_t stream) {
   static int num_sms = 0;
   static bool attr_set = false;
   if (!num_sms) {
@@ -380,7 +419,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   const long long ntiles = p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmR, tmDt, tmRt, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, p);
   ISP_CHECK_LAUNCH("gemm_tc_kernel");
   return ISP_OK;
 }
@@ -418,8 +457,8 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   p.TW = 0;
   p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
-  p.bias = bias; p.has_resid = resid != nullptr; p.alpha = alpha; p.act = act; p.out_bf16 = out_bf16;
-  CUtensorMap tmA, tmB, tmD, tmR;
+  p.bias = bias; p.resid = resid; p.ldr = ldr; p.alpha = alpha; p.act = act; p.out_bf16 = out_bf16;
+  CUtensorMap tmA, tmB, tmD;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)lda * 2};
     const uint32_t box[2] = {gemm::BK, gemm::BM};
@@ -432,22 +471,14 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   }
   const uint32_t cw = out_bf16 ? 64 : 32;
   const uint32_t tailw = (uint32_t)p.BN % cw;  // narrower last chunk of every tile (0 = none)
-  CUtensorMap tmDt, tmRt;
+  CUtensorMap tmDt;
   {
     const uint64_t dims[2] = {(uint64_t)ldd, (uint64_t)M}, str[2] = {(uint64_t)esz, (uint64_t)ldd * esz};
     const uint32_t box[2] = {cw, 32}, boxt[2] = {tailw ? tailw : cw, 32};
     if (int e = make_tmap(&tmD, esz, D, 2, dims, str, box, "gemm_bf16_tc(D)", true)) return e;
     if (int e = make_tmap(&tmDt, esz, D, 2, dims, str, boxt, "gemm_bf16_tc(D tail)", false)) return e;
   }
-  tmR = tmD;
-  tmRt = tmDt;
-  if (resid) {
-    const uint64_t dims[2] = {(uint64_t)ldr, (uint64_t)M}, str[2] = {(uint64_t)esz, (uint64_t)ldr * esz};
-    const uint32_t box[2] = {cw, 32}, boxt[2] = {tailw ? tailw : cw, 32};
-    if (int e = make_tmap(&tmR, esz, resid, 2, dims, str, box, "gemm_bf16_tc(resid)", true)) return e;
-    if (int e = make_tmap(&tmRt, esz, resid, 2, dims, str, boxt, "gemm_bf16_tc(resid tail)", false)) return e;
-  }
-  return gemm::launch(tmA, tmB, tmD, tmR, tmDt, tmRt, p, as_stream(stream));
+  return gemm::launch(tmA, tmB, tmD, tmDt, p, as_stream(stream));
 }
 
 extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
@@ -475,7 +506,7 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   p.tiles_w = (Wd + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
-  p.bias = bias; p.has_resid = 0; p.alpha = 1.f; p.act = act; p.out_bf16 = out_bf16;
+  p.bias = bias; p.resid = nullptr; p.ldr = 0; p.alpha = 1.f; p.act = act; p.out_bf16 = out_bf16;
   CUtensorMap tmA, tmB, tmD, tmDt;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
@@ -497,5 +528,5 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
     if (int e = make_tmap(&tmD, esz, Y, 4, dims, str, box, "conv3x3_bf16_tc(Y)", true)) return e;
     if (int e = make_tmap(&tmDt, esz, Y, 4, dims, str, boxt, "conv3x3_bf16_tc(Y tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmD, tmDt, tmDt, p, as_stream(stream));
+  return gemm::launch(tmA, tmB, tmD, tmDt, p, as_stream(stream));
 }

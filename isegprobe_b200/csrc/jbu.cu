@@ -273,6 +273,102 @@ __global__ void __launch_bounds__(256) bicubic2x_pad_kernel(const float* __restr
   reinterpret_cast<float4*>(out)[idx] = acc;
 }
 
+// Second-generation bicubic x2: one thread produces a 2 (rows) x 4 (cols) block of outputs for
+// 4 channels from a 5 x 6 low-res neighbourhood (3.75 loads per output instead of 16), separable
+// (horizontal then vertical), written straight into the interior of the padded buffer.  The
+// 3-pixel reflect frame is filled afterwards by reflect_border_kernel from that interior.
+__global__ void __launch_bounds__(256) bicubic2x_interior_kernel(const float* __restrict__ src, float* __restrict__ out,
+                                                                 int B, int h, int w, int C) {
+  const int C4 = C / 4, wp = (w + 1) / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * h * wp * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long p = idx / C4;
+  const int lp = (int)(p % wp);
+  p /= wp;
+  const int k = (int)(p % h), b = (int)(p / h);
+  const int l0 = 2 * lp;
+  float cE[4], cO[4];
+  cubic_coeffs(0.75f, cE);  // even outputs: src = k - 0.25 -> floor k-1, t = 0.75
+  cubic_coeffs(0.25f, cO);  // odd outputs:  src = k + 0.25 -> floor k,   t = 0.25
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (long long)b * h * w * C4 + c4;
+  float4 o[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[a][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int yy = min(max(k - 2 + r, 0), h - 1);
+    float4 v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int xx = min(max(l0 - 2 + j, 0), w - 1);
+      v[j] = __ldg(s4 + ((long long)yy * w + xx) * C4);
+    }
+    float4 hh[4];  // horizontal results for output cols 2*l0, 2*l0+1, 2*l0+2, 2*l0+3
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* cc = (q & 1) ? cO : cE;
+      const int o0 = (q >> 1) + (q & 1);  // first tap index into v[]: 0,1,1,2
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a.x = fmaf(v[o0 + j].x, cc[j], a.x);
+        a.y = fmaf(v[o0 + j].y, cc[j], a.y);
+        a.z = fmaf(v[o0 + j].z, cc[j], a.z);
+        a.w = fmaf(v[o0 + j].w, cc[j], a.w);
+      }
+      hh[q] = a;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (r <= 3) {
+        o[0][q].x = fmaf(hh[q].x, cE[r], o[0][q].x); o[0][q].y = fmaf(hh[q].y, cE[r], o[0][q].y);
+        o[0][q].z = fmaf(hh[q].z, cE[r], o[0][q].z); o[0][q].w = fmaf(hh[q].w, cE[r], o[0][q].w);
+      }
+      if (r >= 1) {
+        o[1][q].x = fmaf(hh[q].x, cO[r - 1], o[1][q].x); o[1][q].y = fmaf(hh[q].y, cO[r - 1], o[1][q].y);
+        o[1][q].z = fmaf(hh[q].z, cO[r - 1], o[1][q].z); o[1][q].w = fmaf(hh[q].w, cO[r - 1], o[1][q].w);
+      }
+    }
+  }
+  const int PW = 2 * w + 6, PH = 2 * h + 6;
+  float4* o4 = reinterpret_cast<float4*>(out) + (long long)b * PH * PW * C4 + c4;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ox = 2 * l0 + q;
+      if (ox < 2 * w) o4[((long long)(2 * k + a + 3) * PW + ox + 3) * C4] = o[a][q];
+    }
+}
+
+__global__ void __launch_bounds__(256) reflect_border_kernel(float* __restrict__ out, int B, int GH, int GW, int C) {
+  const int C4 = C / 4, PW = GW + 6, PH = GH + 6;
+  const int nborder = 6 * PW + 6 * GH;  // 3 top + 3 bottom rows, then 3 left + 3 right columns of the middle rows
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * nborder * C4) return;
+  const int c4 = (int)(idx % C4);
+  long long p = idx / C4;
+  const int e = (int)(p % nborder), b = (int)(p / nborder);
+  int py, px;
+  if (e < 6 * PW) {
+    const int r = e / PW;
+    px = e % PW;
+    py = r < 3 ? r : GH + r;  // rows 0..2 and GH+3..GH+5
+  } else {
+    const int m = e - 6 * PW;
+    py = 3 + m / 6;
+    const int cidx = m % 6;
+    px = cidx < 3 ? cidx : GW + cidx;  // cols 0..2 and GW+3..GW+5
+  }
+  const int sy = reflect_idx(py - 3, GH) + 3, sx = reflect_idx(px - 3, GW) + 3;
+  float4* o4 = reinterpret_cast<float4*>(out) + (long long)b * PH * PW * C4 + c4;
+  o4[((long long)py * PW + px) * C4] = o4[((long long)sy * PW + sx) * C4];
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -300,7 +396,7 @@ extern "C" int isp_jbu_range_proj(const float* g, float* proj, long long npix, c
   return ISP_OK;
 }
 
-extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
+extern "C" int isp_jbu_filters_v1(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
                                float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
                                const float* fb1, isp_stream_t stream) {
   ISP_REQUIRE(proj && g && filters && fw0 && fb0 && fw1 && fb1, ISP_ERR_BAD_SHAPE, "jbu_filters: null pointer");
@@ -326,6 +422,15 @@ extern "C" int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B,
   ISP_REQUIRE(B > 0 && h >= 2 && w >= 2 && C > 0 && C % 4 == 0, ISP_ERR_BAD_SHAPE,
               "jbu_bicubic2x_reflectpad: need h,w >= 2 and C %% 4 == 0 (h=%d w=%d C=%d)", h, w, C);
   ISP_REQUIRE(aligned16(src) && aligned16(out), ISP_ERR_MISALIGNED, "jbu_bicubic2x_reflectpad: 16-byte alignment");
+  if (h >= 4 && w >= 4) {  // blocked interior + reflect frame (frame sources lie in the interior)
+    const long long total = (long long)B * h * ((w + 1) / 2) * (C / 4);
+    bicubic2x_interior_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, out, B, h, w, C);
+    ISP_CHECK_LAUNCH("bicubic2x_interior_kernel");
+    const long long nb = (long long)B * (6 * (2 * w + 6) + 6 * 2 * h) * (C / 4);
+    reflect_border_kernel<<<cdiv(nb, 256), 256, 0, as_stream(stream)>>>(out, B, 2 * h, 2 * w, C);
+    ISP_CHECK_LAUNCH("reflect_border_kernel");
+    return ISP_OK;
+  }
   const long long total = (long long)B * (2 * h + 6) * (2 * w + 6) * (C / 4);
   bicubic2x_pad_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, out, B, h, w, C);
   ISP_CHECK_LAUNCH("bicubic2x_pad_kernel");

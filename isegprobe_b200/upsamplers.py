@@ -165,16 +165,16 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         w0, b0, w1, b1 = self._flat(rp[0].weight), rp[0].bias.detach().float(), self._flat(rp[3].weight), rp[3].bias.detach().float()
         _lib.call("isp_jbu_range_proj", _lib.dptr(g), _lib.dptr(proj), B * GH * GW, _lib.dptr(w0), _lib.dptr(b0),
                   _lib.dptr(w1), _lib.dptr(b1), st)
-        filt = torch.empty(B, GH, GW, 49, dtype=torch.float32, device=dev)
+        filt = torch.empty(B, GH, GW, 56, dtype=torch.float32, device=dev)  # row-padded [7][8] filters
         temp = min(max(math.exp(self._scalar(up.range_temp)), 1e-4), 1e4)
         f0, fb0, f1, fb1 = self._flat(fp[0].weight), fp[0].bias.detach().float(), self._flat(fp[3].weight), fp[3].bias.detach().float()
         _lib.call("isp_jbu_filters", _lib.dptr(proj), _lib.dptr(g), _lib.dptr(filt), B, GH, GW, float(temp),
-                  self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), st)
+                  self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), 56, st)
         hr = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
         _lib.call("isp_jbu_bicubic2x_reflectpad", _lib.dptr(src), _lib.dptr(hr), B, h, w, C, st)
         out = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
         with timed_kernel(f"adaptive_conv_{GH}"):
-            _lib.call("isp_adaptive_conv_fwd", _lib.dptr(hr), _lib.dptr(filt), _lib.dptr(out), B, GH, GW, C, st)
+            _lib.call("isp_adaptive_conv_fwd", _lib.dptr(hr), _lib.dptr(filt), _lib.dptr(out), B, GH, GW, C, 56, st)
         return out
 
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:

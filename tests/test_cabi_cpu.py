@@ -58,7 +58,7 @@ def test_argument_validation_without_gpu(built):
     L = _lib.lib()
     assert L.isp_distmaps_fwd(None, None, 1, 1, 8, 8, 5.0, 1.0, 1, None) == -1
     assert b"null" in L.isp_last_error()
-    assert L.isp_adaptive_conv_fwd(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 8, 8, 48, None) == -4
+    assert L.isp_adaptive_conv_fwd(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 8, 8, 48, 49, None) == -4
     assert b"64" in L.isp_last_error()
 
 

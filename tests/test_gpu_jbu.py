@@ -32,8 +32,16 @@ def test_adaptive_conv_nhwc(isp, B, H, W, C):
     want = ojbu.adaptive_conv(x, f)
     xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
     out = torch.empty(B, H, W, C, device=DEV)
-    _call("isp_adaptive_conv_fwd", xin, f.reshape(B, H, W, 49).contiguous().to(DEV), out, B, H, W, C)
+    _call("isp_adaptive_conv_fwd", xin, f.reshape(B, H, W, 49).contiguous().to(DEV), out, B, H, W, C, 49)
+    f56 = torch.zeros(B, H, W, 7, 8)
+    f56[..., :7] = f
+    out56 = torch.empty(B, H, W, C, device=DEV)
+    _call("isp_adaptive_conv_fwd", xin, f56.reshape(B, H, W, 56).contiguous().to(DEV), out56, B, H, W, C, 56)
+    assert torch.equal(out56, out)  # padded-filter (TMA) path computes the same thing
     assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+    out1 = torch.empty(B, H, W, C, device=DEV)
+    _call("isp_adaptive_conv_fwd_v1", xin, f.reshape(B, H, W, 49).contiguous().to(DEV), out1, B, H, W, C)
+    assert relerr(out1.permute(0, 3, 1, 2), want) < 1e-5
     # FeatUp-layout kernel must agree as well (independent implementation)
     out2 = torch.empty(B, C, H, W, device=DEV)
     _call("isp_adaptive_conv_fwd_nchw", x.to(DEV), f.reshape(B, H, W, 49).contiguous().to(DEV), out2, B, H, W, C)
@@ -48,14 +56,14 @@ def test_adaptive_conv_properties_full_size(isp):
     f = torch.zeros(B, H, W, 49, device=DEV)
     f[..., 24] = 1
     out = torch.empty(B, H, W, C, device=DEV)
-    _call("isp_adaptive_conv_fwd", x, f, out, B, H, W, C)
+    _call("isp_adaptive_conv_fwd", x, f, out, B, H, W, C, 49)
     assert torch.equal(out, x[:, 3:-3, 3:-3])
     f = torch.rand(B, H, W, 49, device=DEV)
     y = torch.randn_like(x)
     o1, o2, o3 = (torch.empty(B, H, W, C, device=DEV) for _ in range(3))
-    _call("isp_adaptive_conv_fwd", x, f, o1, B, H, W, C)
-    _call("isp_adaptive_conv_fwd", y, f, o2, B, H, W, C)
-    _call("isp_adaptive_conv_fwd", x + 2 * y, f, o3, B, H, W, C)
+    _call("isp_adaptive_conv_fwd", x, f, o1, B, H, W, C, 49)
+    _call("isp_adaptive_conv_fwd", y, f, o2, B, H, W, C, 49)
+    _call("isp_adaptive_conv_fwd", x + 2 * y, f, o3, B, H, W, C, 49)
     assert relerr(o3, o1 + 2 * o2) < 1e-5
 
 
@@ -110,8 +118,16 @@ def test_filters_and_range_proj(isp):
     filt = torch.empty(2, 30, 22, 49, device=DEV)
     import math
     _call("isp_jbu_filters", proj, g4, filt, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
-          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"])
+          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"], 49)
     assert relerr(filt, want) < 1e-4
+    filt1 = torch.empty(2, 30, 22, 49, device=DEV)
+    _call("isp_jbu_filters_v1", proj, g4, filt1, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
+          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"])
+    assert relerr(filt1, want) < 1e-4
+    filt56 = torch.empty(2, 30, 22, 7, 8, device=DEV)
+    _call("isp_jbu_filters", proj, g4, filt56, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
+          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"], 56)
+    assert torch.equal(filt56[..., :7].reshape(2, 30, 22, 49), filt) and float(filt56[..., 7].abs().max()) == 0
 
 
 @pytest.mark.parametrize("B,h,w,H,W", [(2, 4, 4, 64, 64), (1, 6, 9, 96, 144), (1, 8, 8, 112, 112)])

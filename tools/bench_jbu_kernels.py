@@ -41,7 +41,8 @@ for GH in (64, 128, 256, 512):
     src = torch.randn(B, h, h, C, device=dev)
     g = torch.empty(B, GH, GH, 4, device=dev)
     proj = torch.empty(B, GH, GH, 32, device=dev)
-    filt = torch.empty(B, GH, GH, 49, device=dev)
+    filt = torch.rand(B, GH, GH, 49, device=dev)
+    filt56 = torch.empty(B, GH, GH, 56, device=dev)
     hr = torch.empty(B, GH + 6, GH + 6, C, device=dev)
     out = torch.empty(B, GH, GH, C, device=dev)
     w0, b0 = torch.randn(32, 3, device=dev), torch.randn(32, device=dev)
@@ -50,12 +51,14 @@ for GH in (64, 128, 256, 512):
     f1, fb1 = torch.randn(49, 49, device=dev) * 0.1, torch.randn(49, device=dev)
     res[f"pool_{GH}"] = timeit(lambda: call("isp_jbu_pool_guidance", gd, g, B, 448, 448, GH, GH, *gd.stride()))
     res[f"range_proj_{GH}"] = timeit(lambda: call("isp_jbu_range_proj", g, proj, B * GH * GH, w0, b0, w1, b1))
-    res[f"filters_{GH}"] = timeit(lambda: call("isp_jbu_filters", proj, g, filt, B, GH, GH, 1.0, 1.0, f0, fb0, f1, fb1))
+    res[f"filters_{GH}"] = timeit(lambda: call("isp_jbu_filters", proj, g, filt56, B, GH, GH, 1.0, 1.0, f0, fb0, f1, fb1, 56))
     res[f"bicubic_pad_{GH}"] = timeit(lambda: call("isp_jbu_bicubic2x_reflectpad", src, hr, B, h, h, C))
-    t = timeit(lambda: call("isp_adaptive_conv_fwd", hr, filt, out, B, GH, GH, C))
+    t = timeit(lambda: call("isp_adaptive_conv_fwd", hr, filt56, out, B, GH, GH, C, 56))
     res[f"adaptive_conv_{GH}"] = t
     op_bytes = 4 * B * (C * (GH + 6) ** 2 + 49 * GH * GH + C * GH * GH)
     res[f"adaptive_conv_{GH}_GBs"] = op_bytes / t / 1e6
+    t1 = timeit(lambda: call("isp_adaptive_conv_fwd_v1", hr, filt, out, B, GH, GH, C))
+    res[f"adaptive_conv_v1_{GH}"] = t1
     if GH == 512:
         wf, bf = torch.randn(C, C, device=dev) * 0.05, torch.randn(C, device=dev)
         o2 = torch.empty_like(out)
