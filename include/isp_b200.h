@@ -121,7 +121,8 @@ int isp_gemm_f32_simt(const float* A, const float* W, const float* bias, const f
  * D[M,N] = alpha * act(A[M,K] * W[N,K]^T + bias[N]) + resid[M,N]
  * A, W bf16 row-major (K contiguous; lda, ldw in elements, multiples of 8); D bf16 or f32
  * with row stride ldd >= N (columns N..ldd-1 of a written 8-column group are zeroed);
- * resid bf16 or f32 with row stride ldr, or NULL; act: 0 none, 1 ReLU, 2 GELU(erf), 3 QuickGELU.
+ * resid bf16 or f32 with row stride ldr, or NULL; act: 0 none, 1 ReLU, 2 GELU(erf), 3 QuickGELU,
+ * 4 GELU in tanh form (one MUFU; differs from the erf form by < 5e-4, used by the bf16 pipelines).
  * Replaces the cuBLAS fp32 GEMMs under nn.Linear / Conv2d(1x1) in LoftUp
  * (loftup/layers.py:161-202, loftup/loftup.py:67-70) and the ViT blocks
  * (featurizers/dinov2/layers/attention.py:54-71, mlp.py:34-40). */

@@ -89,12 +89,14 @@ struct Params {
 // erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): 1 RCP + 1 EX2 + 7 FMA instead of erff's ~25
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-ax * ax * 1.4426950408889634f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
   const float r = fmaf(-poly * t, e, 1.f);
   return copysignf(r, x);
 }
@@ -104,6 +106,12 @@ __device__ __forceinline__ float act_fn(float v) {
   if constexpr (ACT == 1) return fmaxf(v, 0.f);
   if constexpr (ACT == 2) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752440f));
   if constexpr (ACT == 3) return v / (1.f + __expf(-1.702f * v));
+  if constexpr (ACT == 4) {  // tanh-form GELU, one MUFU: |gelu_tanh - gelu_erf| < 5e-4, below bf16 output rounding
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(v * fmaf(v * v, 0.0356774081f, 0.7978845608f)));
+    const float hv = 0.5f * v;
+    return fmaf(hv, th, hv);
+  }
   return v;
 }
 
@@ -129,24 +137,34 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
   return c;
 }
 
+// What the (non-inlined) epilogue needs, passed BY VALUE: reading a by-reference Params from the
+// caller's stack cost a local-memory load per use (ncu: 59 % long-scoreboard stalls in the epilogue).
+struct EpiArgs {
+  long long M, ldr;
+  const float* bias;
+  const void* resid;
+  float alpha;
+  int N, BN, TW;
+};
+
 // One epilogue warp, its share of one tile.  CW = columns per 128-byte chunk (64 bf16 / 32 f32).
 // The two warps of a lane quarter take alternate chunks.  Per chunk: prefetch the residual slice
 // with coalesced 16-byte loads (8 lanes = one 128-byte row segment), tcgen05.ld the accumulator,
 // bias/activation in registers, stage into 128B-swizzled smem, add the residual there
 // (row-coalesced pass), TMA-store the chunk.  st_seq counts this warp's stores (staging buffer).
 template <bool OUT_BF16, int ACT>
-__device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmD, const CUtensorMap* tmDt,
-                                              const TileCoord& tc_, uint32_t t_addr, uint8_t* stage, uint32_t& st_seq,
+__device__ __noinline__ void epilogue_tile(const EpiArgs ea, const CUtensorMap* tmD, const CUtensorMap* tmDt,
+                                              const TileCoord tc_, uint32_t t_addr, uint8_t* stage, uint32_t& st_seq,
                                               int q, int half, int lane) {
   constexpr int CW = OUT_BF16 ? 64 : 32;
   constexpr int ESZ = OUT_BF16 ? 2 : 4;
-  const int nchunks = (p.BN + CW - 1) / CW;
+  const int nchunks = (ea.BN + CW - 1) / CW;
   int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
-  if (p.TW) {
-    const int bw = p.TW < 32 ? p.TW : 32;
+  if (ea.TW) {
+    const int bw = ea.TW < 32 ? ea.TW : 32;
     const int pix = q * 32;
-    c1 = tc_.w0 + (p.TW >= 32 ? pix % p.TW : 0);
-    c2 = tc_.h0 + (p.TW >= 32 ? pix / p.TW : q * (32 / bw));
+    c1 = tc_.w0 + (ea.TW >= 32 ? pix % ea.TW : 0);
+    c2 = tc_.h0 + (ea.TW >= 32 ? pix / ea.TW : q * (32 / bw));
     c3 = tc_.img;
   } else {
     c1 = (int)tc_.m0 + q * 32;
@@ -155,22 +173,22 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
   const int sub_r = lane >> 3, sub_u = lane & 7;  // residual pass: lane -> (row within group of 4, 16-byte unit)
   for (int c = half; c < nchunks; c += 2) {
     const int col0 = c * CW;                 // column inside the tile
-    const int ncols = min(CW, p.BN - col0);  // multiple of 16
+    const int ncols = min(CW, ea.BN - col0);  // multiple of 16
     const bool is_tail = ncols < CW;
     const int row_bytes = ncols * ESZ;       // dense row pitch of a tail chunk
     const int nglob = tc_.n0 + col0;         // first global column of the chunk
-    const bool full = nglob + ncols <= p.N;  // no column masking needed
+    const bool full = nglob + ncols <= ea.N;  // no column masking needed
     // ---- residual prefetch (registers), coalesced: 8 lanes cover one row's 128-byte slice
     uint4 rres[8];
     const int units = row_bytes >> 4;
-    if (p.resid) {
+    if (ea.resid) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const long long grow = tc_.m0 + q * 32 + it * 4 + sub_r;
         rres[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < p.M && sub_u < units && nglob + sub_u * (16 / ESZ) < p.ldr)
-          rres[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid) +
-                                                          (grow * p.ldr + nglob) * ESZ + sub_u * 16));
+        if (grow < ea.M && sub_u < units && nglob + sub_u * (16 / ESZ) < ea.ldr)
+          rres[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(ea.resid) +
+                                                          (grow * ea.ldr + nglob) * ESZ + sub_u * 16));
       }
     }
     // ---- staging buffer of this chunk (32 rows x 128 B, 16-byte units XOR-swizzled like TMA's
@@ -198,20 +216,20 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
       for (int e4 = 0; e4 < 32; e4 += 4) {
         const int n = nglob + scol + e4;
         float b[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias) {
-          if (n + 3 < p.N) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (ea.bias) {
+          if (n + 3 < ea.N) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(ea.bias + n));
             b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (n + e < p.N) b[e] = __ldg(p.bias + n + e);
+              if (n + e < ea.N) b[e] = __ldg(ea.bias + n + e);
           }
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float x = act_fn<ACT>(__uint_as_float(vr[e4 + e]) + b[e]) * p.alpha;
-          vr[e4 + e] = __float_as_uint((full || n + e < p.N) ? x : 0.f);
+          const float x = act_fn<ACT>(__uint_as_float(vr[e4 + e]) + b[e]) * ea.alpha;
+          vr[e4 + e] = __float_as_uint((full || n + e < ea.N) ? x : 0.f);
         }
       }
       constexpr int UPS = OUT_BF16 ? 4 : 8;  // 16-byte units produced per 32-column sub-block
@@ -234,7 +252,7 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
       }
     }
     // ---- residual: row-coalesced read-modify-write of the staged chunk
-    if (p.resid) {
+    if (ea.resid) {
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -245,15 +263,17 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
         const uint4 rr = rres[it];
         const int nb = nglob + sub_u * (16 / ESZ);
         if constexpr (OUT_BF16) {
+          // packed bf16x2 adds (HADD2.BF16): one instruction per two elements
           uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-          const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+          uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float lo = __uint_as_float(ow[i] << 16), hi = __uint_as_float(ow[i] & 0xffff0000u);
-            if (full || nb + 2 * i < p.N) lo += __uint_as_float(rw[i] << 16);
-            if (full || nb + 2 * i + 1 < p.N) hi += __uint_as_float(rw[i] & 0xffff0000u);
-            __nv_bfloat162 bb = __floats2bfloat162_rn(lo, hi);
-            ow[i] = *reinterpret_cast<uint32_t*>(&bb);
+            if (!full) {
+              if (nb + 2 * i >= ea.N) rw[i] &= 0xffff0000u;
+              if (nb + 2 * i + 1 >= ea.N) rw[i] &= 0x0000ffffu;
+            }
+            __nv_bfloat162 s2 = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&ow[i]), *reinterpret_cast<__nv_bfloat162*>(&rw[i]));
+            ow[i] = *reinterpret_cast<uint32_t*>(&s2);
           }
           o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         } else {
@@ -261,7 +281,7 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
           const float g[4] = {__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w)};
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (full || nb + i < p.N) f[i] += g[i];
+            if (full || nb + i < ea.N) f[i] += g[i];
           o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
         }
         *reinterpret_cast<uint4*>(sp) = o;
@@ -271,7 +291,7 @@ __device__ __noinline__ void epilogue_tile(const Params& p, const CUtensorMap* t
     __syncwarp();
     if (lane == 0) {
       const CUtensorMap* m = is_tail ? tmDt : tmD;
-      if (p.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
+      if (ea.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
       else tc::tma_store_2d(m, obuf, nglob, c1);
       tc::tma_store_commit();
     }
@@ -363,19 +383,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;    // which of the two warps sharing that quarter (takes chunks half, half+2, ...)
     uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
     uint32_t tl = 0, st_seq = 0;
+    const EpiArgs ea = {p.M, p.ldr, p.bias, p.resid, p.alpha, p.N, p.BN, p.TW};
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       const TileCoord tc_ = tile_coord(p, t);
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-#define ISP_EPI(OB, A) epilogue_tile<OB, A>(p, &tmD, &tmDt, tc_, t_addr, stage, st_seq, q, half, lane)
+#define ISP_EPI(OB, A) epilogue_tile<OB, A>(ea, &tmD, &tmDt, tc_, t_addr, stage, st_seq, q, half, lane)
       if (p.out_bf16) {
         if (p.act == 0) ISP_EPI(true, 0); else if (p.act == 1) ISP_EPI(true, 1);
-        else if (p.act == 2) ISP_EPI(true, 2); else ISP_EPI(true, 3);
+        else if (p.act == 2) ISP_EPI(true, 2); else if (p.act == 3) ISP_EPI(true, 3); else ISP_EPI(true, 4);
       } else {
         if (p.act == 0) ISP_EPI(false, 0); else if (p.act == 1) ISP_EPI(false, 1);
-        else if (p.act == 2) ISP_EPI(false, 2); else ISP_EPI(false, 3);
+        else if (p.act == 2) ISP_EPI(false, 2); else if (p.act == 3) ISP_EPI(false, 3); else ISP_EPI(false, 4);
       }
 #undef ISP_EPI
       tc::tc_fence_before();
@@ -441,7 +462,7 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   ISP_REQUIRE((ldd * esz) % 16 == 0 && aligned16(D), ISP_ERR_MISALIGNED,
               "gemm_bf16_tc: D rows must be 16-byte aligned (ldd=%lld)", ldd);
   ISP_REQUIRE(aligned16(A) && aligned16(W), ISP_ERR_MISALIGNED, "gemm_bf16_tc: A/W must be 16-byte aligned");
-  ISP_REQUIRE(act >= 0 && act <= 3, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: unknown activation %d", act);
+  ISP_REQUIRE(act >= 0 && act <= 4, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: unknown activation %d", act);
   ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "gemm_bf16_tc: bias must be 16-byte aligned");
   ISP_REQUIRE(M < (1ll << 31), ISP_ERR_UNSUPPORTED, "gemm_bf16_tc: M too large for TMA coordinates");
   if (resid) {
@@ -492,7 +513,7 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
               "conv3x3_bf16_tc: output pixels must be 16-byte aligned (ldy=%d)", ldy);
   const int Cin_pad = (Cin + 63) / 64 * 64;  // weights are packed [Cout][9][Cin_pad]; TMA zero-fills c >= Cin
   ISP_REQUIRE(aligned16(X) && aligned16(Wp), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: X/W must be 16-byte aligned");
-  ISP_REQUIRE(act >= 0 && act <= 3, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: unknown activation %d", act);
+  ISP_REQUIRE(act >= 0 && act <= 4, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: unknown activation %d", act);
   ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: bias must be 16-byte aligned");
   gemm::Params p = {};
   p.M = (long long)Nimg * H * Wd; p.N = Cout; p.K = 9 * Cin_pad;

@@ -209,7 +209,7 @@ class DINOv2Featurizer(nn.Module):
             _call("isp_attention_bf16_tc", qkv, 3 * C, hd, Kp, Vt, O, C, hd, B, T, nh, T, 0)
             xs = tc.gemm(O, L["Wproj"], bias=L["bproj"], resid=xs, out_dtype=torch.float32)
             hn = _ln(xs, L["n2w"], L["n2b"], C, 1e-6, bf)
-            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu", out_dtype=bf)
+            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf)
             xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
         xn = _ln(xs, P["nw"], P["nb"], C, 1e-6, torch.float32)
         feats = xn.view(B, T, C)[:, 1:]

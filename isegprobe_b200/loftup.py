@@ -254,7 +254,7 @@ class LoftUpUpsampler(BaseUpsampler):
             x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * 112, ldd=Dp)
             del O
             hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
-            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu", out_dtype=bf, N=C, K=D)
+            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)
             del hn
             x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp)
             del h1

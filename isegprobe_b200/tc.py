@@ -4,7 +4,7 @@ import torch
 
 from . import _lib
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "quick_gelu": 3}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "quick_gelu": 3, "gelu_tanh": 4}
 
 
 def round_up(x, m):
