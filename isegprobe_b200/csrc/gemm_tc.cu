@@ -63,7 +63,7 @@ constexpr int kEpiWarps = 8;                       // two warps per TMEM lane qu
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kEpiBytesPerWarp = 2 * 4096;         // two output staging chunks of 32 rows x 128 B
+constexpr int kEpiBytesPerWarp = 2 * 4096;         // two staging chunks of 32 rows x 128 B
 constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 constexpr int kMainBudget = 160 * 1024;
 constexpr int kSmemBytes = kMainBudget + kEpiBytes;  // 224 KB: also forces one CTA per SM (TMEM: 512 columns)
@@ -73,17 +73,14 @@ struct Params {
   int N, K;           // K = padded reduction length actually looped (multiple of 64)
   int BN;             // tile width, multiple of 16, <= 256
   int stages;
+  int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
   // conv mode (TW == 0 -> plain GEMM)
   int TW, TH, H, W, cin_chunks;
   long long tiles_m, tiles_n;
   int tiles_w, tiles_h;
   // epilogue
   const float* bias;   // [N] or null
-  const void* resid;   // [M, ldr] in the dtype of D, or null (GEMM mode only)
-  long long ldr;
   float alpha;         // out = alpha * act(acc + bias) + resid
-  int act;             // 0 none, 1 relu, 2 gelu(erf), 3 quick-gelu
-  int out_bf16;
 };
 
 // erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): 1 RCP + 1 EX2 + 7 FMA instead of erff's ~25
@@ -137,173 +134,27 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
   return c;
 }
 
-// What the (non-inlined) epilogue needs, passed BY VALUE: reading a by-reference Params from the
-// caller's stack cost a local-memory load per use (ncu: 59 % long-scoreboard stalls in the epilogue).
-struct EpiArgs {
-  long long M, ldr;
-  const float* bias;
-  const void* resid;
-  float alpha;
-  int N, BN, TW;
-};
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
-// One epilogue warp, its share of one tile.  CW = columns per 128-byte chunk (64 bf16 / 32 f32).
-// The two warps of a lane quarter take alternate chunks.  Per chunk: prefetch the residual slice
-// with coalesced 16-byte loads (8 lanes = one 128-byte row segment), tcgen05.ld the accumulator,
-// bias/activation in registers, stage into 128B-swizzled smem, add the residual there
-// (row-coalesced pass), TMA-store the chunk.  st_seq counts this warp's stores (staging buffer).
-template <bool OUT_BF16, int ACT>
-__device__ __noinline__ void epilogue_tile(const EpiArgs ea, const CUtensorMap* tmD, const CUtensorMap* tmDt,
-                                              const TileCoord tc_, uint32_t t_addr, uint8_t* stage, uint32_t& st_seq,
-                                              int q, int half, int lane) {
-  constexpr int CW = OUT_BF16 ? 64 : 32;
-  constexpr int ESZ = OUT_BF16 ? 2 : 4;
-  const int nchunks = (ea.BN + CW - 1) / CW;
-  int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
-  if (ea.TW) {
-    const int bw = ea.TW < 32 ? ea.TW : 32;
-    const int pix = q * 32;
-    c1 = tc_.w0 + (ea.TW >= 32 ? pix % ea.TW : 0);
-    c2 = tc_.h0 + (ea.TW >= 32 ? pix / ea.TW : q * (32 / bw));
-    c3 = tc_.img;
-  } else {
-    c1 = (int)tc_.m0 + q * 32;
-  }
-  const int r7 = lane & 7;
-  const int sub_r = lane >> 3, sub_u = lane & 7;  // residual pass: lane -> (row within group of 4, 16-byte unit)
-  for (int c = half; c < nchunks; c += 2) {
-    const int col0 = c * CW;                 // column inside the tile
-    const int ncols = min(CW, ea.BN - col0);  // multiple of 16
-    const bool is_tail = ncols < CW;
-    const int row_bytes = ncols * ESZ;       // dense row pitch of a tail chunk
-    const int nglob = tc_.n0 + col0;         // first global column of the chunk
-    const bool full = nglob + ncols <= ea.N;  // no column masking needed
-    // ---- residual prefetch (registers), coalesced: 8 lanes cover one row's 128-byte slice
-    uint4 rres[8];
-    const int units = row_bytes >> 4;
-    if (ea.resid) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const long long grow = tc_.m0 + q * 32 + it * 4 + sub_r;
-        rres[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < ea.M && sub_u < units && nglob + sub_u * (16 / ESZ) < ea.ldr)
-          rres[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(ea.resid) +
-                                                          (grow * ea.ldr + nglob) * ESZ + sub_u * 16));
-      }
-    }
-    // ---- staging buffer of this chunk (32 rows x 128 B, 16-byte units XOR-swizzled like TMA's
-    //      SWIZZLE_128B; tail chunks dense and un-swizzled)
-    if (lane == 0) tc::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
-    __syncwarp();
-    uint8_t* obuf = stage + (st_seq & 1) * 4096;
-    uint8_t* ob = obuf + lane * (is_tail ? row_bytes : 128);
-    // ---- accumulator -> registers -> bias / activation / scale -> staging, 32 columns at a time
-    //      (columns >= N give exact zeros: they are K-padding for the next GEMM)
-#pragma unroll
-    for (int sb = 0; sb < CW / 32; ++sb) {
-      const int scol = sb * 32;
-      if (scol >= ncols) break;
-      uint32_t vr[32];
-      if (scol + 32 <= ncols) {
-        tc::tmem_ld32(t_addr + col0 + scol, vr);
-      } else {  // 16 live columns
-        tc::tmem_ld16(t_addr + col0 + scol, *reinterpret_cast<uint32_t(*)[16]>(&vr[0]));
-#pragma unroll
-        for (int e = 16; e < 32; ++e) vr[e] = 0u;
-      }
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int e4 = 0; e4 < 32; e4 += 4) {
-        const int n = nglob + scol + e4;
-        float b[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ea.bias) {
-          if (n + 3 < ea.N) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(ea.bias + n));
-            b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < ea.N) b[e] = __ldg(ea.bias + n + e);
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x = act_fn<ACT>(__uint_as_float(vr[e4 + e]) + b[e]) * ea.alpha;
-          vr[e4 + e] = __float_as_uint((full || n + e < ea.N) ? x : 0.f);
-        }
-      }
-      constexpr int UPS = OUT_BF16 ? 4 : 8;  // 16-byte units produced per 32-column sub-block
-#pragma unroll
-      for (int uu = 0; uu < UPS; ++uu) {
-        const int u = sb * UPS + uu;
-        if (u * 16 >= row_bytes) break;
-        uint4 w;
-        if constexpr (OUT_BF16) {
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 0]), __uint_as_float(vr[uu * 8 + 1]));
-          __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 2]), __uint_as_float(vr[uu * 8 + 3]));
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 4]), __uint_as_float(vr[uu * 8 + 5]));
-          __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(vr[uu * 8 + 6]), __uint_as_float(vr[uu * 8 + 7]));
-          w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
-                         *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
-        } else {
-          w = make_uint4(vr[uu * 4 + 0], vr[uu * 4 + 1], vr[uu * 4 + 2], vr[uu * 4 + 3]);
-        }
-        *reinterpret_cast<uint4*>(ob + (is_tail ? (u << 4) : ((u ^ r7) << 4))) = w;
-      }
-    }
-    // ---- residual: row-coalesced read-modify-write of the staged chunk
-    if (ea.resid) {
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        if (sub_u >= units) continue;
-        const int r = it * 4 + sub_r;
-        uint8_t* sp = obuf + (is_tail ? r * row_bytes + (sub_u << 4) : r * 128 + ((sub_u ^ (r & 7)) << 4));
-        uint4 o = *reinterpret_cast<uint4*>(sp);
-        const uint4 rr = rres[it];
-        const int nb = nglob + sub_u * (16 / ESZ);
-        if constexpr (OUT_BF16) {
-          // packed bf16x2 adds (HADD2.BF16): one instruction per two elements
-          uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-          uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (!full) {
-              if (nb + 2 * i >= ea.N) rw[i] &= 0xffff0000u;
-              if (nb + 2 * i + 1 >= ea.N) rw[i] &= 0x0000ffffu;
-            }
-            __nv_bfloat162 s2 = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&ow[i]), *reinterpret_cast<__nv_bfloat162*>(&rw[i]));
-            ow[i] = *reinterpret_cast<uint32_t*>(&s2);
-          }
-          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        } else {
-          float f[4] = {__uint_as_float(o.x), __uint_as_float(o.y), __uint_as_float(o.z), __uint_as_float(o.w)};
-          const float g[4] = {__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w)};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (full || nb + i < ea.N) f[i] += g[i];
-          o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-        }
-        *reinterpret_cast<uint4*>(sp) = o;
-      }
-    }
-    tc::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      const CUtensorMap* m = is_tail ? tmDt : tmD;
-      if (ea.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
-      else tc::tma_store_2d(m, obuf, nglob, c1);
-      tc::tma_store_commit();
-    }
-    ++st_seq;
-  }
-}
-
+// The kernel is instantiated per (output dtype, activation, residual) so the epilogue is fully
+// inlined: no local-memory arrays, no ABI stack traffic (the earlier non-inlined epilogue spent
+// 60 % of its stalls on STL/LDL of its own arguments).
+//
+// Epilogue, per warp and 128-byte-wide chunk (CW = 64 bf16 / 32 f32 columns) of its 32 rows:
+//   residual chunk: TMA-loaded (by this warp's lane 0, before it waits for the accumulator, so the
+//   load overlaps the MMAs of the tile) into the 128B-swizzled staging buffer;
+//   tcgen05.ld 32 columns -> bias (from smem) / activation / alpha -> + residual read from the
+//   staging buffer (row per thread, swizzle makes it conflict-free) -> written back IN PLACE ->
+//   TMA store of the chunk.  All global traffic is bulk; OOB rows / columns are clipped by TMA.
+template <bool OUT_BF16, int ACT, bool RESID>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDt, const Params p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDt,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRt, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t resid_bar[kEpiWarps][2];
+  __shared__ __align__(16) float bias_s[2][256];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,8 +167,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
     tc::prefetch_tmap(&tmD);
+    if (RESID) tc::prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps); }
+    for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&resid_bar[w][0], 1); tc::mbar_init(&resid_bar[w][1], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -353,12 +206,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
     const uint32_t idesc = tc::idesc_bf16_f32(BM, p.BN);
+    const int last_in = p.TW ? p.cin_chunks - 1 : kblocks - 1;  // k-block (within a tap / the row) that may be partial
+    const int period = p.TW ? p.cin_chunks : kblocks;
     uint32_t it = 0, tl = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       tc::mbar_wait(&tempty_bar[acc], aph ^ 1);
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256u;  // accumulator stages at columns 0 and 256
+      int kin = 0;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
@@ -367,38 +223,168 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t adesc = tc::smem_desc_k_sw128(sa), bdesc = tc::smem_desc_k_sw128(sa + a_bytes);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K step inside the 128B swizzle row
-            tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          // the zero-filled K tail of a row / tap is skipped: those MMAs would add exact zeros
+          const int nsteps = (kin == last_in) ? p.last_steps : BK / 16;
+          // +32 B per 16-element K step inside the 128B swizzle row; fully unrolled so the descriptors
+          // sit in uniform registers (a rolled loop made the issue slower than the MMAs themselves)
+          tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+          if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+          if (nsteps > 2) tc::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+          if (nsteps > 3) tc::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
           tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
           if (kb == kblocks - 1) tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
+        if (++kin == period) kin = 0;
       }
     }
   } else {
     // ------------------------------------------------------------- epilogue (warps 2..9)
+    constexpr int CW = OUT_BF16 ? 64 : 32;    // columns per 128-byte chunk
+    constexpr int ESZ = OUT_BF16 ? 2 : 4;
+    constexpr int UPS = OUT_BF16 ? 4 : 8;     // 16-byte units per 32 accumulator columns
+    constexpr int CPU_ = 16 / ESZ;            // columns per 16-byte unit
     const int ew = warp - 2;
     const int q = warp & 3;      // TMEM lane quarter this warp may access == its 32 rows of the tile
     const int half = ew >> 2;    // which of the two warps sharing that quarter (takes chunks half, half+2, ...)
+    const int etid = ew * 32 + lane;
     uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
-    uint32_t tl = 0, st_seq = 0;
-    const EpiArgs ea = {p.M, p.ldr, p.bias, p.resid, p.alpha, p.N, p.BN, p.TW};
+    uint64_t* rbar = resid_bar[ew];
+    const int nchunks = (p.BN + CW - 1) / CW;
+    const int n_my = (nchunks - half + 1) / 2;
+    const int row = lane, r7 = lane & 7;
+    uint32_t tl = 0, st_seq = 0, rph0 = 0, rph1 = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       const TileCoord tc_ = tile_coord(p, t);
+      int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
+      if (p.TW) {
+        const int bw = p.TW < 32 ? p.TW : 32;
+        const int pix = q * 32;
+        c1 = tc_.w0 + (p.TW >= 32 ? pix % p.TW : 0);
+        c2 = tc_.h0 + (p.TW >= 32 ? pix / p.TW : q * (32 / bw));
+        c3 = tc_.img;
+      } else {
+        c1 = (int)tc_.m0 + q * 32;
+      }
+      // bias slice of this tile -> smem (zeros beyond N, so padded columns come out as exact zeros)
+      if (etid < p.BN) {
+        const int n = tc_.n0 + etid;
+        bias_s[acc][etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      }
+      // residual chunks of this tile: issue the loads now, they land while the tile's MMAs run
+      if (RESID) {
+        if (lane == 0) {
+          tc::tma_store_wait_read<0>();  // both staging buffers have been read by their stores
+          for (int i = 0; i < 2 && i < n_my; ++i) {
+            const int col0 = (half + 2 * i) * CW;
+            const int ncols = min(CW, p.BN - col0);
+            uint8_t* buf = stage + ((st_seq + i) & 1) * 4096;
+            tc::mbar_arrive_expect_tx(&rbar[(st_seq + i) & 1], 32u * ncols * ESZ);
+            tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1);
+          }
+        }
+        __syncwarp();
+      }
+      epi_bar_sync();  // bias visible to all epilogue warps
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-#define ISP_EPI(OB, A) epilogue_tile<OB, A>(ea, &tmD, &tmDt, tc_, t_addr, stage, st_seq, q, half, lane)
-      if (p.out_bf16) {
-        if (p.act == 0) ISP_EPI(true, 0); else if (p.act == 1) ISP_EPI(true, 1);
-        else if (p.act == 2) ISP_EPI(true, 2); else if (p.act == 3) ISP_EPI(true, 3); else ISP_EPI(true, 4);
-      } else {
-        if (p.act == 0) ISP_EPI(false, 0); else if (p.act == 1) ISP_EPI(false, 1);
-        else if (p.act == 2) ISP_EPI(false, 2); else if (p.act == 3) ISP_EPI(false, 3); else ISP_EPI(false, 4);
+      const float* bs = bias_s[acc];
+      for (int i = 0; i < n_my; ++i, ++st_seq) {
+        const int col0 = (half + 2 * i) * CW;     // column inside the tile
+        const int ncols = min(CW, p.BN - col0);   // multiple of 16
+        const bool is_tail = ncols < CW;
+        const int row_bytes = ncols * ESZ;        // dense row pitch of a tail chunk
+        const int nglob = tc_.n0 + col0;          // first global column of the chunk
+        const bool full = nglob + ncols <= p.N;   // no column masking needed
+        const uint32_t b = st_seq & 1;
+        uint8_t* obuf = stage + b * 4096;
+        if (RESID) {
+          if (i >= 2) {  // more than two chunks per warp and tile: reload the buffer once its store has read it
+            if (lane == 0) {
+              tc::tma_store_wait_read<1>();
+              tc::mbar_arrive_expect_tx(&rbar[b], 32u * ncols * ESZ);
+              tc::tma_load_2d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1);
+            }
+            __syncwarp();
+          }
+          tc::mbar_wait(&rbar[b], b ? rph1 : rph0);
+          if (b) rph1 ^= 1; else rph0 ^= 1;
+        } else {
+          if (lane == 0) tc::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+          __syncwarp();
+        }
+        uint8_t* orow = obuf + row * (is_tail ? row_bytes : 128);
+#pragma unroll
+        for (int sb = 0; sb < CW / 32; ++sb) {
+          const int scol = sb * 32;
+          if (scol < ncols) {
+            uint32_t vr[32];
+            if (scol + 32 <= ncols) {
+              tc::tmem_ld32(t_addr + col0 + scol, vr);
+            } else {  // 16 live columns
+              tc::tmem_ld16(t_addr + col0 + scol, *reinterpret_cast<uint32_t(*)[16]>(&vr[0]));
+#pragma unroll
+              for (int e = 16; e < 32; ++e) vr[e] = 0u;
+            }
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int uu = 0; uu < UPS; ++uu) {
+              const int u = sb * UPS + uu;          // 16-byte unit inside the chunk row
+              if (u * 16 < row_bytes) {
+                uint8_t* sp = orow + (is_tail ? (u << 4) : ((u ^ r7) << 4));
+                float x[CPU_];
+#pragma unroll
+                for (int e4 = 0; e4 < CPU_; e4 += 4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(bs + col0 + scol + uu * CPU_ + e4);
+                  x[e4 + 0] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 0]) + bb.x) * p.alpha;
+                  x[e4 + 1] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 1]) + bb.y) * p.alpha;
+                  x[e4 + 2] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 2]) + bb.z) * p.alpha;
+                  x[e4 + 3] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 3]) + bb.w) * p.alpha;
+                }
+                if (RESID) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(sp);
+                  if constexpr (OUT_BF16) {
+                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // bf16 -> f32 is a shift: the add happens in fp32, one rounding
+                      x[2 * k] += __uint_as_float(rw[k] << 16);
+                      x[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                    }
+                  } else {
+                    x[0] += __uint_as_float(rr.x); x[1] += __uint_as_float(rr.y);
+                    x[2] += __uint_as_float(rr.z); x[3] += __uint_as_float(rr.w);
+                  }
+                }
+                if (!full) {
+#pragma unroll
+                  for (int e = 0; e < CPU_; ++e)
+                    if (nglob + scol + uu * CPU_ + e >= p.N) x[e] = 0.f;
+                }
+                uint4 w;
+                if constexpr (OUT_BF16) {
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]), b1 = __floats2bfloat162_rn(x[2], x[3]);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
+                  w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
+                                 *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
+                } else {
+                  w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+                }
+                *reinterpret_cast<uint4*>(sp) = w;
+              }
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const CUtensorMap* m = is_tail ? &tmDt : &tmD;
+          if (p.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
+          else tc::tma_store_2d(m, obuf, nglob, c1);
+          tc::tma_store_commit();
+        }
       }
-#undef ISP_EPI
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
@@ -410,29 +396,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-static int pick_bn(int N) {
-  // widest tile <= 256 that wastes the least: N itself if it fits, else an even split
+static int pick_bn(int N, int max_bn) {
+  // widest tile <= max_bn that wastes the least: N itself if it fits, else an even split
   const int n16 = (N + 15) / 16 * 16;
-  if (n16 <= 256) return n16;
-  for (int parts = 2; parts <= 16; ++parts) {
+  if (n16 <= max_bn) return n16;
+  for (int parts = 2; parts <= 64; ++parts) {
     const int bn = ((N + parts - 1) / parts + 15) / 16 * 16;
-    if (bn <= 256) return bn;
+    if (bn <= max_bn) return bn;
   }
-  return 256;
+  return max_bn;
+}
+
+typedef void (*kernel_fn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Params);
+
+template <bool OB, bool RS>
+static kernel_fn pick_act(int act) {
+  switch (act) {
+    case 0: return gemm_tc_kernel<OB, 0, RS>;
+    case 1: return gemm_tc_kernel<OB, 1, RS>;
+    case 2: return gemm_tc_kernel<OB, 2, RS>;
+    case 3: return gemm_tc_kernel<OB, 3, RS>;
+    default: return gemm_tc_kernel<OB, 4, RS>;
+  }
+}
+
+static kernel_fn pick_kernel(int out_bf16, int act, bool resid) {
+  if (resid) return out_bf16 ? pick_act<true, true>(act) : pick_act<false, true>(act);
+  return out_bf16 ? pick_act<true, false>(act) : pick_act<false, false>(act);
 }
 
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmDt,
-                  Params& p, cudaStream_t stream) {
+                  const CUtensorMap& tmR, const CUtensorMap& tmRt, Params& p, int out_bf16, int act, bool resid,
+                  cudaStream_t stream) {
   static int num_sms = 0;
-  static bool attr_set = false;
   if (!num_sms) {
     int dev = 0;
     ISP_CUDA(cudaGetDevice(&dev));
     ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  kernel_fn fn = pick_kernel(out_bf16, act, resid);
+  static kernel_fn attr_done[32];
+  static int n_attr = 0;
+  bool seen = false;
+  for (int i = 0; i < n_attr; ++i) seen |= attr_done[i] == fn;
+  if (!seen) {
+    ISP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (n_attr < 32) attr_done[n_attr++] = fn;
   }
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
   p.stages = kMainBudget / stage_bytes;
@@ -440,7 +449,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   const long long ntiles = p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, p);
+  fn<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, tmR, tmRt, p);
   ISP_CHECK_LAUNCH("gemm_tc_kernel");
   return ISP_OK;
 }
@@ -474,11 +483,14 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   gemm::Params p = {};
   p.M = M; p.N = N;
   p.K = (K + gemm::BK - 1) / gemm::BK * gemm::BK;  // TMA zero-fills the K tail (global dim = K)
-  p.BN = gemm::pick_bn(N);
+  // with a residual every epilogue warp should own at most two 128-byte chunks per tile, so that
+  // both residual loads are in flight before the accumulator is ready (f32: 32 columns per chunk)
+  p.BN = gemm::pick_bn(N, (resid && !out_bf16) ? 128 : 256);
+  p.last_steps = (K - (p.K - gemm::BK) + 15) / 16;
   p.TW = 0;
   p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
-  p.bias = bias; p.resid = resid; p.ldr = ldr; p.alpha = alpha; p.act = act; p.out_bf16 = out_bf16;
+  p.bias = bias; p.alpha = alpha;
   CUtensorMap tmA, tmB, tmD;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)lda * 2};
@@ -499,7 +511,14 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
     if (int e = make_tmap(&tmD, esz, D, 2, dims, str, box, "gemm_bf16_tc(D)", true)) return e;
     if (int e = make_tmap(&tmDt, esz, D, 2, dims, str, boxt, "gemm_bf16_tc(D tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmDt, p, as_stream(stream));
+  CUtensorMap tmR = tmD, tmRt = tmDt;
+  if (resid) {
+    const uint64_t dims[2] = {(uint64_t)ldr, (uint64_t)M}, str[2] = {(uint64_t)esz, (uint64_t)ldr * esz};
+    const uint32_t box[2] = {cw, 32}, boxt[2] = {tailw ? tailw : cw, 32};
+    if (int e = make_tmap(&tmR, esz, resid, 2, dims, str, box, "gemm_bf16_tc(resid)", true)) return e;
+    if (int e = make_tmap(&tmRt, esz, resid, 2, dims, str, boxt, "gemm_bf16_tc(resid tail)", false)) return e;
+  }
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, resid != nullptr, as_stream(stream));
 }
 
 extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
@@ -517,7 +536,8 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: bias must be 16-byte aligned");
   gemm::Params p = {};
   p.M = (long long)Nimg * H * Wd; p.N = Cout; p.K = 9 * Cin_pad;
-  p.BN = gemm::pick_bn(Cout);
+  p.BN = gemm::pick_bn(Cout, 256);
+  p.last_steps = (Cin - (Cin_pad - 64) + 15) / 16;
   // tile = TH x TW output pixels; prefer wide rows (fewer halo re-reads), fall back to 16x8
   int TW = 16;
   for (int cand : {128, 64, 32, 16, 8}) {
@@ -527,7 +547,7 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   p.tiles_w = (Wd + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
-  p.bias = bias; p.resid = nullptr; p.ldr = 0; p.alpha = 1.f; p.act = act; p.out_bf16 = out_bf16;
+  p.bias = bias; p.alpha = 1.f;
   CUtensorMap tmA, tmB, tmD, tmDt;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
@@ -549,5 +569,5 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
     if (int e = make_tmap(&tmD, esz, Y, 4, dims, str, box, "conv3x3_bf16_tc(Y)", true)) return e;
     if (int e = make_tmap(&tmDt, esz, Y, 4, dims, str, boxt, "conv3x3_bf16_tc(Y tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmDt, p, as_stream(stream));
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmD, tmDt, p, out_bf16, act, false, as_stream(stream));
 }
