@@ -91,54 +91,128 @@ __device__ __forceinline__ void st8(void* p, long long idx, const float (&v)[8])
   }
 }
 
+// Persistent: each warp walks rows with a grid stride, R rows per iteration (all loads of the R
+// rows are issued before the first reduction), gamma / beta staged once per block in shared
+// memory (the per-element __ldg of the first version made the kernel LSU-bound at 1.8 TB/s).
+// bf16 rows stay PACKED in registers (4 per 8 columns) and are unpacked in each of the three
+// passes, so R = 8 rows are in flight per warp: the kernel is latency-bound
+// otherwise (a bf16 row of 416 columns is only 832 bytes); 2 blocks / SM.
+template <bool IN_BF16>
+struct LnRaw {
+  uint4 a, b;  // bf16: a only
+};
+template <bool IN_BF16>
+__device__ __forceinline__ void ln_unpack(LnRaw<IN_BF16>& r, float (&v)[8]) {
+  if constexpr (IN_BF16) {
+    // opaque to the optimiser: otherwise the three passes share one unpack and all R*V*8 floats stay live (spills)
+    asm volatile("" : "+r"(r.a.x), "+r"(r.a.y), "+r"(r.a.z), "+r"(r.a.w));
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  } else {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  }
+}
+
 template <bool IN_BF16, bool OUT_BF16, int V>
-__global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const void* __restrict__ in, long long ldi,
+__global__ void __launch_bounds__(256, 2) layernorm_rows_vec_kernel(const void* __restrict__ in, long long ldi,
                                                                  void* __restrict__ out, long long ldo,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, long long M, int C,
                                                                  float eps) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int R = V <= 2 ? 4 : 2;
+  __shared__ __align__(16) float g_s[V * 256], b_s[V * 256];
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float x[V][8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c0 = (lane + 32 * i) * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[i][e] = 0.f;
-    if (c0 < C && c0 + 8 <= ldi) ld8<IN_BF16>(in, row * ldi + c0, x[i]);
-    else if (c0 < C)
-      for (int e = 0; e < 8 && c0 + e < C; ++e) x[i][e] = ld_any(in, row * ldi + c0 + e, IN_BF16);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (c0 + e >= C) x[i][e] = 0.f;
-      s += x[i][e];
-    }
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (int c = threadIdx.x; c < V * 256; c += 256) {
+    g_s[c] = c < C ? __ldg(gamma + c) : 0.f;
+    b_s[c] = c < C ? __ldg(beta + c) : 0.f;
   }
-  const float mean = warp_sum(s) / (float)C;
-  float v = 0.f;
+  __syncthreads();
+  const float invC = 1.f / (float)C;
+  // columns c0 .. c0+7 of vector i; a vector is live if it starts inside the row (the caller guarantees
+  // 8-element alignment of ldi, so a live vector can always be loaded whole; columns >= C are masked)
+  for (long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R; row0 < M; row0 += nwarps * R) {
+    LnRaw<IN_BF16> raw[R][V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c0 = (lane + 32 * i) * 8;
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = (c0 + e < C) ? x[i][e] - mean : 0.f;
-      v += d * d;
+      for (int i = 0; i < V; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        raw[r][i].a = make_uint4(0u, 0u, 0u, 0u);
+        raw[r][i].b = make_uint4(0u, 0u, 0u, 0u);
+        if (row < M && c0 < C) {
+          if constexpr (IN_BF16) {
+            raw[r][i].a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + row * ldi + c0);
+          } else {
+            raw[r][i].a = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(in) + row * ldi + c0);
+            raw[r][i].b = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(in) + row * ldi + c0 + 4);
+          }
+        }
+      }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    float s[R], v[R], mean[R];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c0 = (lane + 32 * i) * 8;
-    if (c0 >= ldo) continue;
-    float y[8];
+    for (int r = 0; r < R; ++r) {
+      s[r] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
-      y[e] = (c < C) ? (x[i][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+      for (int i = 0; i < V; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        float x[8];
+        ln_unpack<IN_BF16>(raw[r][i], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[r] += (c0 + e < C) ? x[e] : 0.f;  // pad columns of the input row are ignored
+      }
     }
-    st8<OUT_BF16>(out, row * ldo + c0, y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] = s[r] * invC;
+      v[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        float x[8];
+        ln_unpack<IN_BF16>(raw[r][i], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = (c0 + e < C) ? x[e] - mean[r] : 0.f;
+          v[r] = fmaf(d, d, v[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] += __shfl_xor_sync(0xffffffffu, v[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      if (row >= M) break;
+      const float rstd = rsqrtf(v[r] * invC + eps);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        if (c0 >= ldo) continue;
+        float x[8], y[8], g[8], bt[8];
+        ln_unpack<IN_BF16>(raw[r][i], x);
+        *reinterpret_cast<float4*>(&g[0]) = *reinterpret_cast<const float4*>(g_s + c0);
+        *reinterpret_cast<float4*>(&g[4]) = *reinterpret_cast<const float4*>(g_s + c0 + 4);
+        *reinterpret_cast<float4*>(&bt[0]) = *reinterpret_cast<const float4*>(b_s + c0);
+        *reinterpret_cast<float4*>(&bt[4]) = *reinterpret_cast<const float4*>(b_s + c0 + 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = fmaf((x[e] - mean[r]) * rstd, g[e], bt[e]);  // pads: g = b = 0
+        st8<OUT_BF16>(out, row * ldo + c0, y);
+      }
+    }
   }
 }
 
@@ -375,7 +449,7 @@ extern "C" int isp_layernorm_rows(const void* in, int in_bf16, long long ldi, vo
   if (ldi % 8 == 0 && ldo % 8 == 0 && aligned16(in) && aligned16(out) && ldo <= 1024) {
     const int nvec = (int)((ldo + 7) / 8);
     const int V = (nvec + 31) / 32;  // 8-element vectors per lane
-    dim3 grid(cdiv(M, 8));
+    dim3 grid((unsigned)min((long long)cdiv(M, 16), (long long)148 * 8));
 #define ISP_LN_LAUNCH(IB, OB, VV)                                                                        \
   layernorm_rows_vec_kernel<IB, OB, VV><<<grid, 256, 0, as_stream(stream)>>>(in, ldi, out, ldo, gamma, beta, M, C, eps)
 #define ISP_LN_V(IB, OB)                                                           \
