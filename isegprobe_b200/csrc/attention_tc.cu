@@ -5,7 +5,7 @@
 //     materialises [B*4, HW, hw] fp32 = 3.29 GB / image / layer);
 //   * DINOv2 self-attention: 1025 tokens, 6 heads x 64 (dinov2/layers/attention.py:54-71).
 //
-// Work item = (pair of 128-query tiles, head); see the kernel comment for the pipeline.
+// Work item = (128-query tile, head); see the kernel comment for the pipeline.
 // Q is expected pre-scaled by 1/sqrt(head_dim) (folded into the projection weights).
 // Head dims are zero-padded on the K / V^T side only (DK_STEPS*16 >= head_dim, DV >= head_dim).
 #include "tc_common.cuh"
@@ -13,13 +13,14 @@
 namespace isp {
 namespace attn {
 
-constexpr int kSoftmaxWarps = 8;                 // two groups of four: group t owns query tile t of the pair
+constexpr int kSoftmaxWarps = 8;                 // two threads per query row: 64 keys of every block each
 constexpr int kThreads = 64 + 32 * kSoftmaxWarps;
 constexpr int BQ = 128, BKEY = 128;
-constexpr uint32_t kQTile = 2 * 16384;           // one Q tile: two 64-column chunks [128 rows x 64]
+constexpr uint32_t kQBytes = 2 * 16384;          // Q tile: two 64-column chunks [128 rows x 64]
 constexpr uint32_t kKStage = 2 * 16384;          // K block: two 64-column chunks [128 keys x 64]
 constexpr uint32_t kVStage = 2 * 16384;          // V^T block: two 64-key chunks [DV x 64] (DV <= 128)
-constexpr uint32_t kSmem = 2 * kQTile + 2 * kKStage + 2 * kVStage;  // 196608
+constexpr uint32_t kOBytes = 2 * 16384;          // O staging tile for the TMA store: [128 rows x DV] bf16, dense
+constexpr uint32_t kSmem = kQBytes + 2 * kKStage + 2 * kVStage + kOBytes;  // 196608
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThresh = 8.0f;           // log2 units: P stays <= 2^8
 
@@ -27,11 +28,10 @@ struct Params {
   int nkeys, nblocks;          // real keys, blocks of 128 (K / V^T padded with zeros)
   int heads;
   long long rows_per_img;      // queries per image (tile rows never straddle stored rows of 2 images)
-  int pairs_per_img;           // pairs of 128-query tiles per image
-  long long nitems;            // B * pairs_per_img * heads
+  int tiles_per_img;
+  long long nitems;            // B * tiles_per_img * heads
   int q_head_stride;           // column offset between heads in Q (elements)
-  void* out;                   // bf16 [B*rows_per_img, ldo]
-  int ldo, o_head_stride;      // column offset between heads in out
+  int o_head_stride;           // column offset between heads in out
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz); inputs are <= 8
@@ -40,41 +40,47 @@ __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz)
   return y;
 }
 
-// Work item = (pair of 128-query tiles, head).  Both tiles share every K / V^T block that TMA brings
-// in; each tile has its own S and O accumulators in TMEM and its own group of four softmax warps, so
-// while one tile's rows are in exp2 (MUFU-bound) the tensor pipe runs the other tile's MMAs:
-//   warp 0 (TMA)  : Q pair once per item; K block [128 keys x DK], V^T block [DV x 128 keys] -> 2-deep rings
-//   warp 1 (MMA)  : S_t = Q_t K^T (TMEM);  O_t += P_t V  with P_t read FROM TMEM (tcgen05.mma A operand),
-//                   so probabilities never touch shared memory
-//   warps 2-9     : thread per query row: tcgen05.ld S row (once), online softmax in fp32 (exp2, lazy
-//                   rescale of O in TMEM only when the row max grows by > 2^8), P -> bf16 -> tcgen05.st
-//                   over the first 64 columns of S_t (the row's S values are already in registers),
-//                   final O / l -> global bf16.
-// TMEM columns: S_0 @0, S_1 @128, O_0 @256, O_1 @384.  tcgen05.mma instructions execute in issue order,
-// which orders PV_t(j) (reads P_t) before QK_t(j+1) (overwrites S_t / P_t).
+// Work item = (128-query tile, head).  Per item, for each block j of 128 keys:
+//   warp 0 (TMA)  : Q once per item; K block [128 keys x DK], V^T block [DV x 128 keys] -> 2-deep rings
+//   warp 1 (MMA)  : S(j) = Q K(j)^T into TMEM buffer j&1 -- issued TWO blocks ahead, so the softmax of
+//                   block j never waits for the tensor pipe;  O += P(j) V(j) with P read FROM TMEM
+//                   (tcgen05.mma A operand): probabilities never touch shared memory.
+//                   All lanes run the (warp-uniform) loop, one elected lane issues: descriptors stay in
+//                   uniform registers.
+//   warps 2-9     : TWO threads per query row (the two warps sharing a TMEM lane quarter take 64 keys of
+//                   the block each): tcgen05.ld half the S row once, row max exchanged through smem,
+//                   online softmax in fp32 (exp2; O in TMEM is rescaled only when the row max grows by
+//                   more than 2^8), P -> bf16 -> tcgen05.st over the first 64 columns of the S buffer
+//                   (all S values of the row are in registers by then); after the last block
+//                   O / l -> bf16 -> smem -> one TMA store per tile.
+// TMEM columns: S buffers @0 and @128, O @256.  tcgen05.mma instructions execute in issue order, which
+// orders PV(j) (reads P(j) in buffer j&1) before QK(j+2) (overwrites that buffer).
 template <int DK_CHUNKS, int DK_STEPS, int DV>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const Params p) {
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2],
-      o_done[2];
+  __shared__ __align__(8) uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full,
+      pv_done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float xchg[3][2][BQ];  // [slot][half][row]: slots 0/1 = block max (alternating), 2 = partial row sum
 
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 2 * kQTile;
+  uint8_t* sK = sQ + kQBytes;
   uint8_t* sV = sK + 2 * kKStage;
+  uint8_t* sO = sV + 2 * kVStage;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = p.nblocks;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
+    tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); tc::prefetch_tmap(&tmO);
     tc::mbar_init(&q_full, 1); tc::mbar_init(&q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], 1);
       tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], 1);
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 4); tc::mbar_init(&o_done[i], 1);
+      tc::mbar_init(&s_full[i], 1);
     }
+    tc::mbar_init(&p_full, kSoftmaxWarps); tc::mbar_init(&pv_done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
@@ -90,15 +96,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (long long it = blockIdx.x; it < p.nitems; it += gridDim.x, ++item_it) {
         const int h = (int)(it % p.heads);
         const long long tq = it / p.heads;
-        const int b = (int)(tq / p.pairs_per_img);
-        const int pr = (int)(tq % p.pairs_per_img);
-        const long long row0 = (long long)b * p.rows_per_img + (long long)pr * (2 * BQ);
+        const int b = (int)(tq / p.tiles_per_img);
+        const int qt = (int)(tq % p.tiles_per_img);
+        const long long row0 = (long long)b * p.rows_per_img + (long long)qt * BQ;
         tc::mbar_wait(&q_empty, (item_it & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&q_full, 2 * DK_CHUNKS * 16384);
-        for (int t = 0; t < 2; ++t)
-          for (int c = 0; c < DK_CHUNKS; ++c)
-            tc::tma_load_2d(sQ + t * kQTile + c * 16384, &tmQ, &q_full, h * p.q_head_stride + c * 64,
-                            (int)(row0 + t * BQ));
+        tc::mbar_arrive_expect_tx(&q_full, DK_CHUNKS * 16384);
+        for (int c = 0; c < DK_CHUNKS; ++c)
+          tc::tma_load_2d(sQ + c * 16384, &tmQ, &q_full, h * p.q_head_stride + c * 64, (int)row0);
         const long long bh = (long long)b * p.heads + h;
         for (int j = 0; j < nb; ++j, ++kv_it) {
           const int s = kv_it & 1;
@@ -119,109 +123,112 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc_qk = tc::idesc_bf16_f32(BQ, BKEY);
     const uint32_t idesc_pv = tc::idesc_bf16_f32(BQ, DV);
-    uint32_t kv_it = 0, item_it = 0, p_it = 0;
-    // S_t = Q_t K(stage s)^T, then signal the softmax group of tile t
-    auto issue_qk = [&](int t, int s) {
-      if (lane == 0) {
-        const uint32_t d = tmem + t * 128;
+    const bool leader = tc::elect_one();
+    const uint32_t q_lo = tc::smem_u32(sQ), k_lo = tc::smem_u32(sK), v_lo = tc::smem_u32(sV);
+    uint32_t kv_it = 0, item_it = 0, g = 0;  // g: blocks processed so far (all items) == index of the next P / S buffer use
+    // S buffer (gj & 1) = Q K(gj)^T, then signal the softmax warps; frees the K stage
+    auto issue_qk = [&](uint32_t gj) {
+      const int s = gj & 1;
+      tc::mbar_wait(&k_full[s], (gj >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t d = tmem + s * 128;
+      const uint32_t ka = k_lo + s * kKStage;
 #pragma unroll
-        for (int k = 0; k < DK_STEPS; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          tc::umma_bf16(d, tc::smem_desc_k_sw128(tc::smem_u32(sQ) + t * kQTile + off),
-                        tc::smem_desc_k_sw128(tc::smem_u32(sK) + s * kKStage + off), idesc_qk, k ? 1u : 0u);
-        }
-        tc::umma_commit(&s_full[t]);
+      for (int k = 0; k < DK_STEPS; ++k) {
+        const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+        const uint64_t da = tc::smem_desc_k_sw128(q_lo + off), db = tc::smem_desc_k_sw128(ka + off);
+        if (leader) tc::umma_bf16(d, da, db, idesc_qk, k ? 1u : 0u);
       }
-      __syncwarp();
+      if (leader) {
+        tc::umma_commit(&s_full[s]);
+        tc::umma_commit(&k_empty[s]);
+      }
     };
     for (long long it = blockIdx.x; it < p.nitems; it += gridDim.x, ++item_it) {
       tc::mbar_wait(&q_full, item_it & 1);
-      {
-        const int s = kv_it & 1;
-        tc::mbar_wait(&k_full[s], (kv_it >> 1) & 1);
-        tc::tc_fence_after();
-        issue_qk(0, s);
-        issue_qk(1, s);
-        if (lane == 0) {
-          tc::umma_commit(&k_empty[s]);
-          if (nb == 1) tc::umma_commit(&q_empty);
-        }
-        __syncwarp();
-      }
-      for (int j = 0; j < nb; ++j, ++p_it) {
+      issue_qk(kv_it);
+      if (nb > 1) issue_qk(kv_it + 1);
+      if (nb <= 2 && leader) tc::umma_commit(&q_empty);
+      for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t kvi = kv_it + j;
-        const int s = kvi & 1, sn = (kvi + 1) & 1;
+        const int s = kvi & 1;
+        // O += P(j) V(j): P from TMEM (16 keys = 8 packed columns per MMA), V^T from smem
+        tc::mbar_wait(&p_full, g & 1);
+        tc::mbar_wait(&v_full[s], (kvi >> 1) & 1);
+        tc::tc_fence_after();
+        {
+          const uint32_t dO = tmem + 256, aP = tmem + s * 128;
+          const uint32_t va = v_lo + s * kVStage;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          // O_t += P_t(j) V(j): P_t from TMEM (16 keys = 8 packed columns per MMA), V^T from smem
-          tc::mbar_wait(&p_full[t], p_it & 1);
-          if (t == 0) tc::mbar_wait(&v_full[s], (kvi >> 1) & 1);
-          tc::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t dO = tmem + 256 + t * 128, aP = tmem + t * 128;
-#pragma unroll
-            for (int k = 0; k < BKEY / 16; ++k) {
-              const uint32_t boff = (k >> 2) * 16384 + (k & 3) * 32;
-              tc::umma_bf16_ts(dO, aP + k * 8, tc::smem_desc_k_sw128(tc::smem_u32(sV) + s * kVStage + boff), idesc_pv,
-                               (j | k) ? 1u : 0u);
-            }
-            if (t == 1) tc::umma_commit(&v_empty[s]);
-            if (j == nb - 1) tc::umma_commit(&o_done[t]);
+          for (int k = 0; k < BKEY / 16; ++k) {
+            const uint32_t boff = (k >> 2) * 16384 + (k & 3) * 32;
+            const uint64_t db = tc::smem_desc_k_sw128(va + boff);
+            if (leader) tc::umma_bf16_ts(dO, aP + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
           }
-          __syncwarp();
-          if (j + 1 < nb) {
-            if (t == 0) {
-              tc::mbar_wait(&k_full[sn], ((kvi + 1) >> 1) & 1);
-              tc::tc_fence_after();
-            }
-            issue_qk(t, sn);
-            if (t == 1 && lane == 0) {
-              tc::umma_commit(&k_empty[sn]);
-              if (j + 2 == nb) tc::umma_commit(&q_empty);  // last QK of the item issued: Q smem free when it retires
-            }
-            __syncwarp();
+          if (leader) {
+            tc::umma_commit(&v_empty[s]);
+            tc::umma_commit(&pv_done);
           }
+        }
+        if (j + 2 < nb) {
+          issue_qk(kvi + 2);
+          if (j + 3 == nb && leader) tc::umma_commit(&q_empty);  // last QK of the item issued: Q smem free when it retires
         }
       }
       kv_it += nb;
     }
   } else {
     // ------------------------------------------------------------------ softmax / epilogue warps
-    const int t = (warp - 2) >> 2;   // query tile of the pair this group owns
+    const int sw = warp - 2;
+    const int half = sw >> 2;        // which 64 keys of every block (and which half of the O columns)
     const int q = warp & 3;          // TMEM lane quarter
     const int r = q * 32 + lane;     // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem + t * 128 + lane_addr, tO = tmem + 256 + t * 128 + lane_addr;
-    uint32_t s_it = 0, item_it = 0;
+    const uint32_t tO = tmem + 256 + lane_addr;
+    const int bar_id = 1 + q;        // named barrier shared by the two warps of this quarter
+    float* my_x = &xchg[0][half][r];
+    const float* other_x = &xchg[0][half ^ 1][r];
+    constexpr int kSlot = 2 * BQ;    // floats per exchange slot
+    constexpr int DVH0 = ((DV / 2 + 15) / 16) * 16;  // O columns [0, DVH0) belong to half 0, the rest to half 1
+    const int oc0 = half ? DVH0 : 0, oc1 = half ? DV : DVH0;
+    uint32_t g = 0, item_it = 0;     // g: blocks processed so far (all items)
     for (long long it = blockIdx.x; it < p.nitems; it += gridDim.x, ++item_it) {
       const int h = (int)(it % p.heads);
       const long long tq = it / p.heads;
-      const int b = (int)(tq / p.pairs_per_img);
-      const int pr = (int)(tq % p.pairs_per_img);
-      float m_ref = -INFINITY;  // exponent reference, in log2 units (s * log2e)
-      float l = 0.f;
-      for (int j = 0; j < nb; ++j, ++s_it) {
-        tc::mbar_wait(&s_full[t], s_it & 1);
+      const int b = (int)(tq / p.tiles_per_img);
+      const int qt = (int)(tq % p.tiles_per_img);
+      float m_ref = -INFINITY;  // exponent reference, in log2 units (s * log2e); identical in both threads of a row
+      float l = 0.f;            // this thread's part of the row sum
+      for (int j = 0; j < nb; ++j, ++g) {
+        const uint32_t tS = tmem + (g & 1) * 128 + lane_addr;
+        tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc::tc_fence_after();
-        uint32_t sv[128];  // the whole S row of this block, read from TMEM once
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tc::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        uint32_t sv[64];  // this thread's 64 keys of the S row, read from TMEM once
+        tc::tmem_ld32(tS + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tc::tmem_ld32(tS + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         tc::tmem_ld_wait();
-        const int kbase = j * BKEY;
-        if (kbase + BKEY > p.nkeys) {  // only the last key block can hold padded keys (block-uniform)
+        const int kbase = j * BKEY + half * 64;
+        if (kbase + 64 > p.nkeys) {  // only the last key block can hold padded keys (warp-uniform)
 #pragma unroll
-          for (int e = 0; e < 128; ++e)
+          for (int e = 0; e < 64; ++e)
             if (kbase + e >= p.nkeys) sv[e] = __float_as_uint(-INFINITY);
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: the row max is latency-bound otherwise
 #pragma unroll
-        for (int e = 0; e < 128; e += 4) {
+        for (int e = 0; e < 64; e += 4) {
           mx[0] = fmaxf(mx[0], __uint_as_float(sv[e]));
           mx[1] = fmaxf(mx[1], __uint_as_float(sv[e + 1]));
           mx[2] = fmaxf(mx[2], __uint_as_float(sv[e + 2]));
           mx[3] = fmaxf(mx[3], __uint_as_float(sv[e + 3]));
         }
-        const float mj = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
+        const float mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        // Exchange with the thread that holds the other 64 keys of this row.  The barrier also orders
+        // this thread's S loads before the partner's P stores (P aliases the first 64 columns of S).
+        // Slots alternate per block: the partner reads slot (j&1) right after barrier j and cannot pass
+        // barrier j+1 before that, so the write of block j+2 to the same slot is safe.
+        my_x[(j & 1) * kSlot] = mine;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float mj = fmaxf(mine, other_x[(j & 1) * kSlot]) * kLog2e;
         // lazy max update: only move the reference when the row max grew by more than 2^8
         float scale = 1.f;
         bool need = false;
@@ -230,10 +237,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_ref = mj;
           need = (j > 0);
         }
-        if (__any_sync(0xffffffffu, need)) {  // rescale this warp's 32 rows of O_t (PV_t(j-1) has retired: s_full follows it)
+        if (__any_sync(0xffffffffu, need)) {  // rare: rescale this warp's share of O once PV(j-1) has retired
+          tc::mbar_wait(&pv_done, (g - 1) & 1);
+          tc::tc_fence_after();
           const float f = need ? scale : 1.f;
-#pragma unroll
-          for (int c = 0; c < DV; c += 16) {
+          for (int c = oc0; c < oc1; c += 16) {
             uint32_t o[16];
             tc::tmem_ld16(tO + c, o);
             tc::tmem_ld_wait();
@@ -245,7 +253,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float neg_m = -m_ref;
         float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 16 keys -> 8 packed bf16x2 columns of P_t
+        for (int c = 0; c < 4; ++c) {  // 16 keys -> 8 packed bf16x2 columns of P
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
@@ -255,42 +263,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
           }
-          tc::tmem_st8(tS + c * 8, pk);
+          tc::tmem_st8(tS + half * 32 + c * 8, pk);
         }
         l = l * scale + (rs[0] + rs[1]) + (rs[2] + rs[3]);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&p_full[t]);
+        if (lane == 0) tc::mbar_arrive(&p_full);
       }
-      // epilogue: O_t / l -> global
-      tc::mbar_wait(&o_done[t], item_it & 1);
+      // epilogue: O / l -> bf16 -> dense smem tile -> one TMA store (clipped at the image's last row)
+      my_x[2 * kSlot] = l;
+      if (sw == 0 && lane == 0) tc::tma_store_wait_read<0>();  // the previous tile's store has read the staging tile
+      asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+      const float inv = 1.f / (l + other_x[2 * kSlot]);
+      tc::mbar_wait(&pv_done, (g - 1) & 1);
       tc::tc_fence_after();
-      const long long row_local = (long long)pr * (2 * BQ) + t * BQ + r;
-      const bool row_ok = row_local < p.rows_per_img;
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                           ((long long)b * p.rows_per_img + row_local) * p.ldo + h * p.o_head_stride;
-#pragma unroll
-      for (int c = 0; c < DV; c += 16) {
+      uint8_t* orow = sO + r * (DV * 2);
+      for (int c = oc0; c < oc1; c += 16) {
         uint32_t o[16];
         tc::tmem_ld16(tO + c, o);
         tc::tmem_ld_wait();
-        if (row_ok) {
-          uint32_t w[8];
+        uint32_t w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(o[2 * e]) * inv, __uint_as_float(o[2 * e + 1]) * inv);
-            w[e] = *reinterpret_cast<uint32_t*>(&bb);
-          }
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        for (int e = 0; e < 8; ++e) {
+          __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(o[2 * e]) * inv, __uint_as_float(o[2 * e + 1]) * inv);
+          w[e] = *reinterpret_cast<uint32_t*>(&bb);
         }
+        *reinterpret_cast<uint4*>(orow + c * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(orow + c * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
       }
-      // the next item's PV_t(0) overwrites O_t only after this group's next p_full arrival, which
-      // follows these reads in program order; tcgen05.ld completion is covered by the wait above
+      // the next item's PV(0) overwrites O only after all eight warps' next p_full arrivals, which
+      // follow these TMEM reads in program order
       tc::tc_fence_before();
+      tc::fence_proxy_async();
+      asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+      if (sw == 0 && lane == 0) {
+        tc::tma_store_3d(&tmO, sO, h * p.o_head_stride, qt * BQ, b);
+        tc::tma_store_commit();
+      }
     }
+    if (sw == 0 && lane == 0) tc::tma_store_wait_all();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -324,12 +336,18 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
   p.nblocks = (nkeys + attn::BKEY - 1) / attn::BKEY;
   p.heads = heads;
   p.rows_per_img = rows_per_img;
-  p.pairs_per_img = (int)((rows_per_img + 2 * attn::BQ - 1) / (2 * attn::BQ));
-  p.nitems = (long long)B * p.pairs_per_img * heads;
+  p.tiles_per_img = (int)((rows_per_img + attn::BQ - 1) / attn::BQ);
+  p.nitems = (long long)B * p.tiles_per_img * heads;
   p.q_head_stride = q_head_stride;
-  p.out = out; p.ldo = (int)ldo; p.o_head_stride = o_head_stride;
+  p.o_head_stride = o_head_stride;
   const long long nkp = (long long)p.nblocks * attn::BKEY;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  {  // out viewed as [B][rows_per_img][ldo]: a tile's store is clipped at its own image's last row
+    const uint64_t dims[3] = {(uint64_t)ldo, (uint64_t)rows_per_img, (uint64_t)B};
+    const uint64_t str[3] = {2, (uint64_t)ldo * 2, (uint64_t)rows_per_img * ldo * 2};
+    const uint32_t box[3] = {(uint32_t)DV, attn::BQ, 1};
+    if (int e = make_tmap(&tmO, 2, out, 3, dims, str, box, "attention(out)", false)) return e;
+  }
   {
     const uint64_t dims[2] = {(uint64_t)ldq, (uint64_t)B * rows_per_img}, str[2] = {2, (uint64_t)ldq * 2};
     const uint32_t box[2] = {64, attn::BQ};
@@ -361,9 +379,9 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
   }
   const int grid = (int)(p.nitems < num_sms ? p.nitems : num_sms);
   if (variant)
-    attn::attention_kernel<2, 7, 112><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, p);
+    attn::attention_kernel<2, 7, 112><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
   else
-    attn::attention_kernel<1, 4, 64><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, p);
+    attn::attention_kernel<1, 4, 64><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
   ISP_CHECK_LAUNCH("attention_kernel");
   return ISP_OK;
 }
