@@ -72,6 +72,10 @@ int isp_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int B, int C, int H, 
  * basic_upsamplers.py:26-33).  out_bf16 != 0 writes bf16 with Cpad channels. */
 int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int Hout, int Wout,
                          int out_bf16, int Cpad, isp_stream_t stream);
+/* Same resize writing BOTH an f32 result and its bf16 copy (the operand of the tensor-core 1x1
+ * conv that follows) in one pass over the input.  C % 4 == 0. */
+int isp_bilinear_ac_nhwc_dual(const float* in, float* out_f32, void* out_bf16, int B, int C, int Hin, int Win,
+                              int Hout, int Wout, isp_stream_t stream);
 
 /* ---- FeatUp JBU stack (external to the reference tree: JBUFeatUp.py:30-32) --- */
 /* F.adaptive_avg_pool2d(guidance, (OH,OW)): NCHW f32 [B,3,H,W] -> NHWC4 f32 [B,OH,OW,4] (4th = 0) */

@@ -32,10 +32,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 }
 
 // bilinear, align_corners=True (ATen upsample_bilinear2d): NHWC f32 -> NHWC f32|bf16
-template <typename OutT>
+// DUAL: additionally writes a bf16 copy (the tensor-core operand of the next GEMM) in the same pass.
+template <typename OutT, bool DUAL = false>
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(const float* __restrict__ in, OutT* __restrict__ out, int B,
                                                           int C, int Hin, int Win, int Hout, int Wout, int Cpad,
-                                                          float sy, float sx) {
+                                                          float sy, float sx, __nv_bfloat16* __restrict__ out2 = nullptr) {
   const int C4 = Cpad / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * Hout * Wout * C4;
@@ -66,6 +67,13 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(const float* __restric
     reinterpret_cast<uint2*>(out)[idx] = u;
   } else {
     reinterpret_cast<float4*>(out)[idx] = r;
+  }
+  if constexpr (DUAL) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(r.x, r.y), c = __floats2bfloat162_rn(r.z, r.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&a);
+    u.y = *reinterpret_cast<unsigned*>(&c);
+    reinterpret_cast<uint2*>(out2)[idx] = u;
   }
 }
 
@@ -154,6 +162,20 @@ extern "C" int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, in
     bilinear_ac_kernel<float><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), B, C,
                                                                                Hin, Win, Hout, Wout, Cpad, sy, sx);
   ISP_CHECK_LAUNCH("bilinear_ac_kernel");
+  return ISP_OK;
+}
+
+extern "C" int isp_bilinear_ac_nhwc_dual(const float* in, float* out_f32, void* out_bf16, int B, int C, int Hin, int Win,
+                                         int Hout, int Wout, isp_stream_t stream) {
+  ISP_REQUIRE(in && out_f32 && out_bf16 && B > 0 && C > 0 && C % 4 == 0, ISP_ERR_BAD_SHAPE,
+              "bilinear_ac_nhwc_dual: bad arguments (C must be a multiple of 4)");
+  ISP_REQUIRE(Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, ISP_ERR_BAD_SHAPE, "bilinear_ac_nhwc_dual: bad size");
+  const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  const long long total = (long long)B * Hout * Wout * (C / 4);
+  bilinear_ac_kernel<float, true><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
+      in, out_f32, B, C, Hin, Win, Hout, Wout, C, sy, sx, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  ISP_CHECK_LAUNCH("bilinear_ac_kernel(dual)");
   return ISP_OK;
 }
 

@@ -69,7 +69,10 @@ class ISegPipeline(nn.Module):
         norm_img, coord = ops.prepare_input(image, points, self.norm_radius, 1.0, self.use_disks)
         emb = self.embed_coords(coord)
         lr = self.backbone(norm_img, emb)
-        hr = self.upsampler(source=lr, guidance=norm_img)
+        if hasattr(self.upsampler, "forward_resized"):  # upsampler + the resize below in one go (same result)
+            hr = self.upsampler.forward_resized(lr, norm_img, tuple(norm_img.shape[2:]))
+        else:
+            hr = self.upsampler(source=lr, guidance=norm_img)
         if self.upsampler_type != "identity" and tuple(hr.shape[2:]) != tuple(norm_img.shape[2:]):
             hr = bilinear_align_corners_nhwc(to_nhwc_f32(hr), tuple(norm_img.shape[2:])).permute(0, 3, 1, 2)
         return hr

@@ -178,6 +178,15 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         return out
 
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        return self.forward_resized(source, guidance, None)
+
+    def forward_resized(self, source: torch.Tensor, guidance: torch.Tensor, size=None) -> torch.Tensor:
+        """`forward` followed by the bilinear (align_corners=True) resize to `size` that the reference
+        applies right after the upsampler (core/model/iseg_probe_model.py:120-129).  The final
+        `fixup_proj(x) * 0.1 + x` is a per-pixel linear map and the resize a per-channel convex
+        combination of pixels, so they commute exactly (bias included: the weights sum to 1); doing the
+        resize FIRST runs the 1x1 conv on 448^2 instead of 512^2 pixels and writes the bf16 GEMM operand
+        in the resize pass.  size=None keeps the reference's 16x output."""
         if self.training and torch.is_grad_enabled() and source.requires_grad:
             raise NotImplementedError("JBUFeatUpUpsampler: activation backward is not implemented yet")
         x = to_nhwc_f32(source.detach())
@@ -185,6 +194,7 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         for up in (self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4):
             x = self._stage(up, x, guidance)
         B, H, W, C = x.shape
+        OH, OW = (H, W) if size is None else (int(size[0]), int(size[1]))
         conv = self.upsampler.fixup_proj[1]
         # fixup_proj(x) * 0.1 + x  (JBUStack.forward): 1x1 conv on the tcgen05 GEMM (bf16 operands, fp32
         # accumulate, fp32 residual and output; the 0.1 factor keeps the bf16 rounding below 1e-3 of x)
@@ -195,14 +205,22 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             self._fix_b = conv.bias.detach().float().contiguous().to(x.device)
             self._fix_key = key
         if C % 8 == 0:
-            xb = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=x.device)
-            _lib.call("isp_bilinear_ac_nhwc", _lib.dptr(x), _lib.dptr(xb), B, C, H, W, H, W, 1, C, _lib.stream_ptr())
-            out = tc.gemm(xb.view(B * H * W, C), self._fix_w, bias=self._fix_b, resid=x.view(B * H * W, C), alpha=0.1,
-                          out_dtype=torch.float32, N=C, K=C).view(B, H, W, C)
+            xb = torch.empty(B, OH, OW, C, dtype=torch.bfloat16, device=x.device)
+            if (OH, OW) == (H, W):
+                _lib.call("isp_bilinear_ac_nhwc", _lib.dptr(x), _lib.dptr(xb), B, C, H, W, H, W, 1, C, _lib.stream_ptr())
+            else:
+                xr = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
+                _lib.call("isp_bilinear_ac_nhwc_dual", _lib.dptr(x), _lib.dptr(xr), _lib.dptr(xb), B, C, H, W, OH, OW,
+                          _lib.stream_ptr())
+                x = xr
+            out = tc.gemm(xb.view(B * OH * OW, C), self._fix_w, bias=self._fix_b, resid=x.view(B * OH * OW, C),
+                          alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
         else:  # odd channel counts: fp32 SIMT GEMM
+            if (OH, OW) != (H, W):
+                x = bilinear_align_corners_nhwc(x, (OH, OW))
             out = torch.empty_like(x)
             _lib.call("isp_gemm_f32_simt", _lib.dptr(x), _lib.dptr(self._flat(conv.weight)), _lib.dptr(self._fix_b),
-                      _lib.dptr(x), 0.1, _lib.dptr(out), B * H * W, C, C, _lib.stream_ptr())
+                      _lib.dptr(x), 0.1, _lib.dptr(out), B * OH * OW, C, C, _lib.stream_ptr())
         return out.permute(0, 3, 1, 2)
 
 

@@ -144,6 +144,21 @@ def test_jbu_stack_module(isp, B, h, w, H, W):
     assert relerr(out, want) < TOL
 
 
+def test_jbu_forward_resized(isp):
+    """Resize-then-1x1 (what the pipeline runs) equals the reference order, stack then
+    bilinear align_corners resize (iseg_probe_model.py:120-129), to fp32-mode tolerance."""
+    sd = ojbu.init_state_dict(384, seed=0)
+    up = isp.JBUFeatUpUpsampler("dinov2").to(DEV).eval()
+    up.upsampler.load_state_dict(sd)
+    src = synth.lr_features(2, 384, 8, 8, seed=2)
+    gd = (synth.image_batch(2, 112, 112, seed=1) - 0.45) / 0.225
+    with torch.no_grad():
+        out = up.forward_resized(src.to(DEV), gd.to(DEV), (112, 112))
+        want = F.interpolate(ojbu.jbu_stack_forward(sd, src, gd), size=(112, 112), mode="bilinear", align_corners=True)
+    assert tuple(out.shape) == (2, 384, 112, 112)
+    assert relerr(out, want) < TOL
+
+
 def test_jbu_reference_shape_contract(isp):
     """JBUFeatUp.py:36-45: [1,384,14,14] + [1,3,224,224] -> [1,384,224,224]."""
     up = isp.JBUFeatUpUpsampler(backbone_type="dinov2").to(DEV).eval()
