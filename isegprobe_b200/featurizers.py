@@ -216,3 +216,163 @@ class DINOv2Featurizer(nn.Module):
         if inject and self.feats_injection_mode == "after_backbone":
             feats = feats + additional_features.to(feats.dtype)
         return feats.reshape(B, h, w, C).permute(0, 3, 1, 2)
+
+
+class _ClipResBlock(nn.Module):
+    """Parameter container with ResidualAttentionBlock's names (maskclip/model.py:225-243)."""
+
+    def __init__(self, width, heads):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(width, heads)  # container only: in_proj_weight/bias, out_proj.*
+        self.ln_1 = nn.LayerNorm(width)
+        self.mlp = nn.Sequential()
+        self.mlp.add_module("c_fc", nn.Linear(width, width * 4))
+        self.mlp.add_module("gelu", nn.Identity())  # QuickGELU has no parameters
+        self.mlp.add_module("c_proj", nn.Linear(width * 4, width))
+        self.ln_2 = nn.LayerNorm(width)
+
+
+class _ClipViT(nn.Module):
+    """Parameter container with maskclip VisionTransformer's names (maskclip/model.py:286-319)."""
+
+    def __init__(self, input_resolution=224, patch_size=16, width=768, layers=12, heads=12, output_dim=512):
+        super().__init__()
+        self.input_resolution, self.output_dim, self.patch_size = input_resolution, output_dim, patch_size
+        self.width, self.heads = width, heads
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = nn.Module()
+        self.transformer.resblocks = nn.Sequential(*[_ClipResBlock(width, heads) for _ in range(layers)])
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+
+_CLIP_ARCHS = {"ViT-B/16": dict(input_resolution=224, patch_size=16, width=768, layers=12, heads=12, output_dim=512)}
+
+
+class MaskCLIPFeaturizer(nn.Module):
+    """Frozen MaskCLIP (CLIP ViT-B/16) dense features on libisp_b200: same constructor and
+    `forward(x, additional_features)` as the reference adapter (core/model/featurizers/MaskCLIP.py:14-92).
+    11 full blocks, then the last block's value path only (`forward_v`, maskclip/model.py:251-263),
+    `ln_post` and `@ proj` on the patch tokens.  The reference downloads the OpenAI weights
+    (network); here the parameters are `self.model.visual.*` with CLIP's names, random-init
+    unless a state dict is loaded.  bf16 tensor-core GEMMs, fp32 residual stream (the reference
+    runs fp16 on CUDA)."""
+
+    def __init__(self, model_name: str = "ViT-B/16", feats_injection_mode: str = "no_injection") -> None:
+        super().__init__()
+        if model_name not in _CLIP_ARCHS:
+            raise NotImplementedError(f"Only {sorted(_CLIP_ARCHS)} are supported, got {model_name}")
+        self.feats_injection_mode = feats_injection_mode
+        self.model = nn.Module()
+        self.model.visual = _ClipViT(**_CLIP_ARCHS[model_name])
+        self.patch_size = self.model.visual.patch_size
+        self._packed = None
+        self._pos_cache = {}
+
+    def _pack(self, dev):
+        key = (str(dev), sum(p._version for p in self.parameters()))
+        if self._packed is not None and self._packed["key"] == key:
+            return self._packed
+        v = self.model.visual
+        C, nh = v.width, v.heads
+        f32 = lambda t: t.detach().float().contiguous().to(dev)
+        P = {"key": key}
+        P["Wpe"] = tc.pack_linear_weight(v.conv1.weight.detach().float().reshape(C, -1)).to(dev)
+        P["cls"] = f32(v.class_embedding)
+        P["lpw"], P["lpb"] = f32(v.ln_pre.weight), f32(v.ln_pre.bias)
+        sc = (C // nh) ** -0.5
+        blocks = []
+        for blk in v.transformer.resblocks:
+            Wqkv, bqkv = blk.attn.in_proj_weight.detach().float().clone(), blk.attn.in_proj_bias.detach().float().clone()
+            Wv, bv = Wqkv[-C:].clone(), bqkv[-C:].clone()
+            Wqkv[:C] *= sc
+            bqkv[:C] *= sc
+            blocks.append({
+                "n1w": f32(blk.ln_1.weight), "n1b": f32(blk.ln_1.bias),
+                "Wqkv": tc.pack_linear_weight(Wqkv).to(dev), "bqkv": f32(bqkv),
+                "Wv": tc.pack_linear_weight(Wv).to(dev), "bv": f32(bv),
+                "Wo": tc.pack_linear_weight(blk.attn.out_proj.weight).to(dev), "bo": f32(blk.attn.out_proj.bias),
+                "n2w": f32(blk.ln_2.weight), "n2b": f32(blk.ln_2.bias),
+                "W1": tc.pack_linear_weight(blk.mlp.c_fc.weight).to(dev), "b1": f32(blk.mlp.c_fc.bias),
+                "W2": tc.pack_linear_weight(blk.mlp.c_proj.weight).to(dev), "b2": f32(blk.mlp.c_proj.bias),
+            })
+        P["blocks"] = blocks
+        P["npw"], P["npb"] = f32(v.ln_post.weight), f32(v.ln_post.bias)
+        P["Wout"] = tc.pack_linear_weight(v.proj.detach().float().t().contiguous()).to(dev)
+        self._packed = P
+        self._pos_cache = {}
+        return P
+
+    def _pos(self, w_arg, h_arg, n, dev):
+        """interpolate_positional_embedding (maskclip/interpolate.py:5-60), called with the (w, h)
+        the reference passes; parameter preprocessing, cached per size."""
+        v = self.model.visual
+        key = (w_arg, h_arg, str(dev), v.positional_embedding._version)
+        if key not in self._pos_cache:
+            pe = v.positional_embedding.detach().float().cpu()
+            n_og = pe.shape[0] - 1
+            if not (n == n_og and w_arg == h_arg):
+                w0, h0 = w_arg // self.patch_size + 0.1, h_arg // self.patch_size + 0.1
+                s = int(math.sqrt(n_og))
+                pp = F.interpolate(pe[1:].reshape(1, s, s, -1).permute(0, 3, 1, 2), scale_factor=(w0 / s, h0 / s),
+                                   mode="bicubic", align_corners=False, recompute_scale_factor=False)
+                pe = torch.cat([pe[:1], pp.permute(0, 2, 3, 1).reshape(-1, pe.shape[-1])], 0)
+            self._pos_cache[key] = pe.contiguous().to(dev)
+        return self._pos_cache[key]
+
+    def forward(self, x: torch.Tensor, additional_features: torch.Tensor = None) -> torch.Tensor:
+        x = x.detach().float()
+        dev = x.device
+        B, _, H, W = x.shape
+        p = self.patch_size
+        h, w = H // p, W // p
+        v = self.model.visual
+        C, nh, Co = v.width, v.heads, v.output_dim
+        P = self._pack(dev)
+        before = additional_features is not None and self.feats_injection_mode == "before_backbone"
+        extra = None
+        if before:
+            extra = additional_features.detach().float().contiguous()
+            assert tuple(extra.shape) == (B, h * w, C), f"x.shape: {(B, h * w, C)}, additional_features.shape: {tuple(extra.shape)}"
+        N, T = h * w, h * w + 1
+        cols = torch.empty(B * N, P["Wpe"].shape[1], dtype=torch.bfloat16, device=dev)
+        _call("isp_vit_patchify", x, *x.stride(), cols, B, 3, H, W, p, P["Wpe"].shape[1])
+        patch = tc.gemm(cols, P["Wpe"], out_dtype=torch.float32, K=3 * p * p)
+        # VisionTransformer.forward reads `_, _, w, h = x.shape` (w := H, h := W, model.py:321) while
+        # forward_without_patch_embed unpacks `h, w = orig_image_hw` (:388): the two entry points hand
+        # the interpolation opposite orders; mirrored here (they agree for square images).
+        pos = self._pos(W, H, N, dev) if before else self._pos(H, W, N, dev)
+        tok = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+        _call("isp_vit_assemble_tokens", patch, extra, P["cls"], pos, tok, B, N, C)
+        xs = _ln(tok, P["lpw"], P["lpb"], C, 1e-5, torch.float32)
+        Tp = tc.round_up(T, 128)
+        hd = C // nh
+        bf = torch.bfloat16
+        for L in P["blocks"][:-1]:
+            hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-5, bf)
+            qkv = tc.gemm(hn, L["Wqkv"], bias=L["bqkv"], out_dtype=bf)
+            Kp = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
+            Vt = torch.empty(B, nh, 64, Tp, dtype=bf, device=dev)
+            _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Kp, B, T, Tp, nh, 64, 0)
+            _call("isp_repack_heads", qkv, 1, 3 * C, 2 * C, hd, Vt, B, T, Tp, nh, 64, 1)
+            O = torch.empty(B * T, C, dtype=bf, device=dev)
+            _call("isp_attention_bf16_tc", qkv, 3 * C, hd, Kp, Vt, O, C, hd, B, T, nh, T, 0)
+            xs = tc.gemm(O, L["Wo"], bias=L["bo"], resid=xs, out_dtype=torch.float32)
+            hn = _ln(xs, L["n2w"], L["n2b"], C, 1e-5, bf)
+            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="quick_gelu", out_dtype=bf)
+            xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
+        L = P["blocks"][-1]  # forward_v: value projection -> output projection, no residual (model.py:251-263)
+        hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-5, bf)
+        vv = tc.gemm(hn, L["Wv"], bias=L["bv"], out_dtype=bf)
+        vo = tc.gemm(vv, L["Wo"], bias=L["bo"], out_dtype=torch.float32)
+        xn = _ln(vo, P["npw"], P["npb"], C, 1e-5, bf)
+        feats = tc.gemm(xn, P["Wout"], out_dtype=torch.float32).view(B, T, Co)[:, 1:]
+        if additional_features is not None and self.feats_injection_mode == "after_backbone":
+            assert tuple(feats.shape) == tuple(additional_features.shape), \
+                f"features.shape: {tuple(feats.shape)}, additional_features.shape: {tuple(additional_features.shape)}"
+            feats = feats + additional_features.to(feats.dtype)
+        return feats.reshape(B, h, w, Co).permute(0, 3, 1, 2)

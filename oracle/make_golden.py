@@ -125,6 +125,35 @@ def golden_vit():
     save("vit_56x84", out=f)
 
 
+def golden_maskclip():
+    """maskclip/model.py imported BY PATH (the package __init__ pulls the CLIP tokenizer, which needs ftfy)."""
+    import importlib.util
+    base = os.path.join(ref_shim.REFERENCE_ROOT, "core", "model", "featurizers", "maskclip")
+    pkg = __import__("types").ModuleType("maskclip_ref")
+    pkg.__path__ = [base]
+    sys.modules["maskclip_ref"] = pkg
+    for name in ("interpolate", "model"):
+        spec = importlib.util.spec_from_file_location(f"maskclip_ref.{name}", os.path.join(base, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"maskclip_ref.{name}"] = mod
+        spec.loader.exec_module(mod)
+    VT = sys.modules["maskclip_ref.model"].VisionTransformer
+    m = VT(224, 16, 768, 12, 12, 512)
+    sd = synth.maskclip_state_dict(seed=0)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 768, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():
+        plain = m(img, patch_output=True)  # get_patch_encodings (MaskCLIP.py:70)
+        x = m.conv1(img)                   # 'before_backbone' branch (MaskCLIP.py:52-66)
+        x = x.reshape(2, 768, -1).permute(0, 2, 1) + emb
+        inj = m.forward_without_patch_embed(x, (64, 96), patch_output=True)
+        sq = m((synth.image_batch(1, 64, 64, seed=2) - 0.45) / 0.225, patch_output=True)
+    save("maskclip_64x96", plain=plain.reshape(2, 4, 6, 512).permute(0, 3, 1, 2),
+         injected=inj.reshape(2, 4, 6, 512).permute(0, 3, 1, 2), square=sq.reshape(1, 4, 4, 512).permute(0, 3, 1, 2))
+
+
 def golden_jbu_shape():
     """The only anchor the reference holds for JBU is the shape contract of
     JBUFeatUp.py:36-45; record it (parity unpinned, see oracle/jbu.py)."""
@@ -141,4 +170,5 @@ if __name__ == "__main__":
     golden_lift()
     golden_head()
     golden_vit()
+    golden_maskclip()
     golden_jbu_shape()

@@ -136,6 +136,28 @@ def vit_state_dict(dim=384, depth=12, patch=14, n_pos=37 * 37 + 1, mlp_ratio=4, 
     return sd
 
 
+def maskclip_state_dict(width=768, layers=12, patch=16, out_dim=512, resolution=224, seed=0):
+    """Keys/shapes of maskclip.model.VisionTransformer(224, 16, 768, 12, 12, 512).state_dict()
+    (/root/reference/core/model/featurizers/maskclip/model.py:286-319)."""
+    G, sd = _Gen(seed), {}
+    sd["class_embedding"] = G.randn(width, std=width ** -0.5)
+    sd["positional_embedding"] = G.randn((resolution // patch) ** 2 + 1, width, std=width ** -0.5)
+    sd["proj"] = G.randn(width, out_dim, std=width ** -0.5)
+    _conv(sd, G, "conv1", width, 3, patch, bias=False)
+    _ln(sd, G, "ln_pre", width)
+    for i in range(layers):
+        p = f"transformer.resblocks.{i}"
+        sd[f"{p}.attn.in_proj_weight"] = G.randn(3 * width, width, std=width ** -0.5)
+        sd[f"{p}.attn.in_proj_bias"] = G.randn(3 * width, std=0.1)
+        _linear(sd, G, f"{p}.attn.out_proj", width, width)
+        _ln(sd, G, f"{p}.ln_1", width)
+        _linear(sd, G, f"{p}.mlp.c_fc", 4 * width, width)
+        _linear(sd, G, f"{p}.mlp.c_proj", width, 4 * width)
+        _ln(sd, G, f"{p}.ln_2", width)
+    _ln(sd, G, "ln_post", width)
+    return sd
+
+
 def image_batch(b, h, w, seed=1):
     """Synthetic RGB images in [0,1] (north_star: identical synthetic inputs)."""
     return _Gen(seed).rand(b, 3, h, w)

@@ -83,6 +83,31 @@ def test_vit_golden_and_oracle(isp, golden):
     assert tuple(out.shape) == (1, 384, 32, 32) and cosine(out, want) > 0.999, cosine(out, want)
 
 
+def test_maskclip_golden_and_oracle(isp, golden):
+    """MaskCLIP ViT-B/16 dense features: reference golden vectors (64x96, with / without injection)
+    and the oracle at 448^2 (785 tokens); bf16 tensor-core mode: cosine >= 0.999."""
+    from oracle import maskclip as omc
+    sd = synth.maskclip_state_dict(seed=0)
+    g = golden("maskclip_64x96")
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 768, 1, seed=7).squeeze(-1) * 0.1
+    f = isp.MaskCLIPFeaturizer("ViT-B/16", "before_backbone")
+    f.model.visual.load_state_dict(sd, strict=True)  # CLIP's own key layout
+    f = f.to(DEV).eval()
+    with torch.no_grad():
+        inj = f(img.to(DEV), emb.to(DEV))
+        plain = f(img.to(DEV))
+    for out, key in ((inj, "injected"), (plain, "plain")):
+        want = torch.from_numpy(g[key])
+        assert tuple(out.shape) == (2, 512, 4, 6)
+        assert cosine(out, want) > 0.999, (key, cosine(out, want))
+    img = (synth.image_batch(1, 448, 448, seed=3) - 0.45) / 0.225
+    with torch.no_grad():
+        out = f(img.to(DEV))
+        want = omc.maskclip_forward(sd, img)
+    assert tuple(out.shape) == (1, 512, 28, 28) and cosine(out, want) > 0.999, cosine(out, want)
+
+
 def test_lift_golden(isp, golden):
     m = isp.LiFTUpsampler(None, 384, 14)
     m.lift.load_state_dict(synth.lift_state_dict(384, seed=0), strict=True)

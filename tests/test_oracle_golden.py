@@ -8,7 +8,7 @@ from oracle import head as ohead
 from oracle import jbu as ojbu
 from oracle import lift as olift
 from oracle import loftup as oloft
-from oracle import synth, vit as ovit
+from oracle import maskclip as omc, synth, vit as ovit
 
 
 def _relerr(a, b):
@@ -122,3 +122,20 @@ def test_jbu_shape_contract_and_adaptive_conv_identities(golden):
     k = ojbu.range_kernel(sd, "up1", gd[:, :, :6, :8]) * ojbu.spatial_kernel(sd, "up1")
     k = k / k.sum(1, keepdim=True).clamp(1e-7)
     assert torch.allclose(k.sum(1), torch.ones(1, 6, 8), atol=1e-5)
+
+
+def test_maskclip_matches_reference(golden):
+    """Oracle restatement vs the unmodified maskclip VisionTransformer (patch_output path, with and
+    without click-embedding injection; non-square input exercises the (w, h) ordering quirk)."""
+    g = golden("maskclip_64x96")
+    sd = synth.maskclip_state_dict(seed=0)
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 768, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():
+        plain = omc.maskclip_forward(sd, img)
+        inj = omc.maskclip_forward(sd, img, emb)
+        sq = omc.maskclip_forward(sd, (synth.image_batch(1, 64, 64, seed=2) - 0.45) / 0.225)
+    for out, key in ((plain, "plain"), (inj, "injected"), (sq, "square")):
+        want = torch.from_numpy(g[key])
+        assert tuple(out.shape) == tuple(want.shape)
+        assert float((out - want).abs().max() / want.abs().max()) < 1e-4, key
