@@ -16,11 +16,20 @@ namespace attn {
 constexpr int kSoftmaxWarps = 8;                 // two threads per query row: 64 keys of every block each
 constexpr int kThreads = 64 + 32 * kSoftmaxWarps;
 constexpr int BQ = 128, BKEY = 128;
-constexpr uint32_t kQBytes = 2 * 16384;          // Q tile: two 64-column chunks [128 rows x 64]
-constexpr uint32_t kKStage = 2 * 16384;          // K block: two 64-column chunks [128 keys x 64]
-constexpr uint32_t kVStage = 2 * 16384;          // V^T block: two 64-key chunks [DV x 64] (DV <= 128)
-constexpr uint32_t kOBytes = 2 * 16384;          // O staging tile for the TMA store: [128 rows x DV] bf16, dense
-constexpr uint32_t kSmem = kQBytes + 2 * kKStage + 2 * kVStage + kOBytes;  // 196608
+// Shared-memory plan of one instantiation: Q tile = DK_CHUNKS 64-column chunks [128 rows x 64];
+// K block likewise [128 keys x 64] per chunk, 2 stages; V^T block = two 64-key chunks [DV x 64], 2 stages;
+// O staging tile [128 rows x DV] bf16 (dense) for the TMA store when it still fits (DV <= 128).
+template <int DK_CHUNKS, int DV>
+struct Plan {
+  static constexpr uint32_t kQBytes = DK_CHUNKS * 16384;
+  static constexpr uint32_t kKStage = DK_CHUNKS * 16384;
+  static constexpr uint32_t kVChunk = (DV * 128 + 1023) / 1024 * 1024;  // chunk bases stay 1024-byte aligned (swizzle)
+  static constexpr uint32_t kVStage = 2 * kVChunk;
+  static constexpr bool kStageO = DV <= 128;
+  static constexpr uint32_t kOBytes = kStageO ? BQ * DV * 2 : 0;
+  static constexpr uint32_t kBytes = kQBytes + 2 * kKStage + 2 * kVStage + kOBytes;
+};
+constexpr uint32_t kSmemMin = 120 * 1024;        // requested at least: one CTA per SM (each CTA allocates all of TMEM)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThresh = 8.0f;           // log2 units: P stays <= 2^8
 
@@ -32,6 +41,8 @@ struct Params {
   long long nitems;            // B * tiles_per_img * heads
   int q_head_stride;           // column offset between heads in Q (elements)
   int o_head_stride;           // column offset between heads in out
+  void* out;                   // bf16 [B*rows_per_img, ldo] (direct-store epilogue of the wide-head variant)
+  long long ldo;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz); inputs are <= 8
@@ -65,8 +76,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   __shared__ float xchg[3][2][BQ];  // [slot][half][row]: slots 0/1 = block max (alternating), 2 = partial row sum
 
+  using PL = Plan<DK_CHUNKS, DV>;
+  constexpr uint32_t kKStage = PL::kKStage, kVStage = PL::kVStage, kVChunk = PL::kVChunk;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sK = sQ + PL::kQBytes;
   uint8_t* sV = sK + 2 * kKStage;
   uint8_t* sO = sV + 2 * kVStage;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,7 +128,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc::mbar_wait(&v_empty[s], ph ^ 1);
           tc::mbar_arrive_expect_tx(&v_full[s], 2 * DV * 128);
           for (int c = 0; c < 2; ++c)
-            tc::tma_load_2d(sV + s * kVStage + c * 16384, &tmV, &v_full[s], j * BKEY + c * 64, (int)(bh * DV));
+            tc::tma_load_2d(sV + s * kVStage + c * kVChunk, &tmV, &v_full[s], j * BKEY + c * 64, (int)(bh * DV));
         }
       }
     }
@@ -161,7 +174,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t va = v_lo + s * kVStage;
 #pragma unroll
           for (int k = 0; k < BKEY / 16; ++k) {
-            const uint32_t boff = (k >> 2) * 16384 + (k & 3) * 32;
+            const uint32_t boff = (k >> 2) * kVChunk + (k & 3) * 32;
             const uint64_t db = tc::smem_desc_k_sw128(va + boff);
             if (leader) tc::umma_bf16_ts(dO, aP + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
           }
@@ -271,14 +284,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_full);
       }
-      // epilogue: O / l -> bf16 -> dense smem tile -> one TMA store (clipped at the image's last row)
+      // epilogue: O / l -> bf16 -> dense smem tile -> one TMA store (clipped at the image's last row);
+      // the wide-head variant has no smem left for the tile and stores its rows directly
       my_x[2 * kSlot] = l;
-      if (sw == 0 && lane == 0) tc::tma_store_wait_read<0>();  // the previous tile's store has read the staging tile
+      if (PL::kStageO && sw == 0 && lane == 0) tc::tma_store_wait_read<0>();  // previous tile's store has read the staging tile
       asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
       const float inv = 1.f / (l + other_x[2 * kSlot]);
       tc::mbar_wait(&pv_done, (g - 1) & 1);
       tc::tc_fence_after();
-      uint8_t* orow = sO + r * (DV * 2);
+      const long long row_local = (long long)qt * BQ + r;
+      uint8_t* orow = PL::kStageO ? sO + r * (DV * 2)
+                                  : reinterpret_cast<uint8_t*>(p.out) +
+                                        (((long long)b * p.rows_per_img + row_local) * p.ldo + h * p.o_head_stride) * 2;
+      const bool row_ok = PL::kStageO || row_local < p.rows_per_img;
       for (int c = oc0; c < oc1; c += 16) {
         uint32_t o[16];
         tc::tmem_ld16(tO + c, o);
@@ -289,17 +307,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __nv_bfloat162 bb = __floats2bfloat162_rn(__uint_as_float(o[2 * e]) * inv, __uint_as_float(o[2 * e + 1]) * inv);
           w[e] = *reinterpret_cast<uint32_t*>(&bb);
         }
-        *reinterpret_cast<uint4*>(orow + c * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(orow + c * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        if (row_ok) {
+          *reinterpret_cast<uint4*>(orow + c * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(orow + c * 2 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
       }
       // the next item's PV(0) overwrites O only after all eight warps' next p_full arrivals, which
       // follow these TMEM reads in program order
       tc::tc_fence_before();
-      tc::fence_proxy_async();
-      asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
-      if (sw == 0 && lane == 0) {
-        tc::tma_store_3d(&tmO, sO, h * p.o_head_stride, qt * BQ, b);
-        tc::tma_store_commit();
+      if (PL::kStageO) {
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+        if (sw == 0 && lane == 0) {
+          tc::tma_store_3d(&tmO, sO, h * p.o_head_stride, qt * BQ, b);
+          tc::tma_store_commit();
+        }
       }
     }
     if (sw == 0 && lane == 0) tc::tma_store_wait_all();
@@ -317,14 +339,15 @@ using namespace isp;
 // Q: bf16 [B*rows_per_img, ldq]; head h reads columns [h*q_head_stride, +DK) (zero K padding
 // makes any extra columns harmless).  K: bf16 [B, heads, nblocks*128, DKC] (DKC = 64 or 128,
 // zero padded).  Vt: bf16 [B, heads, DV, nblocks*128].  out: bf16 [B*rows_per_img, ldo], head h
-// writes DV columns at h*o_head_stride.  variant 0: head_dim <= 64 (DV = 64); 1: <= 112 (DV = 112).
+// writes DV columns at h*o_head_stride.  variant 0: head_dim <= 64 (DV = 64); 1: <= 112 (DV = 112);
+// 2: <= 144 (DV = 144, K padded to 192 columns).
 extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
                                      void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
                                      int heads, int nkeys, int variant, isp_stream_t stream) {
   ISP_REQUIRE(Q && K && Vt && out, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: null pointer");
   ISP_REQUIRE(B > 0 && rows_per_img > 0 && heads > 0 && nkeys > 0, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: bad shape");
-  ISP_REQUIRE(variant == 0 || variant == 1, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: variant %d", variant);
-  const int DV = variant ? 112 : 64, DKC = variant ? 128 : 64;
+  ISP_REQUIRE(variant >= 0 && variant <= 2, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: variant %d", variant);
+  const int DV = variant == 0 ? 64 : variant == 1 ? 112 : 144, DKC = variant == 0 ? 64 : variant == 1 ? 128 : 192;
   ISP_REQUIRE(ldq % 8 == 0 && ldo % 8 == 0 && o_head_stride % 8 == 0 && q_head_stride % 8 == 0, ISP_ERR_MISALIGNED,
               "attention_bf16_tc: ldq/ldo/q_head_stride/o_head_stride must be multiples of 8 (TMA box starts and "
               "vector stores need 16-byte alignment)");
@@ -340,6 +363,7 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
   p.nitems = (long long)B * p.tiles_per_img * heads;
   p.q_head_stride = q_head_stride;
   p.o_head_stride = o_head_stride;
+  p.out = out; p.ldo = ldo;
   const long long nkp = (long long)p.nblocks * attn::BKEY;
   CUtensorMap tmQ, tmK, tmV, tmO;
   {  // out viewed as [B][rows_per_img][ldo]: a tile's store is clipped at its own image's last row
@@ -370,18 +394,22 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
     ISP_CUDA(cudaGetDevice(&dev));
     ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  auto smem_of = [](uint32_t plan) { return (int)(plan > attn::kSmemMin ? plan : attn::kSmemMin); };
+  const int sm0 = smem_of(attn::Plan<1, 64>::kBytes), sm1 = smem_of(attn::Plan<2, 112>::kBytes),
+            sm2 = smem_of(attn::Plan<3, 144>::kBytes);
   if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<2, 7, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)attn::kSmem));
-    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<1, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)attn::kSmem));
+    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<1, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm0));
+    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<2, 7, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1));
+    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<3, 9, 144>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
     attr_set = true;
   }
   const int grid = (int)(p.nitems < num_sms ? p.nitems : num_sms);
-  if (variant)
-    attn::attention_kernel<2, 7, 112><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  if (variant == 2)
+    attn::attention_kernel<3, 9, 144><<<grid, attn::kThreads, sm2, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  else if (variant == 1)
+    attn::attention_kernel<2, 7, 112><<<grid, attn::kThreads, sm1, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
   else
-    attn::attention_kernel<1, 4, 64><<<grid, attn::kThreads, attn::kSmem, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
+    attn::attention_kernel<1, 4, 64><<<grid, attn::kThreads, sm0, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
   ISP_CHECK_LAUNCH("attention_kernel");
   return ISP_OK;
 }

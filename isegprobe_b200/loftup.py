@@ -129,7 +129,15 @@ class LoftUpUpsampler(BaseUpsampler):
         D = self.n_dim + 20
         hd = D // self.HEADS
         f32 = lambda t: t.detach().float().contiguous().to(dev)
-        P = {"key": key, "D": D, "hd": hd}
+        # head padding of the attention kernel: head_dim <= 112 -> 112-column heads, K rows of 128;
+        # <= 144 (LoftUp(512): 133) -> 144-column heads, K rows of 192
+        if hd <= 112:
+            HP, KP, variant = 112, 128, 1
+        elif hd <= 144:
+            HP, KP, variant = 144, 192, 2
+        else:
+            raise NotImplementedError(f"LoftUp head_dim {hd} > 144 is not supported by the attention kernel")
+        P = {"key": key, "D": D, "hd": hd, "HP": HP, "KP": KP, "variant": variant}
 
         def fold_bn(conv, bn):
             s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
@@ -156,12 +164,12 @@ class LoftUpUpsampler(BaseUpsampler):
             Wi, bi = ca.attention.in_proj_weight.detach().float(), ca.attention.in_proj_bias.detach().float()
             sc = 1.0 / math.sqrt(hd)
             Wo = ca.attention.out_proj.weight.detach().float()
-            Wo_p = torch.zeros(D, self.HEADS * 112)
-            Wq_p, bq_p = torch.zeros(self.HEADS * 112, D), torch.zeros(self.HEADS * 112)
-            for h in range(self.HEADS):  # Q and the attention output are head-padded to 112 columns
-                Wo_p[:, h * 112:h * 112 + hd] = Wo[:, h * hd:(h + 1) * hd]
-                Wq_p[h * 112:h * 112 + hd] = Wi[h * hd:(h + 1) * hd] * sc
-                bq_p[h * 112:h * 112 + hd] = bi[h * hd:(h + 1) * hd] * sc
+            Wo_p = torch.zeros(D, self.HEADS * HP)
+            Wq_p, bq_p = torch.zeros(self.HEADS * HP, D), torch.zeros(self.HEADS * HP)
+            for h in range(self.HEADS):  # Q and the attention output are head-padded to HP columns
+                Wo_p[:, h * HP:h * HP + hd] = Wo[:, h * hd:(h + 1) * hd]
+                Wq_p[h * HP:h * HP + hd] = Wi[h * hd:(h + 1) * hd] * sc
+                bq_p[h * HP:h * HP + hd] = bi[h * hd:(h + 1) * hd] * sc
             layers.append({
                 "nq_w": f32(ca.norm_q.weight), "nq_b": f32(ca.norm_q.bias),
                 "nkv_w": f32(ca.norm_kv.weight), "nkv_b": f32(ca.norm_kv.bias),
@@ -222,6 +230,7 @@ class LoftUpUpsampler(BaseUpsampler):
     def _forward_chunk(self, P, img, src, mm, out, H, W, h, w):
         dev = img.device
         D, hd, C, nh = P["D"], P["hd"], self.n_dim, self.HEADS
+        HP, KP = P["HP"], P["KP"]
         B = img.shape[0]
         M, T = B * H * W, h * w
         Dp = tc.round_up(D, 16)  # row stride of the token matrices (404 -> 416)
@@ -240,18 +249,18 @@ class LoftUpUpsampler(BaseUpsampler):
             kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, tc.round_up(D, 8))
             Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
             Vl = tc.gemm(kvn, L["Wv"], bias=L["bv"], out_dtype=torch.float32, N=D, K=D)
-            Kp = torch.empty(B, nh, Tp, 128, dtype=bf, device=dev)
-            Vt = torch.empty(B, nh, 112, Tp, dtype=bf, device=dev)
-            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, Tp, nh, 128, 0)
-            _call("isp_repack_heads", Vl, 0, D, 0, hd, Vt, B, T, Tp, nh, 112, 1)
+            Kp = torch.empty(B, nh, Tp, KP, dtype=bf, device=dev)
+            Vt = torch.empty(B, nh, HP, Tp, dtype=bf, device=dev)
+            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, Tp, nh, KP, 0)
+            _call("isp_repack_heads", Vl, 0, D, 0, hd, Vt, B, T, Tp, nh, HP, 1)
             qn = self._ln(x, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
-            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * 112, K=D)
+            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
             del qn
-            O = torch.empty(M, nh * 112, dtype=bf, device=dev)
+            O = torch.empty(M, nh * HP, dtype=bf, device=dev)
             with timed_kernel("loftup_attention"):
-                _call("isp_attention_bf16_tc", Q, nh * 112, 112, Kp, Vt, O, nh * 112, 112, B, H * W, nh, T, 1)
+                _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
             del Q
-            x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * 112, ldd=Dp)
+            x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp)
             del O
             hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
             h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)

@@ -48,6 +48,20 @@ def test_loftup_vs_oracle(B, H, W, h, w):
     assert float(per_pixel.min()) > 0.99, float(per_pixel.min())
 
 
+def test_loftup_dim512_vs_oracle():
+    """LoftUp(512) as used on MaskCLIP features (BASELINE config 4): 4 heads x 133 -> the
+    144-column attention variant."""
+    m, sd, cn = _module(512)
+    img = (synth.image_batch(2, 48, 64, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 512, 3, 4, seed=2)
+    with torch.no_grad():
+        out = m(source=lr.to(DEV), guidance=img.to(DEV))
+        want = oloft.loftup_forward(sd, lr, img, cn["norm.weight"], cn["norm.bias"])
+    assert tuple(out.shape) == (2, 512, 48, 64)
+    c = cosine(out, want)
+    assert c >= 0.999, c
+
+
 def test_loftup_state_dict_matches_reference_layout():
     """Reference checkpoints must load: same keys/shapes as LoftUp(dim).state_dict()."""
     from isegprobe_b200.loftup import LoftUpUpsampler
