@@ -143,6 +143,29 @@ int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw,
 int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
                         int Nimg, int H, int W, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream);
 
+/* Backward of that convolution (trainer backward, core/training/trainer.py:213-221, of
+ * ConvSegHead.convs, heads/conv_heads.py:58-66):
+ * dgrad: dX = conv3x3(dY, W') with W' = flipped / transposed weights packed like forward ones
+ *        ([Cin][9][Cout_pad], tap 8 - t); if relu_mask != NULL (the bf16|f32 activation X itself,
+ *        same dtype as dX, pixel stride ldm) the result is zeroed where relu_mask <= 0.
+ * wgrad: dW[co][tap][ci] += sum_pixels dY[p][co] * X[p + tap][ci]  (fp32 [Cout][9][Cin], ACCUMULATED:
+ *        zero it first for a fresh gradient).  Cin, Cout multiples of 64.  Pixel-major tcgen05 GEMM
+ *        with MN-major operands straight from the NHWC tensors. */
+int isp_conv3x3_dgrad_bf16_tc(const void* dY, const void* Wp_flipped, const void* relu_mask, int ldm, void* dX,
+                              int out_bf16, int Nimg, int H, int W, int Cout, int ldy, int Cin, int ldx,
+                              isp_stream_t stream);
+int isp_conv3x3_wgrad_bf16_tc(const void* X, int ldx, const void* dY, int ldy, float* dW, int Nimg, int H, int W,
+                              int Cin, int Cout, isp_stream_t stream);
+
+/* IS-head classifier backward (num_classes == 1; heads/base_head.py:8-18) fused with the ReLU mask
+ * of the last 3x3 layer: dz = act > 0 ? dlogits * wc : 0 (bf16), dwc += act^T dlogits,
+ * dbc += sum dlogits, dbz += column sums of dz (that layer's bias gradient).  All three are
+ * ACCUMULATED.  isp_colsum_bf16: out[c] += sum_m x[m, c] (bias gradient of the other layers). */
+int isp_head_classifier_bwd(const void* act_bf16, long long lda, const float* dlogits, const float* wc,
+                            void* dz_bf16, long long ldz, float* dwc, float* dbc, float* dbz, long long M, int C,
+                            isp_stream_t stream);
+int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, int C, isp_stream_t stream);
+
 /* Flash-style attention on tcgen05: out = softmax(Q K^T) V, scores never leave the SM.
  * Q bf16 [B*rows_per_img, ldq] (pre-scaled by 1/sqrt(d)), head h at column h*q_head_stride;
  * K bf16 [B, heads, ceil128(nkeys), DKC] and Vt bf16 [B, heads, DV, ceil128(nkeys)], zero

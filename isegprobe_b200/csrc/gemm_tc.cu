@@ -281,7 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ncols = min(CW, p.BN - col0);
             uint8_t* buf = stage + ((st_seq + i) & 1) * 4096;
             tc::mbar_arrive_expect_tx(&rbar[(st_seq + i) & 1], 32u * ncols * ESZ);
-            tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1);
+            if (p.TW) tc::tma_load_4d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1, c2, c3);
+            else tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1);
           }
         }
         __syncwarp();
@@ -305,7 +306,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) {
               tc::tma_store_wait_read<1>();
               tc::mbar_arrive_expect_tx(&rbar[b], 32u * ncols * ESZ);
-              tc::tma_load_2d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1);
+              if (p.TW) tc::tma_load_4d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1, c2, c3);
+              else tc::tma_load_2d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1);
             }
             __syncwarp();
           }
@@ -345,7 +347,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (RESID) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(sp);
-                  if constexpr (OUT_BF16) {
+                  if constexpr (ACT == 5) {
+                    // ReLU backward: the "residual" operand is the forward activation; keep the gradient where it is > 0
+                    if constexpr (OUT_BF16) {
+                      const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        if (!(__uint_as_float(rw[k] << 16) > 0.f)) x[2 * k] = 0.f;
+                        if (!(__uint_as_float(rw[k] & 0xffff0000u) > 0.f)) x[2 * k + 1] = 0.f;
+                      }
+                    } else {
+                      if (!(__uint_as_float(rr.x) > 0.f)) x[0] = 0.f;
+                      if (!(__uint_as_float(rr.y) > 0.f)) x[1] = 0.f;
+                      if (!(__uint_as_float(rr.z) > 0.f)) x[2] = 0.f;
+                      if (!(__uint_as_float(rr.w) > 0.f)) x[3] = 0.f;
+                    }
+                  } else if constexpr (OUT_BF16) {
                     const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // bf16 -> f32 is a shift: the add happens in fp32, one rounding
@@ -421,6 +438,7 @@ static kernel_fn pick_act(int act) {
 }
 
 static kernel_fn pick_kernel(int out_bf16, int act, bool resid) {
+  if (act == 5) return out_bf16 ? gemm_tc_kernel<true, 5, true> : gemm_tc_kernel<false, 5, true>;  // ReLU-mask epilogue
   if (resid) return out_bf16 ? pick_act<true, true>(act) : pick_act<false, true>(act);
   return out_bf16 ? pick_act<true, false>(act) : pick_act<false, false>(act);
 }
@@ -521,8 +539,9 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, resid != nullptr, as_stream(stream));
 }
 
-extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
-                                   int Nimg, int H, int Wd, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream) {
+static int conv3x3_common(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16, int Nimg,
+                          int H, int Wd, int Cin, int ldx, int Cout, int ldy, const void* mask, int ldm,
+                          isp_stream_t stream) {
   ISP_REQUIRE(X && Wp && Y, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: null pointer");
   ISP_REQUIRE(Nimg > 0 && H > 0 && Wd > 0 && Cout > 0 && Cin > 0, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: bad shape");
   ISP_REQUIRE(ldx >= Cin && ldx % 8 == 0, ISP_ERR_MISALIGNED,
@@ -534,9 +553,16 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
   ISP_REQUIRE(aligned16(X) && aligned16(Wp), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: X/W must be 16-byte aligned");
   ISP_REQUIRE(act >= 0 && act <= 4, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: unknown activation %d", act);
   ISP_REQUIRE(!bias || aligned16(bias), ISP_ERR_MISALIGNED, "conv3x3_bf16_tc: bias must be 16-byte aligned");
+  if (mask) {
+    ISP_REQUIRE(act == 0, ISP_ERR_UNSUPPORTED, "conv3x3_dgrad_bf16_tc: the ReLU mask replaces the activation");
+    ISP_REQUIRE(ldm >= Cout && (ldm * esz) % 16 == 0 && aligned16(mask), ISP_ERR_MISALIGNED,
+                "conv3x3_dgrad_bf16_tc: mask pixels must be 16-byte aligned (ldm=%d)", ldm);
+    act = 5;
+  }
   gemm::Params p = {};
   p.M = (long long)Nimg * H * Wd; p.N = Cout; p.K = 9 * Cin_pad;
-  p.BN = gemm::pick_bn(Cout, 256);
+  // with a mask operand every epilogue warp should own at most two chunks per tile (see isp_gemm_bf16_tc)
+  p.BN = gemm::pick_bn(Cout, (mask && !out_bf16) ? 128 : 256);
   p.last_steps = (Cin - (Cin_pad - 64) + 15) / 16;
   // tile = TH x TW output pixels; prefer wide rows (fewer halo re-reads), fall back to 16x8
   int TW = 16;
@@ -569,5 +595,29 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
     if (int e = make_tmap(&tmD, esz, Y, 4, dims, str, box, "conv3x3_bf16_tc(Y)", true)) return e;
     if (int e = make_tmap(&tmDt, esz, Y, 4, dims, str, boxt, "conv3x3_bf16_tc(Y tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmDt, tmD, tmDt, p, out_bf16, act, false, as_stream(stream));
+  CUtensorMap tmR = tmD, tmRt = tmDt;
+  if (mask) {
+    const uint32_t bw = TW < 32 ? TW : 32;
+    const uint64_t dims[4] = {(uint64_t)ldm, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
+    const uint64_t str[4] = {(uint64_t)esz, (uint64_t)ldm * esz, (uint64_t)Wd * ldm * esz, (uint64_t)H * Wd * ldm * esz};
+    const uint32_t cw = out_bf16 ? 64u : 32u, tailw = (uint32_t)p.BN % cw;
+    const uint32_t box[4] = {cw, bw, 32 / bw, 1}, boxt[4] = {tailw ? tailw : cw, bw, 32 / bw, 1};
+    if (int e = make_tmap(&tmR, esz, mask, 4, dims, str, box, "conv3x3_dgrad_bf16_tc(mask)", true)) return e;
+    if (int e = make_tmap(&tmRt, esz, mask, 4, dims, str, boxt, "conv3x3_dgrad_bf16_tc(mask tail)", false)) return e;
+  }
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, mask != nullptr, as_stream(stream));
+}
+
+extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
+                                   int Nimg, int H, int Wd, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream) {
+  return conv3x3_common(X, Wp, bias, act, Y, out_bf16, Nimg, H, Wd, Cin, ldx, Cout, ldy, nullptr, 0, stream);
+}
+
+// Data gradient of the same convolution: dX = conv3x3(dY, W') with W'[ci][tap][co] = W[co][ci][8 - tap]
+// (the caller packs the flipped, transposed weights like forward ones), optionally masked by the ReLU
+// of the layer that produced X:  dX = relu_mask > 0 ? conv : 0.  Same kernel, ReLU-mask epilogue.
+extern "C" int isp_conv3x3_dgrad_bf16_tc(const void* dY, const void* Wp_flipped, const void* relu_mask, int ldm,
+                                         void* dX, int out_bf16, int Nimg, int H, int Wd, int Cout, int ldy, int Cin,
+                                         int ldx, isp_stream_t stream) {
+  return conv3x3_common(dY, Wp_flipped, nullptr, 0, dX, out_bf16, Nimg, H, Wd, Cout, ldy, Cin, ldx, relu_mask, ldm, stream);
 }

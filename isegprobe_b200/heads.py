@@ -59,8 +59,69 @@ class BaseClassifierHead(nn.Module):
         return out.permute(0, 3, 1, 2)
 
 
+class _ConvHeadFn(torch.autograd.Function):
+    """ConvSegHead forward + backward on libisp_b200 (the head is the trainable part of the IS model,
+    core/training/trainer.py:213-221).  Forward keeps the bf16 NHWC activations of every layer;
+    backward: fused classifier backward + ReLU mask -> per layer { wgrad (tcgen05, pixel-major GEMM),
+    bias column sums, dgrad (the forward kernel on flipped weights with a ReLU-mask epilogue) }.
+    Parameter gradients are fp32; activation gradients travel in bf16."""
+
+    @staticmethod
+    def forward(ctx, head, x, *params):
+        C, L = head.in_channels, head.num_layers
+        P = head._pack(x.device)
+        f = head._features_bf16(x)
+        acts = [f]
+        for w, b in zip(P["w"], P["b"]):
+            f = tc.conv3x3(f, w, b, C, C, act="relu", ldy=tc.round_up(C, 8))
+            acts.append(f)
+        ctx.head, ctx.acts, ctx.in_shape = head, acts, tuple(x.shape)
+        ctx.need_dx = x.requires_grad
+        return head._classify(f, C)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        head, acts = ctx.head, ctx.acts
+        C, L = head.in_channels, head.num_layers
+        P = head._pack(dlogits.device)
+        B, H, W, ld = acts[-1].shape
+        M = B * H * W
+        dev = dlogits.device
+        dlog = dlogits.detach().float().contiguous().view(M)
+        dz = torch.empty(B, H, W, ld, dtype=torch.bfloat16, device=dev)
+        if ld > C:
+            dz.zero_()
+        dwc = torch.zeros(C, dtype=torch.float32, device=dev)
+        dbc = torch.zeros(1, dtype=torch.float32, device=dev)
+        dbias = [torch.zeros(C, dtype=torch.float32, device=dev) for _ in range(L)]
+        _call("isp_head_classifier_bwd", acts[-1], ld, dlog, P["wc"], dz, ld, dwc, dbc, dbias[L - 1], M, C)
+        dweights = [None] * L
+        dx = None
+        for i in range(L - 1, -1, -1):
+            xin = acts[i]  # input of layer i (bf16 NHWC); for i > 0 also the ReLU output masking dgrad
+            dW = torch.zeros(C, 9, C, dtype=torch.float32, device=dev)
+            _call("isp_conv3x3_wgrad_bf16_tc", xin, xin.shape[3], dz, ld, dW, B, H, W, C, C)
+            dweights[i] = dW.view(C, 3, 3, C).permute(0, 3, 1, 2)
+            if i < L - 1:
+                _call("isp_colsum_bf16", dz, ld, dbias[i], M, C)
+            if i > 0:
+                dprev = torch.empty(B, H, W, ld, dtype=torch.bfloat16, device=dev)
+                _call("isp_conv3x3_dgrad_bf16_tc", dz, P["wT"][i], xin, xin.shape[3], dprev, 1, B, H, W, C, ld, C, ld)
+                dz = dprev
+            elif ctx.need_dx:
+                dxn = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+                _call("isp_conv3x3_dgrad_bf16_tc", dz, P["wT"][0], None, 0, dxn, 0, B, H, W, C, ld, C, C)
+                dx = dxn.permute(0, 3, 1, 2)
+        grads = []
+        for i in range(L):
+            grads += [dweights[i], dbias[i]]
+        grads += [dwc.view(1, C, 1, 1), dbc]
+        return (None, dx, *grads)
+
+
 class ConvSegHead(BaseClassifierHead):
-    """Several 3x3 conv+ReLU layers, then a 1x1 classifier (conv_heads.py:48-73)."""
+    """Several 3x3 conv+ReLU layers, then a 1x1 classifier (conv_heads.py:48-73).  Differentiable
+    (parameters and input) for the 3x3 / one-class configuration every shipped model uses."""
 
     KERNEL = 3
 
@@ -79,6 +140,8 @@ class ConvSegHead(BaseClassifierHead):
                 w = m.conv.weight.detach().float()
                 if self.KERNEL == 3:
                     P["w"].append(tc.pack_conv3x3_weight(w).to(dev))
+                    # dgrad operand: W'[ci][tap][co] = W[co][ci][8 - tap]
+                    P.setdefault("wT", []).append(tc.pack_conv3x3_weight(w.flip(2, 3).transpose(0, 1)).to(dev))
                 else:
                     P["w"].append(tc.pack_linear_weight(w.reshape(C, C)).to(dev))
                 P["b"].append(m.conv.bias.detach().float().contiguous().to(dev))
@@ -87,9 +150,19 @@ class ConvSegHead(BaseClassifierHead):
             self._packed = P
         return self._packed
 
+    def _param_list(self):
+        ps = []
+        for m in self.convs:
+            ps += [m.conv.weight, m.conv.bias]
+        return ps + [self.classifier.weight, self.classifier.bias]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("head backward is not implemented yet (forward/inference only)")
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            if self.KERNEL != 3 or self.num_classes != 1 or self.in_channels % 64 != 0:
+                raise NotImplementedError("head backward is implemented for 3x3 layers, one class and "
+                                          "in_channels % 64 == 0 (the shipped ConvSegHead configurations)")
+            return _ConvHeadFn.apply(self, x, *self._param_list())
         C = self.in_channels
         P = self._pack(x.device)
         f = self._features_bf16(x)
