@@ -1,0 +1,64 @@
+"""Training step of the IS model around the hot path (core/training/trainer.py:377-477, 213-226):
+
+    frozen features (click maps -> embed -> ViT -> upsampler, no_grad)
+      -> ConvSegHead forward / backward on libisp_b200 (heads._ConvHeadFn)
+      -> NormalizedFocalLossSigmoid (core/training/losses.py:42-109; stays torch)
+      -> ONE all-reduce of the flat gradient arena (dist.FlatGradArena; DDP semantics: mean over ranks,
+         core/utils/distributed.py + trainer.py:144-149) -> Adam(lr 5e-5) as models/defaults.py:103-107.
+
+Not covered yet: the gradient of the click embedding (`embed_coords`) -- it needs the activation backward
+of the frozen upsampler and ViT, which are forward-only in this round; `embed_coords` is therefore kept
+frozen here."""
+import torch
+
+from . import dist as idist
+
+
+def normalized_focal_loss(pred: torch.Tensor, label: torch.Tensor, alpha: float = 0.5, gamma: float = 2.0,
+                          eps: float = 1e-12, ignore_label: int = -1, weight: float = 1.0) -> torch.Tensor:
+    """NormalizedFocalLossSigmoid.forward (losses.py:42-109) with its defaults (from_sigmoid=False,
+    detach_delimeter=True, max_mult=-1, size_average=True): per-sample loss [B].  The reference's
+    running `_k_sum` / `_m_max` statistics are logging only and need a host sync each step; omitted."""
+    one_hot = label > 0.5
+    sample_weight = label != ignore_label
+    pred = torch.sigmoid(pred)
+    alpha_t = torch.where(one_hot, alpha * sample_weight, (1 - alpha) * sample_weight)
+    pt = torch.where(sample_weight, 1.0 - torch.abs(label - pred), torch.ones_like(pred))
+    beta = (1 - pt) ** gamma
+    sw_sum = torch.sum(sample_weight, dim=(-2, -1), keepdim=True)
+    beta_sum = torch.sum(beta, dim=(-2, -1), keepdim=True)
+    mult = (sw_sum / (beta_sum + eps)).detach()
+    beta = beta * mult
+    loss = -alpha_t * beta * torch.log(torch.clamp_max(pt + eps, 1.0))
+    loss = weight * (loss * sample_weight)
+    dims = tuple(range(1, loss.dim()))
+    bsum = torch.sum(sample_weight, dim=dims)
+    return torch.sum(loss, dim=dims) / (bsum + eps)
+
+
+class HeadTrainer:
+    """One process per GPU; each rank steps on its own shard of the global batch."""
+
+    def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.pipe = pipeline
+        assert pipeline.head is not None, "the pipeline was built without a head"
+        for p in pipeline.embed_coords.parameters():
+            p.requires_grad = False  # see module docstring
+        self.params = [p for p in pipeline.head.parameters() if p.requires_grad]
+        self.arena = idist.FlatGradArena(self.params)
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps)
+
+    def step(self, image: torch.Tensor, points: torch.Tensor, gt_mask: torch.Tensor) -> torch.Tensor:
+        """image [b,4,H,W] (RGB + previous mask), points [b,2P,3], gt_mask [b,1,H,W] in {0,1,-1}.
+        Returns the (detached) mean loss of this rank's shard."""
+        pipe = self.pipe
+        pipe.head.train()
+        with torch.no_grad():
+            feats = pipe.features(image, points)
+        logits = pipe.head(feats)
+        loss = normalized_focal_loss(logits, gt_mask).mean()
+        self.arena.zero_()
+        loss.backward()
+        self.arena.all_reduce_mean()
+        self.opt.step()
+        return loss.detach()

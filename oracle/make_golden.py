@@ -154,6 +154,29 @@ def golden_maskclip():
          injected=inj.reshape(2, 4, 6, 512).permute(0, 3, 1, 2), square=sq.reshape(1, 4, 4, 512).permute(0, 3, 1, 2))
 
 
+def golden_nfl():
+    """NormalizedFocalLossSigmoid(alpha=0.5, gamma=2) (core/training/losses.py:42-109, models/defaults.py:24)
+    value and gradient.  losses.py imports core.utils.misc, which imports the whole model package; only
+    `get_dims_with_exclusion` (misc.py:28-33) is used, so that one helper is stubbed."""
+    import types
+    tr = types.ModuleType("core.training")
+    tr.__path__ = [os.path.join(ref_shim.REFERENCE_ROOT, "core", "training")]
+    sys.modules["core.training"] = tr
+    m = types.ModuleType("core.utils.misc")
+    m.get_dims_with_exclusion = lambda dim, exclude=None: [d for d in range(dim) if d != exclude]
+    sys.modules["core.utils.misc"] = m
+    sys.modules["core.utils"].misc = m
+    from core.training.losses import NormalizedFocalLossSigmoid
+    g = torch.Generator().manual_seed(11)
+    pred = torch.randn(3, 1, 24, 40, generator=g) * 3
+    label = (torch.rand(3, 1, 24, 40, generator=g) > 0.6).float()
+    label[1, :, :4] = -1
+    pr = pred.clone().requires_grad_(True)
+    out = NormalizedFocalLossSigmoid(alpha=0.5, gamma=2)(pr, label)
+    out.mean().backward()
+    save("nfl_loss", pred=pred, label=label, out=out.detach(), grad=pr.grad)
+
+
 def golden_jbu_shape():
     """The only anchor the reference holds for JBU is the shape contract of
     JBUFeatUp.py:36-45; record it (parity unpinned, see oracle/jbu.py)."""
@@ -171,4 +194,5 @@ if __name__ == "__main__":
     golden_head()
     golden_vit()
     golden_maskclip()
+    golden_nfl()
     golden_jbu_shape()

@@ -110,3 +110,23 @@ def test_convhead_inference_path_unchanged_under_no_grad():
         p.requires_grad = False
     b = head(x)
     assert torch.equal(a, b)
+
+
+def test_head_trainer_step_reduces_loss():
+    """HeadTrainer (frozen features -> head fwd/bwd -> flat-arena all-reduce -> Adam): on a fixed batch
+    the loss must go down, and only the head's parameters may change."""
+    import isegprobe_b200 as isp
+    from isegprobe_b200.training import HeadTrainer
+    torch.manual_seed(0)
+    pipe = isp.ISegPipeline("bilinear", {}).to(DEV)
+    pipe.embed_coords = isp.PatchEmbed((112, 112), (14, 14), 3, 384).to(DEV)
+    tr = HeadTrainer(pipe, lr=5e-5)  # models/defaults.py:105
+    img = torch.cat([synth.image_batch(2, 112, 112, seed=1), torch.zeros(2, 1, 112, 112)], 1).to(DEV)
+    pts = synth.click_points(2, 3, 112, 112, seed=3).to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(112), torch.arange(112), indexing="ij")
+    gt = (((yy - 56) ** 2 + (xx - 50) ** 2) < 30 ** 2).float()[None, None].repeat(2, 1, 1, 1).to(DEV)
+    frozen = {k: v.clone() for k, v in pipe.backbone.state_dict().items()}
+    losses = [float(tr.step(img, pts, gt)) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
+    assert all(torch.equal(v, pipe.backbone.state_dict()[k]) for k, v in frozen.items())
+    assert tr.arena.flat.data_ptr() == tr.params[0].grad.data_ptr()  # gradients live in the single all-reduce buffer

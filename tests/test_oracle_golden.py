@@ -139,3 +139,15 @@ def test_maskclip_matches_reference(golden):
         want = torch.from_numpy(g[key])
         assert tuple(out.shape) == tuple(want.shape)
         assert float((out - want).abs().max() / want.abs().max()) < 1e-4, key
+
+
+def test_nfl_loss_matches_reference(golden):
+    """The training step's loss restatement (isegprobe_b200/training.py) vs the reference's
+    NormalizedFocalLossSigmoid(alpha=0.5, gamma=2): value and gradient, ignore-label rows included."""
+    from isegprobe_b200.training import normalized_focal_loss
+    g = golden("nfl_loss")
+    pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+    out = normalized_focal_loss(pred, torch.from_numpy(g["label"]))
+    out.mean().backward()
+    assert float((out.detach() - torch.from_numpy(g["out"])).abs().max()) < 1e-6
+    assert float((pred.grad - torch.from_numpy(g["grad"])).abs().max()) < 1e-7
