@@ -7,6 +7,10 @@ A step = one pass of  click maps -> click embedding -> DINOv2 ViT-S/14 -> upsamp
 over one batch of synthetic 448x448 images with random-init weights.
   jbu    : BASELINE.json configs[1]  (FeatUp JBU stack / AdaptiveConv, batch 16 per GPU)  [default]
   loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)
+  train  : BASELINE.json configs[4]  (IS training step: frozen DINOv2-S/14 + LoftUp features, ConvSegHead
+           forward/backward, NFL loss, gradient all-reduce, Adam; GLOBAL batch 64 split over the ranks --
+           strong scaling, as the reference's batch_size // ngpus; click-embedding gradient not included,
+           see DESIGN.md section 7)
 Multi-GPU: one process per GPU (torchrun), images sharded across ranks, no data-path
 collective (weak scaling); time = max over ranks of the CUDA-event time of the K steps.
 `--impl reference` times the CPU oracle port of the same path on the host cores.
@@ -29,6 +33,8 @@ WORKLOADS = {
             "name": "DINOv2 ViT-S/14 + FeatUp JBU stack (AdaptiveConv, 32->448 px) forward, batch 16 at 448x448"},
     "loftup": {"batch": 32, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 384},
                "name": "DINOv2 ViT-S/14 + LoftUp cross-attention upsampler to 448x448, bf16, batch 32"},
+    "train": {"batch": 64, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 384},
+              "name": "IS training step: frozen DINOv2-S/14 + LoftUp + ConvSegHead fwd/bwd, global batch 64 at 448x448"},
 }
 H = W = 448
 P_CLICKS = 24
@@ -155,21 +161,34 @@ def main():
     from isegprobe_b200 import _lib, upsamplers
 
     wl = WORKLOADS[args.workload]
-    B = wl["batch"]
+    train = args.workload == "train"
+    B = wl["batch"] // world if train else wl["batch"]  # train: global batch split over ranks (trainer.py:66-68)
     torch.manual_seed(0)
-    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=False).to(dev).eval()
+    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=train).to(dev).eval()
     img_h, pts_h = synth_inputs(B, seed=1 + rank)
     img_h, pts_h = img_h.pin_memory(), pts_h.pin_memory()
     img_d, pts_d = img_h.to(dev), pts_h.to(dev)
+    if train:
+        from isegprobe_b200.training import HeadTrainer
+        trainer = HeadTrainer(pipe)
+        gt_h = (img_h[:, 3:] > 0.5).float().pin_memory()  # synthetic instance masks (the prev-mask channel's blobs)
+        gt_d = gt_h.to(dev)
 
-    def step_device():
-        with torch.no_grad():
-            return pipe.features(img_d, pts_d)
+        def step_device():
+            return trainer.step(img_d, pts_d, gt_d)
 
-    def step_e2e():
-        with torch.no_grad():
-            out = pipe.features(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True))
-            return out.mean(dim=(1, 2, 3)).cpu()  # per-image checksum read back each step
+        def step_e2e():
+            return trainer.step(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True),
+                                gt_h.to(dev, non_blocking=True)).cpu()  # loss read back each step
+    else:
+        def step_device():
+            with torch.no_grad():
+                return pipe.features(img_d, pts_d)
+
+        def step_e2e():
+            with torch.no_grad():
+                out = pipe.features(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True))
+                return out.mean(dim=(1, 2, 3)).cpu()  # per-image checksum read back each step
 
     def barrier():
         if dist is not None:
@@ -232,7 +251,7 @@ def main():
         roofline = {"kernel": "adaptive_conv_nhwc_kernel (JBU stage 512)", "bound": "hbm", "achieved": ach,
                     "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} hbm copy", "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                     "traffic": traffic, "ms_per_launch": t, "algorithmic_bytes_per_launch": alg}
-    elif args.workload == "loftup" and ktimes.get("loftup_attention"):
+    elif args.workload in ("loftup", "train") and ktimes.get("loftup_attention"):
         t = sum(ktimes["loftup_attention"]) / len(ktimes["loftup_attention"])
         imgs = ktimes.get("_loftup_attention_images", [pipe.upsampler.chunk_images])[0]
         flops = 2.0 * 2 * 4 * 200704 * 1024 * 101 * pipe.upsampler.chunk_images  # QK^T + PV, un-padded head dim
@@ -242,23 +261,26 @@ def main():
                     "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "ms_per_launch": t,
                     "algorithmic_flops_per_launch": flops}
     line = {
-        "metric": "images/sec @448^2 DINOv2-S/14 + upsampler forward", "value": value, "unit": "images/s",
+        "metric": ("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd)" if train
+                   else "images/sec @448^2 DINOv2-S/14 + upsampler forward"), "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (JBU SIMT kernels) + bf16 tcgen05 (ViT, 1x1 conv)" if args.workload == "jbu" else "bf16",
+        "higher_is_better": True, "scaling": "strong" if train else "weak", "vs_baseline": None,
+        "dtype": "f32 (JBU SIMT kernels) + bf16 tcgen05 (ViT, 1x1 conv)" if args.workload == "jbu" else
+                 ("bf16 (fp32 parameter gradients, loss and optimizer)" if train else "bf16"),
         "data": "synthetic",
         "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": B * world, "image": "448x448",
                    "clicks_per_polarity": P_CLICKS, "weights": "random init (seed 0)",
                    "l2": "no explicit flush: every step streams > 10 GB of intermediates (>> 126 MB L2)",
                    "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4) * world,
-                "d2h_bytes_per_step": 4 * B * world, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "images/s",
+                "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4 + (gt_h.numel() * 4 if train else 0)) * world,
+                "d2h_bytes_per_step": (4 if train else 4 * B) * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,
         "roofline": roofline,
         "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not train:
         torch.set_num_threads(os.cpu_count())
         t, _ = cpu_port_step(args.workload, 1)
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
