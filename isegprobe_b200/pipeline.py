@@ -13,11 +13,11 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .featurizers import DINOv2Featurizer, PatchEmbed
+from .featurizers import DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed
 from .heads import HEAD_REGISTRY
 from .upsamplers import UPSAMPLER_REGISTRY, bilinear_align_corners_nhwc, to_nhwc_f32
 
-FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "patch_embedding": PatchEmbed}
+FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "maskclip": MaskCLIPFeaturizer, "patch_embedding": PatchEmbed}
 
 
 def install_into_reference() -> None:
@@ -45,14 +45,21 @@ class ISegPipeline(nn.Module):
     def __init__(self, upsampler_type: str = "loftup", upsampler_params: Optional[dict] = None,
                  head_type: str = "convhead", head_params: Optional[dict] = None, backbone_dim: int = 384,
                  patch: int = 14, use_disks: bool = True, norm_radius: int = 5, with_prev_mask: bool = True,
-                 with_head: bool = True):
+                 with_head: bool = True, backbone: str = "dinov2"):
         super().__init__()
+        if backbone not in ("dinov2", "maskclip"):
+            raise ValueError(f"Unknown backbone type: {backbone}")
         if upsampler_type not in UPSAMPLER_REGISTRY:
             raise ValueError(f"Unknown upsampler type: {upsampler_type}")  # model_builder.py:64-65
         self.use_disks, self.norm_radius, self.with_prev_mask = use_disks, norm_radius, with_prev_mask
         self.upsampler_type = upsampler_type
-        self.backbone = DINOv2Featurizer("dinov2_vits14", "before_backbone")
-        self.embed_coords = PatchEmbed((448, 448), (patch, patch), 3 if with_prev_mask else 2, backbone_dim)
+        if backbone == "maskclip":  # models/sbd/maskclip/*.py: ViT-B/16, 768-wide tokens, 512-d features
+            self.backbone = MaskCLIPFeaturizer("ViT-B/16", "before_backbone")
+            patch, backbone_dim, embed_dim = 16, 512, 768
+        else:
+            self.backbone = DINOv2Featurizer("dinov2_vits14", "before_backbone")
+            embed_dim = backbone_dim
+        self.embed_coords = PatchEmbed((448, 448), (patch, patch), 3 if with_prev_mask else 2, embed_dim)
         self.upsampler = UPSAMPLER_REGISTRY[upsampler_type](**(upsampler_params or {}))
         self.head = None
         if with_head:

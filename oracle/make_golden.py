@@ -177,6 +177,55 @@ def golden_nfl():
     save("nfl_loss", pred=pred, label=label, out=out.detach(), grad=pr.grad)
 
 
+def golden_noc_driver():
+    """Click sequences and IoU curves of the reference's evaluate_sample (core/inference/evaluation.py:43-88)
+    with BasePredictor + ZoomIn(skip_clicks=-1) + flip (the eval_mode='fixedNNN' stack) around oracle/stubnet.py.
+    Real reference code: clicker.py, transforms/*, predictors/base_predictor.py, evaluation.py.  Stubs:
+    core.utils.misc's model import, core.inference.utils.get_iou (same 3-line formula; checked again in the
+    test with an independent expression), dataset / logging imports."""
+    import importlib.util
+    import types
+    from isegprobe_b200.evaluation import synthetic_dataset
+    from oracle.stubnet import StubNet
+    root = ref_shim.REFERENCE_ROOT
+    sys.modules["core.model"].iSegBaseModel = object
+    log = types.ModuleType("core.utils.log")
+    log.logger = __import__("logging").getLogger("ref")
+    sys.modules["core.utils.log"] = log
+    sys.modules.pop("core.utils.misc", None)
+    for name, rel in (("core.inference", "core/inference"), ("core.inference.predictors", "core/inference/predictors"),
+                      ("core.data", "core/data")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(root, rel)]
+        sys.modules[name] = m
+    bd = types.ModuleType("core.data.base_dataset")
+    bd.iSegBaseDataset = object
+    sys.modules["core.data.base_dataset"] = bd
+    iu = types.ModuleType("core.inference.utils")
+
+    def get_iou(gt_mask, pred_mask, ignore_label=-1):
+        keep, obj = gt_mask != ignore_label, gt_mask == 1
+        return (np.logical_and(np.logical_and(pred_mask, obj), keep).sum()
+                / np.logical_and(np.logical_or(pred_mask, obj), keep).sum())
+    iu.get_iou = get_iou
+    sys.modules["core.inference.utils"] = iu
+    sys.modules["core.inference"].utils = iu
+    from core.inference.predictors.base_predictor import BasePredictor  # by path: the package __init__ pulls the BRS code
+    sys.modules["core.inference.predictors"].BasePredictor = BasePredictor
+    from core.inference.evaluation import evaluate_sample
+    from core.inference.transforms import ZoomIn
+    arrays = {}
+    samples = synthetic_dataset("grabcut", n=3, seed=5)
+    for si, (img, gt) in enumerate(samples):
+        pred = BasePredictor(StubNet(), torch.device("cpu"), zoom_in=ZoomIn(skip_clicks=-1, target_size=(96, 128)),
+                             with_flip=True)
+        clicks, ious, probs = evaluate_sample(img, gt, pred, max_iou_thr=0.95, pred_thr=0.49, max_clicks=8)
+        arrays[f"clicks_{si}"] = np.array([[int(c.is_positive), c.coords[0], c.coords[1]] for c in clicks], dtype=np.int64)
+        arrays[f"ious_{si}"] = ious
+        arrays[f"probs_{si}"] = probs.astype(np.float32)
+    save("noc_driver", **arrays)
+
+
 def golden_jbu_shape():
     """The only anchor the reference holds for JBU is the shape contract of
     JBUFeatUp.py:36-45; record it (parity unpinned, see oracle/jbu.py)."""
@@ -195,4 +244,5 @@ if __name__ == "__main__":
     golden_vit()
     golden_maskclip()
     golden_nfl()
+    golden_noc_driver()
     golden_jbu_shape()

@@ -176,3 +176,60 @@ def test_pipeline_masks_vs_oracle(isp, up_type, params):
     decided = want.abs() > margin
     agree = ((logits > 0) == (want > 0))[decided].float().mean()
     assert float(agree) >= 0.999, float(agree)
+
+
+def test_noc_loop_maskclip_loftup(isp):
+    """BASELINE config 4 shape on one GPU: MaskCLIP ViT-B/16 + LoftUp(512) + ConvSegHead(512) driven by the
+    evaluation loop (fixed-size zoom-in, flip TTA, up to 3 clicks) on two synthetic GrabCut-shaped samples;
+    the first click's probability map is checked against the oracle chain on the same transformed input."""
+    from isegprobe_b200 import evaluation as ev
+    from oracle import maskclip as omc
+    torch.manual_seed(0)
+    S = 112  # evaluation crop (divisible by the 16-pixel patch)
+    pipe = isp.ISegPipeline("loftup", {"upsampler_path": None, "n_dim": 512}, backbone="maskclip",
+                            head_params={"in_channels": 512, "num_layers": 2, "num_classes": 1}).to(DEV).eval()
+    pipe.embed_coords = isp.PatchEmbed((S, S), (16, 16), 3, 768).to(DEV).eval()
+    msd = synth.maskclip_state_dict(seed=0)
+    pipe.backbone.model.visual.load_state_dict(msd)
+    usd, cn = synth.loftup_state_dict(512, seed=0), synth.channelnorm_state_dict(512, seed=1)
+    pipe.upsampler.upsampler.upsampler.load_state_dict(usd)
+    pipe.upsampler.upsampler.channelnorm.load_state_dict(cn)
+    hsd = synth.convhead_state_dict(512, 2, 1, seed=0)
+    pipe.head.load_state_dict(hsd)
+    psd = synth.patch_embed_state_dict(768, 16, 3, seed=0)
+    pipe.embed_coords.load_state_dict(psd)
+    samples = ev.synthetic_dataset("grabcut", n=2, seed=9)
+    pred = ev.FixedSizePredictor(pipe, torch.device(DEV), target_size=(S, S), with_flip=True)
+    curves = ev.evaluate_dataset_sharded(samples, pred, max_iou_thr=1.01, max_clicks=3)
+    assert len(curves) == 2 and all(len(c) == 3 and np.all(np.isfinite(c)) for c in curves)
+    noc, _, over = ev.compute_noc_metric(curves, [0.85, 0.90], max_clicks=3)
+    assert len(noc) == 2
+    # first-click parity: same transformed input through the oracle chain (MaskCLIP -> LoftUp -> head)
+    img, gt = samples[0]
+    clicker = ev.Clicker(gt_mask=gt)
+    clicker.make_next_click(np.zeros_like(gt))
+    pred.set_input_image(img)
+    with torch.no_grad():  # evaluate_sample's own context (evaluation.py:58)
+        probs = pred.get_prediction(clicker)
+    im = torch.from_numpy(img.transpose(2, 0, 1).copy()).float().div(255)[None]
+    x = torch.cat([im, torch.zeros(1, 1, *im.shape[2:])], 1)
+    x = torch.nn.functional.interpolate(x, size=(S, S), mode="bilinear", align_corners=True)
+    c = clicker.clicks_list[0]
+    pt = (S * c.coords[0] / im.shape[2], S * c.coords[1] / im.shape[3])
+    outs = []
+    with torch.no_grad():
+        for flip in (False, True):
+            xi = torch.flip(x, dims=[3]) if flip else x
+            p = torch.tensor([[[pt[0], (S - pt[1] - 1) if flip else pt[1], 0.0], [-1.0, -1.0, -1.0]]])
+            nimg = ohead.normalize_image(xi[:, :3])
+            maps = torch.from_numpy(odm.distmaps(p.numpy(), S, S, 5, 1.0, True))
+            emb = ohead.patch_embed_forward(psd, torch.cat([xi[:, 3:], maps], 1))
+            lr = omc.maskclip_forward(msd, nimg, emb)
+            hr = oloft.loftup_forward(usd, lr, nimg, cn["norm.weight"], cn["norm.bias"])
+            lo = ohead.convhead_forward(hsd, hr)
+            outs.append(torch.flip(lo, dims=[3]) if flip else lo)
+    want = torch.sigmoid(0.5 * (outs[0] + outs[1]))
+    want = torch.nn.functional.interpolate(want, size=im.shape[2:], mode="bilinear", align_corners=True)[0, 0].numpy()
+    decided = np.abs(want - 0.49) > 0.02
+    agree = ((probs > 0.49) == (want > 0.49))[decided].mean()
+    assert agree >= 0.999, agree
