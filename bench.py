@@ -7,6 +7,8 @@ A step = one pass of  click maps -> click embedding -> DINOv2 ViT-S/14 -> upsamp
 over one batch of synthetic 448x448 images with random-init weights.
   jbu    : BASELINE.json configs[1]  (FeatUp JBU stack / AdaptiveConv, batch 16 per GPU)  [default]
   loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)
+  eval   : BASELINE.json configs[3]  (20-click NoC evaluation loop, MaskCLIP ViT-B/16 + LoftUp(512) + head,
+           eval_mode fixed448 with flip TTA, one synthetic GrabCut-shaped sample per rank and step; clicks/s)
   train  : BASELINE.json configs[4]  (IS training step: frozen DINOv2-S/14 + LoftUp features, ConvSegHead
            forward/backward, NFL loss, gradient all-reduce, Adam; GLOBAL batch 64 split over the ranks --
            strong scaling, as the reference's batch_size // ngpus; click-embedding gradient not included,
@@ -33,6 +35,9 @@ WORKLOADS = {
             "name": "DINOv2 ViT-S/14 + FeatUp JBU stack (AdaptiveConv, 32->448 px) forward, batch 16 at 448x448"},
     "loftup": {"batch": 32, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 384},
                "name": "DINOv2 ViT-S/14 + LoftUp cross-attention upsampler to 448x448, bf16, batch 32"},
+    "eval": {"batch": 2, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 512},
+             "name": "20-click NoC loop, MaskCLIP ViT-B/16 + LoftUp(512) + ConvSegHead, fixed448 + flip, synthetic "
+                     "GrabCut-shaped samples sharded over the ranks"},
     "train": {"batch": 64, "upsampler": "loftup", "params": {"upsampler_path": None, "n_dim": 384},
               "name": "IS training step: frozen DINOv2-S/14 + LoftUp + ConvSegHead fwd/bwd, global batch 64 at 448x448"},
 }
@@ -134,6 +139,75 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_eval(args, rank, world, dev, dist):
+    """Config 4: every rank runs the 20-click loop on its own samples (no collective in the timed region;
+    the IoU curves are gathered once at the end).  value = clicks/s over all ranks; a click = one
+    predictor call = one batch-2 (image + flip) forward of the whole model + the host-side click simulator."""
+    import numpy as np
+    import isegprobe_b200 as isp
+    from isegprobe_b200 import _lib, evaluation as ev
+    from isegprobe_b200 import dist as idist
+    wl = WORKLOADS["eval"]
+    torch.manual_seed(0)
+    pipe = isp.ISegPipeline("loftup", wl["params"], backbone="maskclip",
+                            head_params={"in_channels": 512, "num_layers": 2, "num_classes": 1}).to(dev).eval()
+    pipe.embed_coords = isp.PatchEmbed((448, 448), (16, 16), 3, 768).to(dev).eval()
+    n_w, n_t = max(args.warmup, 3), args.steps
+    samples = ev.synthetic_dataset("grabcut", n=(n_w + n_t) * world, seed=0)
+    mine = [samples[i] for i in idist.shard_indices(len(samples), world, rank)]
+    pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True)
+    for img, gt in mine[:n_w]:
+        ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=3)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0.record()
+    curves = [ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=20)[1] for img, gt in mine[n_w:n_w + n_t]]
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    rows = torch.tensor(np.stack(curves), device=dev)
+    allr = idist.gather_sample_results(rows, n_t * world).cpu().numpy()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    noc, _, over = ev.compute_noc_metric(list(allr), [0.85, 0.90], max_clicks=20)
+    clicks = 20 * n_t * world
+    v = clicks / (ms / 1e3)
+    line = {"metric": "clicks/sec, 20-click NoC loop @448^2 MaskCLIP ViT-B/16 + LoftUp + head (flip TTA)", "value": v,
+            "unit": "clicks/s", "n_gpus": world, "steps": n_t, "warmup": n_w, "ms_per_step": ms / n_t,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "samples_per_rank": n_t, "clicks_per_sample": 20, "weights": "random init (seed 0)",
+                       "l2": "inputs change every click; every forward streams > 2 GB of intermediates",
+                       "parallelism": f"dp{world} (samples sharded round-robin, final IoU gather only)"},
+            "e2e": {"value": v, "unit": "clicks/s", "h2d_bytes_per_step": int(20 * 2 * 4 * 448 * 448 * 4) * world,
+                    "d2h_bytes_per_step": int(20 * 448 * 448 * 4) * world, "ms_per_step": ms / n_t,
+                    "note": "the loop is end-to-end by construction: image / clicks go host->device and the "
+                            "probability map comes back to the host clicker every click"},
+            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "roofline": None,
+            "noc": {"NoC@85": float(noc[0]), "NoC@90": float(noc[1]), ">=20@85": int(over[0]), ">=20@90": int(over[1]),
+                    "note": "random-init weights: the values only show the metric path runs"}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +234,8 @@ def main():
     import isegprobe_b200 as isp
     from isegprobe_b200 import _lib, upsamplers
 
+    if args.workload == "eval":
+        return run_eval(args, rank, world, dev, dist)
     wl = WORKLOADS[args.workload]
     train = args.workload == "train"
     B = wl["batch"] // world if train else wl["batch"]  # train: global batch split over ranks (trainer.py:66-68)
