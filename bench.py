@@ -332,9 +332,14 @@ def main():
         imgs = ktimes.get("_loftup_attention_images", [pipe.upsampler.chunk_images])[0]
         flops = 2.0 * 2 * 4 * 200704 * 1024 * 101 * pipe.upsampler.chunk_images  # QK^T + PV, un-padded head dim
         ach = flops / (t * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("loftup_attention_bytes_per_image")
+            traffic = traffic * pipe.upsampler.chunk_images if traffic else None
         roofline = {"kernel": "attention_kernel<2,7,112> (LoftUp cross-attention, per layer call)", "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_tflops_sustained"], "peak_kind": f"{pk_kind} cuBLAS bf16 sustained",
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "ms_per_launch": t,
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "ms_per_launch": t,
                     "algorithmic_flops_per_launch": flops}
     line = {
         "metric": ("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd)" if train
