@@ -257,14 +257,18 @@ def main():
             return trainer.step(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True),
                                 gt_h.to(dev, non_blocking=True)).cpu()  # loss read back each step
     else:
+        # the step is replayed from a CUDA graph (ISegPipeline.features_graphed); the e2e variant copies the
+        # pinned host inputs straight into the graph's static input buffers
         def step_device():
-            with torch.no_grad():
-                return pipe.features(img_d, pts_d)
+            return pipe.features_graphed(img_d, pts_d)
 
         def step_e2e():
+            out = pipe.features_graphed(img_h, pts_h)
+            return out.mean(dim=(1, 2, 3)).cpu()  # per-image checksum read back each step
+
+        def step_eager():
             with torch.no_grad():
-                out = pipe.features(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True))
-                return out.mean(dim=(1, 2, 3)).cpu()  # per-image checksum read back each step
+                return pipe.features(img_d, pts_d)
 
     def barrier():
         if dist is not None:
@@ -292,10 +296,14 @@ def main():
     if sampler:
         sampler.start()
     upsamplers.KERNEL_TIMERS.clear()
-    upsamplers.KERNEL_TIMING = True
-    l0 = _lib.launch_count()
+    upsamplers.KERNEL_TIMING = train  # events cannot be recorded inside a graph replay: the graphed workloads
+    l0 = _lib.launch_count()          # time their dominant kernel in a few eager steps right after the timed region
     ms = timed(step_device, args.steps)
-    launches = _lib.launch_count() - l0
+    launches = (_lib.launch_count() - l0) if train else pipe.graphed_launches() * args.steps
+    if not train:
+        upsamplers.KERNEL_TIMING = True
+        for _ in range(2):
+            step_eager()
     upsamplers.KERNEL_TIMING = False
     torch.cuda.synchronize()
     ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
@@ -351,6 +359,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": B * world, "image": "448x448",
                    "clicks_per_polarity": P_CLICKS, "weights": "random init (seed 0)",
+                   "launch": "eager" if train else "CUDA graph replay (one graph per step)",
                    "l2": "no explicit flush: every step streams > 10 GB of intermediates (>> 126 MB L2)",
                    "parallelism": f"dp{world} (images sharded, no data-path collective)"},
         "e2e": {"value": e2e, "unit": "images/s",

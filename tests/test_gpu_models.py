@@ -233,3 +233,22 @@ def test_noc_loop_maskclip_loftup(isp):
     decided = np.abs(want - 0.49) > 0.02
     agree = ((probs > 0.49) == (want > 0.49))[decided].mean()
     assert agree >= 0.999, agree
+
+
+@pytest.mark.parametrize("up_type,params", [("jbu_featup", {"backbone_type": "dinov2", "use_norm": True}),
+                                            ("loftup", {"upsampler_path": None, "n_dim": 384})])
+def test_features_graphed_equals_eager(isp, up_type, params):
+    """CUDA-graph replay of the feature path returns bit-identical results to the eager calls, also
+    after the inputs change (static input buffers are refreshed before every replay)."""
+    torch.manual_seed(0)
+    H = W = 112
+    pipe = isp.ISegPipeline(up_type, params, with_head=False).to(DEV).eval()
+    pipe.embed_coords = isp.PatchEmbed((H, W), (14, 14), 3, 384).to(DEV).eval()
+    for seed in (1, 2):
+        image = torch.cat([synth.image_batch(2, H, W, seed=seed), torch.zeros(2, 1, H, W)], 1).to(DEV)
+        pts = synth.click_points(2, 3, H, W, seed=seed + 2).to(DEV)
+        with torch.no_grad():
+            a = pipe.features(image, pts).clone()
+            b = pipe.features_graphed(image, pts).clone()
+        assert torch.equal(a, b)
+    assert pipe.graphed_launches() > 50
