@@ -143,6 +143,25 @@ int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw,
 int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
                         int Nimg, int H, int W, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream);
 
+/* The same two kernels with a LayerNorm fused on either side, so that LN(x) between two GEMMs of the
+ * LoftUp transformer (loftup/layers.py:186-202: norm_q -> in_proj, :161-174: LayerNorm -> Linear) is never
+ * materialised:
+ *  - ln_stats != NULL: D = alpha * act(LN(A) W^T + bias) + resid.  W must hold W[n,k]*gamma[k] (bf16),
+ *    ln_g[n] = sum_k of those bf16 values, bias[n] = sum_k W[n,k]*beta[k] + b[n]; ln_stats is
+ *    [M][ln_slots][2] partial (sum, sum of squares) of each A row over its K real columns.
+ *    LN(A) W^T = rstd * (A W'^T - mean * ln_g), applied per row in the epilogue.
+ *  - stats_out != NULL: also writes those partial sums for the rows of D / pixels of Y (of the values as
+ *    stored, columns < N), [M][stats_slots][2], stats_slots = isp_gemm_stats_slots(N, out_bf16, resid != NULL);
+ *    one slot per (column tile, 128-byte chunk): no atomics, bit-reproducible. */
+int isp_gemm_stats_slots(int N, int out_bf16, int has_resid);
+int isp_gemm_bf16_tc_ex(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                        const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
+                        long long ldd, int out_bf16, long long M, int N, int K, const float* ln_stats, int ln_slots,
+                        const float* ln_g, float ln_eps, float* stats_out, int stats_slots, isp_stream_t stream);
+int isp_conv3x3_bf16_tc_ex(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
+                           int Nimg, int H, int W, int Cin, int ldx, int Cout, int ldy, float* stats_out,
+                           int stats_slots, isp_stream_t stream);
+
 /* Backward of that convolution (trainer backward, core/training/trainer.py:213-221, of
  * ConvSegHead.convs, heads/conv_heads.py:58-66):
  * dgrad: dX = conv3x3(dY, W') with W' = flipped / transposed weights packed like forward ones

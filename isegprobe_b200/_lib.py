@@ -35,6 +35,9 @@ SIGNATURES = {
     "isp_gemm_f32_simt": [_P, _P, _P, _P, _F, _P, _LL, _I, _I, _S],
     "isp_gemm_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _F, _I, _P, _LL, _I, _LL, _I, _I, _S],
     "isp_conv3x3_bf16_tc": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S],
+    "isp_gemm_stats_slots": [_I, _I, _I],
+    "isp_gemm_bf16_tc_ex": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _F, _I, _P, _LL, _I, _LL, _I, _I, _P, _I, _P, _F, _P, _I, _S],
+    "isp_conv3x3_bf16_tc_ex": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _S],
     "isp_conv3x3_dgrad_bf16_tc": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S],
     "isp_conv3x3_wgrad_bf16_tc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _S],
     "isp_head_classifier_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _LL, _I, _S],

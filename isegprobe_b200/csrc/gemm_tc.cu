@@ -81,6 +81,14 @@ struct Params {
   // epilogue
   const float* bias;   // [N] or null
   float alpha;         // out = alpha * act(acc + bias) + resid
+  // fused LayerNorm of the A rows (see isp_gemm_bf16_tc_ex): acc -> rstd * (acc - mean * ln_g[n]) before bias / act
+  const float* ln_stats;  // [M][ln_slots][2] partial (sum, sum of squares) of every A row, or null
+  const float* ln_g;      // [N] column sums of the (gamma-scaled) weights
+  int ln_slots;
+  float ln_invC, ln_eps;
+  // row statistics of the OUTPUT (over columns < N, of the values as stored), for the next fused LayerNorm
+  float* stats_out;       // [M][stats_slots][2] or null; slot = n_tile * chunks_per_tile + chunk: no atomics, deterministic
+  int stats_slots;
 };
 
 // erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): 1 RCP + 1 EX2 + 7 FMA instead of erff's ~25
@@ -154,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t resid_bar[kEpiWarps][2];
-  __shared__ __align__(16) float bias_s[2][256];
+  __shared__ __align__(16) float bias_s[256], lng_s[256];  // single-buffered: two epilogue barriers per tile
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -268,9 +276,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         c1 = (int)tc_.m0 + q * 32;
       }
       // bias slice of this tile -> smem (zeros beyond N, so padded columns come out as exact zeros)
+      epi_bar_sync();  // every epilogue warp is done with the previous tile's bias / g slice
       if (etid < p.BN) {
         const int n = tc_.n0 + etid;
-        bias_s[acc][etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        bias_s[etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        if (p.ln_stats) lng_s[etid] = n < p.N ? __ldg(p.ln_g + n) : 0.f;
+      }
+      // this thread's row of the tile: global row index (conv mode: linear pixel index) and validity
+      long long grow;
+      bool row_ok;
+      if (p.TW) {
+        const int pix = q * 32 + lane;
+        const int hh = tc_.h0 + pix / p.TW, ww = tc_.w0 + pix % p.TW;
+        row_ok = hh < p.H && ww < p.W;
+        grow = ((long long)tc_.img * p.H + hh) * p.W + ww;
+      } else {
+        grow = tc_.m0 + q * 32 + lane;
+        row_ok = grow < p.M;
+      }
+      float ln_rstd = 1.f, ln_nrm = 0.f;  // x_norm . W = rstd * acc + (-rstd * mean) * g[n]
+      if (p.ln_stats && row_ok) {
+        float su = 0.f, sq = 0.f;
+        const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
+        for (int k = 0; k < p.ln_slots; ++k) {  // fixed order: deterministic
+          const float2 v = __ldg(sp2 + k);
+          su += v.x;
+          sq += v.y;
+        }
+        const float mean = su * p.ln_invC;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_invC - mean * mean, 0.f) + p.ln_eps);
+        ln_nrm = -ln_rstd * mean;
       }
       // residual chunks of this tile: issue the loads now, they land while the tile's MMAs run
       if (RESID) {
@@ -291,8 +326,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-      const float* bs = bias_s[acc];
+      const float* bs = bias_s;
+      const float* gs = lng_s;
+      const bool ln_on = p.ln_stats != nullptr;
       for (int i = 0; i < n_my; ++i, ++st_seq) {
+        float st_sum = 0.f, st_sq = 0.f;
         const int col0 = (half + 2 * i) * CW;     // column inside the tile
         const int ncols = min(CW, p.BN - col0);   // multiple of 16
         const bool is_tail = ncols < CW;
@@ -339,11 +377,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float x[CPU_];
 #pragma unroll
                 for (int e4 = 0; e4 < CPU_; e4 += 4) {
-                  const float4 bb = *reinterpret_cast<const float4*>(bs + col0 + scol + uu * CPU_ + e4);
-                  x[e4 + 0] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 0]) + bb.x) * p.alpha;
-                  x[e4 + 1] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 1]) + bb.y) * p.alpha;
-                  x[e4 + 2] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 2]) + bb.z) * p.alpha;
-                  x[e4 + 3] = act_fn<ACT>(__uint_as_float(vr[uu * CPU_ + e4 + 3]) + bb.w) * p.alpha;
+                  float4 bb = *reinterpret_cast<const float4*>(bs + col0 + scol + uu * CPU_ + e4);
+                  float a0 = __uint_as_float(vr[uu * CPU_ + e4 + 0]), a1 = __uint_as_float(vr[uu * CPU_ + e4 + 1]);
+                  float a2 = __uint_as_float(vr[uu * CPU_ + e4 + 2]), a3 = __uint_as_float(vr[uu * CPU_ + e4 + 3]);
+                  if (ln_on) {  // fused LayerNorm of the A row
+                    const float4 gg = *reinterpret_cast<const float4*>(gs + col0 + scol + uu * CPU_ + e4);
+                    a0 = fmaf(ln_rstd, a0, ln_nrm * gg.x); a1 = fmaf(ln_rstd, a1, ln_nrm * gg.y);
+                    a2 = fmaf(ln_rstd, a2, ln_nrm * gg.z); a3 = fmaf(ln_rstd, a3, ln_nrm * gg.w);
+                  }
+                  x[e4 + 0] = act_fn<ACT>(a0 + bb.x) * p.alpha;
+                  x[e4 + 1] = act_fn<ACT>(a1 + bb.y) * p.alpha;
+                  x[e4 + 2] = act_fn<ACT>(a2 + bb.z) * p.alpha;
+                  x[e4 + 3] = act_fn<ACT>(a3 + bb.w) * p.alpha;
                 }
                 if (RESID) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(sp);
@@ -385,13 +430,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   __nv_bfloat162 b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
                   w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
                                  *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
+                  if (p.stats_out) {  // statistics of the values the consumer will read (after bf16 rounding)
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const float lo = __uint_as_float(ww[k] << 16), hi = __uint_as_float(ww[k] & 0xffff0000u);
+                      st_sum += lo + hi;
+                      st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+                    }
+                  }
                 } else {
+                  if (p.stats_out) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { st_sum += x[k]; st_sq = fmaf(x[k], x[k], st_sq); }
+                  }
                   w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
                 }
                 *reinterpret_cast<uint4*>(sp) = w;
               }
             }
           }
+        }
+        if (p.stats_out && row_ok) {
+          const int slot = (tc_.n0 / p.BN) * nchunks + (half + 2 * i);
+          reinterpret_cast<float2*>(p.stats_out)[grow * p.stats_slots + slot] = make_float2(st_sum, st_sq);
         }
         tc::fence_proxy_async();
         __syncwarp();
@@ -477,9 +539,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 
 using namespace isp;
 
-extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                                const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
-                                long long ldd, int out_bf16, long long M, int N, int K, isp_stream_t stream) {
+static int gemm_common(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
+                       int resid_bf16, long long ldr, float alpha, int act, void* D, long long ldd, int out_bf16,
+                       long long M, int N, int K, const float* ln_stats, int ln_slots, const float* ln_g, float ln_eps,
+                       float* stats_out, int stats_slots, isp_stream_t stream) {
   ISP_REQUIRE(A && W && D, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: null pointer");
   ISP_REQUIRE(M > 0 && N > 0 && K > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: bad shape M=%lld N=%d K=%d", M, N, K);
   ISP_REQUIRE(lda >= K && ldw >= K && ldd >= N, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: leading dimensions too small");
@@ -509,6 +572,16 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
   p.bias = bias; p.alpha = alpha;
+  if (ln_stats) {
+    ISP_REQUIRE(ln_g && ln_slots > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_ex: ln_stats needs ln_g and ln_slots > 0");
+    p.ln_stats = ln_stats; p.ln_g = ln_g; p.ln_slots = ln_slots; p.ln_invC = 1.f / (float)K; p.ln_eps = ln_eps;
+  }
+  if (stats_out) {
+    const int need = (int)p.tiles_n * ((p.BN + (out_bf16 ? 64 : 32) - 1) / (out_bf16 ? 64 : 32));
+    ISP_REQUIRE(stats_slots == need, ISP_ERR_BAD_SHAPE,
+                "gemm_bf16_tc_ex: stats_slots must be %d for N=%d (ask isp_gemm_stats_slots)", need, N);
+    p.stats_out = stats_out; p.stats_slots = stats_slots;
+  }
   CUtensorMap tmA, tmB, tmD;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)lda * 2};
@@ -539,9 +612,39 @@ extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, lon
   return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, resid != nullptr, as_stream(stream));
 }
 
+extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                                const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
+                                long long ldd, int out_bf16, long long M, int N, int K, isp_stream_t stream) {
+  return gemm_common(A, lda, W, ldw, bias, resid, resid_bf16, ldr, alpha, act, D, ldd, out_bf16, M, N, K, nullptr, 0,
+                     nullptr, 0.f, nullptr, 0, stream);
+}
+
+// Number of (sum, sum of squares) slots per row that a GEMM / conv with N output columns writes.
+extern "C" int isp_gemm_stats_slots(int N, int out_bf16, int has_resid) {
+  const int bn = gemm::pick_bn(N, (has_resid && !out_bf16) ? 128 : 256);
+  const int cw = out_bf16 ? 64 : 32;
+  return ((N + bn - 1) / bn) * ((bn + cw - 1) / cw);
+}
+
+// isp_gemm_bf16_tc with a LayerNorm fused on either side:
+//  * ln_stats != NULL: D = alpha * act( LN(A) W^T + bias ) + resid, where W must hold the gamma-scaled weights
+//    W[n,k] * gamma[k] (bf16), ln_g[n] = sum_k of those bf16 values, bias[n] = sum_k W[n,k] beta[k] + b[n], and
+//    ln_stats[M][ln_slots][2] the partial (sum, sum of squares) of every A row over its K real columns:
+//    LN(A) W^T = rstd * (A W'^T - mean * ln_g).  The normalised activations are never materialised.
+//  * stats_out != NULL: additionally writes those partial sums for the rows of D (values as stored),
+//    [M][stats_slots][2] with stats_slots = isp_gemm_stats_slots(N, out_bf16, resid != NULL).
+extern "C" int isp_gemm_bf16_tc_ex(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                                   const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
+                                   long long ldd, int out_bf16, long long M, int N, int K, const float* ln_stats,
+                                   int ln_slots, const float* ln_g, float ln_eps, float* stats_out, int stats_slots,
+                                   isp_stream_t stream) {
+  return gemm_common(A, lda, W, ldw, bias, resid, resid_bf16, ldr, alpha, act, D, ldd, out_bf16, M, N, K, ln_stats,
+                     ln_slots, ln_g, ln_eps, stats_out, stats_slots, stream);
+}
+
 static int conv3x3_common(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16, int Nimg,
                           int H, int Wd, int Cin, int ldx, int Cout, int ldy, const void* mask, int ldm,
-                          isp_stream_t stream) {
+                          float* stats_out, int stats_slots, isp_stream_t stream) {
   ISP_REQUIRE(X && Wp && Y, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: null pointer");
   ISP_REQUIRE(Nimg > 0 && H > 0 && Wd > 0 && Cout > 0 && Cin > 0, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc: bad shape");
   ISP_REQUIRE(ldx >= Cin && ldx % 8 == 0, ISP_ERR_MISALIGNED,
@@ -574,6 +677,11 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
   p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
   p.bias = bias; p.alpha = 1.f;
+  if (stats_out) {
+    const int need = (int)p.tiles_n * ((p.BN + (out_bf16 ? 64 : 32) - 1) / (out_bf16 ? 64 : 32));
+    ISP_REQUIRE(stats_slots == need, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc_ex: stats_slots must be %d for Cout=%d", need, Cout);
+    p.stats_out = stats_out; p.stats_slots = stats_slots;
+  }
   CUtensorMap tmA, tmB, tmD, tmDt;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
@@ -610,7 +718,16 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
 
 extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
                                    int Nimg, int H, int Wd, int Cin, int ldx, int Cout, int ldy, isp_stream_t stream) {
-  return conv3x3_common(X, Wp, bias, act, Y, out_bf16, Nimg, H, Wd, Cin, ldx, Cout, ldy, nullptr, 0, stream);
+  return conv3x3_common(X, Wp, bias, act, Y, out_bf16, Nimg, H, Wd, Cin, ldx, Cout, ldy, nullptr, 0, nullptr, 0, stream);
+}
+
+// isp_conv3x3_bf16_tc that also writes the row statistics of Y (see isp_gemm_bf16_tc_ex); rows = pixels in
+// NHWC order.  stats_slots = isp_gemm_stats_slots(Cout, out_bf16, 0).
+extern "C" int isp_conv3x3_bf16_tc_ex(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
+                                      int Nimg, int H, int Wd, int Cin, int ldx, int Cout, int ldy, float* stats_out,
+                                      int stats_slots, isp_stream_t stream) {
+  return conv3x3_common(X, Wp, bias, act, Y, out_bf16, Nimg, H, Wd, Cin, ldx, Cout, ldy, nullptr, 0, stats_out,
+                        stats_slots, stream);
 }
 
 // Data gradient of the same convolution: dX = conv3x3(dY, W') with W'[ci][tap][co] = W[co][ci][8 - tap]
@@ -619,5 +736,6 @@ extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* b
 extern "C" int isp_conv3x3_dgrad_bf16_tc(const void* dY, const void* Wp_flipped, const void* relu_mask, int ldm,
                                          void* dX, int out_bf16, int Nimg, int H, int Wd, int Cout, int ldy, int Cin,
                                          int ldx, isp_stream_t stream) {
-  return conv3x3_common(dY, Wp_flipped, nullptr, 0, dX, out_bf16, Nimg, H, Wd, Cout, ldy, Cin, ldx, relu_mask, ldm, stream);
+  return conv3x3_common(dY, Wp_flipped, nullptr, 0, dX, out_bf16, Nimg, H, Wd, Cout, ldy, Cin, ldx, relu_mask, ldm,
+                        nullptr, 0, stream);
 }

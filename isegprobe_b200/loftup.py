@@ -96,6 +96,9 @@ class LoftUpUpsampler(BaseUpsampler):
 
     HEADS = 4
     chunk_images = 4  # images per internal pass (bounds the [B*HW, 416] intermediates)
+    # LayerNorms of the query stream (norm_q, FeedForward's, the transformer's final one) are applied inside the
+    # epilogue of the GEMM that consumes them, from row statistics the producing GEMM / conv wrote (tc.gemm ln_stats=)
+    fuse_layernorm = True
 
     def __init__(self, upsampler_path: str = None, n_dim: int = 384, lr_pe_type: str = "sine", lr_size: int = 16):
         super().__init__()
@@ -180,11 +183,18 @@ class LoftUpUpsampler(BaseUpsampler):
                 "nf_w": f32(ff.net[0].weight), "nf_b": f32(ff.net[0].bias),
                 "W1": tc.pack_linear_weight(ff.net[1].weight).to(dev), "b1": f32(ff.net[1].bias),
                 "W2": tc.pack_linear_weight(ff.net[4].weight).to(dev), "b2": f32(ff.net[4].bias),
+                # LayerNorm folded into the Linear that follows it (tc.pack_ln_linear): (W*gamma, column sums, bias')
+                "Wq_ln": [t.to(dev) for t in tc.pack_ln_linear(Wq_p, bq_p, ca.norm_q.weight, ca.norm_q.bias)],
+                "W1_ln": [t.to(dev) for t in tc.pack_ln_linear(ff.net[1].weight, ff.net[1].bias, ff.net[0].weight,
+                                                               ff.net[0].bias)],
             })
         P["layers"] = layers
         P["n_w"], P["n_b"] = f32(up.ca_transformer.norm.weight), f32(up.ca_transformer.norm.bias)
         P["Wf"] = tc.pack_linear_weight(up.final_conv[0].weight.detach().float().reshape(self.n_dim, D)).to(dev)
         P["bf"] = f32(up.final_conv[0].bias)
+        P["Wf_ln"] = [t.to(dev) for t in tc.pack_ln_linear(up.final_conv[0].weight.detach().float().reshape(self.n_dim, D),
+                                                           up.final_conv[0].bias, up.ca_transformer.norm.weight,
+                                                           up.ca_transformer.norm.bias)]
         P["lnf_w"], P["lnf_b"] = f32(up.final_conv[1].weight), f32(up.final_conv[1].bias)
         P["grids"] = {}
         self._packed = P
@@ -240,7 +250,12 @@ class LoftUpUpsampler(BaseUpsampler):
               P["freqs20"], P["fb_sin"], P["fb_cos"], P["cn203_w"], P["cn203_b"], ff, B, H, W, 208, 1e-5)
         x = tc.conv3x3(ff, P["conv1_w"], P["conv1_b"], 203, D, act="relu", ldy=Dp)
         del ff
-        x = tc.conv3x3(x, P["conv2_w"], P["conv2_b"], D, D, act="relu", ldy=Dp).view(M, Dp)
+        fuse = self.fuse_layernorm
+        st_a = st_b = None
+        if fuse:  # per-row (sum, sum of squares) slots: conv2 / FFN2 write st_a, out-proj writes st_b
+            st_a = torch.empty(M, tc.stats_slots(D, bf, False), 2, dtype=torch.float32, device=dev)
+            st_b = torch.empty(M, tc.stats_slots(D, bf, True), 2, dtype=torch.float32, device=dev)
+        x = tc.conv3x3(x, P["conv2_w"], P["conv2_b"], D, D, act="relu", ldy=Dp, stats_out=st_a).view(M, Dp)
         kv = torch.empty(B * T, D, dtype=torch.float32, device=dev)
         _call("isp_loftup_lr_prepare", src, *src.stride(), P["cn_w"], P["cn_b"], self._grid(P, h, dev),
               self._grid(P, w, dev), P["freqs5"], P["lb_sin"], P["lb_cos"], kv, B, C, h, w, 1e-5)
@@ -253,22 +268,36 @@ class LoftUpUpsampler(BaseUpsampler):
             Vt = torch.empty(B, nh, HP, Tp, dtype=bf, device=dev)
             _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, Tp, nh, KP, 0)
             _call("isp_repack_heads", Vl, 0, D, 0, hd, Vt, B, T, Tp, nh, HP, 1)
-            qn = self._ln(x, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
-            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
-            del qn
+            if fuse:
+                Wq, gq, bq = L["Wq_ln"]
+                Q = tc.gemm(x, Wq, bias=bq, out_dtype=bf, N=nh * HP, K=D, ln_stats=st_a, ln_g=gq, ln_eps=1e-5)
+            else:
+                qn = self._ln(x, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
+                Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
+                del qn
             O = torch.empty(M, nh * HP, dtype=bf, device=dev)
             with timed_kernel("loftup_attention"):
                 _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
             del Q
-            x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp)
+            x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp, stats_out=st_b)
             del O
-            hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
-            h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)
-            del hn
-            x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp)
+            if fuse:
+                W1, g1, b1 = L["W1_ln"]
+                h1 = tc.gemm(x, W1, bias=b1, act="gelu_tanh", out_dtype=bf, N=C, K=D, ln_stats=st_b, ln_g=g1,
+                             ln_eps=1e-5)
+            else:
+                hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
+                h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)
+                del hn
+            x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp, stats_out=st_a)
             del h1
-        xn = self._ln(x, P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
-        del x
-        y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
-        del xn
+        if fuse:
+            Wf, gf, bfin = P["Wf_ln"]
+            y = tc.gemm(x, Wf, bias=bfin, out_dtype=torch.float32, N=C, K=D, ln_stats=st_a, ln_g=gf, ln_eps=1e-5)
+            del x
+        else:
+            xn = self._ln(x, P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
+            del x
+            y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
+            del xn
         _call("isp_layernorm_rows", y, 0, C, out.view(M, C), 0, C, P["lnf_w"], P["lnf_b"], M, C, 1e-6)

@@ -72,3 +72,21 @@ def test_loftup_state_dict_matches_reference_layout():
     ckpt = {"upsampler." + k: v for k, v in synth.loftup_state_dict(384, seed=3).items()}
     ckpt.update({"model.1." + k: v for k, v in synth.channelnorm_state_dict(384, seed=4).items()})
     m.load_reference_checkpoint(ckpt)
+
+
+def test_loftup_fused_layernorm_matches_unfused():
+    """LayerNorm applied in the consuming GEMM's epilogue (default) vs the stand-alone LayerNorm kernel: same
+    function, different bf16 rounding points; both must sit within the bf16 tolerance of the oracle."""
+    m, sd, cn = _module()
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 384, 8, 12, seed=2)
+    with torch.no_grad():
+        want = oloft.loftup_forward(sd, lr, img, cn["norm.weight"], cn["norm.bias"])
+        outs = {}
+        for fuse in (True, False):
+            m.fuse_layernorm = fuse
+            outs[fuse] = m(source=lr.to(DEV), guidance=img.to(DEV)).cpu().float()
+    assert cosine(outs[True], outs[False]) > 0.9995
+    ct, cf = cosine(outs[True], want), cosine(outs[False], want)
+    assert ct >= 0.999 and cf >= 0.999, (ct, cf)
+    assert ct > cf - 2e-4, (ct, cf)  # fusing must not cost accuracy

@@ -65,3 +65,49 @@ def test_conv3x3(tc, B, H, W, Cin, Cout):
                    out_dtype=torch.float32)
     want = torch.relu(F.conv2d(x.float(), w.float(), b, padding=1)).permute(0, 2, 3, 1)
     assert relerr(y[..., :Cout], want) < 1e-4, relerr(y[..., :Cout], want)
+
+
+@pytest.mark.parametrize("M,D,N2", [(1000, 404, 448), (70001, 404, 384), (300, 384, 1536)])
+def test_gemm_fused_layernorm(tc, M, D, N2):
+    """Producer GEMM writes per-row (sum, sum of squares) slots of its stored output; the consumer GEMM applies
+    LayerNorm(gamma, beta) of those rows in its epilogue (isp_gemm_bf16_tc_ex).  Checked against LN-then-Linear in
+    fp32 on the same bf16-stored activations (loftup/layers.py:161-174,186-202)."""
+    g = torch.Generator().manual_seed(M + D)
+    K0 = 384
+    A = torch.randn(M, K0, generator=g).to(torch.bfloat16)
+    W0 = (torch.randn(D, K0, generator=g) * K0 ** -0.5).to(torch.bfloat16)
+    b0 = torch.randn(D, generator=g) * 0.5 + 0.7   # a mean well away from zero (cancellation in rstd*(acc - mean*g))
+    Dp = tc.round_up(D, 16)
+    R = torch.zeros(M, Dp, dtype=torch.bfloat16)
+    R[:, :D] = torch.randn(M, D, generator=g).to(torch.bfloat16)
+    for resid in (None, R):
+        slots = tc.stats_slots(D, torch.bfloat16, resid is not None)
+        st = torch.full((M, slots, 2), float("nan"), device=DEV)
+        x = tc.gemm(A.to(DEV), W0.to(DEV), bias=b0.to(DEV), resid=None if resid is None else resid.to(DEV),
+                    out_dtype=torch.bfloat16, N=D, ldd=Dp, stats_out=st)
+        xs = x[:, :D].float().cpu()
+        ssum = st.sum(1).cpu()
+        assert torch.allclose(ssum[:, 0], xs.sum(1), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(ssum[:, 1], (xs * xs).sum(1), rtol=1e-4, atol=1e-3)
+        gamma, beta = torch.randn(D, generator=g) * 0.3 + 1.0, torch.randn(D, generator=g) * 0.2
+        W1 = torch.randn(N2, D, generator=g) * D ** -0.5
+        b1 = torch.randn(N2, generator=g)
+        Wg, gsum, bias = tc.pack_ln_linear(W1, b1, gamma, beta)
+        out = tc.gemm(x, Wg.to(DEV), bias=bias.to(DEV), out_dtype=torch.float32, N=N2, K=D, ln_stats=st,
+                      ln_g=gsum.to(DEV), ln_eps=1e-5)
+        want = F.layer_norm(xs, (D,), gamma, beta, 1e-5) @ W1.T + b1
+        assert relerr(out, want) < 1e-2 and cosine(out, want) > 0.9999, (relerr(out, want), cosine(out, want))
+
+
+def test_conv3x3_row_stats(tc):
+    g = torch.Generator().manual_seed(11)
+    B, H, W, Cin, Cout = 2, 9, 21, 64, 404
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g)
+    st = torch.full((B * H * W, tc.stats_slots(Cout), 2), float("nan"), device=DEV)
+    y = tc.conv3x3(x.to(DEV), tc.pack_conv3x3_weight(w).to(DEV), b.to(DEV), Cin, Cout, act="relu", ldy=416,
+                   stats_out=st)
+    ys = y.view(-1, 416)[:, :Cout].float()
+    assert torch.allclose(st.sum(1)[:, 0], ys.sum(1), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(st.sum(1)[:, 1], (ys * ys).sum(1), rtol=1e-4, atol=1e-3)
