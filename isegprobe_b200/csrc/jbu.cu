@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) bicubic2x_pad_kernel(const float* __restr
 // 4 channels from a 5 x 6 low-res neighbourhood (3.75 loads per output instead of 16), separable
 // (horizontal then vertical), written straight into the interior of the padded buffer.  The
 // 3-pixel reflect frame is filled afterwards by reflect_border_kernel from that interior.
-__global__ void __launch_bounds__(256) bicubic2x_interior_kernel(const float* __restrict__ src, float* __restrict__ out,
+__global__ void __launch_bounds__(256, 3) bicubic2x_interior_kernel(const float* __restrict__ src, float* __restrict__ out,
                                                                  int B, int h, int w, int C) {
   const int C4 = C / 4, wp = (w + 1) / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

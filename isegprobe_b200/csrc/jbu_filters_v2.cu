@@ -147,39 +147,84 @@ __device__ __forceinline__ void mlp_layer(float2 (&acc)[kWP], const float* vcol,
   }
 }
 
+// k of this block's pixels, global <-> smem [tap][pixel].  The padded layout (56 floats = 14 float4 per pixel,
+// slots 7, 15, ... are the zero 8th entries) moves as float4 with 7 independent loads in flight per thread;
+// the dense layout (49) moves as scalars.  All index arithmetic is by compile-time constants.
+template <int OUT_LD, bool STORE>
+__device__ __forceinline__ void slab_rw(float* __restrict__ slab, float* v, int nlive, int tid) {
+  if (OUT_LD == 56) {
+    float4* s4 = reinterpret_cast<float4*>(slab);
+    constexpr int N4 = B_PIX * 14, PER = N4 / B_THREADS;  // 28 float4 per thread
+    static_assert(N4 % B_THREADS == 0 && PER % 7 == 0, "slab_rw tiling");
+#pragma unroll 1
+    for (int it = 0; it < PER; it += 7) {
+      float4 x[7];
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int e4 = (it + u) * B_THREADS + tid, px = e4 / 14;
+        x[u] = px < nlive ? s4[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int e4 = (it + u) * B_THREADS + tid, px = e4 / 14, s14 = e4 - px * 14;
+        const int tap = (s14 >> 1) * 7 + (s14 & 1) * 4;
+        float* vp = v + tap * B_VS + px;
+        if (!STORE) {
+          vp[0] = x[u].x; vp[B_VS] = x[u].y; vp[2 * B_VS] = x[u].z;
+          if (!(s14 & 1)) vp[3 * B_VS] = x[u].w;
+        } else if (px < nlive) {
+          x[u].x = fmaf(0.1f, vp[0], x[u].x); x[u].y = fmaf(0.1f, vp[B_VS], x[u].y);
+          x[u].z = fmaf(0.1f, vp[2 * B_VS], x[u].z);
+          if (!(s14 & 1)) x[u].w = fmaf(0.1f, vp[3 * B_VS], x[u].w);
+          s4[e4] = x[u];
+        }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int e = tid; e < B_PIX * 49; e += B_THREADS) {
+      const int px = e / 49, tap = e - px * 49;
+      if (!STORE) v[tap * B_VS + px] = px < nlive ? slab[e] : 0.f;
+      else if (px < nlive) slab[e] = fmaf(0.1f, v[tap * B_VS + px], slab[e]);
+    }
+  }
+}
+
+template <int OUT_LD>
 __global__ void __launch_bounds__(B_THREADS, 3)
 jbu_fixup_kernel(const float4* __restrict__ g, float* __restrict__ filters, long long npix,
                  const float* __restrict__ fw0, const float* __restrict__ fb0, const float* __restrict__ fw1,
-                 const float* __restrict__ fb1, int out_ld) {
+                 const float* __restrict__ fb1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemB& S = *reinterpret_cast<SmemB*>(smem_raw);
   const int tid = threadIdx.x;
   const long long pix0 = (long long)blockIdx.x * B_PIX;
   const int nlive = (int)min((long long)B_PIX, npix - pix0);
-  for (int i = tid; i < 52 * kWP; i += B_THREADS) {
-    const int c = i / kWP, r = i % kWP;
-    S.w0t[i] = (r < 49) ? __ldg(fw0 + r * 52 + c) : 0.f;
-  }
-  for (int i = tid; i < 49 * kWP; i += B_THREADS) {
-    const int c = i / kWP, r = i % kWP;
-    S.w1t[i] = (r < 49) ? __ldg(fw1 + r * 49 + c) : 0.f;
-  }
-  for (int i = tid; i < kWP; i += B_THREADS) {
-    S.b0[i] = (i < 49) ? fb0[i] : 0.f;
-    S.b1[i] = (i < 49) ? fb1[i] : 0.f;
-  }
-  // k (from kernel A) and g -> smem [c][pixel], coalesced reads
-  float* slab = filters + pix0 * out_ld;
-  for (int e = tid; e < B_PIX * out_ld; e += B_THREADS) {
-    const int px = e / out_ld, tap = slot_to_tap(e - px * out_ld, out_ld);
-    if (tap >= 0) S.v[tap * B_VS + px] = px < nlive ? slab[e] : 0.f;
-  }
+  float* slab = filters + pix0 * OUT_LD;
+  // k (from kernel A) and g -> smem [c][pixel]
+  slab_rw<OUT_LD, false>(slab, S.v, nlive, tid);
   for (int px = tid; px < B_PIX; px += B_THREADS) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px < nlive) t = g[pix0 + px];
     S.v[49 * B_VS + px] = t.x;
     S.v[50 * B_VS + px] = t.y;
     S.v[51 * B_VS + px] = t.z;
+  }
+  // weights: coalesced global reads, transposed on the way into smem ([c][r], rows 49..51 of r are zero)
+  for (int i = tid; i < 52 * kWP; i += B_THREADS) S.w0t[i] = 0.f;
+  for (int i = tid; i < 49 * kWP; i += B_THREADS) S.w1t[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < 49 * 52; i += B_THREADS) {
+    const int r = i / 52, c = i - r * 52;
+    S.w0t[c * kWP + r] = __ldg(fw0 + i);
+  }
+  for (int i = tid; i < 49 * 49; i += B_THREADS) {
+    const int r = i / 49, c = i - r * 49;
+    S.w1t[c * kWP + r] = __ldg(fw1 + i);
+  }
+  for (int i = tid; i < kWP; i += B_THREADS) {
+    S.b0[i] = (i < 49) ? fb0[i] : 0.f;
+    S.b1[i] = (i < 49) ? fb1[i] : 0.f;
   }
   __syncthreads();
   float* vcol = S.v + 2 * tid;  // this thread's pixel pair
@@ -192,10 +237,7 @@ jbu_fixup_kernel(const float4* __restrict__ g, float* __restrict__ filters, long
 #pragma unroll
   for (int t = 0; t < 49; ++t) *reinterpret_cast<float2*>(vcol + t * B_VS) = acc[t];
   __syncthreads();
-  for (int e = tid; e < nlive * out_ld; e += B_THREADS) {  // filters = k + 0.1 * o
-    const int px = e / out_ld, tap = slot_to_tap(e - px * out_ld, out_ld);
-    if (tap >= 0) slab[e] = fmaf(0.1f, S.v[tap * B_VS + px], slab[e]);
-  }
+  slab_rw<OUT_LD, true>(slab, S.v, nlive, tid);  // filters = k + 0.1 * o
 }
 
 }  // namespace jf2
@@ -216,7 +258,8 @@ extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters
   const int smemA = (int)sizeof(jf2::SmemA), smemB = (int)sizeof(jf2::SmemB);
   if (!attr_set) {
     ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA));
-    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
+    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_fixup_kernel<49>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
+    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_fixup_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
     attr_set = true;
   }
   const float inv2s2 = 1.f / (2.f * sigma_spatial * sigma_spatial);
@@ -224,8 +267,14 @@ extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters
   jf2::jbu_range_kernel<<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2, out_ld);
   ISP_CHECK_LAUNCH("jbu_range_kernel");
   const long long npix = (long long)B * H * W;
-  jf2::jbu_fixup_kernel<<<cdiv(npix, jf2::B_PIX), jf2::B_THREADS, smemB, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(g), filters, npix, fw0, fb0, fw1, fb1, out_ld);
+  if (out_ld == 56) {
+    ISP_REQUIRE(aligned16(filters), ISP_ERR_MISALIGNED, "jbu_filters: padded filters must be 16-byte aligned");
+    jf2::jbu_fixup_kernel<56><<<cdiv(npix, jf2::B_PIX), jf2::B_THREADS, smemB, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(g), filters, npix, fw0, fb0, fw1, fb1);
+  } else {
+    jf2::jbu_fixup_kernel<49><<<cdiv(npix, jf2::B_PIX), jf2::B_THREADS, smemB, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(g), filters, npix, fw0, fb0, fw1, fb1);
+  }
   ISP_CHECK_LAUNCH("jbu_fixup_kernel");
   return ISP_OK;
 }

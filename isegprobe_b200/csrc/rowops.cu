@@ -353,20 +353,37 @@ __global__ void __launch_bounds__(256) lr_prepare_kernel(const float* __restrict
 // Attention operand repack.  src: [B*T, ld] (f32|bf16) holding per-head slices at column
 // col0 + head*hd.  Writes K-style [B, heads, Tpad, DKC] (row = token, zero padded) when
 // transpose == 0, or V^T-style [B, heads, DV, Tpad] when transpose == 1 (bf16).
+// One block = 64 tokens of one (batch, head): the [64][hd] slice is read with d fastest (coalesced rows),
+// staged in shared memory, and written either as padded rows (transpose == 0) or transposed with the
+// token index fastest (transpose == 1), so both sides move in full 128-byte segments.
+constexpr int kRepackT = 64;
 __global__ void __launch_bounds__(256) repack_heads_kernel(const void* __restrict__ src, int src_bf16, long long ld,
                                                            int col0, int hd, __nv_bfloat16* __restrict__ dst, int B,
                                                            int T, int Tpad, int heads, int D, int transpose) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * heads * Tpad * D;
-  if (idx >= total) return;
-  int t, d;
-  long long bh;
-  if (!transpose) { d = (int)(idx % D); t = (int)((idx / D) % Tpad); bh = idx / ((long long)D * Tpad); }
-  else { t = (int)(idx % Tpad); d = (int)((idx / Tpad) % D); bh = idx / ((long long)D * Tpad); }
-  const int hh = (int)(bh % heads), b = (int)(bh / heads);
-  float v = 0.f;
-  if (t < T && d < hd) v = ld_any(src, ((long long)b * T + t) * ld + col0 + hh * hd + d, src_bf16);
-  dst[idx] = __float2bfloat16(v);
+  extern __shared__ __nv_bfloat16 rp_tile[];  // [kRepackT][hd | 1] (odd pitch in 16-bit words pairs)
+  const int t0 = blockIdx.x * kRepackT, hh = blockIdx.y, b = blockIdx.z;
+  const int pitch = hd | 1;
+  const int nt = min(kRepackT, Tpad - t0);
+  for (int e = threadIdx.x; e < kRepackT * hd; e += blockDim.x) {
+    const int tt = e / hd, d = e - tt * hd, t = t0 + tt;
+    float v = 0.f;
+    if (t < T) v = ld_any(src, ((long long)b * T + t) * ld + col0 + hh * hd + d, src_bf16);
+    rp_tile[tt * pitch + d] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  __nv_bfloat16* out = dst + ((long long)b * heads + hh) * (long long)Tpad * D;
+  if (!transpose) {
+    for (int e = threadIdx.x; e < nt * D; e += blockDim.x) {
+      const int tt = e / D, d = e - tt * D;
+      out[(long long)(t0 + tt) * D + d] = d < hd ? rp_tile[tt * pitch + d] : zero;
+    }
+  } else {
+    for (int e = threadIdx.x; e < D * kRepackT; e += blockDim.x) {
+      const int d = e / kRepackT, tt = e - d * kRepackT;
+      if (tt < nt) out[(long long)d * Tpad + t0 + tt] = d < hd ? rp_tile[tt * pitch + d] : zero;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -520,10 +537,12 @@ extern "C" int isp_repack_heads(const void* src, int src_bf16, long long ld, int
   ISP_REQUIRE(src && dst_bf16, ISP_ERR_BAD_SHAPE, "repack_heads: null pointer");
   ISP_REQUIRE(B > 0 && T > 0 && Tpad >= T && heads > 0 && D >= head_dim && head_dim > 0, ISP_ERR_BAD_SHAPE,
               "repack_heads: bad shape");
-  const long long total = (long long)B * heads * Tpad * D;
-  repack_heads_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, src_bf16, ld, col0, head_dim,
-                                                                     reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, T,
-                                                                     Tpad, heads, D, transpose);
+  ISP_REQUIRE(B <= 65535 && heads <= 65535 && head_dim <= 512, ISP_ERR_UNSUPPORTED, "repack_heads: grid too large");
+  const dim3 grid((unsigned)cdiv(Tpad, kRepackT), (unsigned)heads, (unsigned)B);
+  const size_t smem = (size_t)kRepackT * (head_dim | 1) * sizeof(__nv_bfloat16);
+  repack_heads_kernel<<<grid, 256, smem, as_stream(stream)>>>(src, src_bf16, ld, col0, head_dim,
+                                                              reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, T, Tpad,
+                                                              heads, D, transpose);
   ISP_CHECK_LAUNCH("repack_heads_kernel");
   return ISP_OK;
 }

@@ -1,4 +1,3 @@
-set -x
-python -m pytest tests/test_gpu_tc.py tests/test_gpu_loftup.py -x -q -m gpu 2>&1 | tail -15
-python bench.py --workload loftup --steps 5 --warmup 3 > gpurun_out/bench_loftup_ln.json 2> gpurun_out/bench_loftup_ln.err
-tail -c 1500 gpurun_out/bench_loftup_ln.json; tail -5 gpurun_out/bench_loftup_ln.err
+python -m pytest tests/test_gpu_jbu.py tests/test_gpu_models.py tests/test_gpu_attention.py -x -q -m gpu 2>&1 | tail -5
+python tools/bench_jbu_kernels.py > gpurun_out/jbu_kernels.txt 2>&1; tail -30 gpurun_out/jbu_kernels.txt
+WORKLOAD=jbu BATCH=16 python tools/stage_times.py 2>&1 | grep -v "n=   1     0.0" | tail -30
