@@ -73,6 +73,9 @@ struct Params {
   int N, K;           // K = padded reduction length actually looped (multiple of 64)
   int BN;             // tile width, multiple of 16, <= 256
   int stages;
+  int pair;           // 1: a CTA works on TWO vertically adjacent 128-row tiles at once (both TMEM accumulators), loading
+                      // the weight tile once for both -- 0.67x the L2->SM operand bytes per MAC (the conv kernels sit at
+                      // the ~12 TB/s L2->SM ceiling); the epilogue then does not overlap the next tile's MMAs
   int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
   // conv mode (TW == 0 -> plain GEMM)
   int TW, TH, H, W, cin_chunks;
@@ -166,8 +169,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
-  const long long ntiles = p.tiles_m * p.tiles_n;
+  const uint32_t a_half = BM * BK * 2;
+  const uint32_t a_bytes = a_half << p.pair, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+  // work unit = one tile, or (pair mode) the tiles (2i, n) and (2i+1, n); tiles_m is even in pair mode
+  const long long ntiles = (p.tiles_m >> p.pair) * p.tiles_n;
+  auto unit_tile = [&](long long u, int sub) -> long long {
+    return p.pair ? ((2 * (u / p.tiles_n) + sub) * p.tiles_n + u % p.tiles_n) : u;
+  };
   const int kblocks = p.K / BK;
   uint8_t* epi_smem = smem + kMainBudget;
 
@@ -192,7 +200,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const TileCoord tc_ = tile_coord(p, t);
+        const TileCoord tc_ = tile_coord(p, unit_tile(t, 0));
+        const TileCoord tc2 = tile_coord(p, unit_tile(t, 1));
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -204,8 +213,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
             const int r = tap / 3, q = tap - r * 3;
             tc::tma_load_4d(sa, &tmA, &full_bar[s], cc * BK, tc_.w0 + q - 1, tc_.h0 + r - 1, tc_.img);
+            if (p.pair) tc::tma_load_4d(sa + a_half, &tmA, &full_bar[s], cc * BK, tc2.w0 + q - 1, tc2.h0 + r - 1, tc2.img);
           } else {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0);
+            if (p.pair) tc::tma_load_2d(sa + a_half, &tmA, &full_bar[s], kb * BK, (int)tc2.m0);
           }
           tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0);
         }
@@ -218,8 +229,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int period = p.TW ? p.cin_chunks : kblocks;
     uint32_t it = 0, tl = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
-      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+      // pair mode: the unit owns both accumulators (virtual tiles 2*tl and 2*tl+1 of the epilogue's numbering)
+      const uint32_t acc = p.pair ? 0u : (tl & 1), aph = p.pair ? (tl & 1) : ((tl >> 1) & 1);
       tc::mbar_wait(&tempty_bar[acc], aph ^ 1);
+      if (p.pair) tc::mbar_wait(&tempty_bar[1], aph ^ 1);
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256u;  // accumulator stages at columns 0 and 256
       int kin = 0;
@@ -239,8 +252,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
           if (nsteps > 2) tc::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
           if (nsteps > 3) tc::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+          if (p.pair) {  // second tile of the pair: A rows 128..255 of the stage (+16 KB), same weight tile
+            const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
+            tc::umma_bf16(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
+            if (nsteps > 1) tc::umma_bf16(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
+            if (nsteps > 2) tc::umma_bf16(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
+            if (nsteps > 3) tc::umma_bf16(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
+          }
           tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
-          if (kb == kblocks - 1) tc::umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if (kb == kblocks - 1) {                                 // accumulator(s) complete
+            tc::umma_commit(&tfull_bar[acc]);
+            if (p.pair) tc::umma_commit(&tfull_bar[1]);
+          }
         }
         __syncwarp();
         if (++kin == period) kin = 0;
@@ -262,9 +285,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_my = (nchunks - half + 1) / 2;
     const int row = lane, r7 = lane & 7;
     uint32_t tl = 0, st_seq = 0, rph0 = 0, rph1 = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+    const long long nvirt = ntiles << p.pair;  // virtual tiles of this kernel: accumulator tl & 1, in MMA completion order
+    for (long long vt = (long long)blockIdx.x << p.pair; vt < nvirt;
+         vt += (vt & p.pair) ? (((long long)gridDim.x << 1) - 1) : (p.pair ? 1 : gridDim.x), ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-      const TileCoord tc_ = tile_coord(p, t);
+      const TileCoord tc_ = tile_coord(p, unit_tile(vt >> p.pair, (int)(vt & p.pair)));
       int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
       if (p.TW) {
         const int bw = p.TW < 32 ? p.TW : 32;
@@ -523,11 +548,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     ISP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (n_attr < 32) attr_done[n_attr++] = fn;
   }
-  const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  // pairing halves the number of work units: only when there are at least two waves of pairs
+  if (p.pair && ((p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
+  const int stage_bytes = (BM * BK * 2 << p.pair) + p.BN * BK * 2;
   p.stages = kMainBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
-  const long long ntiles = p.tiles_m * p.tiles_n;
+  const long long ntiles = (p.tiles_m >> p.pair) * p.tiles_n;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   fn<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, tmR, tmRt, p);
   ISP_CHECK_LAUNCH("gemm_tc_kernel");
@@ -676,6 +703,7 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
   p.tiles_w = (Wd + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
   p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
+  p.pair = 1;  // K loop of >= 9 k-blocks: the un-overlapped epilogue is small against the saved operand traffic
   p.bias = bias; p.alpha = 1.f;
   if (stats_out) {
     const int need = (int)p.tiles_n * ((p.BN + (out_bf16 ? 64 : 32) - 1) / (out_bf16 ? 64 : 32));

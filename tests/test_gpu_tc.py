@@ -111,3 +111,38 @@ def test_conv3x3_row_stats(tc):
     ys = y.view(-1, 416)[:, :Cout].float()
     assert torch.allclose(st.sum(1)[:, 0], ys.sum(1), rtol=1e-4, atol=1e-3)
     assert torch.allclose(st.sum(1)[:, 1], (ys * ys).sum(1), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 224, 352, 64, 96), (1, 160, 256, 128, 404), (2, 161, 250, 64, 80)])
+def test_conv3x3_paired_tiles(tc, B, H, W, Cin, Cout):
+    """Sizes with at least two waves of tile PAIRS: the kernel computes two vertically adjacent 128-pixel tiles per CTA
+    from one weight tile (gemm_tc.cu Params::pair); also the row statistics and the ReLU-mask dgrad in that mode."""
+    from isegprobe_b200 import _lib
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    ldy = tc.round_up(Cout, 16)
+    st = torch.full((B * H * W, tc.stats_slots(Cout), 2), float("nan"), device=DEV)
+    y = tc.conv3x3(xn.to(DEV), tc.pack_conv3x3_weight(w).to(DEV), b.to(DEV), Cin, Cout, act="relu", ldy=ldy, stats_out=st)
+    want = torch.relu(F.conv2d(x.float(), w.float(), b, padding=1)).permute(0, 2, 3, 1)
+    ys = y[..., :Cout].float().cpu()
+    assert relerr(ys, want) < 1e-2 and cosine(ys, want) > 0.9999
+    assert float(y[..., Cout:].float().abs().max()) == 0 if ldy > Cout else True
+    ysf = ys.reshape(-1, Cout)
+    assert torch.allclose(st.sum(1)[:, 0].cpu(), ysf.sum(1), rtol=1e-4, atol=1e-3)
+    y32 = tc.conv3x3(xn.to(DEV), tc.pack_conv3x3_weight(w).to(DEV), b.to(DEV), Cin, Cout, act=None, out_dtype=torch.float32)
+    want32 = F.conv2d(x.float(), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    assert relerr(y32[..., :Cout], want32) < 1e-4
+    if Cin == Cout or Cin % 8 == 0 and Cout % 8 == 0:
+        # dgrad of that conv with the ReLU mask of its input: dX = conv_transpose(dY, W) * (act > 0)
+        dy = torch.randn(B, H, W, Cout, generator=g).to(torch.bfloat16)
+        act = torch.relu(torch.randn(B, H, W, Cin, generator=g)).to(torch.bfloat16)
+        wT = tc.pack_conv3x3_weight(w.float().flip(2, 3).transpose(0, 1)).to(DEV)
+        dx = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=DEV)
+        dy_d, act_d = dy.to(DEV), act.to(DEV)  # keep the device copies alive across the raw-pointer call
+        _lib.call("isp_conv3x3_dgrad_bf16_tc", _lib.dptr(dy_d), _lib.dptr(wT), _lib.dptr(act_d), Cin,
+                  _lib.dptr(dx), 1, B, H, W, Cout, Cout, Cin, Cin, _lib.stream_ptr())
+        wantd = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1) * (act.float() > 0)
+        assert relerr(dx.float(), wantd) < 1e-2 and cosine(dx.float(), wantd) > 0.9999

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_jbu.py tests/test_gpu_models.py tests/test_gpu_attention.py -x -q -m gpu 2>&1 | tail -5
-python tools/bench_jbu_kernels.py > gpurun_out/jbu_kernels.txt 2>&1; tail -30 gpurun_out/jbu_kernels.txt
-WORKLOAD=jbu BATCH=16 python tools/stage_times.py 2>&1 | grep -v "n=   1     0.0" | tail -30
+python -m pytest tests/ -x -q -m gpu 2>&1 | tail -8
+for wl in loftup train eval jbu; do python bench.py --workload $wl --steps 5 --warmup 3 2>/dev/null > gpurun_out/bench_${wl}_r1b.json; python -c "
+import sys,json; d=json.loads(open('gpurun_out/bench_${wl}_r1b.json').read()); print('$wl', d['value'], d['unit'], 'e2e', d['e2e']['value'], 'ms', d['ms_per_step'], (d.get('roofline') or {}).get('frac'), d['clocks'])"; done
