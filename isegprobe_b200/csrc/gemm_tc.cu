@@ -76,6 +76,8 @@ struct Params {
   int pair;           // 1: a CTA works on TWO vertically adjacent 128-row tiles at once (both TMEM accumulators), loading
                       // the weight tile once for both -- 0.67x the L2->SM operand bytes per MAC (the conv kernels sit at
                       // the ~12 TB/s L2->SM ceiling); the epilogue then does not overlap the next tile's MMAs
+  int epi_bufs;       // staging chunks per epilogue warp: 2, or 1 (pair mode without residual: the 32 KB go to a third
+                      // pipeline stage instead)
   int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
   // conv mode (TW == 0 -> plain GEMM)
   int TW, TH, H, W, cin_chunks;
@@ -177,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     return p.pair ? ((2 * (u / p.tiles_n) + sub) * p.tiles_n + u % p.tiles_n) : u;
   };
   const int kblocks = p.K / BK;
-  uint8_t* epi_smem = smem + kMainBudget;
+  uint8_t* epi_smem = smem + kSmemBytes - kEpiWarps * 4096 * p.epi_bufs;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -279,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;      // TMEM lane quarter this warp may access == its 32 rows of the tile
     const int half = ew >> 2;    // which of the two warps sharing that quarter (takes chunks half, half+2, ...)
     const int etid = ew * 32 + lane;
-    uint8_t* stage = epi_smem + ew * kEpiBytesPerWarp;
+    uint8_t* stage = epi_smem + ew * 4096 * p.epi_bufs;
     uint64_t* rbar = resid_bar[ew];
     const int nchunks = (p.BN + CW - 1) / CW;
     const int n_my = (nchunks - half + 1) / 2;
@@ -362,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row_bytes = ncols * ESZ;        // dense row pitch of a tail chunk
         const int nglob = tc_.n0 + col0;          // first global column of the chunk
         const bool full = nglob + ncols <= p.N;   // no column masking needed
-        const uint32_t b = st_seq & 1;
+        const uint32_t b = p.epi_bufs == 2 ? (st_seq & 1) : 0u;
         uint8_t* obuf = stage + b * 4096;
         if (RESID) {
           if (i >= 2) {  // more than two chunks per warp and tile: reload the buffer once its store has read it
@@ -377,7 +379,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(&rbar[b], b ? rph1 : rph0);
           if (b) rph1 ^= 1; else rph0 ^= 1;
         } else {
-          if (lane == 0) tc::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+          if (lane == 0) {  // the store that used this buffer (two chunks ago / the previous one) has read it
+            if (p.epi_bufs == 2) tc::tma_store_wait_read<1>();
+            else tc::tma_store_wait_read<0>();
+          }
           __syncwarp();
         }
         uint8_t* orow = obuf + row * (is_tail ? row_bytes : 128);
@@ -551,7 +556,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   // pairing halves the number of work units: only when there are at least two waves of pairs
   if (p.pair && ((p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
   const int stage_bytes = (BM * BK * 2 << p.pair) + p.BN * BK * 2;
-  p.stages = kMainBudget / stage_bytes;
+  p.epi_bufs = (p.pair && !resid) ? 1 : 2;
+  p.stages = (kSmemBytes - kEpiWarps * 4096 * p.epi_bufs) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   const long long ntiles = (p.tiles_m >> p.pair) * p.tiles_n;
