@@ -604,6 +604,7 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
   p.TW = 0;
   p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
+  p.pair = 0;  // K is short here: the exposed epilogue costs more than the shared weight tile saves (measured)
   p.bias = bias; p.alpha = alpha;
   if (ln_stats) {
     ISP_REQUIRE(ln_g && ln_slots > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_ex: ln_stats needs ln_g and ln_slots > 0");

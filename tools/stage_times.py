@@ -13,11 +13,20 @@ batch = int(os.environ.get("BATCH", "4"))
 cfg = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-pipe = ISegPipeline(upsampler_type=cfg["upsampler"], upsampler_params=cfg["params"], with_head=False).to(dev).eval()
+train = wl == "train"
+pipe = ISegPipeline(upsampler_type=cfg["upsampler"], upsampler_params=cfg["params"], with_head=train).to(dev).eval()
 img, pts = bench.synth_inputs(batch, 1)
 img, pts = img.to(dev), pts.to(dev)
+if train:
+    from isegprobe_b200.training import HeadTrainer
+    trainer = HeadTrainer(pipe)
+    gt = (torch.rand(batch, 1, bench.H, bench.W, device=dev) > 0.5).float()
+    run = lambda: trainer.step(img, pts, gt)
+else:
+    run = lambda: pipe.features(img, pts)
 rec, orig = [], _lib.call
-SHAPE_ARGS = {"isp_gemm_bf16_tc": (13, 14, 15, 9, 12), "isp_gemm_bf16_tc_ex": (13, 14, 15, 9, 12),
+SHAPE_ARGS = {"isp_conv3x3_dgrad_bf16_tc": (6, 7, 8, 9, 11), "isp_conv3x3_wgrad_bf16_tc": (5, 6, 7, 8, 9),
+              "isp_gemm_bf16_tc": (13, 14, 15, 9, 12), "isp_gemm_bf16_tc_ex": (13, 14, 15, 9, 12),
               "isp_conv3x3_bf16_tc": (6, 7, 8, 9, 11), "isp_conv3x3_bf16_tc_ex": (6, 7, 8, 9, 11)}
 
 def timed(name, *a):
@@ -29,9 +38,10 @@ def timed(name, *a):
     key = tuple(a[i] for i in idx) if idx else tuple(x for x in a[:-1] if isinstance(x, int) and 0 <= x < 10**7)[:8]
     rec.append((name, key, e0, e1))
 
-with torch.no_grad():
+import contextlib
+with (contextlib.nullcontext() if train else torch.no_grad()):
     for _ in range(2):
-        pipe.features(img, pts)
+        run()
     torch.cuda.synchronize()
     _lib.call = timed
     for m in list(sys.modules.values()):
@@ -39,7 +49,7 @@ with torch.no_grad():
             pass  # modules call _lib.call through the module attribute, patched above
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    pipe.features(img, pts)
+    run()
     t1.record()
     torch.cuda.synchronize()
 _lib.call = orig
