@@ -99,6 +99,9 @@ class LoftUpUpsampler(BaseUpsampler):
     # LayerNorms of the query stream (norm_q, FeedForward's, the transformer's final one) are applied inside the
     # epilogue of the GEMM that consumes them, from row statistics the producing GEMM / conv wrote (tc.gemm ln_stats=)
     fuse_layernorm = True
+    # dtype of the returned features; ISegPipeline switches to bf16 when a head consumes them (the head rounds its
+    # input to bf16 anyway: same bits, one 1.2 GB/8-image conversion pass less)
+    out_dtype = torch.float32
 
     def __init__(self, upsampler_path: str = None, n_dim: int = 384, lr_pe_type: str = "sine", lr_size: int = 16):
         super().__init__()
@@ -231,7 +234,7 @@ class LoftUpUpsampler(BaseUpsampler):
         # batch-global min/max is computed once, then images go through in chunks
         mm = torch.empty(6, dtype=torch.int32, device=dev)
         _call("isp_minmax_per_channel", img, mm, B, H, W, img.stride(0), img.stride(1))
-        out = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+        out = torch.empty(B, H, W, C, dtype=self.out_dtype, device=dev)
         for b0 in range(0, B, self.chunk_images):
             b1 = min(B, b0 + self.chunk_images)
             self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w)
@@ -300,4 +303,5 @@ class LoftUpUpsampler(BaseUpsampler):
             del x
             y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
             del xn
-        _call("isp_layernorm_rows", y, 0, C, out.view(M, C), 0, C, P["lnf_w"], P["lnf_b"], M, C, 1e-6)
+        _call("isp_layernorm_rows", y, 0, C, out.view(M, C), int(out.dtype == torch.bfloat16), C, P["lnf_w"], P["lnf_b"],
+              M, C, 1e-6)

@@ -67,6 +67,8 @@ class ISegPipeline(nn.Module):
                 raise ValueError(f"Unknown head type: {head_type}")  # model_builder.py:81-82
             self.head = HEAD_REGISTRY[head_type](**(head_params or {"in_channels": backbone_dim, "num_layers": 2,
                                                                     "num_classes": 1}))
+        if self.head is not None and hasattr(self.upsampler, "out_dtype") and hasattr(self.head, "_features_bf16"):
+            self.upsampler.out_dtype = torch.bfloat16  # the head's own input format: no fp32 round trip in between
         for m in (self.backbone, self.upsampler):  # frozen, as ModelBuilder(freeze=True)
             for p in m.parameters():
                 p.requires_grad = False
