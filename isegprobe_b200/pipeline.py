@@ -86,16 +86,20 @@ class ISegPipeline(nn.Module):
             hr = bilinear_align_corners_nhwc(to_nhwc_f32(hr), tuple(norm_img.shape[2:])).permute(0, 3, 1, 2)
         return hr
 
-    def features_graphed(self, image: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    def features_graphed(self, image: torch.Tensor, points: torch.Tensor, slot: int = 0,
+                         h2d_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """`features` replayed from a CUDA graph (one capture per input shape): the ~700 kernel launches of a
         step -- most of them tens of microseconds in the ViT -- are issued by the GPU front-end instead of
         ~700 Python/ctypes calls, which otherwise leave the device waiting between the small kernels.
         Inference only (no autograd); the result lives in a buffer owned by the graph and is overwritten by
-        the next call with the same shapes."""
+        the next call with the same shapes and the same `slot`.
+        Pipelined serving: alternate `slot` 0/1 and pass a copy stream -- the host->device copy of the next request then
+        runs on `h2d_stream` while the previous request's graph executes (each slot has its own static input / output
+        buffers; the copy waits for the slot's previous replay, the replay waits for the copy)."""
         assert not torch.is_grad_enabled() or not any(p.requires_grad for p in self.embed_coords.parameters()) or \
             not self.training, "features_graphed is an inference path"
         dev = next(self.backbone.parameters()).device  # inputs may be (pinned) host tensors: copied straight into the static buffers
-        key = (tuple(image.shape), tuple(points.shape), image.dtype, points.dtype)
+        key = (tuple(image.shape), tuple(points.shape), image.dtype, points.dtype, slot)
         graphs = self.__dict__.setdefault("_graphs", {})
         entry = graphs.get(key)
         if entry is None:
@@ -111,12 +115,23 @@ class ISegPipeline(nn.Module):
             l0 = _lib.launch_count()
             with torch.cuda.graph(graph), torch.no_grad():
                 out = self.features(s_img, s_pts)
-            entry = (graph, s_img, s_pts, out, _lib.launch_count() - l0)
+            entry = (graph, s_img, s_pts, out, _lib.launch_count() - l0, torch.cuda.Event())
             graphs[key] = entry
-        graph, s_img, s_pts, out, _ = entry
-        s_img.copy_(image, non_blocking=True)
-        s_pts.copy_(points, non_blocking=True)
+        graph, s_img, s_pts, out, _, done = entry
+        cur = torch.cuda.current_stream()
+        if h2d_stream is None:
+            s_img.copy_(image, non_blocking=True)
+            s_pts.copy_(points, non_blocking=True)
+        else:
+            h2d_stream.wait_event(done)  # the slot's previous replay has consumed its inputs
+            with torch.cuda.stream(h2d_stream):
+                s_img.copy_(image, non_blocking=True)
+                s_pts.copy_(points, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(h2d_stream)
+            cur.wait_event(ready)
         graph.replay()
+        done.record(cur)
         return out
 
     def graphed_launches(self) -> int:
