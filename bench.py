@@ -349,7 +349,7 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("adaptive_conv_512_bytes_per_image")
             traffic = traffic * B if traffic else None
-        roofline = {"kernel": "adaptive_conv_nhwc_kernel (JBU stage 512)", "bound": "hbm", "achieved": ach,
+        roofline = {"kernel": "adaptive_conv_v3_kernel (JBU stage 512)", "bound": "hbm", "achieved": ach,
                     "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} hbm copy", "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                     "traffic": traffic, "ms_per_launch": t, "algorithmic_bytes_per_launch": alg}
     elif args.workload in ("loftup", "train") and ktimes.get("loftup_attention"):
