@@ -345,6 +345,88 @@ __global__ void __launch_bounds__(256, 3) bicubic2x_interior_kernel(const float*
     }
 }
 
+// Third generation: the thread marches down a strip of kMarchR low-res rows for its 4 output columns x 4 channels.
+// Every low-res row is loaded once per strip (6 float4) and filtered horizontally once; the last five horizontal
+// results stay in registers and produce two output rows per step (1.1 loads per output float4 instead of 3.75;
+// ncu on the 2x4-blocked kernel: 44 % of the stalls were the loads).  Same summation order as the blocked kernel.
+constexpr int kMarchR = 8;
+__global__ void __launch_bounds__(128, 3) bicubic2x_march_kernel(const float* __restrict__ src, float* __restrict__ out,
+                                                                 int B, int h, int w, int C) {
+  const int C4 = C / 4, wp = (w + 1) / 2, nstrips = (h + kMarchR - 1) / kMarchR;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * nstrips * wp * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long p = idx / C4;
+  const int lp = (int)(p % wp);
+  p /= wp;
+  const int ks = (int)(p % nstrips) * kMarchR, b = (int)(p / nstrips);
+  const int l0 = 2 * lp;
+  float cE[4], cO[4];
+  cubic_coeffs(0.75f, cE);
+  cubic_coeffs(0.25f, cO);
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (long long)b * h * w * C4 + c4;
+  long long xoff[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) xoff[j] = (long long)min(max(l0 - 2 + j, 0), w - 1) * C4;
+  const int PW = 2 * w + 6, PH = 2 * h + 6;
+  float4* o4 = reinterpret_cast<float4*>(out) + (long long)b * PH * PW * C4 + c4;
+  float4 hh[5][4];  // horizontal results of the five most recent rows (oldest first)
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = __ldg(s4 + (long long)min(max(ks - 2, 0), h - 1) * w * C4 + xoff[j]);
+#pragma unroll
+  for (int m = 0; m < kMarchR + 4; ++m) {  // input row ks - 2 + m
+    float4 vn[6];
+    if (m + 1 < kMarchR + 4) {             // next row in flight while this one is filtered
+      const long long yoff = (long long)min(max(ks - 1 + m, 0), h - 1) * w * C4;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) vn[j] = __ldg(s4 + yoff + xoff[j]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hh[r][q] = hh[r + 1][q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* cc = (q & 1) ? cO : cE;
+      const int o0 = (q >> 1) + (q & 1);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a.x = fmaf(v[o0 + j].x, cc[j], a.x);
+        a.y = fmaf(v[o0 + j].y, cc[j], a.y);
+        a.z = fmaf(v[o0 + j].z, cc[j], a.z);
+        a.w = fmaf(v[o0 + j].w, cc[j], a.w);
+      }
+      hh[4][q] = a;
+    }
+    if (m >= 4) {  // rows k-2 .. k+2 are in the window: k = ks + m - 4
+      const int k = ks + m - 4;
+      if (k < h) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float cw = a ? cO[r] : cE[r];
+              const float4 t = hh[r + a][q];
+              o.x = fmaf(t.x, cw, o.x); o.y = fmaf(t.y, cw, o.y); o.z = fmaf(t.z, cw, o.z); o.w = fmaf(t.w, cw, o.w);
+            }
+            const int ox = 2 * l0 + q;
+            if (ox < 2 * w) o4[((long long)(2 * k + a + 3) * PW + ox + 3) * C4] = o;
+          }
+      }
+    }
+    if (m + 1 < kMarchR + 4) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] = vn[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) reflect_border_kernel(float* __restrict__ out, int B, int GH, int GW, int C) {
   const int C4 = C / 4, PW = GW + 6, PH = GH + 6;
   const int nborder = 6 * PW + 6 * GH;  // 3 top + 3 bottom rows, then 3 left + 3 right columns of the middle rows
@@ -423,9 +505,9 @@ extern "C" int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B,
               "jbu_bicubic2x_reflectpad: need h,w >= 2 and C %% 4 == 0 (h=%d w=%d C=%d)", h, w, C);
   ISP_REQUIRE(aligned16(src) && aligned16(out), ISP_ERR_MISALIGNED, "jbu_bicubic2x_reflectpad: 16-byte alignment");
   if (h >= 4 && w >= 4) {  // blocked interior + reflect frame (frame sources lie in the interior)
-    const long long total = (long long)B * h * ((w + 1) / 2) * (C / 4);
-    bicubic2x_interior_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(src, out, B, h, w, C);
-    ISP_CHECK_LAUNCH("bicubic2x_interior_kernel");
+    const long long total = (long long)B * cdiv(h, kMarchR) * ((w + 1) / 2) * (C / 4);
+    bicubic2x_march_kernel<<<cdiv(total, 128), 128, 0, as_stream(stream)>>>(src, out, B, h, w, C);
+    ISP_CHECK_LAUNCH("bicubic2x_march_kernel");
     const long long nb = (long long)B * (6 * (2 * w + 6) + 6 * 2 * h) * (C / 4);
     reflect_border_kernel<<<cdiv(nb, 256), 256, 0, as_stream(stream)>>>(out, B, 2 * h, 2 * w, C);
     ISP_CHECK_LAUNCH("reflect_border_kernel");
