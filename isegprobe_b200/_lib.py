@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisp_b200.so")
+LIB_PATH = os.environ.get("ISP_B200_LIB") or os.path.join(_HERE, "libisp_b200.so")
 
 _c = ctypes
 _P, _I, _F, _LL, _S = _c.c_void_p, _c.c_int, _c.c_float, _c.c_longlong, _c.c_void_p

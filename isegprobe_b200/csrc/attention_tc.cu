@@ -43,6 +43,7 @@ struct Params {
   int o_head_stride;           // column offset between heads in out
   void* out;                   // bf16 [B*rows_per_img, ldo] (direct-store epilogue of the wide-head variant)
   long long ldo;
+  int stagger_ns;              // split mode: the second half's warps start every tile this much later
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz); inputs are <= 8
@@ -71,8 +72,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full,
+  __shared__ __align__(8) uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2],
       pv_done;
+  // Split mode (TMEM has room for two O accumulators: 256 + 2*DV <= 512): the two threads of a query row are fully
+  // independent -- each keeps its own running max / sum for ITS 64 keys of every block and its own accumulator
+  // O_h += P[:, half] V[half] (two K=64 MMAs instead of one K=128); the halves are merged once per tile in the
+  // epilogue.  No per-block max exchange and no barrier between the two warps that share an SM sub-partition, so
+  // one of them can run its exponentials while the other waits for TMEM (measured: the kernel was bound by the
+  // latency of that lock-step chain, not by MUFU -- removing every MUFU only took it from 1.60 to 1.42 ms).
+  constexpr bool kSplit = 256 + 2 * DV <= 512;
   __shared__ uint32_t tmem_base_s;
   __shared__ float xchg[3][2][BQ];  // [slot][half][row]: slots 0/1 = block max (alternating), 2 = partial row sum
 
@@ -93,7 +101,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], 1);
       tc::mbar_init(&s_full[i], 1);
     }
-    tc::mbar_init(&p_full, kSoftmaxWarps); tc::mbar_init(&pv_done, 1);
+    tc::mbar_init(&p_full[0], kSplit ? kSoftmaxWarps / 2 : kSoftmaxWarps);
+    tc::mbar_init(&p_full[1], kSoftmaxWarps / 2);
+    tc::mbar_init(&pv_done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
@@ -166,17 +176,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t kvi = kv_it + j;
         const int s = kvi & 1;
         // O += P(j) V(j): P from TMEM (16 keys = 8 packed columns per MMA), V^T from smem
-        tc::mbar_wait(&p_full, g & 1);
+        tc::mbar_wait(&p_full[0], g & 1);
         tc::mbar_wait(&v_full[s], (kvi >> 1) & 1);
         tc::tc_fence_after();
         {
           const uint32_t dO = tmem + 256, aP = tmem + s * 128;
           const uint32_t va = v_lo + s * kVStage;
+          if constexpr (kSplit) {
 #pragma unroll
-          for (int k = 0; k < BKEY / 16; ++k) {
-            const uint32_t boff = (k >> 2) * kVChunk + (k & 3) * 32;
-            const uint64_t db = tc::smem_desc_k_sw128(va + boff);
-            if (leader) tc::umma_bf16_ts(dO, aP + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
+            for (int k = 0; k < BKEY / 32; ++k) {  // keys 0..63 -> accumulator 0 (P at S columns 0..31)
+              const uint64_t db = tc::smem_desc_k_sw128(va + (k & 3) * 32);
+              if (leader) tc::umma_bf16_ts(dO, aP + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
+            }
+            tc::mbar_wait(&p_full[1], g & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < BKEY / 32; ++k) {  // keys 64..127 -> accumulator 1 (P at S columns 64..95)
+              const uint64_t db = tc::smem_desc_k_sw128(va + kVChunk + (k & 3) * 32);
+              if (leader) tc::umma_bf16_ts(dO + DV, aP + 64 + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BKEY / 16; ++k) {
+              const uint32_t boff = (k >> 2) * kVChunk + (k & 3) * 32;
+              const uint64_t db = tc::smem_desc_k_sw128(va + boff);
+              if (leader) tc::umma_bf16_ts(dO, aP + k * 8, db, idesc_pv, (j | k) ? 1u : 0u);
+            }
           }
           if (leader) {
             tc::umma_commit(&v_empty[s]);
@@ -198,6 +223,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int r = q * 32 + lane;     // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t tO = tmem + 256 + lane_addr;
+    const uint32_t tOh = tO + (kSplit ? half * DV : 0);  // split mode: this thread's own accumulator
     const int bar_id = 1 + q;        // named barrier shared by the two warps of this quarter
     float* my_x = &xchg[0][half][r];
     const float* other_x = &xchg[0][half ^ 1][r];
@@ -210,6 +236,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const long long tq = it / p.heads;
       const int b = (int)(tq / p.tiles_per_img);
       const int qt = (int)(tq % p.tiles_per_img);
+      if (kSplit && half && p.stagger_ns) __nanosleep(p.stagger_ns);
       float m_ref = -INFINITY;  // exponent reference, in log2 units (s * log2e); identical in both threads of a row
       float l = 0.f;            // this thread's part of the row sum
       for (int j = 0; j < nb; ++j, ++g) {
@@ -239,9 +266,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // this thread's S loads before the partner's P stores (P aliases the first 64 columns of S).
         // Slots alternate per block: the partner reads slot (j&1) right after barrier j and cannot pass
         // barrier j+1 before that, so the write of block j+2 to the same slot is safe.
-        my_x[(j & 1) * kSlot] = mine;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        const float mj = fmaxf(mine, other_x[(j & 1) * kSlot]) * kLog2e;
+        float mj;
+        if constexpr (kSplit) {
+          mj = mine * kLog2e;  // this half's own reference: nothing to exchange
+        } else {
+          my_x[(j & 1) * kSlot] = mine;
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          mj = fmaxf(mine, other_x[(j & 1) * kSlot]) * kLog2e;
+        }
         // lazy max update: only move the reference when the row max grew by more than 2^8
         float scale = 1.f;
         bool need = false;
@@ -254,16 +286,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc::mbar_wait(&pv_done, (g - 1) & 1);
           tc::tc_fence_after();
           const float f = need ? scale : 1.f;
-          for (int c = oc0; c < oc1; c += 16) {
+          for (int c = kSplit ? 0 : oc0; c < (kSplit ? DV : oc1); c += 16) {
             uint32_t o[16];
-            tc::tmem_ld16(tO + c, o);
+            tc::tmem_ld16(tOh + c, o);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-            tc::tmem_st16(tO + c, o);
+            tc::tmem_st16(tOh + c, o);
           }
         }
-        const float neg_m = -m_ref;
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;  // a half with no valid key yet: P = 2^-inf = 0
         float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // 16 keys -> 8 packed bf16x2 columns of P
@@ -276,20 +308,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             __nv_bfloat162 bb = __floats2bfloat162_rn(p0, p1);
             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&bb);
           }
-          tc::tmem_st8(tS + half * 32 + c * 8, pk);
+          tc::tmem_st8(tS + half * (kSplit ? 64 : 32) + c * 8, pk);  // split mode: inside this thread's own S columns
         }
         l = l * scale + (rs[0] + rs[1]) + (rs[2] + rs[3]);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&p_full);
+        if (lane == 0) tc::mbar_arrive(&p_full[kSplit ? half : 0]);
       }
       // epilogue: O / l -> bf16 -> dense smem tile -> one TMA store (clipped at the image's last row);
       // the wide-head variant has no smem left for the tile and stores its rows directly
       my_x[2 * kSlot] = l;
+      if constexpr (kSplit) my_x[0] = m_ref;
       if (PL::kStageO && sw == 0 && lane == 0) tc::tma_store_wait_read<0>();  // previous tile's store has read the staging tile
       asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
-      const float inv = 1.f / (l + other_x[2 * kSlot]);
+      float inv, f0 = 1.f, f1 = 0.f;  // O = (O_0 f0 + O_1 f1) * inv
+      if constexpr (kSplit) {
+        const float m_o = other_x[0], l_o = other_x[2 * kSlot];
+        const float m = fmaxf(m_ref, m_o);
+        const float f_me = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m);
+        const float f_o = (m_o == -INFINITY) ? 0.f : ex2_approx(m_o - m);
+        inv = 1.f / (l * f_me + l_o * f_o);
+        f0 = half ? f_o : f_me;
+        f1 = half ? f_me : f_o;
+      } else {
+        inv = 1.f / (l + other_x[2 * kSlot]);
+      }
       tc::mbar_wait(&pv_done, (g - 1) & 1);
       tc::tc_fence_after();
       const long long row_local = (long long)qt * BQ + r;
@@ -300,7 +344,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int c = oc0; c < oc1; c += 16) {
         uint32_t o[16];
         tc::tmem_ld16(tO + c, o);
-        tc::tmem_ld_wait();
+        if constexpr (kSplit) {
+          uint32_t o1[16];
+          tc::tmem_ld16(tO + DV + c, o1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            o[e] = __float_as_uint(fmaf(__uint_as_float(o[e]), f0, __uint_as_float(o1[e]) * f1));
+        } else {
+          tc::tmem_ld_wait();
+        }
         uint32_t w[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -364,6 +417,8 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
   p.q_head_stride = q_head_stride;
   p.o_head_stride = o_head_stride;
   p.out = out; p.ldo = ldo;
+  p.stagger_ns = 400;  // measured 150..800 ns: 1.53 -> 1.48 ms on the LoftUp shape (the two warps of an SM sub-partition
+                       // then alternate between their TMEM-load and exponential phases instead of colliding)
   const long long nkp = (long long)p.nblocks * attn::BKEY;
   CUtensorMap tmQ, tmK, tmV, tmO;
   {  // out viewed as [B][rows_per_img][ldo]: a tile's store is clipped at its own image's last row
