@@ -155,7 +155,7 @@ def run_eval(args, rank, world, dev, dist):
     n_w, n_t = max(args.warmup, 3), args.steps
     samples = ev.synthetic_dataset("grabcut", n=(n_w + n_t) * world, seed=0)
     mine = [samples[i] for i in idist.shard_indices(len(samples), world, rank)]
-    pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True)
+    pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True, use_graph=True)
     for img, gt in mine[:n_w]:
         ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=3)
     if dist is not None:
@@ -176,7 +176,10 @@ def run_eval(args, rank, world, dev, dist):
         sampler.stop_flag = True
         sampler.join()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0  # eager launches (none when every click replays the graph) ...
+    fwd_graphs = pipe.__dict__.get("_fwd_graphs", {})
+    if fwd_graphs:                         # ... plus the kernels inside each replayed graph
+        launches += list(fwd_graphs.values())[-1][4] * 20 * n_t
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

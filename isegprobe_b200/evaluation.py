@@ -220,8 +220,12 @@ class FixedSizePredictor:
     """BasePredictor with the transform stack [ZoomIn, SigmoidForPred, AddHorizontalFlip]."""
 
     def __init__(self, net, device, target_size=(448, 448), with_flip: bool = True, net_clicks_limit: Optional[int] = None,
-                 zoom_in: Optional[ZoomIn] = "default") -> None:
+                 zoom_in: Optional[ZoomIn] = "default", use_graph: bool = False, graph_clicks: int = 24) -> None:
+        """use_graph: run the network through ISegPipeline.forward_graphed.  The click tensor is then padded to
+        `graph_clicks` entries per polarity with (-1,-1,-1) rows -- invalid clicks, which DistMaps ignores
+        (core/model/ops.py:44-52), so the prediction is unchanged -- to keep one graph for every click count."""
         self.net, self.device = net, device
+        self.use_graph, self.graph_clicks = use_graph and hasattr(net, "forward_graphed"), graph_clicks
         self.with_flip, self.net_clicks_limit = with_flip, net_clicks_limit
         self.zoom_in = ZoomIn(skip_clicks=-1, target_size=tuple(target_size)) if zoom_in == "default" else zoom_in
         self.original_image = None
@@ -247,6 +251,8 @@ class FixedSizePredictor:
         if self.net_clicks_limit is not None:
             n = min(self.net_clicks_limit, n)
         n = max(1, n)
+        if self.use_graph and n <= self.graph_clicks:
+            n = self.graph_clicks
         total = []
         for cl in clicks_lists:
             cl = cl[: self.net_clicks_limit]
@@ -268,7 +274,11 @@ class FixedSizePredictor:
             image = torch.cat([image, torch.flip(image, dims=[3])], dim=0)
             clicks_lists = clicks_lists + [[c.copy(coords=(c.coords[0], width - c.coords[1] - 1)) for c in cl]
                                            for cl in clicks_lists]
-        logits = self.net(image, self.get_points_nd(clicks_lists))["instances"]
+        points = self.get_points_nd(clicks_lists)
+        if self.use_graph and points.shape[1] == 2 * self.graph_clicks:
+            logits = self.net.forward_graphed(image, points)
+        else:
+            logits = self.net(image, points)["instances"]
         pred = F.interpolate(logits.float(), mode="bilinear", align_corners=True, size=image.shape[2:])
         if self.with_flip:  # inverse transforms run in reverse order: flip, sigmoid, zoom-in
             n = pred.shape[0] // 2

@@ -252,3 +252,27 @@ def test_features_graphed_equals_eager(isp, up_type, params):
             b = pipe.features_graphed(image, pts).clone()
         assert torch.equal(a, b)
     assert pipe.graphed_launches() > 50
+
+
+def test_predictor_graph_replay_equals_eager(isp):
+    """FixedSizePredictor(use_graph=True): the network call is one CUDA-graph replay with the click tensor padded by
+    invalid (-1,-1,-1) rows; IoU curves and probability maps are identical to the eager predictor's."""
+    from isegprobe_b200 import evaluation as ev
+    torch.manual_seed(0)
+    S = 112
+    pipe = isp.ISegPipeline("loftup", {"upsampler_path": None, "n_dim": 384}).to(DEV).eval()
+    pipe.embed_coords = isp.PatchEmbed((S, S), (14, 14), 3, 384).to(DEV).eval()
+    samples = ev.synthetic_dataset("grabcut", n=2, seed=4)
+    res = {}
+    for use_graph in (False, True):
+        pred = ev.FixedSizePredictor(pipe, torch.device(DEV), target_size=(S, S), with_flip=True, use_graph=use_graph)
+        res[use_graph] = ev.evaluate_dataset_sharded(samples, pred, max_iou_thr=1.01, max_clicks=4)
+        img, gt = samples[0]
+        clicker = ev.Clicker(gt_mask=gt)
+        clicker.make_next_click(np.zeros_like(gt))
+        pred.set_input_image(img)
+        with torch.no_grad():
+            res[(use_graph, "p")] = pred.get_prediction(clicker)
+    assert all(np.array_equal(a, b) for a, b in zip(res[False], res[True]))
+    assert np.array_equal(res[(False, "p")], res[(True, "p")])
+    assert len(pipe.__dict__["_fwd_graphs"]) == 1
