@@ -76,6 +76,11 @@ struct Params {
   int pair;           // 1: a CTA works on TWO vertically adjacent 128-row tiles at once (both TMEM accumulators), loading
                       // the weight tile once for both -- 0.67x the L2->SM operand bytes per MAC (the conv kernels sit at
                       // the ~12 TB/s L2->SM ceiling); the epilogue then does not overlap the next tile's MMAs
+  int cta2;           // 1: launched as clusters of two CTAs that form a CTA pair (tcgen05 cta_group::2).  The pair computes
+                      // two vertically adjacent tiles (or tile pairs) of one column tile with ONE 256-row MMA: each CTA
+                      // loads its own 128 A rows and only HALF of the weight tile, the tensor cores read both halves.
+                      // Per-SM operand fill per MAC x0.67 (x0.78 on top of pair mode) -- the fill rate (~49 B/clk/SM)
+                      // is what bounds these kernels -- while every CTA keeps its own accumulators and epilogue.
   int epi_bufs;       // staging chunks per epilogue warp: 2, or 1 (pair mode without residual: the 32 KB go to a third
                       // pipeline stage instead)
   int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
@@ -159,11 +164,12 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 //   tcgen05.ld 32 columns -> bias (from smem) / activation / alpha -> + residual read from the
 //   staging buffer (row per thread, swizzle makes it conflict-free) -> written back IN PLACE ->
 //   TMA store of the chunk.  All global traffic is bulk; OOB rows / columns are clipped by TMA.
-template <bool OUT_BF16, int ACT, bool RESID>
+template <bool OUT_BF16, int ACT, bool RESID, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmDt,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRt, const Params p) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRt,
+               const __grid_constant__ CUtensorMap tmBh, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t resid_bar[kEpiWarps][2];
@@ -172,11 +178,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_half = BM * BK * 2;
-  const uint32_t a_bytes = a_half << p.pair, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
-  // work unit = one tile, or (pair mode) the tiles (2i, n) and (2i+1, n); tiles_m is even in pair mode
-  const long long ntiles = (p.tiles_m >> p.pair) * p.tiles_n;
+  // this CTA's share of the weight tile: all of it, or (CTA pair) its half
+  const uint32_t a_bytes = a_half << p.pair, b_bytes = ((uint32_t)p.BN >> (CTA2 ? 1 : 0)) * BK * 2, stage_bytes = a_bytes + b_bytes;
+  // work unit of a CTA = one tile, or (pair mode) two vertically adjacent tiles; the two CTAs of a CTA pair take
+  // adjacent units of the same column tile.  tiles_m is a multiple of the tiles per cluster unit.
+  const uint32_t crank = CTA2 ? tc::cluster_ctarank() : 0u;
+  const int gshift = p.pair + (CTA2 ? 1 : 0);
+  const long long ntiles = (p.tiles_m >> gshift) * p.tiles_n;   // units per CTA stream
+  const long long u0 = blockIdx.x >> (CTA2 ? 1 : 0), ustep = gridDim.x >> (CTA2 ? 1 : 0);
   auto unit_tile = [&](long long u, int sub) -> long long {
-    return p.pair ? ((2 * (u / p.tiles_n) + sub) * p.tiles_n + u % p.tiles_n) : u;
+    return gshift ? ((((u / p.tiles_n) << gshift) + (crank << p.pair) + sub) * p.tiles_n + u % p.tiles_n) : u;
   };
   const int kblocks = p.K / BK;
   uint8_t* epi_smem = smem + kSmemBytes - kEpiWarps * 4096 * p.epi_bufs;
@@ -186,14 +197,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::prefetch_tmap(&tmB);
     tc::prefetch_tmap(&tmD);
     if (RESID) tc::prefetch_tmap(&tmR);
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps); }
+    // CTA pair: the leader's full barrier also counts the peer's producer, its tempty barrier the peer's epilogue warps
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1u << (CTA2 ? 1 : 0)); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps << (CTA2 ? 1 : 0)); }
     for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&resid_bar[w][0], 1); tc::mbar_init(&resid_bar[w][1], 1); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+  if (warp == 1) {
+    if (CTA2) tc::tmem_alloc_2sm(&tmem_base_s, kTmemCols);
+    else tc::tmem_alloc(&tmem_base_s, kTmemCols);
+  }
   tc::tc_fence_before();
   __syncthreads();
+  if (CTA2) tc::cluster_sync();  // the peer's barriers exist before anything is signalled across the pair
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -201,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (long long t = u0; t < ntiles; t += ustep) {
         const TileCoord tc_ = tile_coord(p, unit_tile(t, 0));
         const TileCoord tc2 = tile_coord(p, unit_tile(t, 1));
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -210,6 +226,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
+          if (CTA2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            else tc::mbar_arrive_leader(&full_bar[s]);
+            if (p.TW) {
+              const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+              const int r = tap / 3, q = tap - r * 3;
+              tc::tma_load_4d_2sm(sa, &tmA, &full_bar[s], cc * BK, tc_.w0 + q - 1, tc_.h0 + r - 1, tc_.img);
+              if (p.pair)
+                tc::tma_load_4d_2sm(sa + a_half, &tmA, &full_bar[s], cc * BK, tc2.w0 + q - 1, tc2.h0 + r - 1, tc2.img);
+            } else {
+              tc::tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0);
+              if (p.pair) tc::tma_load_2d_2sm(sa + a_half, &tmA, &full_bar[s], kb * BK, (int)tc2.m0);
+            }
+            tc::tma_load_2d_2sm(sb, &tmBh, &full_bar[s], kb * BK, tc_.n0 + (int)crank * (p.BN >> 1));
+            continue;
+          }
           tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           if (p.TW) {
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
@@ -225,12 +258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = tc::idesc_bf16_f32(BM, p.BN);
+    // ------------------------------------------------------------- MMA issuer (CTA pair: the leader CTA only)
+    const uint32_t idesc = tc::idesc_bf16_f32(BM << (CTA2 ? 1 : 0), p.BN);
     const int last_in = p.TW ? p.cin_chunks - 1 : kblocks - 1;  // k-block (within a tap / the row) that may be partial
     const int period = p.TW ? p.cin_chunks : kblocks;
     uint32_t it = 0, tl = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+    for (long long t = u0; t < ntiles && crank == 0; t += ustep, ++tl) {
       // pair mode: the unit owns both accumulators (virtual tiles 2*tl and 2*tl+1 of the epilogue's numbering)
       const uint32_t acc = p.pair ? 0u : (tl & 1), aph = p.pair ? (tl & 1) : ((tl >> 1) & 1);
       tc::mbar_wait(&tempty_bar[acc], aph ^ 1);
@@ -250,21 +283,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nsteps = (kin == last_in) ? p.last_steps : BK / 16;
           // +32 B per 16-element K step inside the 128B swizzle row; fully unrolled so the descriptors
           // sit in uniform registers (a rolled loop made the issue slower than the MMAs themselves)
-          tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
-          if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-          if (nsteps > 2) tc::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-          if (nsteps > 3) tc::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-          if (p.pair) {  // second tile of the pair: A rows 128..255 of the stage (+16 KB), same weight tile
-            const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
-            tc::umma_bf16(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
-            if (nsteps > 1) tc::umma_bf16(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
-            if (nsteps > 2) tc::umma_bf16(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
-            if (nsteps > 3) tc::umma_bf16(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
-          }
-          tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
-          if (kb == kblocks - 1) {                                 // accumulator(s) complete
-            tc::umma_commit(&tfull_bar[acc]);
-            if (p.pair) tc::umma_commit(&tfull_bar[1]);
+          if (CTA2) {
+            tc::umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+            if (nsteps > 1) tc::umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            if (nsteps > 2) tc::umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            if (nsteps > 3) tc::umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            if (p.pair) {
+              const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
+              tc::umma_bf16_2sm(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
+              if (nsteps > 1) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
+              if (nsteps > 2) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
+              if (nsteps > 3) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
+            }
+            tc::umma_commit_2sm(&empty_bar[s]);                    // both CTAs' smem slots free when these retire
+            if (kb == kblocks - 1) {                                 // accumulators complete in both CTAs
+              tc::umma_commit_2sm(&tfull_bar[acc]);
+              if (p.pair) tc::umma_commit_2sm(&tfull_bar[1]);
+            }
+          } else {
+            tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+            if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            if (nsteps > 2) tc::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            if (nsteps > 3) tc::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            if (p.pair) {  // second tile of the pair: A rows 128..255 of the stage (+16 KB), same weight tile
+              const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
+              tc::umma_bf16(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
+              if (nsteps > 1) tc::umma_bf16(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
+              if (nsteps > 2) tc::umma_bf16(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
+              if (nsteps > 3) tc::umma_bf16(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
+            }
+            tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
+            if (kb == kblocks - 1) {                                 // accumulator(s) complete
+              tc::umma_commit(&tfull_bar[acc]);
+              if (p.pair) tc::umma_commit(&tfull_bar[1]);
+            }
           }
         }
         __syncwarp();
@@ -288,8 +340,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = lane, r7 = lane & 7;
     uint32_t tl = 0, st_seq = 0, rph0 = 0, rph1 = 0;
     const long long nvirt = ntiles << p.pair;  // virtual tiles of this kernel: accumulator tl & 1, in MMA completion order
-    for (long long vt = (long long)blockIdx.x << p.pair; vt < nvirt;
-         vt += (vt & p.pair) ? (((long long)gridDim.x << 1) - 1) : (p.pair ? 1 : gridDim.x), ++tl) {
+    for (long long vt = u0 << p.pair; vt < nvirt;
+         vt += (vt & p.pair) ? ((ustep << 1) - 1) : (p.pair ? 1 : ustep), ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       const TileCoord tc_ = tile_coord(p, unit_tile(vt >> p.pair, (int)(vt & p.pair)));
       int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
@@ -496,13 +548,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {  // accumulator drained (CTA pair: only the leader's MMA warp waits, on the leader's barrier)
+        if (CTA2) tc::mbar_arrive_leader(&tempty_bar[acc]);
+        else tc::mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA retires
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (CTA2) tc::cluster_sync();  // no CTA leaves (or frees TMEM) while its peer may still signal / the pair MMA runs
+  if (warp == 1) {
+    if (CTA2) tc::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 static int pick_bn(int N, int max_bn) {
@@ -516,53 +575,92 @@ static int pick_bn(int N, int max_bn) {
   return max_bn;
 }
 
-typedef void (*kernel_fn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Params);
+typedef void (*kernel_fn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Params);
 
-template <bool OB, bool RS>
+template <bool OB, bool RS, bool C2>
 static kernel_fn pick_act(int act) {
   switch (act) {
-    case 0: return gemm_tc_kernel<OB, 0, RS>;
-    case 1: return gemm_tc_kernel<OB, 1, RS>;
-    case 2: return gemm_tc_kernel<OB, 2, RS>;
-    case 3: return gemm_tc_kernel<OB, 3, RS>;
-    default: return gemm_tc_kernel<OB, 4, RS>;
+    case 0: return gemm_tc_kernel<OB, 0, RS, C2>;
+    case 1: return gemm_tc_kernel<OB, 1, RS, C2>;
+    case 2: return gemm_tc_kernel<OB, 2, RS, C2>;
+    case 3: return gemm_tc_kernel<OB, 3, RS, C2>;
+    default: return gemm_tc_kernel<OB, 4, RS, C2>;
   }
 }
 
+// C2: the CTA-pair instantiation (cta_group::2 instructions: it can only be launched in clusters of two CTAs)
+template <bool C2>
 static kernel_fn pick_kernel(int out_bf16, int act, bool resid) {
-  if (act == 5) return out_bf16 ? gemm_tc_kernel<true, 5, true> : gemm_tc_kernel<false, 5, true>;  // ReLU-mask epilogue
-  if (resid) return out_bf16 ? pick_act<true, true>(act) : pick_act<false, true>(act);
-  return out_bf16 ? pick_act<true, false>(act) : pick_act<false, false>(act);
+  if (act == 5) return out_bf16 ? gemm_tc_kernel<true, 5, true, C2> : gemm_tc_kernel<false, 5, true, C2>;  // ReLU-mask epilogue
+  if (resid) return out_bf16 ? pick_act<true, true, C2>(act) : pick_act<false, true, C2>(act);
+  return out_bf16 ? pick_act<true, false, C2>(act) : pick_act<false, false, C2>(act);
 }
 
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmDt,
-                  const CUtensorMap& tmR, const CUtensorMap& tmRt, Params& p, int out_bf16, int act, bool resid,
-                  cudaStream_t stream) {
+                  const CUtensorMap& tmR, const CUtensorMap& tmRt, const CUtensorMap& tmBh, Params& p, int out_bf16,
+                  int act, bool resid, cudaStream_t stream) {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     ISP_CUDA(cudaGetDevice(&dev));
     ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  kernel_fn fn = pick_kernel(out_bf16, act, resid);
-  static kernel_fn attr_done[32];
-  static int n_attr = 0;
-  bool seen = false;
-  for (int i = 0; i < n_attr; ++i) seen |= attr_done[i] == fn;
-  if (!seen) {
-    ISP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    if (n_attr < 32) attr_done[n_attr++] = fn;
-  }
   // pairing halves the number of work units: only when there are at least two waves of pairs
   if (p.pair && ((p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
-  const int stage_bytes = (BM * BK * 2 << p.pair) + p.BN * BK * 2;
+  auto prepare = [](kernel_fn f) -> int {  // opt in to 224 KB of dynamic shared memory, once per instantiation
+    static kernel_fn attr_done[64];
+    static int n_attr = 0;
+    for (int i = 0; i < n_attr; ++i)
+      if (attr_done[i] == f) return ISP_OK;
+    ISP_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (n_attr < 64) attr_done[n_attr++] = f;
+    return ISP_OK;
+  };
+  // CTA-pair mode: tiles per cluster unit divide tiles_m (the weight tile always splits into two swizzle-aligned
+  // halves: BN % 16 == 0) and there are at least two waves of cluster units
+  static int max_clusters = -1;  // co-resident 2-CTA clusters of the pair kernel (224 KB smem: one CTA per SM)
+  static const int cta2_env = getenv("ISP_GEMM_CTA2") ? atoi(getenv("ISP_GEMM_CTA2")) : 1;
+  if (max_clusters < 0) {
+    kernel_fn f2 = pick_kernel<true>(out_bf16, act, resid);
+    if (int e = prepare(f2)) return e;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(num_sms & ~1); q.blockDim = dim3(kThreads); q.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, f2, &q) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    max_clusters = n;
+  }
+  const int G = 2 << p.pair;
+  p.cta2 = (cta2_env && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
+            (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters) ? 1 : 0;
+  const int stage_bytes = (BM * BK * 2 << p.pair) + (p.BN >> p.cta2) * BK * 2;
   p.epi_bufs = (p.pair && !resid) ? 1 : 2;
   p.stages = (kSmemBytes - kEpiWarps * 4096 * p.epi_bufs) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
+  if (p.cta2) {
+    kernel_fn fn = pick_kernel<true>(out_bf16, act, resid);
+    if (int e = prepare(fn)) return e;
+    const long long nunits = (p.tiles_m / G) * p.tiles_n;
+    const int ncl = (int)(nunits < max_clusters ? nunits : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ISP_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmD, tmDt, tmR, tmRt, tmBh, p));
+    ::isp::count_launch(1);
+    return ISP_OK;
+  }
+  kernel_fn fn = pick_kernel<false>(out_bf16, act, resid);
+  if (int e = prepare(fn)) return e;
   const long long ntiles = (p.tiles_m >> p.pair) * p.tiles_n;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  fn<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, tmR, tmRt, p);
+  fn<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmD, tmDt, tmR, tmRt, tmBh, p);
   ISP_CHECK_LAUNCH("gemm_tc_kernel");
   return ISP_OK;
 }
@@ -616,7 +714,7 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
                 "gemm_bf16_tc_ex: stats_slots must be %d for N=%d (ask isp_gemm_stats_slots)", need, N);
     p.stats_out = stats_out; p.stats_slots = stats_slots;
   }
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmD, tmBh;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)lda * 2};
     const uint32_t box[2] = {gemm::BK, gemm::BM};
@@ -626,6 +724,8 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {2, (uint64_t)ldw * 2};
     const uint32_t box[2] = {gemm::BK, (uint32_t)p.BN};
     if (int e = make_tmap_bf16(&tmB, W, 2, dims, str, box, "gemm_bf16_tc(W)")) return e;
+    const uint32_t boxh[2] = {gemm::BK, (uint32_t)p.BN / 2};  // half tile (CTA-pair mode: one half per CTA)
+    if (int e = make_tmap_bf16(&tmBh, W, 2, dims, str, boxh, "gemm_bf16_tc(W half)")) return e;
   }
   const uint32_t cw = out_bf16 ? 64 : 32;
   const uint32_t tailw = (uint32_t)p.BN % cw;  // narrower last chunk of every tile (0 = none)
@@ -643,7 +743,7 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
     if (int e = make_tmap(&tmR, esz, resid, 2, dims, str, box, "gemm_bf16_tc(resid)", true)) return e;
     if (int e = make_tmap(&tmRt, esz, resid, 2, dims, str, boxt, "gemm_bf16_tc(resid tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, resid != nullptr, as_stream(stream));
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, tmBh, p, out_bf16, act, resid != nullptr, as_stream(stream));
 }
 
 extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias,
@@ -717,7 +817,7 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
     ISP_REQUIRE(stats_slots == need, ISP_ERR_BAD_SHAPE, "conv3x3_bf16_tc_ex: stats_slots must be %d for Cout=%d", need, Cout);
     p.stats_out = stats_out; p.stats_slots = stats_slots;
   }
-  CUtensorMap tmA, tmB, tmD, tmDt;
+  CUtensorMap tmA, tmB, tmD, tmDt, tmBh;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)Nimg};
     const uint64_t str[4] = {2, (uint64_t)ldx * 2, (uint64_t)Wd * ldx * 2, (uint64_t)H * Wd * ldx * 2};
@@ -728,6 +828,8 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
     const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)Cout}, str[2] = {2, (uint64_t)p.K * 2};
     const uint32_t box[2] = {gemm::BK, (uint32_t)p.BN};
     if (int e = make_tmap_bf16(&tmB, Wp, 2, dims, str, box, "conv3x3_bf16_tc(W)")) return e;
+    const uint32_t boxh[2] = {gemm::BK, (uint32_t)p.BN / 2};
+    if (int e = make_tmap_bf16(&tmBh, Wp, 2, dims, str, boxh, "conv3x3_bf16_tc(W half)")) return e;
   }
   {
     const uint32_t bw = TW < 32 ? TW : 32;
@@ -748,7 +850,7 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
     if (int e = make_tmap(&tmR, esz, mask, 4, dims, str, box, "conv3x3_dgrad_bf16_tc(mask)", true)) return e;
     if (int e = make_tmap(&tmRt, esz, mask, 4, dims, str, boxt, "conv3x3_dgrad_bf16_tc(mask tail)", false)) return e;
   }
-  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, p, out_bf16, act, mask != nullptr, as_stream(stream));
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, tmBh, p, out_bf16, act, mask != nullptr, as_stream(stream));
 }
 
 extern "C" int isp_conv3x3_bf16_tc(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16,
