@@ -185,6 +185,35 @@ int isp_head_classifier_bwd(const void* act_bf16, long long lda, const float* dl
                             isp_stream_t stream);
 int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, int C, isp_stream_t stream);
 
+/* Activation backward through the frozen ViT: the reference trains the click embedding THROUGH the frozen
+ * backbone (core/model/featurizers/DINOv2.py:518-523 injects it before the blocks; trainer backward
+ * core/training/trainer.py:213-221), so d(loss)/d(additional_features) needs every block's input gradient
+ * (dinov2/layers/block.py:92-117, attention.py:54-71, mlp.py:34-40).  Weight-side GEMMs of that backward are
+ * isp_gemm_bf16_tc with transposed packed weights; the per-head attention products use
+ *   isp_gemm_bf16_tc_batched: for every (batch b, head h)  D[b,h] (M x N) = alpha * A[b,h] (M x K) . W[b,h]^T (N x K),
+ *     bf16 operands with unit stride along K, D bf16 | f32 with unit stride along N, all other strides
+ *     (row, head, batch; in elements) explicit -- heads may be column slices of a packed [tokens, 3C] matrix.
+ * Row / element kernels:
+ *   isp_layernorm_rows_bwd: dx = LN'(x)^T (gamma * dy) + resid (fp32; optional bf16 copy of dx), C <= 1024;
+ *   isp_gelu_bwd_bf16:      dpre = dh * gelu'(pre)  (nn.GELU, erf form), n even;
+ *   isp_softmax_rows:       P[r, :ncols] = softmax(S[r, :ncols]) (fp32 -> bf16), zeros up to ncols_pad;
+ *   isp_attn_ds_rows:       dS = P * (dP - sum_j P dP) per row, zeros up to ncols_pad;
+ *   isp_transpose_bf16_batched: dst[z][c][r] = src[z][r][c]. */
+int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
+                             long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
+                             long long d_sb, int out_bf16, int M, int N, int K, int H, int B, float alpha,
+                             isp_stream_t stream);
+int isp_layernorm_rows_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+                           const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
+                           long long M, int C, float eps, isp_stream_t stream);
+int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream);
+int isp_softmax_rows(const float* S, long long lds, void* P_bf16, long long ldp, long long R, int ncols, int ncols_pad,
+                     isp_stream_t stream);
+int isp_attn_ds_rows(const void* P_bf16, long long ldp, const float* dP, long long lddp, void* dS_bf16, long long ldds,
+                     long long R, int ncols, int ncols_pad, isp_stream_t stream);
+int isp_transpose_bf16_batched(const void* src, long long lds, long long src_z, void* dst, long long ldd, long long dst_z,
+                               int Z, int R, int C, isp_stream_t stream);
+
 /* Flash-style attention on tcgen05: out = softmax(Q K^T) V, scores never leave the SM.
  * Q bf16 [B*rows_per_img, ldq] (pre-scaled by 1/sqrt(d)), head h at column h*q_head_stride;
  * K bf16 [B, heads, ceil128(nkeys), DKC] and Vt bf16 [B, heads, DV, ceil128(nkeys)], zero

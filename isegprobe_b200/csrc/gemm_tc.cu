@@ -76,6 +76,8 @@ struct Params {
   int pair;           // 1: a CTA works on TWO vertically adjacent 128-row tiles at once (both TMEM accumulators), loading
                       // the weight tile once for both -- 0.67x the L2->SM operand bytes per MAC (the conv kernels sit at
                       // the ~12 TB/s L2->SM ceiling); the epilogue then does not overlap the next tile's MMAs
+  int batched;        // > 0: `batched` independent problems per "head" x `nbatch` "batches" with their own A / W / D
+  int nbatch;         // (4-D tensor maps: column, row, head, batch); tiles_m then counts the row tiles of ALL problems
   int cta2;           // 1: launched as clusters of two CTAs that form a CTA pair (tcgen05 cta_group::2).  The pair computes
                       // two vertically adjacent tiles (or tile pairs) of one column tile with ONE 256-row MMA: each CTA
                       // loads its own 128 A rows and only HALF of the weight tile, the tensor cores read both halves.
@@ -142,7 +144,13 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
   c.n0 = (int)(t % p.tiles_n) * p.BN;
   c.m0 = tm * BM;
   c.img = c.h0 = c.w0 = 0;
-  if (p.TW) {
+  if (p.batched) {  // problem z = (batch, head), row tile inside it
+    const long long per = p.tiles_m / ((long long)p.batched * p.nbatch);
+    const long long z = tm / per;
+    c.m0 = (tm % per) * BM;
+    c.h0 = (int)(z % p.batched);
+    c.img = (int)(z / p.batched);
+  } else if (p.TW) {
     const int per_img = p.tiles_w * p.tiles_h;
     c.img = (int)(tm / per_img);
     const int r = (int)(tm % per_img);
@@ -244,6 +252,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             continue;
           }
           tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          if (p.batched) {
+            tc::tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0, tc_.h0, tc_.img);
+            tc::tma_load_4d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0, tc_.h0, tc_.img);
+            continue;
+          }
           if (p.TW) {
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
             const int r = tap / 3, q = tap - r * 3;
@@ -353,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         c3 = tc_.img;
       } else {
         c1 = (int)tc_.m0 + q * 32;
+        if (p.batched) { c2 = tc_.h0; c3 = tc_.img; }
       }
       // bias slice of this tile -> smem (zeros beyond N, so padded columns come out as exact zeros)
       epi_bar_sync();  // every epilogue warp is done with the previous tile's bias / g slice
@@ -541,7 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) {
           const CUtensorMap* m = is_tail ? &tmDt : &tmD;
-          if (p.TW) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
+          if (p.TW || p.batched) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
           else tc::tma_store_2d(m, obuf, nglob, c1);
           tc::tma_store_commit();
         }
@@ -606,7 +620,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   // pairing halves the number of work units: only when there are at least two waves of pairs
-  if (p.pair && ((p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
+  if (p.pair && (p.batched || (p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
   auto prepare = [](kernel_fn f) -> int {  // opt in to 224 KB of dynamic shared memory, once per instantiation
     static kernel_fn attr_done[64];
     static int n_attr = 0;
@@ -634,7 +648,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     max_clusters = n;
   }
   const int G = 2 << p.pair;
-  p.cta2 = (cta2_env && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
+  p.cta2 = (cta2_env && !p.batched && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
             (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters) ? 1 : 0;
   const int stage_bytes = (BM * BK * 2 << p.pair) + (p.BN >> p.cta2) * BK * 2;
   p.epi_bufs = (p.pair && !resid) ? 1 : 2;
@@ -774,6 +788,59 @@ extern "C" int isp_gemm_bf16_tc_ex(const void* A, long long lda, const void* W, 
                                    isp_stream_t stream) {
   return gemm_common(A, lda, W, ldw, bias, resid, resid_bf16, ldr, alpha, act, D, ldd, out_bf16, M, N, K, ln_stats,
                      ln_slots, ln_g, ln_eps, stats_out, stats_slots, stream);
+}
+
+// Batched GEMM: for every (batch b, head h)   D[b,h] (M x N) = alpha * A[b,h] (M x K) . W[b,h]^T (N x K),
+// bf16 operands with unit stride along K, D bf16 | f32 with unit stride along N; every other stride (row, head,
+// batch; in elements) is explicit, so heads can be column slices of a packed [tokens, 3C] qkv matrix.  Rows /
+// columns beyond M / N / K are zero-filled on load and clipped on store by TMA (no bleed between problems).
+// Used by the attention backward of the frozen ViT (dinov2/layers/attention.py:54-71 under autograd).
+extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
+                                        long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm,
+                                        long long d_sh, long long d_sb, int out_bf16, int M, int N, int K, int H, int B,
+                                        float alpha, isp_stream_t stream) {
+  ISP_REQUIRE(A && W && D, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_batched: null pointer");
+  ISP_REQUIRE(M > 0 && N > 0 && K > 0 && H > 0 && B > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_batched: bad shape");
+  const int esz = out_bf16 ? 2 : 4;
+  ISP_REQUIRE(a_sm % 8 == 0 && a_sh % 8 == 0 && a_sb % 8 == 0 && w_sn % 8 == 0 && w_sh % 8 == 0 && w_sb % 8 == 0,
+              ISP_ERR_MISALIGNED, "gemm_bf16_tc_batched: A / W strides must be multiples of 8 elements");
+  ISP_REQUIRE((d_sm * esz) % 16 == 0 && (d_sh * esz) % 16 == 0 && (d_sb * esz) % 16 == 0, ISP_ERR_MISALIGNED,
+              "gemm_bf16_tc_batched: D strides must be multiples of 16 bytes");
+  ISP_REQUIRE(aligned16(A) && aligned16(W) && aligned16(D), ISP_ERR_MISALIGNED, "gemm_bf16_tc_batched: 16-byte alignment");
+  gemm::Params p = {};
+  p.M = M; p.N = N;
+  p.K = (K + gemm::BK - 1) / gemm::BK * gemm::BK;
+  p.BN = gemm::pick_bn(N, 256);
+  p.last_steps = (K - (p.K - gemm::BK) + 15) / 16;
+  p.TW = 0;
+  p.batched = H; p.nbatch = B;
+  p.tiles_m = (long long)((M + gemm::BM - 1) / gemm::BM) * H * B;
+  p.tiles_n = (N + p.BN - 1) / p.BN;
+  p.pair = 0;
+  p.bias = nullptr; p.alpha = alpha;
+  CUtensorMap tmA, tmB, tmD, tmDt;
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {2, (uint64_t)a_sm * 2, (uint64_t)a_sh * 2, (uint64_t)a_sb * 2};
+    const uint32_t box[4] = {gemm::BK, gemm::BM, 1, 1};
+    if (int e = make_tmap_bf16(&tmA, A, 4, dims, str, box, "gemm_bf16_tc_batched(A)")) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {2, (uint64_t)w_sn * 2, (uint64_t)w_sh * 2, (uint64_t)w_sb * 2};
+    const uint32_t box[4] = {gemm::BK, (uint32_t)p.BN, 1, 1};
+    if (int e = make_tmap_bf16(&tmB, W, 4, dims, str, box, "gemm_bf16_tc_batched(W)")) return e;
+  }
+  const uint32_t cw = out_bf16 ? 64 : 32;
+  const uint32_t tailw = (uint32_t)p.BN % cw;
+  {
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {(uint64_t)esz, (uint64_t)d_sm * esz, (uint64_t)d_sh * esz, (uint64_t)d_sb * esz};
+    const uint32_t box[4] = {cw, 32, 1, 1}, boxt[4] = {tailw ? tailw : cw, 32, 1, 1};
+    if (int e = make_tmap(&tmD, esz, D, 4, dims, str, box, "gemm_bf16_tc_batched(D)", true)) return e;
+    if (int e = make_tmap(&tmDt, esz, D, 4, dims, str, boxt, "gemm_bf16_tc_batched(D tail)", false)) return e;
+  }
+  return gemm::launch(tmA, tmB, tmD, tmDt, tmD, tmDt, tmB, p, out_bf16, 0, false, as_stream(stream));
 }
 
 static int conv3x3_common(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16, int Nimg,

@@ -1,0 +1,221 @@
+// Row / element kernels of the activation backward through the frozen ViT (the reference trains the click embedding
+// through the frozen backbone: core/model/featurizers/DINOv2.py:518-523, core/model/iseg_probe_model.py:93-99,
+// trainer backward core/training/trainer.py:213-221).  The GEMMs of that backward run on gemm_tc_kernel (transposed
+// packed weights, isp_gemm_bf16_tc_batched for the per-head attention products); what is left is bandwidth work:
+//   layernorm_bwd_kernel   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ residual gradient)
+//   gelu_bwd_kernel        dpre = dh * (Phi(pre) + pre * phi(pre))          (nn.GELU, exact erf form)
+//   softmax_rows_kernel    P = softmax(S) over the valid keys of a score row (recomputed from Q K^T)
+//   attn_ds_kernel         dS = P * (dP - sum_j P dP)                       (softmax backward, row-wise)
+//   transpose_kernel       [Z][R][C] -> [Z][C][R] bf16 (P^T, dS^T and d_emb^T operands)
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace isp {
+namespace vb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one warp per row; C <= 32 * kMaxPerLane
+constexpr int kMaxPerLane = 32;
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy,
+                                                            const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ resid, long long ldr,
+                                                            float* __restrict__ dx, long long lddx,
+                                                            __nv_bfloat16* __restrict__ dx_bf, long long ldb, long long M,
+                                                            int C, float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + row * ldx;
+  const float* dr = dy + row * lddy;
+  float xv[kMaxPerLane], gv[kMaxPerLane];
+  float s = 0.f;
+  const int n = (C + 31) / 32;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    if (i < n) {
+      const int c = lane + 32 * i;
+      xv[i] = c < C ? xr[c] : 0.f;
+      gv[i] = c < C ? dr[c] * __ldg(gamma + c) : 0.f;
+      s += xv[i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < n) {
+      const float d = (lane + 32 * i < C) ? xv[i] - mean : 0.f;
+      var += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+  float a = 0.f, b = 0.f;  // sum(g*dy), sum(g*dy*xhat)
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < n) {
+      const float xh = (xv[i] - mean) * rstd;
+      xv[i] = xh;
+      a += gv[i];
+      b += (lane + 32 * i < C) ? gv[i] * xh : 0.f;
+    }
+  a = warp_sum(a) / (float)C;
+  b = warp_sum(b) / (float)C;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < n) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        float v = rstd * (gv[i] - a - xv[i] * b);
+        if (resid) v += resid[row * ldr + c];
+        dx[row * lddx + c] = v;
+        if (dx_bf) dx_bf[row * ldb + c] = __float2bfloat16(v);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat162* __restrict__ dh,
+                                                       const __nv_bfloat162* __restrict__ pre,
+                                                       __nv_bfloat162* __restrict__ out, long long n2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float2 d = __bfloat1622float2(dh[i]), x = __bfloat1622float2(pre[i]);
+  auto g = [](float v) {  // d/dv [ v * Phi(v) ] = Phi(v) + v * phi(v)
+    const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+    return cdf + v * pdf;
+  };
+  out[i] = __floats2bfloat162_rn(d.x * g(x.x), d.y * g(x.y));
+}
+
+// one warp per row of scores; ncols valid entries, row pitch lds / ldp; padded P entries are written as zero
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long lds,
+                                                           __nv_bfloat16* __restrict__ P, long long ldp, long long R,
+                                                           int ncols, int ncols_pad) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* s = S + row * lds;
+  float mx = -INFINITY;
+  for (int c = lane; c < ncols; c += 32) mx = fmaxf(mx, s[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < ncols; c += 32) sum += __expf(s[c] - mx);
+  const float inv = 1.f / warp_sum(sum);
+  __nv_bfloat16* p = P + row * ldp;
+  for (int c = lane; c < ncols_pad; c += 32) p[c] = __float2bfloat16(c < ncols ? __expf(s[c] - mx) * inv : 0.f);
+}
+
+__global__ void __launch_bounds__(256) attn_ds_kernel(const __nv_bfloat16* __restrict__ P, long long ldp,
+                                                      const float* __restrict__ dP, long long lddp,
+                                                      __nv_bfloat16* __restrict__ dS, long long ldds, long long R,
+                                                      int ncols, int ncols_pad) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const __nv_bfloat16* p = P + row * ldp;
+  const float* dp = dP + row * lddp;
+  float dot = 0.f;
+  for (int c = lane; c < ncols; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+  dot = warp_sum(dot);
+  __nv_bfloat16* o = dS + row * ldds;
+  for (int c = lane; c < ncols_pad; c += 32)
+    o[c] = __float2bfloat16(c < ncols ? __bfloat162float(p[c]) * (dp[c] - dot) : 0.f);
+}
+
+// [Z][R][lds] (C valid columns) -> [Z][C][ldd] (R valid columns); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __restrict__ src, long long lds,
+                                                        long long src_z, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                        long long dst_z, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const __nv_bfloat16* s = src + (long long)blockIdx.z * src_z;
+  __nv_bfloat16* d = dst + (long long)blockIdx.z * dst_z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? s[(long long)r * lds + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) d[(long long)c * ldd + r] = tile[tx][i];
+  }
+}
+
+}  // namespace vb
+}  // namespace isp
+
+using namespace isp;
+
+// Backward of LayerNorm over the last dimension of x [M, C] (fp32, row pitch ldx), affine weight gamma:
+// dx = LN'(x)^T (gamma * dy) (+ resid, the gradient arriving through the residual connection).  dx_bf16 (optional)
+// receives a bf16 copy for the next GEMM.  C <= 1024.
+extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+                                      const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16,
+                                      long long ldb, long long M, int C, float eps, isp_stream_t stream) {
+  ISP_REQUIRE(dy && x && gamma && dx, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: null pointer");
+  ISP_REQUIRE(M > 0 && C > 0 && C <= 32 * vb::kMaxPerLane, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: bad shape (C <= 1024)");
+  vb::layernorm_bwd_kernel<<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx,
+                                                                     reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C,
+                                                                     eps);
+  ISP_CHECK_LAUNCH("layernorm_bwd_kernel");
+  return ISP_OK;
+}
+
+// dpre = dh * gelu'(pre) on dense bf16 arrays of n elements (n even; nn.GELU erf form, dinov2/layers/mlp.py:34-40).
+extern "C" int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream) {
+  ISP_REQUIRE(dh && pre && out && n > 0 && n % 2 == 0, ISP_ERR_BAD_SHAPE, "gelu_bwd_bf16: bad arguments");
+  vb::gelu_bwd_kernel<<<cdiv(n / 2, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat162*>(dh), reinterpret_cast<const __nv_bfloat162*>(pre),
+      reinterpret_cast<__nv_bfloat162*>(out), n / 2);
+  ISP_CHECK_LAUNCH("gelu_bwd_kernel");
+  return ISP_OK;
+}
+
+// P[r, :ncols] = softmax(S[r, :ncols]) (fp32 scores -> bf16 probabilities), P[r, ncols:ncols_pad] = 0.
+extern "C" int isp_softmax_rows(const float* S, long long lds, void* P_bf16, long long ldp, long long R, int ncols,
+                                int ncols_pad, isp_stream_t stream) {
+  ISP_REQUIRE(S && P_bf16 && R > 0 && ncols > 0 && ncols_pad >= ncols && lds >= ncols && ldp >= ncols_pad, ISP_ERR_BAD_SHAPE,
+              "softmax_rows: bad arguments");
+  vb::softmax_rows_kernel<<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(S, lds, reinterpret_cast<__nv_bfloat16*>(P_bf16), ldp,
+                                                                    R, ncols, ncols_pad);
+  ISP_CHECK_LAUNCH("softmax_rows_kernel");
+  return ISP_OK;
+}
+
+// dS[r, c] = P[r, c] * (dP[r, c] - sum_j P[r, j] dP[r, j]) for c < ncols, 0 up to ncols_pad.
+extern "C" int isp_attn_ds_rows(const void* P_bf16, long long ldp, const float* dP, long long lddp, void* dS_bf16,
+                                long long ldds, long long R, int ncols, int ncols_pad, isp_stream_t stream) {
+  ISP_REQUIRE(P_bf16 && dP && dS_bf16 && R > 0 && ncols > 0 && ncols_pad >= ncols, ISP_ERR_BAD_SHAPE,
+              "attn_ds_rows: bad arguments");
+  vb::attn_ds_kernel<<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(P_bf16), ldp, dP, lddp,
+                                                               reinterpret_cast<__nv_bfloat16*>(dS_bf16), ldds, R, ncols,
+                                                               ncols_pad);
+  ISP_CHECK_LAUNCH("attn_ds_kernel");
+  return ISP_OK;
+}
+
+// dst[z][c][r] = src[z][r][c] for Z matrices of R x C bf16 (row pitches lds / ldd, matrix pitches src_z / dst_z).
+extern "C" int isp_transpose_bf16_batched(const void* src, long long lds, long long src_z, void* dst, long long ldd,
+                                          long long dst_z, int Z, int R, int C, isp_stream_t stream) {
+  ISP_REQUIRE(src && dst && Z > 0 && R > 0 && C > 0 && lds >= C && ldd >= R && Z <= 65535, ISP_ERR_BAD_SHAPE,
+              "transpose_bf16_batched: bad arguments");
+  ISP_REQUIRE(cdiv(R, 32) <= 65535, ISP_ERR_UNSUPPORTED, "transpose_bf16_batched: too many rows");
+  const dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32), (unsigned)Z);
+  vb::transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, src_z,
+                                                           reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_z, R, C);
+  ISP_CHECK_LAUNCH("transpose_kernel");
+  return ISP_OK;
+}

@@ -176,6 +176,15 @@ class DINOv2Featurizer(nn.Module):
         return self._pos_cache[key]
 
     def forward(self, x, additional_features=None):
+        """Frozen backbone.  When the click embedding requires grad (training: it is injected before the blocks,
+        DINOv2.py:518-523) the call goes through an autograd Function whose backward runs the activation backward
+        of all twelve blocks on libisp_b200 and returns d(loss)/d(additional_features)."""
+        if (torch.is_grad_enabled() and additional_features is not None and additional_features.requires_grad
+                and self.feats_injection_mode == "before_backbone"):
+            return _DinoBackboneFn.apply(self, x, additional_features)
+        return self._forward_impl(x, additional_features, None)
+
+    def _forward_impl(self, x, additional_features, saved):
         x = x.detach().float()
         dev = x.device
         B, _, H, W = x.shape
@@ -198,7 +207,10 @@ class DINOv2Featurizer(nn.Module):
         Tp = tc.round_up(T, 128)
         hd = C // nh
         bf = torch.bfloat16
+        if saved is not None:
+            saved.update({"B": B, "T": T, "h": h, "w": w, "blocks": []})
         for L in P["blocks"]:
+            x_in = xs
             hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-6, bf)
             qkv = tc.gemm(hn, L["Wqkv"], bias=L["bqkv"], out_dtype=bf)
             Kp = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
@@ -210,12 +222,128 @@ class DINOv2Featurizer(nn.Module):
             xs = tc.gemm(O, L["Wproj"], bias=L["bproj"], resid=xs, out_dtype=torch.float32)
             hn = _ln(xs, L["n2w"], L["n2b"], C, 1e-6, bf)
             h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf)
+            if saved is not None:  # block input, qkv and the MLP's input: what the backward re-reads
+                saved["blocks"].append((x_in, qkv, xs))
             xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
+        if saved is not None:
+            saved["x_final"] = xs
         xn = _ln(xs, P["nw"], P["nb"], C, 1e-6, torch.float32)
         feats = xn.view(B, T, C)[:, 1:]
         if inject and self.feats_injection_mode == "after_backbone":
             feats = feats + additional_features.to(feats.dtype)
         return feats.reshape(B, h, w, C).permute(0, 3, 1, 2)
+
+    # ---------------------------------------------------------------- activation backward
+    def _pack_bwd(self, dev):
+        """Transposed packed weights of every block (dgrad of y = a W^T is dy W, i.e. a GEMM with W^T as weight)."""
+        P = self._pack(dev)
+        if "bwd" not in P:
+            m = self.model
+            C, nh = m.embed_dim, m.num_heads
+            sc = (C // nh) ** -0.5
+            out = []
+            for blk in m.blocks:
+                Wqkv = blk.attn.qkv.weight.detach().float().clone()
+                Wqkv[:C] *= sc
+                g1, g2 = blk.ls1.gamma.detach().float(), blk.ls2.gamma.detach().float()
+                out.append({
+                    "WqkvT": tc.pack_linear_weight(Wqkv.t().contiguous()).to(dev),
+                    "WprojT": tc.pack_linear_weight((blk.attn.proj.weight.detach().float() * g1[:, None]).t().contiguous()).to(dev),
+                    "W1T": tc.pack_linear_weight(blk.mlp.fc1.weight.detach().float().t().contiguous()).to(dev),
+                    "W2T": tc.pack_linear_weight((blk.mlp.fc2.weight.detach().float() * g2[:, None]).t().contiguous()).to(dev),
+                })
+            P["bwd"] = out
+        return P, P["bwd"]
+
+    @staticmethod
+    def _ln_bwd(dy, x, gamma, resid, C, eps=1e-6):
+        M = x.shape[0]
+        dx = torch.empty(M, C, dtype=torch.float32, device=x.device)
+        dxb = torch.empty(M, C, dtype=torch.bfloat16, device=x.device)
+        _call("isp_layernorm_rows_bwd", dy, dy.stride(0), x, x.stride(0), gamma, resid,
+              0 if resid is None else resid.stride(0), dx, C, dxb, C, M, C, float(eps))
+        return dx, dxb
+
+    def _attention_bwd(self, qkv, dO, B, T, C, nh):
+        """d(qkv) of O = softmax(Q K^T) V per (image, head), probabilities recomputed from Q and K
+        (dinov2/layers/attention.py:54-71; Q already carries the 1/sqrt(d) scale).  All products are batched
+        tcgen05 GEMMs over (image, head); P, dP, dS are materialised (T x T per head: 2 MB)."""
+        dev, bf, hd = qkv.device, torch.bfloat16, C // nh
+        Tp = tc.round_up(T, 8)
+        st = _lib.stream_ptr()
+        q0 = _lib.dptr(qkv)
+        S = torch.empty(B, nh, T, Tp, dtype=torch.float32, device=dev)
+        dP = torch.empty(B, nh, T, Tp, dtype=torch.float32, device=dev)
+        Pm = torch.empty(B, nh, T, Tp, dtype=bf, device=dev)
+        dS = torch.empty(B, nh, T, Tp, dtype=bf, device=dev)
+
+        def bgemm(A, a_str, W, w_str, D, d_str, out_bf16, M, N, K):
+            _lib.call("isp_gemm_bf16_tc_batched", A, *a_str, W, *w_str, D, *d_str, int(out_bf16), M, N, K, nh, B, 1.0, st)
+
+        tok = (3 * C, hd, T * 3 * C)            # (row, head, image) strides of a head slice of qkv
+        sq = (Tp, T * Tp, nh * T * Tp)          # ... of the [B, nh, T, Tp] score-shaped tensors
+        tr = (Tp, hd * Tp, nh * hd * Tp)        # ... of the transposed [B, nh, hd, Tp] operands
+        bgemm(q0, tok, q0 + 2 * C, tok, _lib.dptr(S), sq, False, T, T, hd)                     # S = Q K^T
+        _call("isp_softmax_rows", S, Tp, Pm, Tp, B * nh * T, T, Tp)
+        bgemm(_lib.dptr(dO), (C, hd, T * C), q0 + 4 * C, tok, _lib.dptr(dP), sq, False, T, T, hd)  # dP = dO V^T
+        _call("isp_attn_ds_rows", Pm, Tp, dP, Tp, dS, Tp, B * nh * T, T, Tp)
+        del S, dP
+        dqkv = torch.empty(B * T, 3 * C, dtype=bf, device=dev)
+        d0 = _lib.dptr(dqkv)
+        Xt = torch.empty(B, nh, hd, Tp, dtype=bf, device=dev)   # K^T, then Q^T, then dO^T
+        Mt = torch.empty(B, nh, T, Tp, dtype=bf, device=dev)    # dS^T, then P^T
+        _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Xt, B, T, Tp, nh, hd, 1)
+        bgemm(_lib.dptr(dS), sq, _lib.dptr(Xt), tr, d0, tok, True, T, hd, T)                   # dQ = dS K
+        _call("isp_transpose_bf16_batched", dS, Tp, T * Tp, Mt, Tp, T * Tp, B * nh, T, T)
+        _call("isp_repack_heads", qkv, 1, 3 * C, 0, hd, Xt, B, T, Tp, nh, hd, 1)
+        bgemm(_lib.dptr(Mt), sq, _lib.dptr(Xt), tr, d0 + 2 * C, tok, True, T, hd, T)           # dK = dS^T Q
+        _call("isp_transpose_bf16_batched", Pm, Tp, T * Tp, Mt, Tp, T * Tp, B * nh, T, T)
+        _call("isp_repack_heads", dO, 1, C, 0, hd, Xt, B, T, Tp, nh, hd, 1)
+        bgemm(_lib.dptr(Mt), sq, _lib.dptr(Xt), tr, d0 + 4 * C, tok, True, T, hd, T)           # dV = P^T dO
+        return dqkv
+
+    def _backward_impl(self, saved, grad_feats):
+        dev = grad_feats.device
+        m = self.model
+        C, nh = m.embed_dim, m.num_heads
+        P, PB = self._pack_bwd(dev)
+        B, T, h, w = saved["B"], saved["T"], saved["h"], saved["w"]
+        M = B * T
+        bf = torch.bfloat16
+        dxn = torch.zeros(B, T, C, dtype=torch.float32, device=dev)  # the CLS token is not part of the features
+        dxn[:, 1:] = grad_feats.detach().float().permute(0, 2, 3, 1).reshape(B, h * w, C)
+        dx, dxb = self._ln_bwd(dxn.view(M, C), saved["x_final"], P["nw"], None, C)
+        for L, LB, (x_in, qkv, x_mid) in zip(reversed(P["blocks"]), reversed(PB), reversed(saved["blocks"])):
+            # MLP: x_out = x_mid + fc2(gelu(fc1(LN2 x_mid)))   (LayerScale folded into fc2)
+            hn = _ln(x_mid, L["n2w"], L["n2b"], C, 1e-6, bf)
+            pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf)
+            dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf)
+            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel())
+            dn = tc.gemm(dh, LB["W1T"], out_dtype=torch.float32)
+            dx, dxb = self._ln_bwd(dn, x_mid, L["n2w"], dx, C)
+            # attention: x_mid = x_in + proj(attn(qkv(LN1 x_in)))
+            dO = tc.gemm(dxb, LB["WprojT"], out_dtype=bf)
+            dqkv = self._attention_bwd(qkv, dO, B, T, C, nh)
+            dn = tc.gemm(dqkv, LB["WqkvT"], out_dtype=torch.float32)
+            dx, dxb = self._ln_bwd(dn, x_in, L["n1w"], dx, C)
+        return dx.view(B, T, C)[:, 1:].contiguous()
+
+
+class _DinoBackboneFn(torch.autograd.Function):
+    """Frozen DINOv2 backbone with an input gradient for the injected click embedding."""
+
+    @staticmethod
+    def forward(ctx, feat, x, additional_features):
+        saved = {}
+        out = feat._forward_impl(x, additional_features, saved)
+        ctx.feat, ctx.saved = feat, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d_extra = ctx.feat._backward_impl(ctx.saved, grad_out)
+        ctx.saved = None
+        return None, None, d_extra
 
 
 class _ClipResBlock(nn.Module):

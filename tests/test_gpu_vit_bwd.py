@@ -1,0 +1,114 @@
+"""GPU parity: activation backward through the frozen ViT (gradient of the injected click embedding) against torch
+autograd through the fp32 oracle (oracle/vit.py; reference: core/model/featurizers/DINOv2.py:500-546 under
+trainer.py:213-221), plus the kernels it is made of.  bf16 tensor-core mode: cosine >= 0.99 on the gradient."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import head as ohead
+from oracle import synth
+from oracle import vit as ovit
+from tests.gpu_util import DEV, cosine, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _call(name, *a):
+    from isegprobe_b200 import _lib
+    _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
+
+
+def test_batched_gemm_head_slices():
+    """Heads as column slices of a packed [tokens, 3C] matrix; odd row / reduction counts (zero-fill, clipping)."""
+    from isegprobe_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    B, nh, T, hd = 3, 6, 65, 64
+    C = nh * hd
+    qkv = (torch.randn(B * T, 3 * C, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+    Tp = 72
+    S = torch.full((B, nh, T, Tp), float("nan"), device=DEV)
+    tok, sq = (3 * C, hd, T * 3 * C), (Tp, T * Tp, nh * T * Tp)
+    q0 = _lib.dptr(qkv)
+    _lib.call("isp_gemm_bf16_tc_batched", q0, *tok, q0 + 2 * C, *tok, _lib.dptr(S), *sq, 0, T, T, hd, nh, B, 0.5,
+              _lib.stream_ptr())
+    q = qkv.float().view(B, T, 3, nh, hd)
+    want = 0.5 * torch.einsum("bthd,bshd->bhts", q[:, :, 0], q[:, :, 1])
+    assert relerr(S[..., :T], want) < 1e-4
+    assert bool(torch.isnan(S[..., 68:]).all())  # columns beyond N (up to the next 16-byte boundary) are not written
+    # reduction over the (odd) token count: dV-style product  D[b,h] (T x hd) = P^T-like [T x T] . X^T [hd x T]
+    Pm = (torch.randn(B, nh, T, Tp, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    Xt = (torch.randn(B, nh, hd, Tp, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    out = torch.zeros(B * T, 3 * C, dtype=torch.bfloat16, device=DEV)
+    _lib.call("isp_gemm_bf16_tc_batched", _lib.dptr(Pm), *sq, _lib.dptr(Xt), Tp, hd * Tp, nh * hd * Tp,
+              _lib.dptr(out) + 2 * C, *tok, 1, T, hd, T, nh, B, 1.0, _lib.stream_ptr())
+    want = torch.einsum("bhts,bhds->bthd", Pm[..., :T].float(), Xt[..., :T].float()).reshape(B * T, C)
+    got = out.view(B * T, 3, C)[:, 1].float()
+    assert relerr(got, want) < 1e-2 and cosine(got, want) > 0.9999
+    assert float(out.view(B * T, 3, C)[:, 0].abs().max()) == 0 and float(out.view(B * T, 3, C)[:, 2].abs().max()) == 0
+
+
+def test_layernorm_gelu_softmax_backward_kernels():
+    g = torch.Generator().manual_seed(1)
+    M, C = 333, 384
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=g) * 0.3 + 1, torch.randn(C, generator=g)
+    dy, res = torch.randn(M, C, generator=g), torch.randn(M, C, generator=g)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (C,), gamma, beta, 1e-6).backward(dy)
+    dx = torch.empty(M, C, device=DEV)
+    dxb = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    _call("isp_layernorm_rows_bwd", dy.to(DEV), C, x.to(DEV), C, gamma.to(DEV), res.to(DEV), C, dx, C, dxb, C, M, C, 1e-6)
+    assert relerr(dx, xr.grad + res) < 1e-5
+    assert relerr(dxb.float(), xr.grad + res) < 1e-2
+    # GELU backward (erf form)
+    pre = (torch.randn(M, 1536, generator=g) * 1.5).to(torch.bfloat16)
+    dh = torch.randn(M, 1536, generator=g).to(torch.bfloat16)
+    pr = pre.float().requires_grad_(True)
+    F.gelu(pr).backward(dh.float())
+    out = torch.empty_like(dh, device=DEV)
+    _call("isp_gelu_bwd_bf16", dh.to(DEV), pre.to(DEV), out, dh.numel())
+    assert relerr(out.float(), pr.grad) < 1e-2
+    # softmax rows and its backward
+    R, T, Tp = 200, 65, 72
+    S = torch.randn(R, Tp, generator=g) * 3
+    dP = torch.randn(R, Tp, generator=g)
+    Pm = torch.empty(R, Tp, dtype=torch.bfloat16, device=DEV)
+    _call("isp_softmax_rows", S.to(DEV), Tp, Pm, Tp, R, T, Tp)
+    want = torch.softmax(S[:, :T], -1)
+    assert relerr(Pm[:, :T].float(), want) < 1e-2 and float(Pm[:, T:].float().abs().max()) == 0
+    dS = torch.empty(R, Tp, dtype=torch.bfloat16, device=DEV)
+    _call("isp_attn_ds_rows", Pm, Tp, dP.to(DEV), Tp, dS, Tp, R, T, Tp)
+    Pf = Pm[:, :T].float().cpu()
+    wantd = Pf * (dP[:, :T] - (Pf * dP[:, :T]).sum(-1, keepdim=True))
+    assert relerr(dS[:, :T].float(), wantd) < 1e-2 and float(dS[:, T:].float().abs().max()) == 0
+    # batched transpose
+    src = torch.randn(5, 65, 72, generator=g).to(torch.bfloat16).to(DEV)
+    dst = torch.zeros(5, 70, 72, dtype=torch.bfloat16, device=DEV)
+    _call("isp_transpose_bf16_batched", src, 72, 65 * 72, dst, 72, 70 * 72, 5, 65, 70)
+    assert torch.equal(dst[:, :, :65], src[:, :, :70].transpose(1, 2))
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 56, 56), (3, 56, 84), (1, 112, 112)])
+def test_vit_click_embedding_gradient_vs_oracle_autograd(B, H, W):
+    import isegprobe_b200 as isp
+    torch.manual_seed(0)
+    f = isp.DINOv2Featurizer("dinov2_vits14", "before_backbone")
+    vsd = synth.vit_state_dict(384, depth=12, seed=0)
+    f.model.load_state_dict(vsd)
+    f = f.to(DEV).eval()
+    img = ohead.normalize_image(synth.image_batch(B, H, W, seed=1))
+    n = (H // 14) * (W // 14)
+    emb = torch.randn(B, n, 384, generator=torch.Generator().manual_seed(2)) * 0.5
+    gout = torch.randn(B, 384, H // 14, W // 14, generator=torch.Generator().manual_seed(3))
+    e_ref = emb.clone().requires_grad_(True)
+    ovit.dinov2_forward(vsd, img, e_ref).backward(gout)
+    e = emb.to(DEV).requires_grad_(True)
+    out = f(img.to(DEV), e)
+    out.backward(gout.to(DEV))
+    assert e.grad is not None and tuple(e.grad.shape) == (B, n, 384)
+    c = cosine(e.grad, e_ref.grad)
+    assert c > 0.99, c
+    assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
+    # forward value under autograd equals the inference path bit for bit
+    with torch.no_grad():
+        assert torch.equal(out.detach(), f(img.to(DEV), emb.to(DEV)))
