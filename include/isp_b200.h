@@ -72,6 +72,10 @@ int isp_nchw_to_nhwc_bf16(const float* in, void* out_bf16, int B, int C, int H, 
  * basic_upsamplers.py:26-33).  out_bf16 != 0 writes bf16 with Cpad channels. */
 int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int Hout, int Wout,
                          int out_bf16, int Cpad, isp_stream_t stream);
+/* Gradient of isp_bilinear_ac_nhwc w.r.t. its input (adjoint of the align_corners=True resize,
+ * core/model/iseg_probe_model.py:120-129 under autograd): gin [B,Hin,Win,C] from gout [B,Hout,Wout,C], fp32 NHWC. */
+int isp_bilinear_ac_nhwc_bwd(const float* gout, float* gin, int B, int C, int Hin, int Win, int Hout, int Wout,
+                             isp_stream_t stream);
 /* Same resize writing BOTH an f32 result and its bf16 copy (the operand of the tensor-core 1x1
  * conv that follows) in one pass over the input.  C % 4 == 0. */
 int isp_bilinear_ac_nhwc_dual(const float* in, float* out_f32, void* out_bf16, int B, int C, int Hin, int Win,

@@ -77,6 +77,56 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(const float* __restric
   }
 }
 
+// Adjoint of bilinear_ac_kernel (gradient w.r.t. its input): every input pixel gathers, with the forward's own
+// fp32 coordinates and weights, from the output pixels it contributed to.  VEC = 4: float4 over channels.
+template <int VEC>
+__global__ void __launch_bounds__(256) bilinear_ac_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int B,
+                                                              int C, int Hin, int Win, int Hout, int Wout, float sy,
+                                                              float sx) {
+  const int CV = C / VEC;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Hin * Win * CV;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  const long long p = idx / CV;
+  const int xi = (int)(p % Win), yi = (int)((p / Win) % Hin), b = (int)(p / ((long long)Win * Hin));
+  // output rows / columns whose source coordinate lies within one pixel of (yi, xi)
+  const int oy0 = sy > 0.f ? max(0, (int)floorf((float)(yi - 1) / sy)) : 0;
+  const int oy1 = sy > 0.f ? min(Hout - 1, (int)ceilf((float)(yi + 1) / sy)) : Hout - 1;
+  const int ox0 = sx > 0.f ? max(0, (int)floorf((float)(xi - 1) / sx)) : 0;
+  const int ox1 = sx > 0.f ? min(Wout - 1, (int)ceilf((float)(xi + 1) / sx)) : Wout - 1;
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  const float* g = gout + (size_t)b * Hout * Wout * C + (size_t)cv * VEC;
+  for (int oy = oy0; oy <= oy1; ++oy) {
+    const float fy = sy * (float)oy;
+    const int y0 = (int)fy, y1 = y0 + (y0 < Hin - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0;
+    const float wy = (y0 == yi ? 1.f - ly1 : 0.f) + (y1 == yi ? ly1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = ox0; ox <= ox1; ++ox) {
+      const float fx = sx * (float)ox;
+      const int x0 = (int)fx, x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+      const float lx1 = fx - (float)x0;
+      const float wx = (x0 == xi ? 1.f - lx1 : 0.f) + (x1 == xi ? lx1 : 0.f);
+      if (wx == 0.f) continue;
+      const float wgt = wy * wx;
+      const float* gp = g + ((size_t)oy * Wout + ox) * C;
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gp));
+        acc[0] = fmaf(wgt, t.x, acc[0]); acc[1] = fmaf(wgt, t.y, acc[1]);
+        acc[2 % VEC] = fmaf(wgt, t.z, acc[2 % VEC]); acc[3 % VEC] = fmaf(wgt, t.w, acc[3 % VEC]);
+      } else {
+        acc[0] = fmaf(wgt, __ldg(gp), acc[0]);
+      }
+    }
+  }
+  float* o = gin + ((size_t)(b * Hin + yi) * Win + xi) * C + (size_t)cv * VEC;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) o[v] = acc[v];
+}
+
 // C[M,N] = alpha * (A[M,K] W[N,K]^T + bias) + resid   -- fp32 SIMT, 64x64x16 tiles, 4x4 per thread
 __global__ void __launch_bounds__(256) gemm_f32_simt_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
                                                             const float* __restrict__ bias,
@@ -162,6 +212,24 @@ extern "C" int isp_bilinear_ac_nhwc(const float* in, void* out, int B, int C, in
     bilinear_ac_kernel<float><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), B, C,
                                                                                Hin, Win, Hout, Wout, Cpad, sy, sx);
   ISP_CHECK_LAUNCH("bilinear_ac_kernel");
+  return ISP_OK;
+}
+
+// Gradient of isp_bilinear_ac_nhwc w.r.t. its input: gin [B,Hin,Win,C] = resize^T gout [B,Hout,Wout,C] (fp32 NHWC).
+extern "C" int isp_bilinear_ac_nhwc_bwd(const float* gout, float* gin, int B, int C, int Hin, int Win, int Hout, int Wout,
+                                        isp_stream_t stream) {
+  ISP_REQUIRE(gout && gin && B > 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, ISP_ERR_BAD_SHAPE,
+              "bilinear_ac_nhwc_bwd: bad arguments");
+  const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  if (C % 4 == 0 && aligned16(gout)) {
+    const long long total = (long long)B * Hin * Win * (C / 4);
+    bilinear_ac_bwd_kernel<4><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(gout, gin, B, C, Hin, Win, Hout, Wout, sy, sx);
+  } else {
+    const long long total = (long long)B * Hin * Win * C;
+    bilinear_ac_bwd_kernel<1><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(gout, gin, B, C, Hin, Win, Hout, Wout, sy, sx);
+  }
+  ISP_CHECK_LAUNCH("bilinear_ac_bwd_kernel");
   return ISP_OK;
 }
 

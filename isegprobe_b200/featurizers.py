@@ -53,9 +53,7 @@ class PatchEmbed(nn.Module):
             self._packed = (key, tc.pack_linear_weight(w).to(dev), self.proj.bias.detach().float().to(dev))
         return self._packed[1], self._packed[2]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and self.proj.weight.requires_grad and self.training:
-            raise NotImplementedError("PatchEmbed: weight gradient is not implemented yet")
+    def _embed(self, x: torch.Tensor):
         x = x.detach().float()
         B, Cin, H, W = x.shape
         p = self.patch_size[0]
@@ -65,10 +63,49 @@ class PatchEmbed(nn.Module):
         cols = torch.empty(B * N, Wp.shape[1], dtype=torch.bfloat16, device=x.device)
         _call("isp_vit_patchify", x, *x.stride(), cols, B, Cin, H, W, p, Wp.shape[1])
         y = tc.gemm(cols, Wp, bias=b, out_dtype=torch.float32, K=K)
-        y = y.view(B, N, -1)
+        return y.view(B, N, -1), cols, K
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, Cin, H, W = x.shape
+        p = self.patch_size[0]
+        if torch.is_grad_enabled() and (self.proj.weight.requires_grad or self.proj.bias.requires_grad):
+            y = _PatchEmbedFn.apply(self, x, self.proj.weight, self.proj.bias)  # trainable click embedding
+        else:
+            y = self._embed(x)[0]
         if not self.flatten:
             y = y.transpose(1, 2).reshape(B, -1, H // p, W // p)
         return self.norm(y)
+
+
+class _PatchEmbedFn(torch.autograd.Function):
+    """Conv2d(k = s = patch) as a GEMM over patch rows; backward = weight / bias gradient (the input is the click
+    map: no gradient).  dW = d_y^T cols on the batched tcgen05 GEMM (reduction over the tokens), fp32 result."""
+
+    @staticmethod
+    def forward(ctx, mod, x, weight, bias):
+        y, cols, K = mod._embed(x)
+        ctx.cols, ctx.K, ctx.wshape = cols, K, tuple(weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        cols, K = ctx.cols, ctx.K
+        dev, bf = gy.device, torch.bfloat16
+        M, Kp = cols.shape
+        D = gy.shape[-1]
+        g = gy.detach().reshape(M, D).to(bf).contiguous()
+        Mp = tc.round_up(M, 8)
+        gT = torch.empty(D, Mp, dtype=bf, device=dev)
+        cT = torch.empty(K, Mp, dtype=bf, device=dev)
+        _call("isp_transpose_bf16_batched", g, D, 0, gT, Mp, 0, 1, M, D)
+        _call("isp_transpose_bf16_batched", cols, Kp, 0, cT, Mp, 0, 1, M, K)
+        ldw = tc.round_up(K, 4)
+        dW = torch.empty(D, ldw, dtype=torch.float32, device=dev)
+        _lib.call("isp_gemm_bf16_tc_batched", _lib.dptr(gT), Mp, D * Mp, D * Mp, _lib.dptr(cT), Mp, K * Mp, K * Mp,
+                  _lib.dptr(dW), ldw, D * ldw, D * ldw, 0, D, K, M, 1, 1, 1.0, _lib.stream_ptr())
+        db = torch.zeros(D, dtype=torch.float32, device=dev)
+        _call("isp_colsum_bf16", g, D, db, M, D)
+        return None, None, dW[:, :K].reshape(ctx.wshape), db
 
 
 class _Block(nn.Module):

@@ -6,9 +6,11 @@
       -> ONE all-reduce of the flat gradient arena (dist.FlatGradArena; DDP semantics: mean over ranks,
          core/utils/distributed.py + trainer.py:144-149) -> Adam(lr 5e-5) as models/defaults.py:103-107.
 
-Not covered yet: the gradient of the click embedding (`embed_coords`) -- it needs the activation backward
-of the frozen upsampler and ViT, which are forward-only in this round; `embed_coords` is therefore kept
-frozen here."""
+The click embedding (`embed_coords`) is trained THROUGH the frozen backbone and upsampler in the reference
+(DINOv2.py:518-523).  The DINOv2 backbone has its activation backward (featurizers._DinoBackboneFn); of the
+upsamplers, the resize-only ones (`identity` = the "noup" configs, `bilinear`, and torch's `nearest` / `bicubic`) are
+differentiable, so those configurations train `embed_coords` exactly like the reference.  LoftUp / JBU / LiFT are
+still forward-only: with them `embed_coords` is kept frozen and the step is head-only."""
 import torch
 
 from . import dist as idist
@@ -42,9 +44,13 @@ class HeadTrainer:
     def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8):
         self.pipe = pipeline
         assert pipeline.head is not None, "the pipeline was built without a head"
+        self.train_embedding = (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic")
+                                and hasattr(pipeline.backbone, "_backward_impl"))
         for p in pipeline.embed_coords.parameters():
-            p.requires_grad = False  # see module docstring
+            p.requires_grad = self.train_embedding  # see module docstring
         self.params = [p for p in pipeline.head.parameters() if p.requires_grad]
+        if self.train_embedding:
+            self.params += list(pipeline.embed_coords.parameters())
         self.arena = idist.FlatGradArena(self.params)
         self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps)
 
@@ -53,9 +59,12 @@ class HeadTrainer:
         Returns the (detached) mean loss of this rank's shard."""
         pipe = self.pipe
         pipe.head.train()
-        with torch.no_grad():
-            feats = pipe.features(image, points)
-        logits = pipe.head(feats)
+        if self.train_embedding:  # gradients flow head -> resize -> frozen ViT -> click embedding
+            logits = pipe(image, points)["instances"]
+        else:
+            with torch.no_grad():
+                feats = pipe.features(image, points)
+            logits = pipe.head(feats)
         loss = normalized_focal_loss(logits, gt_mask).mean()
         self.arena.zero_()
         loss.backward()

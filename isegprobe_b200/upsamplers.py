@@ -57,6 +57,8 @@ def to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
     v = x.permute(0, 2, 3, 1)
     if v.is_contiguous():
         return v
+    if torch.is_grad_enabled() and x.requires_grad:
+        return v.contiguous()  # autograd-tracked copy (training path only)
     B, C, H, W = x.shape
     out = torch.empty(B, H, W, C, dtype=torch.float32, device=x.device)
     sb, sc, sh, sw = x.stride()
@@ -64,13 +66,39 @@ def to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def bilinear_align_corners_nhwc(x_nhwc: torch.Tensor, size) -> torch.Tensor:
-    """F.interpolate(mode='bilinear', align_corners=True) on a dense NHWC fp32 tensor."""
+def _bilinear_fwd(x_nhwc, size):
     B, H, W, C = x_nhwc.shape
+    if C % 4:  # the kernel moves float4 channel groups: pad narrow maps (the 1-channel logits) to 4 channels
+        return _bilinear_fwd(F.pad(x_nhwc, (0, 4 - C % 4)), size)[..., :C].contiguous()
     out = torch.empty(B, size[0], size[1], C, dtype=torch.float32, device=x_nhwc.device)
     _lib.call("isp_bilinear_ac_nhwc", _lib.dptr(x_nhwc), _lib.dptr(out), B, C, H, W, size[0], size[1], 0, C,
               _lib.stream_ptr())
     return out
+
+
+class _BilinearFn(torch.autograd.Function):
+    """align_corners=True resize with its adjoint as backward (isp_bilinear_ac_nhwc_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, size):
+        ctx.in_hw = (x_nhwc.shape[1], x_nhwc.shape[2])
+        return _bilinear_fwd(x_nhwc.contiguous(), size)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.detach().float().contiguous()
+        B, OH, OW, C = g.shape
+        H, W = ctx.in_hw
+        gin = torch.empty(B, H, W, C, dtype=torch.float32, device=g.device)
+        _lib.call("isp_bilinear_ac_nhwc_bwd", _lib.dptr(g), _lib.dptr(gin), B, C, H, W, OH, OW, _lib.stream_ptr())
+        return gin, None
+
+
+def bilinear_align_corners_nhwc(x_nhwc: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(mode='bilinear', align_corners=True) on a dense NHWC fp32 tensor; differentiable w.r.t. x."""
+    if torch.is_grad_enabled() and x_nhwc.requires_grad:
+        return _BilinearFn.apply(x_nhwc, (int(size[0]), int(size[1])))
+    return _bilinear_fwd(x_nhwc, size)
 
 
 class IdentityUpsampler(BaseUpsampler):

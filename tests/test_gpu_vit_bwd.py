@@ -112,3 +112,62 @@ def test_vit_click_embedding_gradient_vs_oracle_autograd(B, H, W):
     # forward value under autograd equals the inference path bit for bit
     with torch.no_grad():
         assert torch.equal(out.detach(), f(img.to(DEV), emb.to(DEV)))
+
+
+def test_bilinear_resize_adjoint():
+    from isegprobe_b200.upsamplers import bilinear_align_corners_nhwc
+    g = torch.Generator().manual_seed(5)
+    for (B, h, w, C, H, W) in [(2, 4, 6, 384, 56, 84), (1, 32, 32, 8, 448, 448), (2, 8, 8, 1, 56, 56), (1, 56, 56, 4, 20, 30)]:
+        x = torch.randn(B, h, w, C, generator=g)
+        go = torch.randn(B, H, W, C, generator=g)
+        xr = x.clone().requires_grad_(True)
+        F.interpolate(xr.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).backward(go.permute(0, 3, 1, 2))
+        xd = x.to(DEV).requires_grad_(True)
+        bilinear_align_corners_nhwc(xd, (H, W)).backward(go.to(DEV))
+        assert relerr(xd.grad, xr.grad) < 1e-5, (B, h, w, C, H, W)
+
+
+@pytest.mark.parametrize("up_type", ["bilinear", "identity"])
+def test_pipeline_gradients_vs_oracle_autograd(up_type):
+    """Whole differentiable chain of the 'noup' / 'bilinear' configs (models/sbd/dinov2/patch-embed_{noup,bilinear}.py):
+    click maps -> trainable PatchEmbed -> frozen ViT -> resize -> trainable ConvSegHead.  Gradients of
+    embed_coords.proj.* and of the head against torch autograd through the fp32 oracle chain."""
+    import isegprobe_b200 as isp
+    from oracle import distmaps as odm
+    torch.manual_seed(0)
+    B, H, W = 2, 56, 84
+    pipe = isp.ISegPipeline(up_type, {}).to(DEV)
+    pipe.embed_coords = isp.PatchEmbed((H, W), (14, 14), 3, 384).to(DEV)
+    vsd = synth.vit_state_dict(384, depth=12, seed=0)
+    pipe.backbone.model.load_state_dict(vsd)
+    hsd = synth.convhead_state_dict(384, 2, 1, seed=0)
+    pipe.head.load_state_dict(hsd)
+    psd = synth.patch_embed_state_dict(384, 14, 3, seed=0)
+    pipe.embed_coords.load_state_dict(psd)
+    image = torch.cat([synth.image_batch(B, H, W, seed=1), (synth.image_batch(B, H, W, seed=8)[:, :1] > 0.5).float()], 1)
+    pts = synth.click_points(B, 3, H, W, seed=3)
+    gout = torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(4))
+    # oracle chain under autograd
+    pr = {k: v.clone().requires_grad_(True) for k, v in psd.items()}
+    hr_ = {k: v.clone().requires_grad_(True) for k, v in hsd.items()}
+    nimg = ohead.normalize_image(image[:, :3])
+    maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
+    emb = ohead.patch_embed_forward(pr, torch.cat([image[:, 3:], maps], 1))
+    lr = ovit.dinov2_forward(vsd, nimg, emb)
+    feats = ohead.bilinear_align_corners(lr, (H, W)) if up_type == "bilinear" else lr
+    want = ohead.convhead_forward(hr_, feats)
+    if tuple(want.shape[2:]) != (H, W):
+        want = ohead.bilinear_align_corners(want, (H, W))
+    (want * gout).sum().backward()
+    # ours
+    pipe.train()
+    logits = pipe(image.to(DEV), pts.to(DEV))["instances"]
+    (logits * gout.to(DEV)).sum().backward()
+    assert cosine(logits, want) > 0.998
+    gw, gb = pipe.embed_coords.proj.weight.grad, pipe.embed_coords.proj.bias.grad
+    assert gw is not None and gb is not None
+    assert cosine(gw, pr["proj.weight"].grad) > 0.98, cosine(gw, pr["proj.weight"].grad)
+    assert cosine(gb, pr["proj.bias"].grad) > 0.98, cosine(gb, pr["proj.bias"].grad)
+    for k, v in hr_.items():
+        got = dict(pipe.head.named_parameters())[k].grad
+        assert cosine(got, v.grad) > 0.99, (k, cosine(got, v.grad))
