@@ -105,6 +105,9 @@ int isp_jbu_filters_v1(const float* proj, const float* g, float* filters, int B,
  * src NHWC [B,h,w,C] -> out NHWC [B,2h+6,2w+6,C] */
 int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,
                                  isp_stream_t stream);
+/* Its adjoint (gradient w.r.t. src, for the activation backward of the frozen JBU stack):
+ * gsrc [B,h,w,C] from gpad [B,2h+6,2w+6,C]. */
+int isp_jbu_bicubic2x_reflectpad_bwd(const float* gpad, float* gsrc, int B, int h, int w, int C, isp_stream_t stream);
 /* AdaptiveConv.forward: out[b,y,x,c] = sum_{i,j<7} in[b,y+i,x+j,c] * filt[b,y,x,i*7+j].
  * NHWC fast path: in [B,H+6,W+6,C], out [B,H,W,C], C % 64 == 0.  filt_ld: 49 = dense filters
  * [B,H,W,49] (FeatUp's layout), 56 = row-padded [B,H,W,7,8] (see isp_jbu_filters). */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "isp_jbu_filters": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _I, _S],
     "isp_jbu_filters_v1": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _S],
     "isp_jbu_bicubic2x_reflectpad": [_P, _P, _I, _I, _I, _I, _S],
+    "isp_jbu_bicubic2x_reflectpad_bwd": [_P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_fwd_v1": [_P, _P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_fwd_nchw": [_P, _P, _P, _I, _I, _I, _I, _S],

@@ -451,6 +451,66 @@ __global__ void __launch_bounds__(256) reflect_border_kernel(float* __restrict__
   o4[((long long)py * PW + px) * C4] = o4[((long long)sy * PW + sx) * C4];
 }
 
+// Adjoint of isp_jbu_bicubic2x_reflectpad (gradient w.r.t. the low-res source of one JBU stage): every source pixel
+// gathers from the up-sampled pixels it fed (bicubic A = -0.75, align_corners = False, border clamp), each of which
+// collects the gradient of its interior position and of the reflect-pad copies of it.
+__device__ __forceinline__ float bicubic_adj_weight(int Y, int m, int n, const float* cE, const float* cO) {
+  // weight of source index m in up-sampled index Y (2n outputs): Y = 2k uses k-2..k+1 (cE), Y = 2k+1 uses k-1..k+2 (cO)
+  const int k = Y >> 1;
+  const float* c = (Y & 1) ? cO : cE;
+  const int base = (Y & 1) ? k - 1 : k - 2;
+  float wgt = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (min(max(base + i, 0), n - 1) == m) wgt += c[i];
+  return wgt;
+}
+// sum of the padded-gradient entries that are copies of up-sampled index Y (size G, pad 3, reflect): positions
+// Y + 3 (interior), 3 - Y (left frame, 1 <= Y <= 3), 2G + 1 - Y (right frame, G-4 <= Y <= G-2)
+__device__ __forceinline__ int reflect_sources(int Y, int G, int (&pos)[3]) {
+  int n = 0;
+  pos[n++] = Y + 3;
+  if (Y >= 1 && Y <= 3) pos[n++] = 3 - Y;
+  if (Y >= G - 4 && Y <= G - 2) pos[n++] = 2 * G + 1 - Y;
+  return n;
+}
+__global__ void __launch_bounds__(256) bicubic2x_pad_bwd_kernel(const float* __restrict__ gpad, float* __restrict__ gsrc,
+                                                               int B, int h, int w, int C) {
+  const int C4 = C / 4, GH = 2 * h, GW = 2 * w, PW = GW + 6, PH = GH + 6;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * h * w * C4) return;
+  const int c4 = (int)(idx % C4);
+  long long p = idx / C4;
+  const int l = (int)(p % w);
+  p /= w;
+  const int m = (int)(p % h), b = (int)(p / h);
+  float cE[4], cO[4];
+  cubic_coeffs(0.75f, cE);
+  cubic_coeffs(0.25f, cO);
+  const float4* g4 = reinterpret_cast<const float4*>(gpad) + (long long)b * PH * PW * C4 + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int Y = max(0, 2 * m - 4); Y <= min(GH - 1, 2 * m + 5); ++Y) {
+    const float wy = bicubic_adj_weight(Y, m, h, cE, cO);
+    if (wy == 0.f) continue;
+    int py[3];
+    const int ny = reflect_sources(Y, GH, py);
+    for (int X = max(0, 2 * l - 4); X <= min(GW - 1, 2 * l + 5); ++X) {
+      const float wx = bicubic_adj_weight(X, l, w, cE, cO);
+      if (wx == 0.f) continue;
+      int px[3];
+      const int nx = reflect_sources(X, GW, px);
+      const float wgt = wy * wx;
+      for (int a = 0; a < ny; ++a)
+        for (int c = 0; c < nx; ++c) {
+          const float4 t = __ldg(g4 + ((long long)py[a] * PW + px[c]) * C4);
+          acc.x = fmaf(wgt, t.x, acc.x); acc.y = fmaf(wgt, t.y, acc.y);
+          acc.z = fmaf(wgt, t.z, acc.z); acc.w = fmaf(wgt, t.w, acc.w);
+        }
+    }
+  }
+  reinterpret_cast<float4*>(gsrc)[idx] = acc;
+}
+
 }  // namespace isp
 
 using namespace isp;
@@ -475,6 +535,18 @@ extern "C" int isp_jbu_range_proj(const float* g, float* proj, long long npix, c
   range_proj_kernel<<<cdiv(npix, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g),
                                                                     reinterpret_cast<float4*>(proj), npix, w0, b0, w1, b1);
   ISP_CHECK_LAUNCH("range_proj_kernel");
+  return ISP_OK;
+}
+
+// Gradient of isp_jbu_bicubic2x_reflectpad w.r.t. src: gsrc [B,h,w,C] from gpad [B,2h+6,2w+6,C] (fp32 NHWC, C % 4 == 0).
+extern "C" int isp_jbu_bicubic2x_reflectpad_bwd(const float* gpad, float* gsrc, int B, int h, int w, int C,
+                                                isp_stream_t stream) {
+  ISP_REQUIRE(gpad && gsrc && B > 0 && h >= 2 && w >= 2 && C > 0 && C % 4 == 0, ISP_ERR_BAD_SHAPE,
+              "jbu_bicubic2x_reflectpad_bwd: need h,w >= 2 and C %% 4 == 0");
+  ISP_REQUIRE(aligned16(gpad) && aligned16(gsrc), ISP_ERR_MISALIGNED, "jbu_bicubic2x_reflectpad_bwd: 16-byte alignment");
+  const long long total = (long long)B * h * w * (C / 4);
+  bicubic2x_pad_bwd_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(gpad, gsrc, B, h, w, C);
+  ISP_CHECK_LAUNCH("bicubic2x_pad_bwd_kernel");
   return ISP_OK;
 }
 

@@ -180,10 +180,11 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             cache[key] = hit
         return hit[2]
 
-    def _stage(self, up: _JBULearnedRange, src: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
-        B, h, w, C = src.shape
-        GH, GW = 2 * h, 2 * w
-        dev, st = src.device, _lib.stream_ptr()
+    def _filters(self, up: _JBULearnedRange, guidance: torch.Tensor, GH: int, GW: int, ld: int) -> torch.Tensor:
+        """Combined per-pixel 7x7 kernels of one stage from the guidance image: [B,GH,GW,ld], ld = 56 (rows padded
+        to 8, the layout isp_adaptive_conv_fwd fetches with one TMA box) or 49 (dense, for the input-gradient kernel)."""
+        B = guidance.shape[0]
+        dev, st = guidance.device, _lib.stream_ptr()
         g = torch.empty(B, GH, GW, 4, dtype=torch.float32, device=dev)
         sb, sc, sh, sw = guidance.stride()
         _lib.call("isp_jbu_pool_guidance", _lib.dptr(guidance), _lib.dptr(g), B, guidance.shape[2], guidance.shape[3],
@@ -193,11 +194,18 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         w0, b0, w1, b1 = self._flat(rp[0].weight), rp[0].bias.detach().float(), self._flat(rp[3].weight), rp[3].bias.detach().float()
         _lib.call("isp_jbu_range_proj", _lib.dptr(g), _lib.dptr(proj), B * GH * GW, _lib.dptr(w0), _lib.dptr(b0),
                   _lib.dptr(w1), _lib.dptr(b1), st)
-        filt = torch.empty(B, GH, GW, 56, dtype=torch.float32, device=dev)  # row-padded [7][8] filters
+        filt = torch.empty(B, GH, GW, ld, dtype=torch.float32, device=dev)
         temp = min(max(math.exp(self._scalar(up.range_temp)), 1e-4), 1e4)
         f0, fb0, f1, fb1 = self._flat(fp[0].weight), fp[0].bias.detach().float(), self._flat(fp[3].weight), fp[3].bias.detach().float()
         _lib.call("isp_jbu_filters", _lib.dptr(proj), _lib.dptr(g), _lib.dptr(filt), B, GH, GW, float(temp),
-                  self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), 56, st)
+                  self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), ld, st)
+        return filt
+
+    def _stage(self, up: _JBULearnedRange, src: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        B, h, w, C = src.shape
+        GH, GW = 2 * h, 2 * w
+        dev, st = src.device, _lib.stream_ptr()
+        filt = self._filters(up, guidance, GH, GW, 56)
         hr = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
         _lib.call("isp_jbu_bicubic2x_reflectpad", _lib.dptr(src), _lib.dptr(hr), B, h, w, C, st)
         out = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
@@ -215,8 +223,44 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         combination of pixels, so they commute exactly (bias included: the weights sum to 1); doing the
         resize FIRST runs the 1x1 conv on 448^2 instead of 512^2 pixels and writes the bf16 GEMM operand
         in the resize pass.  size=None keeps the reference's 16x output."""
-        if self.training and torch.is_grad_enabled() and source.requires_grad:
-            raise NotImplementedError("JBUFeatUpUpsampler: activation backward is not implemented yet")
+        if torch.is_grad_enabled() and source.requires_grad:  # frozen stack, but the features' gradient flows through
+            return _JBUFn.apply(self, source, guidance, size)
+        return self._forward_impl(source, guidance, size)
+
+    def _backward_impl(self, grad_out: torch.Tensor, guidance: torch.Tensor, src_hw, size):
+        """d(loss)/d(source) of forward_resized: the stack is linear in `source` (the 7x7 kernels depend on the guidance
+        image only), so the backward is the chain of adjoints -- 1x1 conv dgrad (+ identity), resize adjoint, and per
+        stage isp_adaptive_conv_grad_input followed by the bicubic / reflect-pad adjoint."""
+        from . import tc
+        g = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()  # [B,OH,OW,C]
+        B, OH, OW, C = g.shape
+        if C % 8:
+            raise NotImplementedError("JBUFeatUpUpsampler backward needs a channel count that is a multiple of 8")
+        dev, st = g.device, _lib.stream_ptr()
+        guidance = guidance.detach().float()
+        conv = self.upsampler.fixup_proj[1]
+        key = (conv.weight._version, str(dev))
+        if getattr(self, "_fixT_key", None) != key:
+            self._fixT_w = tc.pack_linear_weight(self._flat(conv.weight).t().contiguous()).to(dev)
+            self._fixT_key = key
+        M = B * OH * OW
+        gb = g.view(M, C).to(torch.bfloat16)
+        dx = tc.gemm(gb, self._fixT_w, resid=g.view(M, C), alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
+        GH, GW = 16 * src_hw[0], 16 * src_hw[1]
+        if (OH, OW) != (GH, GW):
+            d = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
+            _lib.call("isp_bilinear_ac_nhwc_bwd", _lib.dptr(dx), _lib.dptr(d), B, C, GH, GW, OH, OW, st)
+            dx = d
+        for up in (self.upsampler.up4, self.upsampler.up3, self.upsampler.up2, self.upsampler.up1):
+            filt = self._filters(up, guidance, GH, GW, 49)
+            dpad = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
+            _lib.call("isp_adaptive_conv_grad_input", _lib.dptr(dx), _lib.dptr(filt), _lib.dptr(dpad), B, GH, GW, C, st)
+            GH, GW = GH // 2, GW // 2
+            dx = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
+            _lib.call("isp_jbu_bicubic2x_reflectpad_bwd", _lib.dptr(dpad), _lib.dptr(dx), B, GH, GW, C, st)
+        return dx.permute(0, 3, 1, 2)
+
+    def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, size=None) -> torch.Tensor:
         x = to_nhwc_f32(source.detach())
         guidance = guidance.detach().float()
         for up in (self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4):
@@ -250,6 +294,20 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             _lib.call("isp_gemm_f32_simt", _lib.dptr(x), _lib.dptr(self._flat(conv.weight)), _lib.dptr(self._fix_b),
                       _lib.dptr(x), 0.1, _lib.dptr(out), B * OH * OW, C, C, _lib.stream_ptr())
         return out.permute(0, 3, 1, 2)
+
+
+class _JBUFn(torch.autograd.Function):
+    """Frozen JBU stack with an input gradient for `source` (the backbone features)."""
+
+    @staticmethod
+    def forward(ctx, mod, source, guidance, size):
+        ctx.mod, ctx.guidance, ctx.size = mod, guidance, size
+        ctx.src_hw = (source.shape[2], source.shape[3])
+        return mod._forward_impl(source, guidance, size)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, ctx.mod._backward_impl(grad_out, ctx.guidance, ctx.src_hw, ctx.size), None, None
 
 
 UPSAMPLER_REGISTRY = {

@@ -127,7 +127,7 @@ def test_bilinear_resize_adjoint():
         assert relerr(xd.grad, xr.grad) < 1e-5, (B, h, w, C, H, W)
 
 
-@pytest.mark.parametrize("up_type", ["bilinear", "identity"])
+@pytest.mark.parametrize("up_type", ["bilinear", "identity", "jbu_featup"])
 def test_pipeline_gradients_vs_oracle_autograd(up_type):
     """Whole differentiable chain of the 'noup' / 'bilinear' configs (models/sbd/dinov2/patch-embed_{noup,bilinear}.py):
     click maps -> trainable PatchEmbed -> frozen ViT -> resize -> trainable ConvSegHead.  Gradients of
@@ -136,7 +136,11 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     from oracle import distmaps as odm
     torch.manual_seed(0)
     B, H, W = 2, 56, 84
-    pipe = isp.ISegPipeline(up_type, {}).to(DEV)
+    pipe = isp.ISegPipeline(up_type, {"backbone_type": "dinov2"} if up_type == "jbu_featup" else {}).to(DEV)
+    if up_type == "jbu_featup":
+        from oracle import jbu as ojbu
+        usd = ojbu.init_state_dict(384, seed=0)
+        pipe.upsampler.upsampler.load_state_dict(usd)
     pipe.embed_coords = isp.PatchEmbed((H, W), (14, 14), 3, 384).to(DEV)
     vsd = synth.vit_state_dict(384, depth=12, seed=0)
     pipe.backbone.model.load_state_dict(vsd)
@@ -154,7 +158,10 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
     emb = ohead.patch_embed_forward(pr, torch.cat([image[:, 3:], maps], 1))
     lr = ovit.dinov2_forward(vsd, nimg, emb)
-    feats = ohead.bilinear_align_corners(lr, (H, W)) if up_type == "bilinear" else lr
+    if up_type == "jbu_featup":
+        feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
+    else:
+        feats = ohead.bilinear_align_corners(lr, (H, W)) if up_type == "bilinear" else lr
     want = ohead.convhead_forward(hr_, feats)
     if tuple(want.shape[2:]) != (H, W):
         want = ohead.bilinear_align_corners(want, (H, W))
@@ -171,3 +178,38 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     for k, v in hr_.items():
         got = dict(pipe.head.named_parameters())[k].grad
         assert cosine(got, v.grad) > 0.99, (k, cosine(got, v.grad))
+
+
+def test_bicubic_reflectpad_adjoint():
+    g = torch.Generator().manual_seed(6)
+    for (B, h, w, C) in [(2, 4, 4, 8), (1, 5, 7, 64), (1, 16, 16, 384), (1, 2, 3, 4)]:
+        x = torch.randn(B, C, h, w, generator=g)
+        go = torch.randn(B, C, 2 * h + 6, 2 * w + 6, generator=g)
+        xr = x.clone().requires_grad_(True)
+        up = F.interpolate(xr, size=(2 * h, 2 * w), mode="bicubic", align_corners=False)
+        F.pad(up, [3] * 4, mode="reflect").backward(go)
+        gs = torch.empty(B, h, w, C, device=DEV)
+        _call("isp_jbu_bicubic2x_reflectpad_bwd", go.permute(0, 2, 3, 1).contiguous().to(DEV), gs, B, h, w, C)
+        assert relerr(gs.permute(0, 3, 1, 2), xr.grad) < 1e-5, (B, h, w, C)
+
+
+@pytest.mark.parametrize("size", [None, (56, 56)])
+def test_jbu_source_gradient_vs_oracle_autograd(size):
+    import isegprobe_b200 as isp
+    from oracle import jbu as ojbu
+    up = isp.JBUFeatUpUpsampler("dinov2").to(DEV).eval()
+    sd = ojbu.init_state_dict(384, seed=0)
+    up.upsampler.load_state_dict(sd)
+    src = synth.lr_features(2, 384, 4, 4, seed=2)
+    gd = (synth.image_batch(2, 56, 56, seed=1) - 0.45) / 0.225
+    sr = src.clone().requires_grad_(True)
+    want = ojbu.jbu_stack_forward(sd, sr, gd)
+    if size is not None:
+        want = ohead.bilinear_align_corners(want, size)
+    gout = torch.randn(want.shape, generator=torch.Generator().manual_seed(7))
+    want.backward(gout)
+    s = src.to(DEV).requires_grad_(True)
+    out = up.forward_resized(s, gd.to(DEV), size)
+    out.backward(gout.to(DEV))
+    assert relerr(out, want) < 1e-3
+    assert relerr(s.grad, sr.grad) < 5e-3 and cosine(s.grad, sr.grad) > 0.9999, (relerr(s.grad, sr.grad), cosine(s.grad, sr.grad))
