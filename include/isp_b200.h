@@ -201,7 +201,7 @@ int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, i
  *     bf16 operands with unit stride along K, D bf16 | f32 with unit stride along N, all other strides
  *     (row, head, batch; in elements) explicit -- heads may be column slices of a packed [tokens, 3C] matrix.
  * Row / element kernels:
- *   isp_layernorm_rows_bwd: dx = LN'(x)^T (gamma * dy) + resid (fp32; optional bf16 copy of dx), C <= 1024;
+ *   isp_layernorm_rows_bwd: dx = LN'(x)^T (gamma * dy) + resid (x fp32 | bf16, dx fp32 + optional bf16 copy), C <= 1024;
  *   isp_gelu_bwd_bf16:      dpre = dh * gelu'(pre)  (nn.GELU, erf form), n even;
  *   isp_softmax_rows:       P[r, :ncols] = softmax(S[r, :ncols]) (fp32 -> bf16), zeros up to ncols_pad;
  *   isp_attn_ds_rows:       dS = P * (dP - sum_j P dP) per row, zeros up to ncols_pad;
@@ -210,7 +210,7 @@ int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long
                              long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
                              long long d_sb, int out_bf16, int M, int N, int K, int H, int B, float alpha,
                              isp_stream_t stream);
-int isp_layernorm_rows_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, const float* gamma,
                            const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
                            long long M, int C, float eps, isp_stream_t stream);
 int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream);

@@ -28,8 +28,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // one warp per row; C <= 32 * kMaxPerLane
 constexpr int kMaxPerLane = 32;
 
+template <bool X_BF16>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy,
-                                                            const float* __restrict__ x, long long ldx,
+                                                            const void* __restrict__ xv_, long long ldx,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ resid, long long ldr,
                                                             float* __restrict__ dx, long long lddx,
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* xr = x + row * ldx;
+  const float* xr = reinterpret_cast<const float*>(xv_) + row * ldx;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv_) + row * ldx;
   const float* dr = dy + row * lddy;
   float xv[kMaxPerLane], gv[kMaxPerLane];
   float s = 0.f;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = 0; i < kMaxPerLane; ++i) {
     if (i < n) {
       const int c = lane + 32 * i;
-      xv[i] = c < C ? xr[c] : 0.f;
+      xv[i] = c < C ? (X_BF16 ? __bfloat162float(xb[c]) : xr[c]) : 0.f;
       gv[i] = c < C ? dr[c] * __ldg(gamma + c) : 0.f;
       s += xv[i];
     }
@@ -159,17 +161,20 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __r
 
 using namespace isp;
 
-// Backward of LayerNorm over the last dimension of x [M, C] (fp32, row pitch ldx), affine weight gamma:
+// Backward of LayerNorm over the last dimension of x [M, C] (fp32 | bf16, row pitch ldx), affine weight gamma:
 // dx = LN'(x)^T (gamma * dy) (+ resid, the gradient arriving through the residual connection).  dx_bf16 (optional)
 // receives a bf16 copy for the next GEMM.  C <= 1024.
-extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, const float* gamma,
                                       const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16,
                                       long long ldb, long long M, int C, float eps, isp_stream_t stream) {
   ISP_REQUIRE(dy && x && gamma && dx, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: null pointer");
   ISP_REQUIRE(M > 0 && C > 0 && C <= 32 * vb::kMaxPerLane, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: bad shape (C <= 1024)");
-  vb::layernorm_bwd_kernel<<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx,
-                                                                     reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C,
-                                                                     eps);
+  if (x_bf16)
+    vb::layernorm_bwd_kernel<true><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
+        dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
+  else
+    vb::layernorm_bwd_kernel<false><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
+        dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
   ISP_CHECK_LAUNCH("layernorm_bwd_kernel");
   return ISP_OK;
 }

@@ -293,12 +293,16 @@ class DINOv2Featurizer(nn.Module):
         return P, P["bwd"]
 
     @staticmethod
-    def _ln_bwd(dy, x, gamma, resid, C, eps=1e-6):
+    def _ln_bwd(dy, x, gamma, resid, C, eps=1e-6, ldb=None):
+        """LayerNorm backward over rows (x fp32 or bf16): returns (dx fp32 [M,C], bf16 copy [M,ldb])."""
         M = x.shape[0]
         dx = torch.empty(M, C, dtype=torch.float32, device=x.device)
-        dxb = torch.empty(M, C, dtype=torch.bfloat16, device=x.device)
-        _call("isp_layernorm_rows_bwd", dy, dy.stride(0), x, x.stride(0), gamma, resid,
-              0 if resid is None else resid.stride(0), dx, C, dxb, C, M, C, float(eps))
+        ldb = C if ldb is None else ldb
+        dxb = torch.empty(M, ldb, dtype=torch.bfloat16, device=x.device)
+        if ldb > C:
+            dxb[:, C:].zero_()
+        _call("isp_layernorm_rows_bwd", dy, dy.stride(0), x, int(x.dtype == torch.bfloat16), x.stride(0), gamma, resid,
+              0 if resid is None else resid.stride(0), dx, C, dxb, dxb.stride(0), M, C, float(eps))
         return dx, dxb
 
     def _attention_bwd(self, qkv, dO, B, T, C, nh):

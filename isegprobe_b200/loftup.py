@@ -220,8 +220,11 @@ class LoftUpUpsampler(BaseUpsampler):
 
     # ---------------------------------------------------------------- forward
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and source.requires_grad:
-            raise NotImplementedError("LoftUpUpsampler: activation backward is not implemented yet")
+        if torch.is_grad_enabled() and source.requires_grad:  # frozen weights, but the features' gradient flows through
+            return _LoftUpFn.apply(self, source, guidance)
+        return self._forward_impl(source, guidance, None)
+
+    def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, saved) -> torch.Tensor:
         dev = guidance.device
         P = self._pack(dev)
         D, hd, C = P["D"], P["hd"], self.n_dim
@@ -235,12 +238,17 @@ class LoftUpUpsampler(BaseUpsampler):
         mm = torch.empty(6, dtype=torch.int32, device=dev)
         _call("isp_minmax_per_channel", img, mm, B, H, W, img.stride(0), img.stride(1))
         out = torch.empty(B, H, W, C, dtype=self.out_dtype, device=dev)
+        if saved is not None:
+            saved.update({"src": src, "chunks": [], "H": H, "W": W, "h": h, "w": w})
         for b0 in range(0, B, self.chunk_images):
             b1 = min(B, b0 + self.chunk_images)
-            self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w)
+            keep = None if saved is None else {"b0": b0, "b1": b1}
+            self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w, keep)
+            if saved is not None:
+                saved["chunks"].append(keep)
         return out.permute(0, 3, 1, 2)
 
-    def _forward_chunk(self, P, img, src, mm, out, H, W, h, w):
+    def _forward_chunk(self, P, img, src, mm, out, H, W, h, w, keep=None):
         dev = img.device
         D, hd, C, nh = P["D"], P["hd"], self.n_dim, self.HEADS
         HP, KP = P["HP"], P["KP"]
@@ -263,6 +271,8 @@ class LoftUpUpsampler(BaseUpsampler):
         _call("isp_loftup_lr_prepare", src, *src.stride(), P["cn_w"], P["cn_b"], self._grid(P, h, dev),
               self._grid(P, w, dev), P["freqs5"], P["lb_sin"], P["lb_cos"], kv, B, C, h, w, 1e-5)
         Tp = tc.round_up(T, 128)
+        if keep is not None:  # what the activation backward re-reads: the query stream at every residual point, kv
+            keep["kv"], keep["xs"] = kv, [x]
         for L in P["layers"]:
             kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, tc.round_up(D, 8))
             Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
@@ -284,6 +294,8 @@ class LoftUpUpsampler(BaseUpsampler):
             del Q
             x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp, stats_out=st_b)
             del O
+            if keep is not None:
+                keep["xs"].append(x)
             if fuse:
                 W1, g1, b1 = L["W1_ln"]
                 h1 = tc.gemm(x, W1, bias=b1, act="gelu_tanh", out_dtype=bf, N=C, K=D, ln_stats=st_b, ln_g=g1,
@@ -294,6 +306,8 @@ class LoftUpUpsampler(BaseUpsampler):
                 del hn
             x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp, stats_out=st_a)
             del h1
+            if keep is not None:
+                keep["xs"].append(x)
         if fuse:
             Wf, gf, bfin = P["Wf_ln"]
             y = tc.gemm(x, Wf, bias=bfin, out_dtype=torch.float32, N=C, K=D, ln_stats=st_a, ln_g=gf, ln_eps=1e-5)
@@ -305,3 +319,182 @@ class LoftUpUpsampler(BaseUpsampler):
             del xn
         _call("isp_layernorm_rows", y, 0, C, out.view(M, C), int(out.dtype == torch.bfloat16), C, P["lnf_w"], P["lnf_b"],
               M, C, 1e-6)
+
+
+    # ---------------------------------------------------------------- activation backward (d loss / d source)
+    def _pack_bwd(self, dev):
+        """Transposed packed weights: the dgrad of y = a W^T is dy W, a GEMM with W^T as the weight."""
+        P = self._pack(dev)
+        if "bwd" not in P:
+            up = self.upsampler.upsampler
+            D, hd, nh, HP = P["D"], P["hd"], self.HEADS, P["HP"]
+            pw = lambda w: tc.pack_linear_weight(w.detach().float().t().contiguous()).to(dev)
+            out = []
+            for ca, ff in up.ca_transformer.layers:
+                Wi = ca.attention.in_proj_weight.detach().float()
+                sc = 1.0 / math.sqrt(hd)
+                Wo = ca.attention.out_proj.weight.detach().float()
+                Wo_p = torch.zeros(D, nh * HP)
+                Wq_p = torch.zeros(nh * HP, D)
+                for hh in range(nh):
+                    Wo_p[:, hh * HP:hh * HP + hd] = Wo[:, hh * hd:(hh + 1) * hd]
+                    Wq_p[hh * HP:hh * HP + hd] = Wi[hh * hd:(hh + 1) * hd] * sc
+                out.append({"WqT": pw(Wq_p), "WoT": pw(Wo_p), "WkT": pw(Wi[D:2 * D]), "WvT": pw(Wi[2 * D:]),
+                            "W1T": pw(ff.net[1].weight), "W2T": pw(ff.net[4].weight)})
+            P["bwd"] = out
+            P["WfT"] = pw(up.final_conv[0].weight.detach().float().reshape(self.n_dim, D))
+        return P, P["bwd"]
+
+    def _ln_bwd(self, dy, x, gamma, resid, C, eps, ldb):
+        from .featurizers import DINOv2Featurizer
+        return DINOv2Featurizer._ln_bwd(dy, x, gamma, resid, C, eps, ldb)
+
+    def _attention_bwd_image(self, Q, dO, Kp, Vp, Kt, need_dq, HW, T, nh, HP):
+        """One image: Q, dO [HW, nh*HP] bf16; Kp, Vp [nh, T, HP] bf16 (rows = keys), Kt [nh, HP, T8] -> (dQ [HW, nh*HP] bf16
+        or None, dK, dV [nh, T, HP] fp32).  Probabilities are recomputed and materialised per image ([nh, HW, T])."""
+        dev, bf = Q.device, torch.bfloat16
+        st = _lib.stream_ptr()
+
+        def bgemm(A, a_str, Wm, w_str, Dm, d_str, out_bf16, M, N, K):
+            _lib.call("isp_gemm_bf16_tc_batched", A, *a_str, Wm, *w_str, Dm, *d_str, int(out_bf16), M, N, K, nh, 1, 1.0, st)
+
+        row = (nh * HP, HP, HW * nh * HP)   # (row, head, image) strides of a head slice of Q / dO / dQ
+        key = (HP, T * HP, nh * T * HP)     # ... of Kp / Vp / dK / dV  [nh, T, HP]
+        Tp = tc.round_up(T, 8)                # row pitch of the score-shaped tensors (TMA: 16-byte strides)
+        sq = (Tp, HW * Tp, nh * HW * Tp)      # ... of the score-shaped [nh, HW, Tp] tensors
+        tr = (Tp, HP * Tp, nh * HP * Tp)      # ... of Kt [nh, HP, Tp]
+        S = torch.empty(nh, HW, Tp, dtype=torch.float32, device=dev)
+        bgemm(_lib.dptr(Q), row, _lib.dptr(Kp), key, _lib.dptr(S), sq, False, HW, T, HP)           # S = Q K^T
+        Pm = torch.empty(nh, HW, Tp, dtype=bf, device=dev)
+        _call("isp_softmax_rows", S, Tp, Pm, Tp, nh * HW, T, Tp)
+        bgemm(_lib.dptr(dO), row, _lib.dptr(Vp), key, _lib.dptr(S), sq, False, HW, T, HP)          # dP = dO V^T (reuses S)
+        dS = torch.empty(nh, HW, Tp, dtype=bf, device=dev)
+        _call("isp_attn_ds_rows", Pm, Tp, S, Tp, dS, Tp, nh * HW, T, Tp)
+        del S
+        dQ = None
+        if need_dq:
+            dQ = torch.empty(HW, nh * HP, dtype=bf, device=dev)
+            bgemm(_lib.dptr(dS), sq, _lib.dptr(Kt), tr, _lib.dptr(dQ), row, True, HW, HP, T)      # dQ = dS K
+        HWp = tc.round_up(HW, 8)
+        tq = (HWp, T * HWp, nh * T * HWp)   # transposed score-shaped [nh, T, HWp]
+        tx = (HWp, HP * HWp, nh * HP * HWp)  # Q^T / dO^T [nh, HP, HWp]
+        Mt = torch.empty(nh, T, HWp, dtype=bf, device=dev)
+        Xt = torch.empty(nh, HP, HWp, dtype=bf, device=dev)
+        dK = torch.empty(nh, T, HP, dtype=torch.float32, device=dev)
+        dV = torch.empty(nh, T, HP, dtype=torch.float32, device=dev)
+        _call("isp_transpose_bf16_batched", dS, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
+        _call("isp_repack_heads", Q, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
+        bgemm(_lib.dptr(Mt), tq, _lib.dptr(Xt), tx, _lib.dptr(dK), key, False, T, HP, HW)          # dK = dS^T Q
+        _call("isp_transpose_bf16_batched", Pm, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
+        _call("isp_repack_heads", dO, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
+        bgemm(_lib.dptr(Mt), tq, _lib.dptr(Xt), tx, _lib.dptr(dV), key, False, T, HP, HW)          # dV = P^T dO
+        return dQ, dK, dV
+
+    def _backward_chunk(self, P, PB, keep, g, H, W, h, w):
+        """g: [B,H,W,C] fp32 gradient of this chunk's output -> gradient w.r.t. the chunk's kv rows [B*T, D] fp32."""
+        dev, bf = g.device, torch.bfloat16
+        D, hd, C, nh, HP = P["D"], P["hd"], self.n_dim, self.HEADS, P["HP"]
+        Dp, D8 = tc.round_up(D, 16), tc.round_up(D, 8)
+        B = g.shape[0]
+        HW, T = H * W, h * w
+        M = B * HW
+        xs, kv = keep["xs"], keep["kv"]
+        # out = LN2d(y), y = conv1x1(LN_n(x_last))
+        xn = self._ln(xs[-1], P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
+        y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
+        del xn
+        dy, dyb = self._ln_bwd(g.reshape(M, C), y, P["lnf_w"], None, C, 1e-6, C)
+        del y, dy
+        dn = tc.gemm(dyb, P["WfT"], out_dtype=torch.float32, N=D, K=C)
+        dx, dxb = self._ln_bwd(dn, xs[-1], P["n_w"], None, D, 1e-5, Dp)
+        del dn, dyb
+        dkv = None
+        for li in range(len(P["layers"]) - 1, -1, -1):
+            L, LB = P["layers"][li], PB[li]
+            x_in, x_a = xs[2 * li], xs[2 * li + 1]
+            # FeedForward: x_f = x_a + W2 gelu(W1 LN_f(x_a) + b1) + b2
+            hn = self._ln(x_a, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
+            pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf, N=C, K=D)
+            del hn
+            dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf, N=C, K=D)
+            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel())
+            del pre
+            dn = tc.gemm(dh, LB["W1T"], out_dtype=torch.float32, N=D, K=C)
+            del dh
+            dx, dxb = self._ln_bwd(dn, x_a, L["nf_w"], dx, D, 1e-5, Dp)
+            del dn
+            # cross-attention: x_a = x_in + Wo attn(Wq LN_q(x_in), K, V) + bo
+            dO = tc.gemm(dxb, LB["WoT"], out_dtype=bf, N=nh * HP, K=D)
+            qn = self._ln(x_in, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
+            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
+            del qn
+            kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, D8)
+            Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
+            Vl = tc.gemm(kvn, L["Wv"], bias=L["bv"], out_dtype=torch.float32, N=D, K=D)
+            Kp = torch.empty(B, nh, T, HP, dtype=bf, device=dev)
+            Vp = torch.empty(B, nh, T, HP, dtype=bf, device=dev)
+            Kt = torch.empty(B, nh, HP, tc.round_up(T, 8), dtype=bf, device=dev)
+            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, T, nh, HP, 0)
+            _call("isp_repack_heads", Vl, 0, D, 0, hd, Vp, B, T, T, nh, HP, 0)
+            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kt, B, T, tc.round_up(T, 8), nh, HP, 1)
+            need_dq = li > 0  # the first layer's queries come from the image only
+            dQ = torch.empty(M, nh * HP, dtype=bf, device=dev) if need_dq else None
+            dK = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
+            dV = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
+            for b in range(B):
+                dq_b, dK[b], dV[b] = self._attention_bwd_image(Q[b * HW:(b + 1) * HW], dO[b * HW:(b + 1) * HW], Kp[b], Vp[b],
+                                                               Kt[b], need_dq, HW, T, nh, HP)
+                if need_dq:
+                    dQ[b * HW:(b + 1) * HW] = dq_b
+            del Q, dO
+            if need_dq:
+                dn = tc.gemm(dQ, LB["WqT"], out_dtype=torch.float32, N=D, K=nh * HP)
+                dx, dxb = self._ln_bwd(dn, x_in, L["nq_w"], dx, D, 1e-5, Dp)
+                del dn, dQ
+            # back through the K / V projections and LN_kv
+            dKl = dK[..., :hd].permute(0, 2, 1, 3).reshape(B * T, D)
+            dVl = dV[..., :hd].permute(0, 2, 1, 3).reshape(B * T, D)
+            dKb = torch.zeros(B * T, D8, dtype=bf, device=dev)
+            dVb = torch.zeros(B * T, D8, dtype=bf, device=dev)
+            dKb[:, :D], dVb[:, :D] = dKl.to(bf), dVl.to(bf)
+            dkvn = tc.gemm(dKb, LB["WkT"], out_dtype=torch.float32, N=D, K=D)
+            dkvn = tc.gemm(dVb, LB["WvT"], resid=dkvn, out_dtype=torch.float32, N=D, K=D)
+            dkv, _ = self._ln_bwd(dkvn, kv, L["nkv_w"], dkv, D, 1e-5, D8)
+        return dkv
+
+    def _backward_impl(self, saved, grad_out):
+        dev = grad_out.device
+        P, PB = self._pack_bwd(dev)
+        C, D = self.n_dim, P["D"]
+        H, W, h, w = saved["H"], saved["W"], saved["h"], saved["w"]
+        g = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()
+        src = saved["src"]
+        B = src.shape[0]
+        T = h * w
+        src_rows = src.permute(0, 2, 3, 1).reshape(B * T, C).contiguous()
+        dsrc = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+        for keep in saved["chunks"]:
+            b0, b1 = keep["b0"], keep["b1"]
+            dkv = self._backward_chunk(P, PB, keep, g[b0:b1], H, W, h, w)
+            # kv = [ChannelNorm(src) | sine PE]: only the first C columns depend on the source
+            d, _ = self._ln_bwd(dkv, src_rows[b0 * T:b1 * T], P["cn_w"], None, C, 1e-5, C)
+            dsrc[b0 * T:b1 * T] = d
+            keep.clear()
+        return dsrc.view(B, h, w, C).permute(0, 3, 1, 2)
+
+
+class _LoftUpFn(torch.autograd.Function):
+    """Frozen LoftUp with an input gradient for `source` (the backbone features)."""
+
+    @staticmethod
+    def forward(ctx, mod, source, guidance):
+        saved = {}
+        out = mod._forward_impl(source, guidance, saved)
+        ctx.mod, ctx.saved = mod, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d = ctx.mod._backward_impl(ctx.saved, grad_out)
+        ctx.saved = None
+        return None, d, None

@@ -57,7 +57,7 @@ def test_layernorm_gelu_softmax_backward_kernels():
     F.layer_norm(xr, (C,), gamma, beta, 1e-6).backward(dy)
     dx = torch.empty(M, C, device=DEV)
     dxb = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
-    _call("isp_layernorm_rows_bwd", dy.to(DEV), C, x.to(DEV), C, gamma.to(DEV), res.to(DEV), C, dx, C, dxb, C, M, C, 1e-6)
+    _call("isp_layernorm_rows_bwd", dy.to(DEV), C, x.to(DEV), 0, C, gamma.to(DEV), res.to(DEV), C, dx, C, dxb, C, M, C, 1e-6)
     assert relerr(dx, xr.grad + res) < 1e-5
     assert relerr(dxb.float(), xr.grad + res) < 1e-2
     # GELU backward (erf form)
@@ -127,7 +127,7 @@ def test_bilinear_resize_adjoint():
         assert relerr(xd.grad, xr.grad) < 1e-5, (B, h, w, C, H, W)
 
 
-@pytest.mark.parametrize("up_type", ["bilinear", "identity", "jbu_featup"])
+@pytest.mark.parametrize("up_type", ["bilinear", "identity", "jbu_featup", "loftup"])
 def test_pipeline_gradients_vs_oracle_autograd(up_type):
     """Whole differentiable chain of the 'noup' / 'bilinear' configs (models/sbd/dinov2/patch-embed_{noup,bilinear}.py):
     click maps -> trainable PatchEmbed -> frozen ViT -> resize -> trainable ConvSegHead.  Gradients of
@@ -136,7 +136,13 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     from oracle import distmaps as odm
     torch.manual_seed(0)
     B, H, W = 2, 56, 84
-    pipe = isp.ISegPipeline(up_type, {"backbone_type": "dinov2"} if up_type == "jbu_featup" else {}).to(DEV)
+    params = {"jbu_featup": {"backbone_type": "dinov2"}, "loftup": {"upsampler_path": None, "n_dim": 384}}.get(up_type, {})
+    pipe = isp.ISegPipeline(up_type, params).to(DEV)
+    if up_type == "loftup":
+        from oracle import loftup as oloft
+        lsd, lcn = synth.loftup_state_dict(384, seed=0), synth.channelnorm_state_dict(384, seed=1)
+        pipe.upsampler.upsampler.upsampler.load_state_dict(lsd)
+        pipe.upsampler.upsampler.channelnorm.load_state_dict(lcn)
     if up_type == "jbu_featup":
         from oracle import jbu as ojbu
         usd = ojbu.init_state_dict(384, seed=0)
@@ -158,7 +164,9 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
     emb = ohead.patch_embed_forward(pr, torch.cat([image[:, 3:], maps], 1))
     lr = ovit.dinov2_forward(vsd, nimg, emb)
-    if up_type == "jbu_featup":
+    if up_type == "loftup":
+        feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"])
+    elif up_type == "jbu_featup":
         feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
     else:
         feats = ohead.bilinear_align_corners(lr, (H, W)) if up_type == "bilinear" else lr
@@ -213,3 +221,28 @@ def test_jbu_source_gradient_vs_oracle_autograd(size):
     out.backward(gout.to(DEV))
     assert relerr(out, want) < 1e-3
     assert relerr(s.grad, sr.grad) < 5e-3 and cosine(s.grad, sr.grad) > 0.9999, (relerr(s.grad, sr.grad), cosine(s.grad, sr.grad))
+
+
+@pytest.mark.parametrize("B,H,W,h,w", [(2, 28, 42, 2, 3), (3, 56, 56, 4, 4)])
+def test_loftup_source_gradient_vs_oracle_autograd(B, H, W, h, w):
+    from isegprobe_b200.loftup import LoftUpUpsampler
+    from oracle import loftup as oloft
+    m = LoftUpUpsampler(None, n_dim=384)
+    sd, cn = synth.loftup_state_dict(384, seed=0), synth.channelnorm_state_dict(384, seed=1)
+    m.upsampler.upsampler.load_state_dict(sd, strict=True)
+    m.upsampler.channelnorm.load_state_dict(cn, strict=True)
+    m = m.to(DEV).eval()
+    m.chunk_images = 2
+    img = (synth.image_batch(B, H, W, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(B, 384, h, w, seed=2)
+    gout = torch.randn(B, 384, H, W, generator=torch.Generator().manual_seed(9))
+    lr_ref = lr.clone().requires_grad_(True)
+    want = oloft.loftup_forward(sd, lr_ref, img, cn["norm.weight"], cn["norm.bias"])
+    want.backward(gout)
+    s = lr.to(DEV).requires_grad_(True)
+    out = m(source=s, guidance=img.to(DEV))
+    out.backward(gout.to(DEV))
+    assert cosine(out, want) >= 0.999
+    c = cosine(s.grad, lr_ref.grad)
+    assert c > 0.99, c
+    assert relerr(s.grad, lr_ref.grad) < 0.2, relerr(s.grad, lr_ref.grad)
