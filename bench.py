@@ -9,10 +9,11 @@ over one batch of synthetic 448x448 images with random-init weights.
   loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)
   eval   : BASELINE.json configs[3]  (20-click NoC evaluation loop, MaskCLIP ViT-B/16 + LoftUp(512) + head,
            eval_mode fixed448 with flip TTA, one synthetic GrabCut-shaped sample per rank and step; clicks/s)
-  train  : BASELINE.json configs[4]  (IS training step: frozen DINOv2-S/14 + LoftUp features, ConvSegHead
-           forward/backward, NFL loss, gradient all-reduce, Adam; GLOBAL batch 64 split over the ranks --
-           strong scaling, as the reference's batch_size // ngpus; click-embedding gradient not included,
-           see DESIGN.md section 7)
+  train  : BASELINE.json configs[4]  (IS training step as the reference runs it: click maps -> trainable click
+           embedding -> frozen DINOv2-S/14 -> frozen LoftUp -> ConvSegHead, NFL loss, backward through the head AND
+           through the frozen upsampler / backbone down to the click embedding, gradient all-reduce, Adam; GLOBAL
+           batch 64 split over the ranks -- strong scaling, as the reference's batch_size // ngpus).
+           `--train-head-only` freezes the click embedding (features under no_grad, head forward/backward only).
 Multi-GPU: one process per GPU (torchrun), images sharded across ranks, no data-path
 collective (weak scaling); time = max over ranks of the CUDA-event time of the K steps.
 `--impl reference` times the CPU oracle port of the same path on the host cores.
@@ -219,6 +220,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="jbu")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-head-only", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -249,7 +251,7 @@ def main():
     img_d, pts_d = img_h.to(dev), pts_h.to(dev)
     if train:
         from isegprobe_b200.training import HeadTrainer
-        trainer = HeadTrainer(pipe)
+        trainer = HeadTrainer(pipe, train_embedding=not args.train_head_only)
         gt_h = (img_h[:, 3:] > 0.5).float().pin_memory()  # synthetic instance masks (the prev-mask channel's blobs)
         gt_d = gt_h.to(dev)
 
@@ -370,7 +372,8 @@ def main():
                     "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "ms_per_launch": t,
                     "algorithmic_flops_per_launch": flops}
     line = {
-        "metric": ("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd)" if train
+        "metric": (("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd"
+                    + (")" if args.train_head_only else " + click-embedding gradient through the frozen path)")) if train
                    else "images/sec @448^2 DINOv2-S/14 + upsampler forward"), "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if train else "weak", "vs_baseline": None,

@@ -42,10 +42,10 @@ def normalized_focal_loss(pred: torch.Tensor, label: torch.Tensor, alpha: float 
 class HeadTrainer:
     """One process per GPU; each rank steps on its own shard of the global batch."""
 
-    def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, train_embedding: bool = True):
         self.pipe = pipeline
         assert pipeline.head is not None, "the pipeline was built without a head"
-        self.train_embedding = (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic", "jbu_featup", "loftup")
+        self.train_embedding = train_embedding and (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic", "jbu_featup", "loftup")
                                 and hasattr(pipeline.backbone, "_backward_impl"))
         for p in pipeline.embed_coords.parameters():
             p.requires_grad = self.train_embedding  # see module docstring
