@@ -204,7 +204,7 @@ int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, i
  *   isp_layernorm_rows_bwd: dx = LN'(x)^T (gamma * dy) + resid (x fp32 | bf16, dx fp32 + optional bf16 copy), C <= 1024;
  *   isp_gelu_bwd_bf16:      dpre = dh * gelu'(pre)  (nn.GELU, erf form), n even;
  *   isp_softmax_rows:       P[r, :ncols] = softmax(S[r, :ncols]) (fp32 -> bf16), zeros up to ncols_pad;
- *   isp_attn_ds_rows:       dS = P * (dP - sum_j P dP) per row, zeros up to ncols_pad;
+ *   isp_attn_ds_rows:       dS = P * (dP - sum_j P dP) per row (dP fp32 | bf16), zeros up to ncols_pad;
  *   isp_transpose_bf16_batched: dst[z][c][r] = src[z][r][c]. */
 int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
                              long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
@@ -216,8 +216,8 @@ int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x
 int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream);
 int isp_softmax_rows(const float* S, long long lds, void* P_bf16, long long ldp, long long R, int ncols, int ncols_pad,
                      isp_stream_t stream);
-int isp_attn_ds_rows(const void* P_bf16, long long ldp, const float* dP, long long lddp, void* dS_bf16, long long ldds,
-                     long long R, int ncols, int ncols_pad, isp_stream_t stream);
+int isp_attn_ds_rows(const void* P_bf16, long long ldp, const void* dP, int dp_bf16, long long lddp, void* dS_bf16,
+                     long long ldds, long long R, int ncols, int ncols_pad, isp_stream_t stream);
 int isp_transpose_bf16_batched(const void* src, long long lds, long long src_z, void* dst, long long ldd, long long dst_z,
                                int Z, int R, int C, isp_stream_t stream);
 

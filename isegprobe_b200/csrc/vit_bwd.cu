@@ -87,6 +87,84 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
 }
 
+// Same, C % 4 == 0 and 16-byte aligned rows: a lane moves float4 (8 bytes of bf16 x) per step -- the scalar kernel ran
+// at 1 TB/s on the [802816, 404] query stream of the LoftUp backward.
+template <bool X_BF16>
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ dy, long long lddy,
+                                                                const void* __restrict__ xv_, long long ldx,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ resid, long long ldr,
+                                                                float* __restrict__ dx, long long lddx,
+                                                                __nv_bfloat16* __restrict__ dx_bf, long long ldb,
+                                                                long long M, int C, float eps) {
+  constexpr int kIt = 8;  // C <= 1024
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int C4 = C >> 2;
+  const float4* d4 = reinterpret_cast<const float4*>(dy + row * lddy);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 xv[kIt], gv[kIt];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kIt; ++i) {
+    const int c = lane + 32 * i;
+    xv[i] = gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C4) {
+      if (X_BF16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xv_) + row * ldx + 4 * c);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        xv[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        xv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv_) + row * ldx + 4 * c);
+      }
+      const float4 d = d4[c], g = __ldg(g4 + c);
+      gv[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kIt; ++i)
+    if (lane + 32 * i < C4) {
+      const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+      var += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < kIt; ++i)
+    if (lane + 32 * i < C4) {
+      xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd);
+      sa += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      sb += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    }
+  sa = warp_sum(sa) / (float)C;
+  sb = warp_sum(sb) / (float)C;
+#pragma unroll
+  for (int i = 0; i < kIt; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) {
+      float4 v = make_float4(rstd * (gv[i].x - sa - xv[i].x * sb), rstd * (gv[i].y - sa - xv[i].y * sb),
+                             rstd * (gv[i].z - sa - xv[i].z * sb), rstd * (gv[i].w - sa - xv[i].w * sb));
+      if (resid) {
+        const float4 r = *reinterpret_cast<const float4*>(resid + row * ldr + 4 * c);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dx + row * lddx + 4 * c) = v;
+      if (dx_bf) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned*>(&lo);
+        u.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(dx_bf + row * ldb + 4 * c) = u;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat162* __restrict__ dh,
                                                        const __nv_bfloat162* __restrict__ pre,
                                                        __nv_bfloat162* __restrict__ out, long long n2) {
@@ -119,21 +197,22 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int c = lane; c < ncols_pad; c += 32) p[c] = __float2bfloat16(c < ncols ? __expf(s[c] - mx) * inv : 0.f);
 }
 
+template <typename DPT>
 __global__ void __launch_bounds__(256) attn_ds_kernel(const __nv_bfloat16* __restrict__ P, long long ldp,
-                                                      const float* __restrict__ dP, long long lddp,
+                                                      const DPT* __restrict__ dP, long long lddp,
                                                       __nv_bfloat16* __restrict__ dS, long long ldds, long long R,
                                                       int ncols, int ncols_pad) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
   const __nv_bfloat16* p = P + row * ldp;
-  const float* dp = dP + row * lddp;
+  const DPT* dp = dP + row * lddp;
   float dot = 0.f;
-  for (int c = lane; c < ncols; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+  for (int c = lane; c < ncols; c += 32) dot += __bfloat162float(p[c]) * (float)dp[c];
   dot = warp_sum(dot);
   __nv_bfloat16* o = dS + row * ldds;
   for (int c = lane; c < ncols_pad; c += 32)
-    o[c] = __float2bfloat16(c < ncols ? __bfloat162float(p[c]) * (dp[c] - dot) : 0.f);
+    o[c] = __float2bfloat16(c < ncols ? __bfloat162float(p[c]) * ((float)dp[c] - dot) : 0.f);
 }
 
 // [Z][R][lds] (C valid columns) -> [Z][C][ldd] (R valid columns); 32 x 32 tiles through shared memory
@@ -156,6 +235,35 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __r
   }
 }
 
+// 64 x 64 tiles, 32-bit global accesses on both sides (two bf16 along the contiguous dimension); needs even R, C and
+// pitches.  The 32 x 32 / 16-bit kernel above moved the 1.6 GB score matrices of the LoftUp backward at 1.7 TB/s.
+__global__ void __launch_bounds__(256) transpose64_kernel(const __nv_bfloat16* __restrict__ src, long long lds,
+                                                          long long src_z, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                          long long dst_z, int R, int C) {
+  __shared__ unsigned short tile[64][65];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const unsigned short* s = reinterpret_cast<const unsigned short*>(src) + (long long)blockIdx.z * src_z;
+  unsigned short* d = reinterpret_cast<unsigned short*>(dst) + (long long)blockIdx.z * dst_z;
+  const int w = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k;
+    unsigned v = 0;
+    if (r0 + r < R && c0 + 2 * w < C) v = *reinterpret_cast<const unsigned*>(s + (long long)(r0 + r) * lds + c0 + 2 * w);
+    tile[r][2 * w] = (unsigned short)(v & 0xffffu);
+    tile[r][2 * w + 1] = (unsigned short)(v >> 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = ty + 8 * k;
+    if (c0 + c < C && r0 + 2 * w < R) {
+      const unsigned v = (unsigned)tile[2 * w][c] | ((unsigned)tile[2 * w + 1][c] << 16);
+      *reinterpret_cast<unsigned*>(d + (long long)(c0 + c) * ldd + r0 + 2 * w) = v;
+    }
+  }
+}
+
 }  // namespace vb
 }  // namespace isp
 
@@ -169,6 +277,20 @@ extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const voi
                                       long long ldb, long long M, int C, float eps, isp_stream_t stream) {
   ISP_REQUIRE(dy && x && gamma && dx, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: null pointer");
   ISP_REQUIRE(M > 0 && C > 0 && C <= 32 * vb::kMaxPerLane, ISP_ERR_BAD_SHAPE, "layernorm_rows_bwd: bad shape (C <= 1024)");
+  const int xs = x_bf16 ? 2 : 4;
+  const bool vec = C % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (ldx * xs) % (x_bf16 ? 8 : 16) == 0 && aligned16(dy) &&
+                   aligned16(dx) && aligned16(gamma) && ((uintptr_t)x % 16 == 0) && (!resid || (ldr % 4 == 0 && aligned16(resid))) &&
+                   (!dx_bf16 || (ldb % 4 == 0 && (uintptr_t)dx_bf16 % 8 == 0));
+  if (vec) {
+    if (x_bf16)
+      vb::layernorm_bwd_vec_kernel<true><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
+          dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
+    else
+      vb::layernorm_bwd_vec_kernel<false><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
+          dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
+    ISP_CHECK_LAUNCH("layernorm_bwd_vec_kernel");
+    return ISP_OK;
+  }
   if (x_bf16)
     vb::layernorm_bwd_kernel<true><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
         dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
@@ -201,13 +323,18 @@ extern "C" int isp_softmax_rows(const float* S, long long lds, void* P_bf16, lon
 }
 
 // dS[r, c] = P[r, c] * (dP[r, c] - sum_j P[r, j] dP[r, j]) for c < ncols, 0 up to ncols_pad.
-extern "C" int isp_attn_ds_rows(const void* P_bf16, long long ldp, const float* dP, long long lddp, void* dS_bf16,
-                                long long ldds, long long R, int ncols, int ncols_pad, isp_stream_t stream) {
+extern "C" int isp_attn_ds_rows(const void* P_bf16, long long ldp, const void* dP, int dp_bf16, long long lddp,
+                                void* dS_bf16, long long ldds, long long R, int ncols, int ncols_pad, isp_stream_t stream) {
   ISP_REQUIRE(P_bf16 && dP && dS_bf16 && R > 0 && ncols > 0 && ncols_pad >= ncols, ISP_ERR_BAD_SHAPE,
               "attn_ds_rows: bad arguments");
-  vb::attn_ds_kernel<<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(P_bf16), ldp, dP, lddp,
-                                                               reinterpret_cast<__nv_bfloat16*>(dS_bf16), ldds, R, ncols,
-                                                               ncols_pad);
+  if (dp_bf16)
+    vb::attn_ds_kernel<__nv_bfloat16><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(P_bf16), ldp, reinterpret_cast<const __nv_bfloat16*>(dP), lddp,
+        reinterpret_cast<__nv_bfloat16*>(dS_bf16), ldds, R, ncols, ncols_pad);
+  else
+    vb::attn_ds_kernel<float><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(P_bf16), ldp, reinterpret_cast<const float*>(dP), lddp,
+        reinterpret_cast<__nv_bfloat16*>(dS_bf16), ldds, R, ncols, ncols_pad);
   ISP_CHECK_LAUNCH("attn_ds_kernel");
   return ISP_OK;
 }
@@ -218,6 +345,14 @@ extern "C" int isp_transpose_bf16_batched(const void* src, long long lds, long l
   ISP_REQUIRE(src && dst && Z > 0 && R > 0 && C > 0 && lds >= C && ldd >= R && Z <= 65535, ISP_ERR_BAD_SHAPE,
               "transpose_bf16_batched: bad arguments");
   ISP_REQUIRE(cdiv(R, 32) <= 65535, ISP_ERR_UNSUPPORTED, "transpose_bf16_batched: too many rows");
+  if (R % 2 == 0 && C % 2 == 0 && lds % 2 == 0 && ldd % 2 == 0 && src_z % 2 == 0 && dst_z % 2 == 0 &&
+      (uintptr_t)src % 4 == 0 && (uintptr_t)dst % 4 == 0) {
+    const dim3 grid64((unsigned)cdiv(C, 64), (unsigned)cdiv(R, 64), (unsigned)Z);
+    vb::transpose64_kernel<<<grid64, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, src_z,
+                                                               reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_z, R, C);
+    ISP_CHECK_LAUNCH("transpose64_kernel");
+    return ISP_OK;
+  }
   const dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32), (unsigned)Z);
   vb::transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, src_z,
                                                            reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_z, R, C);

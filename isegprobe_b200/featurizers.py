@@ -327,7 +327,7 @@ class DINOv2Featurizer(nn.Module):
         bgemm(q0, tok, q0 + 2 * C, tok, _lib.dptr(S), sq, False, T, T, hd)                     # S = Q K^T
         _call("isp_softmax_rows", S, Tp, Pm, Tp, B * nh * T, T, Tp)
         bgemm(_lib.dptr(dO), (C, hd, T * C), q0 + 4 * C, tok, _lib.dptr(dP), sq, False, T, T, hd)  # dP = dO V^T
-        _call("isp_attn_ds_rows", Pm, Tp, dP, Tp, dS, Tp, B * nh * T, T, Tp)
+        _call("isp_attn_ds_rows", Pm, Tp, dP, 0, Tp, dS, Tp, B * nh * T, T, Tp)
         del S, dP
         dqkv = torch.empty(B * T, 3 * C, dtype=bf, device=dev)
         d0 = _lib.dptr(dqkv)

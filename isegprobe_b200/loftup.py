@@ -367,10 +367,10 @@ class LoftUpUpsampler(BaseUpsampler):
         bgemm(_lib.dptr(Q), row, _lib.dptr(Kp), key, _lib.dptr(S), sq, False, HW, T, HP)           # S = Q K^T
         Pm = torch.empty(nh, HW, Tp, dtype=bf, device=dev)
         _call("isp_softmax_rows", S, Tp, Pm, Tp, nh * HW, T, Tp)
-        bgemm(_lib.dptr(dO), row, _lib.dptr(Vp), key, _lib.dptr(S), sq, False, HW, T, HP)          # dP = dO V^T (reuses S)
-        dS = torch.empty(nh, HW, Tp, dtype=bf, device=dev)
-        _call("isp_attn_ds_rows", Pm, Tp, S, Tp, dS, Tp, nh * HW, T, Tp)
         del S
+        dS = torch.empty(nh, HW, Tp, dtype=bf, device=dev)  # holds dP (bf16: dS is stored in bf16 anyway), then dS in place
+        bgemm(_lib.dptr(dO), row, _lib.dptr(Vp), key, _lib.dptr(dS), sq, True, HW, T, HP)          # dP = dO V^T
+        _call("isp_attn_ds_rows", Pm, Tp, dS, 1, Tp, dS, Tp, nh * HW, T, Tp)
         dQ = None
         if need_dq:
             dQ = torch.empty(HW, nh * HP, dtype=bf, device=dev)

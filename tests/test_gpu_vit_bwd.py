@@ -60,6 +60,23 @@ def test_layernorm_gelu_softmax_backward_kernels():
     _call("isp_layernorm_rows_bwd", dy.to(DEV), C, x.to(DEV), 0, C, gamma.to(DEV), res.to(DEV), C, dx, C, dxb, C, M, C, 1e-6)
     assert relerr(dx, xr.grad + res) < 1e-5
     assert relerr(dxb.float(), xr.grad + res) < 1e-2
+    # scalar fallback (odd channel count) and bf16 x
+    C2 = 203
+    x2, dy2, g2 = torch.randn(50, C2, generator=g), torch.randn(50, C2, generator=g), torch.randn(C2, generator=g)
+    x2r = x2.clone().requires_grad_(True)
+    F.layer_norm(x2r, (C2,), g2, None, 1e-5).backward(dy2)
+    dx2 = torch.empty(50, C2, device=DEV)
+    _call("isp_layernorm_rows_bwd", dy2.to(DEV), C2, x2.to(DEV), 0, C2, g2.to(DEV), None, 0, dx2, C2, None, 0, 50, C2, 1e-5)
+    assert relerr(dx2, x2r.grad) < 1e-5
+    xb = (torch.randn(M, 416, generator=g) * 2).to(torch.bfloat16)
+    C3 = 404
+    g3, dy3 = torch.randn(C3, generator=g), torch.randn(M, C3, generator=g)
+    xbr = xb[:, :C3].float().requires_grad_(True)
+    F.layer_norm(xbr, (C3,), g3, None, 1e-5).backward(dy3)
+    dx3 = torch.empty(M, C3, device=DEV)
+    dx3b = torch.empty(M, 416, dtype=torch.bfloat16, device=DEV)
+    _call("isp_layernorm_rows_bwd", dy3.to(DEV), C3, xb.to(DEV), 1, 416, g3.to(DEV), None, 0, dx3, C3, dx3b, 416, M, C3, 1e-5)
+    assert relerr(dx3, xbr.grad) < 1e-5 and relerr(dx3b[:, :C3].float(), xbr.grad) < 1e-2
     # GELU backward (erf form)
     pre = (torch.randn(M, 1536, generator=g) * 1.5).to(torch.bfloat16)
     dh = torch.randn(M, 1536, generator=g).to(torch.bfloat16)
@@ -77,11 +94,15 @@ def test_layernorm_gelu_softmax_backward_kernels():
     want = torch.softmax(S[:, :T], -1)
     assert relerr(Pm[:, :T].float(), want) < 1e-2 and float(Pm[:, T:].float().abs().max()) == 0
     dS = torch.empty(R, Tp, dtype=torch.bfloat16, device=DEV)
-    _call("isp_attn_ds_rows", Pm, Tp, dP.to(DEV), Tp, dS, Tp, R, T, Tp)
+    _call("isp_attn_ds_rows", Pm, Tp, dP.to(DEV), 0, Tp, dS, Tp, R, T, Tp)
     Pf = Pm[:, :T].float().cpu()
     wantd = Pf * (dP[:, :T] - (Pf * dP[:, :T]).sum(-1, keepdim=True))
     assert relerr(dS[:, :T].float(), wantd) < 1e-2 and float(dS[:, T:].float().abs().max()) == 0
-    # batched transpose
+    # batched transpose: even sizes take the 64x64 / 32-bit kernel
+    src2 = torch.randn(3, 130, 200, generator=g).to(torch.bfloat16).to(DEV)
+    dst2 = torch.zeros(3, 198, 136, dtype=torch.bfloat16, device=DEV)
+    _call("isp_transpose_bf16_batched", src2, 200, 130 * 200, dst2, 136, 198 * 136, 3, 130, 198)
+    assert torch.equal(dst2[:, :, :130], src2[:, :, :198].transpose(1, 2)) and float(dst2[:, :, 130:].abs().max()) == 0
     src = torch.randn(5, 65, 72, generator=g).to(torch.bfloat16).to(DEV)
     dst = torch.zeros(5, 70, 72, dtype=torch.bfloat16, device=DEV)
     _call("isp_transpose_bf16_batched", src, 72, 65 * 72, dst, 72, 70 * 72, 5, 65, 70)
