@@ -375,19 +375,27 @@ class LoftUpUpsampler(BaseUpsampler):
         if need_dq:
             dQ = torch.empty(HW, nh * HP, dtype=bf, device=dev)
             bgemm(_lib.dptr(dS), sq, _lib.dptr(Kt), tr, _lib.dptr(dQ), row, True, HW, HP, T)      # dQ = dS K
+        # dK = dS^T Q and dV = P^T dO reduce over the HW queries: only (T / 128) x heads = 32 output tiles, so the
+        # reduction is split nsplit ways over the GEMM's batch dimension (batch stride = a column offset inside the
+        # transposed operands) and the fp32 partial results are summed afterwards.
         HWp = tc.round_up(HW, 8)
-        tq = (HWp, T * HWp, nh * T * HWp)   # transposed score-shaped [nh, T, HWp]
-        tx = (HWp, HP * HWp, nh * HP * HWp)  # Q^T / dO^T [nh, HP, HWp]
+        nsplit = next((n for n in (14, 16, 8, 7, 4, 2) if HW % n == 0 and (HW // n) % 8 == 0 and HW // n >= 1024), 1)
+        ck = HW // nsplit
         Mt = torch.empty(nh, T, HWp, dtype=bf, device=dev)
         Xt = torch.empty(nh, HP, HWp, dtype=bf, device=dev)
-        dK = torch.empty(nh, T, HP, dtype=torch.float32, device=dev)
-        dV = torch.empty(nh, T, HP, dtype=torch.float32, device=dev)
+        part = torch.empty(nsplit, nh, T, HP, dtype=torch.float32, device=dev)
+
+        def reduce_gemm():
+            _lib.call("isp_gemm_bf16_tc_batched", _lib.dptr(Mt), HWp, T * HWp, ck, _lib.dptr(Xt), HWp, HP * HWp, ck,
+                      _lib.dptr(part), HP, T * HP, nh * T * HP, 0, T, HP, ck, nh, nsplit, 1.0, st)
+            return part.sum(0) if nsplit > 1 else part[0].clone()
+
         _call("isp_transpose_bf16_batched", dS, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
         _call("isp_repack_heads", Q, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
-        bgemm(_lib.dptr(Mt), tq, _lib.dptr(Xt), tx, _lib.dptr(dK), key, False, T, HP, HW)          # dK = dS^T Q
+        dK = reduce_gemm()                                                                          # dK = dS^T Q
         _call("isp_transpose_bf16_batched", Pm, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
         _call("isp_repack_heads", dO, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
-        bgemm(_lib.dptr(Mt), tq, _lib.dptr(Xt), tx, _lib.dptr(dV), key, False, T, HP, HW)          # dV = P^T dO
+        dV = reduce_gemm()                                                                          # dV = P^T dO
         return dQ, dK, dV
 
     def _backward_chunk(self, P, PB, keep, g, H, W, h, w):
