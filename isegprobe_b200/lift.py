@@ -100,8 +100,11 @@ class LiFTUpsampler(BaseUpsampler):
         return P
 
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and source.requires_grad:
-            raise NotImplementedError("LiFTUpsampler: activation backward is not implemented yet")
+        if torch.is_grad_enabled() and source.requires_grad:  # frozen weights, but the features' gradient flows through
+            return _LiFTFn.apply(self, source, guidance)
+        return self._forward_impl(source, guidance, None)
+
+    def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, saved) -> torch.Tensor:
         dev = guidance.device
         P = self._pack(dev)
         img, src = guidance.detach().float(), source.detach().float()
@@ -138,7 +141,73 @@ class LiFTUpsampler(BaseUpsampler):
         _call("isp_copy_channels", i1p, 0, GH * GW * 32, 1, GW * 32, 32, cat2[..., Co:], 1, GH * GW * C2, GW * C2, C2,
               B, 32, GH, GW)
         Ch = C // 2
-        x = tc.conv3x3(cat2, P["dc1"][0], P["dc1"][1], C2, Ch, act="relu", ldy=tc.round_up(Ch, 8))
-        x = tc.conv3x3(x, P["dc2"][0], P["dc2"][1], Ch, Ch, act="relu", ldy=tc.round_up(Ch, 8))
+        x1 = tc.conv3x3(cat2, P["dc1"][0], P["dc1"][1], C2, Ch, act="relu", ldy=tc.round_up(Ch, 8))
+        x = tc.conv3x3(x1, P["dc2"][0], P["dc2"][1], Ch, Ch, act="relu", ldy=tc.round_up(Ch, 8))
+        if saved is not None:  # ReLU outputs (masks of the two dgrads) and the shapes
+            saved.update({"x1": x1, "x2": x, "B": B, "h": h, "w": w, "C": C})
         out = tc.gemm(x.view(B * GH * GW, -1), P["out_w"], bias=P["out_b"], out_dtype=torch.float32, N=C, K=Ch)
         return out.view(B, GH, GW, C).permute(0, 3, 1, 2)
+
+
+    # ---------------------------------------------------------------- activation backward (d loss / d source)
+    def _pack_bwd(self, dev):
+        P = self._pack(dev)
+        if "bwd" not in P:
+            L, C = self.lift, self.n_dim
+            dc = L.up1.conv_1.double_conv
+            w1, _ = _fold(dc[0], dc[1])
+            w2, _ = _fold(dc[3], dc[4])
+            flipT = lambda w: tc.pack_conv3x3_weight(w.detach().float().flip(2, 3).transpose(0, 1).contiguous()).to(dev)
+            up = L.up1.up
+            Cin, Co = up.weight.shape[0], up.weight.shape[1]
+            wt = up.weight.detach().float().permute(2, 3, 1, 0).reshape(4 * Co, Cin)
+            P["bwd"] = {"dc1T": flipT(w1), "dc2T": flipT(w2),
+                        "outT": tc.pack_linear_weight(L.outc.weight.detach().float().reshape(C, C // 2).t().contiguous()).to(dev),
+                        "upT": tc.pack_linear_weight(wt.t().contiguous()).to(dev)}
+        return P, P["bwd"]
+
+    def _backward_impl(self, saved, grad_out):
+        """Chain of dgrads back to the source channels: 1x1 conv, two 3x3 convs (ReLU masks), inverse pixel shuffle,
+        transposed conv (LiFT.py:106-122; the image branch carries no gradient)."""
+        dev, bf = grad_out.device, torch.bfloat16
+        P, PB = self._pack_bwd(dev)
+        B, h, w, C = saved["B"], saved["h"], saved["w"], saved["C"]
+        GH, GW = 2 * h, 2 * w
+        Cc, Ch = C + 32, C // 2
+        Co = Cc // 2
+        C2 = Co + 32
+        x1, x2 = saved["x1"], saved["x2"]
+        ldh = x2.shape[3]
+        g = grad_out.detach().float().permute(0, 2, 3, 1).contiguous().view(B * GH * GW, C).to(bf)
+        dz = tc.gemm(g, PB["outT"], out_dtype=bf, N=Ch, K=C, ldd=ldh).view(B, GH, GW, ldh)
+        dz = dz * (x2 > 0)  # ReLU of the second 3x3 conv
+        d1 = torch.empty(B, GH, GW, ldh, dtype=bf, device=dev)
+        if ldh > Ch:
+            d1.zero_()
+        _call("isp_conv3x3_dgrad_bf16_tc", dz.contiguous(), PB["dc2T"], x1, ldh, d1, 1, B, GH, GW, Ch, ldh, Ch, ldh)
+        ld2 = tc.round_up(C2, 8)
+        dcat2 = torch.empty(B, GH, GW, ld2, dtype=bf, device=dev)
+        _call("isp_conv3x3_dgrad_bf16_tc", d1, PB["dc1T"], None, 0, dcat2, 1, B, GH, GW, Ch, ldh, C2, ld2)
+        dup = torch.empty(B, h, w, 4 * Co, dtype=bf, device=dev)  # inverse of the pixel shuffle
+        for dy in range(2):
+            for dx in range(2):
+                dup[..., (dy * 2 + dx) * Co:(dy * 2 + dx + 1) * Co] = dcat2[:, dy::2, dx::2, :Co]
+        dcat1 = tc.gemm(dup.view(B * h * w, 4 * Co), PB["upT"], out_dtype=torch.float32, N=Cc, K=4 * Co)
+        return dcat1[:, :C].reshape(B, h, w, C).permute(0, 3, 1, 2)
+
+
+class _LiFTFn(torch.autograd.Function):
+    """Frozen LiFT with an input gradient for `source`."""
+
+    @staticmethod
+    def forward(ctx, mod, source, guidance):
+        saved = {}
+        out = mod._forward_impl(source, guidance, saved)
+        ctx.mod, ctx.saved = mod, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d = ctx.mod._backward_impl(ctx.saved, grad_out)
+        ctx.saved = None
+        return None, d, None

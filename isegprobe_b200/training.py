@@ -11,7 +11,7 @@ The click embedding (`embed_coords`) is trained THROUGH the frozen backbone and 
 upsamplers, the resize-only ones (`identity` = the "noup" configs, `bilinear`, and torch's `nearest` / `bicubic`) and the
 FeatUp JBU stack (linear in its source: chain of adjoint kernels) and LoftUp (cross-attention backward w.r.t. keys /
 values with recomputed, materialised probabilities) are differentiable, so those configurations train `embed_coords`
-exactly like the reference.  LiFT is still forward-only: with them `embed_coords` is kept frozen and the step is head-only."""
+exactly like the reference, as does LiFT (dgrads of its source branch).  Only the MaskCLIP backbone is still forward-only: with them `embed_coords` is kept frozen and the step is head-only."""
 import torch
 
 from . import dist as idist
@@ -45,7 +45,7 @@ class HeadTrainer:
     def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, train_embedding: bool = True):
         self.pipe = pipeline
         assert pipeline.head is not None, "the pipeline was built without a head"
-        self.train_embedding = train_embedding and (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic", "jbu_featup", "loftup")
+        self.train_embedding = train_embedding and (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic", "jbu_featup", "loftup", "lift")
                                 and hasattr(pipeline.backbone, "_backward_impl"))
         for p in pipeline.embed_coords.parameters():
             p.requires_grad = self.train_embedding  # see module docstring

@@ -148,7 +148,7 @@ def test_bilinear_resize_adjoint():
         assert relerr(xd.grad, xr.grad) < 1e-5, (B, h, w, C, H, W)
 
 
-@pytest.mark.parametrize("up_type", ["bilinear", "identity", "jbu_featup", "loftup"])
+@pytest.mark.parametrize("up_type", ["bilinear", "identity", "jbu_featup", "loftup", "lift"])
 def test_pipeline_gradients_vs_oracle_autograd(up_type):
     """Whole differentiable chain of the 'noup' / 'bilinear' configs (models/sbd/dinov2/patch-embed_{noup,bilinear}.py):
     click maps -> trainable PatchEmbed -> frozen ViT -> resize -> trainable ConvSegHead.  Gradients of
@@ -157,7 +157,8 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     from oracle import distmaps as odm
     torch.manual_seed(0)
     B, H, W = 2, 56, 84
-    params = {"jbu_featup": {"backbone_type": "dinov2"}, "loftup": {"upsampler_path": None, "n_dim": 384}}.get(up_type, {})
+    params = {"jbu_featup": {"backbone_type": "dinov2"}, "loftup": {"upsampler_path": None, "n_dim": 384},
+              "lift": {"lift_path": None, "n_dim": 384, "patch": 14}}.get(up_type, {})
     pipe = isp.ISegPipeline(up_type, params).to(DEV)
     if up_type == "loftup":
         from oracle import loftup as oloft
@@ -185,7 +186,12 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
     emb = ohead.patch_embed_forward(pr, torch.cat([image[:, 3:], maps], 1))
     lr = ovit.dinov2_forward(vsd, nimg, emb)
-    if up_type == "loftup":
+    if up_type == "lift":
+        from oracle import lift as olift
+        tsd = synth.lift_state_dict(384, seed=0)
+        pipe.upsampler.lift.load_state_dict(tsd)
+        feats = ohead.bilinear_align_corners(olift.lift_forward(tsd, lr, nimg), (H, W))
+    elif up_type == "loftup":
         feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"])
     elif up_type == "jbu_featup":
         feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
