@@ -202,7 +202,7 @@ int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, i
  *     (row, head, batch; in elements) explicit -- heads may be column slices of a packed [tokens, 3C] matrix.
  * Row / element kernels:
  *   isp_layernorm_rows_bwd: dx = LN'(x)^T (gamma * dy) + resid (x fp32 | bf16, dx fp32 + optional bf16 copy), C <= 1024;
- *   isp_gelu_bwd_bf16:      dpre = dh * gelu'(pre)  (nn.GELU, erf form), n even;
+ *   isp_gelu_bwd_bf16:      dpre = dh * act'(pre)  (quick = 0: nn.GELU erf form; 1: CLIP QuickGELU), n even;
  *   isp_softmax_rows:       P[r, :ncols] = softmax(S[r, :ncols]) (fp32 -> bf16), zeros up to ncols_pad;
  *   isp_attn_ds_rows:       dS = P * (dP - sum_j P dP) per row (dP fp32 | bf16), zeros up to ncols_pad;
  *   isp_transpose_bf16_batched: dst[z][c][r] = src[z][r][c]. */
@@ -213,7 +213,7 @@ int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long
 int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, const float* gamma,
                            const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
                            long long M, int C, float eps, isp_stream_t stream);
-int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream);
+int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, int quick, isp_stream_t stream);
 int isp_softmax_rows(const float* S, long long lds, void* P_bf16, long long ldp, long long R, int ncols, int ncols_pad,
                      isp_stream_t stream);
 int isp_attn_ds_rows(const void* P_bf16, long long ldp, const void* dP, int dp_bf16, long long lddp, void* dS_bf16,

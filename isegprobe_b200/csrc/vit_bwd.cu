@@ -165,13 +165,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
   }
 }
 
+template <int KIND>  // 0: nn.GELU (erf form), 1: QuickGELU x * sigmoid(1.702 x) (maskclip/model.py:166-168)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat162* __restrict__ dh,
                                                        const __nv_bfloat162* __restrict__ pre,
                                                        __nv_bfloat162* __restrict__ out, long long n2) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2) return;
   const float2 d = __bfloat1622float2(dh[i]), x = __bfloat1622float2(pre[i]);
-  auto g = [](float v) {  // d/dv [ v * Phi(v) ] = Phi(v) + v * phi(v)
+  auto g = [](float v) {
+    if (KIND == 1) {  // d/dv [ v * s(av) ] = s + a v s (1 - s)
+      const float sg = 1.f / (1.f + __expf(-1.702f * v));
+      return sg * (1.f + 1.702f * v * (1.f - sg));
+    }
+    // d/dv [ v * Phi(v) ] = Phi(v) + v * phi(v)
     const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
     const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
     return cdf + v * pdf;
@@ -301,12 +307,18 @@ extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const voi
   return ISP_OK;
 }
 
-// dpre = dh * gelu'(pre) on dense bf16 arrays of n elements (n even; nn.GELU erf form, dinov2/layers/mlp.py:34-40).
-extern "C" int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, isp_stream_t stream) {
+// dpre = dh * act'(pre) on dense bf16 arrays of n elements (n even); quick == 0: nn.GELU erf form
+// (dinov2/layers/mlp.py:34-40), quick == 1: CLIP's QuickGELU.
+extern "C" int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, int quick, isp_stream_t stream) {
   ISP_REQUIRE(dh && pre && out && n > 0 && n % 2 == 0, ISP_ERR_BAD_SHAPE, "gelu_bwd_bf16: bad arguments");
-  vb::gelu_bwd_kernel<<<cdiv(n / 2, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat162*>(dh), reinterpret_cast<const __nv_bfloat162*>(pre),
-      reinterpret_cast<__nv_bfloat162*>(out), n / 2);
+  if (quick)
+    vb::gelu_bwd_kernel<1><<<cdiv(n / 2, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat162*>(dh), reinterpret_cast<const __nv_bfloat162*>(pre),
+        reinterpret_cast<__nv_bfloat162*>(out), n / 2);
+  else
+    vb::gelu_bwd_kernel<0><<<cdiv(n / 2, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat162*>(dh), reinterpret_cast<const __nv_bfloat162*>(pre),
+        reinterpret_cast<__nv_bfloat162*>(out), n / 2);
   ISP_CHECK_LAUNCH("gelu_bwd_kernel");
   return ISP_OK;
 }

@@ -359,7 +359,7 @@ class DINOv2Featurizer(nn.Module):
             hn = _ln(x_mid, L["n2w"], L["n2b"], C, 1e-6, bf)
             pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf)
             dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf)
-            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel())
+            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel(), 0)
             dn = tc.gemm(dh, LB["W1T"], out_dtype=torch.float32)
             dx, dxb = self._ln_bwd(dn, x_mid, L["n2w"], dx, C)
             # attention: x_mid = x_in + proj(attn(qkv(LN1 x_in)))
@@ -494,6 +494,14 @@ class MaskCLIPFeaturizer(nn.Module):
         return self._pos_cache[key]
 
     def forward(self, x: torch.Tensor, additional_features: torch.Tensor = None) -> torch.Tensor:
+        """Frozen backbone; like DINOv2Featurizer the call is differentiable w.r.t. a click embedding injected before
+        the blocks (models/sbd/maskclip/patch-embed_noup.py trains it through the frozen CLIP ViT)."""
+        if (torch.is_grad_enabled() and additional_features is not None and additional_features.requires_grad
+                and self.feats_injection_mode == "before_backbone"):
+            return _MaskClipBackboneFn.apply(self, x, additional_features)
+        return self._forward_impl(x, additional_features, None)
+
+    def _forward_impl(self, x, additional_features, saved):
         x = x.detach().float()
         dev = x.device
         B, _, H, W = x.shape
@@ -521,7 +529,10 @@ class MaskCLIPFeaturizer(nn.Module):
         Tp = tc.round_up(T, 128)
         hd = C // nh
         bf = torch.bfloat16
+        if saved is not None:
+            saved.update({"B": B, "T": T, "h": h, "w": w, "tok": tok, "blocks": []})
         for L in P["blocks"][:-1]:
+            x_in = xs
             hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-5, bf)
             qkv = tc.gemm(hn, L["Wqkv"], bias=L["bqkv"], out_dtype=bf)
             Kp = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
@@ -533,11 +544,15 @@ class MaskCLIPFeaturizer(nn.Module):
             xs = tc.gemm(O, L["Wo"], bias=L["bo"], resid=xs, out_dtype=torch.float32)
             hn = _ln(xs, L["n2w"], L["n2b"], C, 1e-5, bf)
             h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="quick_gelu", out_dtype=bf)
+            if saved is not None:
+                saved["blocks"].append((x_in, qkv, xs))
             xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
         L = P["blocks"][-1]  # forward_v: value projection -> output projection, no residual (model.py:251-263)
         hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-5, bf)
         vv = tc.gemm(hn, L["Wv"], bias=L["bv"], out_dtype=bf)
         vo = tc.gemm(vv, L["Wo"], bias=L["bo"], out_dtype=torch.float32)
+        if saved is not None:
+            saved["x_last"], saved["vo"] = xs, vo
         xn = _ln(vo, P["npw"], P["npb"], C, 1e-5, bf)
         feats = tc.gemm(xn, P["Wout"], out_dtype=torch.float32).view(B, T, Co)[:, 1:]
         if additional_features is not None and self.feats_injection_mode == "after_backbone":
@@ -545,3 +560,69 @@ class MaskCLIPFeaturizer(nn.Module):
                 f"features.shape: {tuple(feats.shape)}, additional_features.shape: {tuple(additional_features.shape)}"
             feats = feats + additional_features.to(feats.dtype)
         return feats.reshape(B, h, w, Co).permute(0, 3, 1, 2)
+
+    # ---------------------------------------------------------------- activation backward
+    def _pack_bwd(self, dev):
+        P = self._pack(dev)
+        if "bwd" not in P:
+            v = self.model.visual
+            C, nh = v.width, v.heads
+            sc = (C // nh) ** -0.5
+            pw = lambda w: tc.pack_linear_weight(w.detach().float().t().contiguous()).to(dev)
+            out = []
+            for blk in v.transformer.resblocks:
+                Wqkv = blk.attn.in_proj_weight.detach().float().clone()
+                Wv = Wqkv[-C:].clone()
+                Wqkv[:C] *= sc
+                out.append({"WqkvT": pw(Wqkv), "WvT": pw(Wv), "WoT": pw(blk.attn.out_proj.weight),
+                            "W1T": pw(blk.mlp.c_fc.weight), "W2T": pw(blk.mlp.c_proj.weight)})
+            P["bwd"] = out
+            P["WoutT"] = tc.pack_linear_weight(v.proj.detach().float().contiguous()).to(dev)  # (proj^T)^T
+        return P, P["bwd"]
+
+    def _backward_impl(self, saved, grad_feats):
+        dev = grad_feats.device
+        v = self.model.visual
+        C, nh, Co = v.width, v.heads, v.output_dim
+        P, PB = self._pack_bwd(dev)
+        B, T, h, w = saved["B"], saved["T"], saved["h"], saved["w"]
+        M, bf = B * T, torch.bfloat16
+        ln_bwd, attn_bwd = DINOv2Featurizer._ln_bwd, DINOv2Featurizer._attention_bwd
+        df = torch.zeros(B, T, Co, dtype=bf, device=dev)  # the class token is not part of the features
+        df[:, 1:] = grad_feats.detach().permute(0, 2, 3, 1).reshape(B, h * w, Co).to(bf)
+        dn = tc.gemm(df.view(M, Co), P["WoutT"], out_dtype=torch.float32)          # through `@ proj`
+        _, dvo = ln_bwd(dn, saved["vo"], P["npw"], None, C, 1e-5)                  # ln_post
+        L, LB = P["blocks"][-1], PB[-1]
+        dvv = tc.gemm(dvo, LB["WoT"], out_dtype=bf)                                # out_proj of forward_v
+        dn = tc.gemm(dvv, LB["WvT"], out_dtype=torch.float32)                      # value projection
+        dx, dxb = ln_bwd(dn, saved["x_last"], L["n1w"], None, C, 1e-5)
+        for L, LB, (x_in, qkv, x_mid) in zip(reversed(P["blocks"][:-1]), reversed(PB[:-1]), reversed(saved["blocks"])):
+            hn = _ln(x_mid, L["n2w"], L["n2b"], C, 1e-5, bf)
+            pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf)
+            dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf)
+            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel(), 1)                 # QuickGELU
+            dn = tc.gemm(dh, LB["W1T"], out_dtype=torch.float32)
+            dx, dxb = ln_bwd(dn, x_mid, L["n2w"], dx, C, 1e-5)
+            dO = tc.gemm(dxb, LB["WoT"], out_dtype=bf)
+            dqkv = attn_bwd(None, qkv, dO, B, T, C, nh)
+            dn = tc.gemm(dqkv, LB["WqkvT"], out_dtype=torch.float32)
+            dx, dxb = ln_bwd(dn, x_in, L["n1w"], dx, C, 1e-5)
+        dtok, _ = ln_bwd(dx, saved["tok"], P["lpw"], None, C, 1e-5)               # ln_pre
+        return dtok.view(B, T, C)[:, 1:].contiguous()
+
+
+class _MaskClipBackboneFn(torch.autograd.Function):
+    """Frozen MaskCLIP ViT with an input gradient for the injected click embedding."""
+
+    @staticmethod
+    def forward(ctx, feat, x, additional_features):
+        saved = {}
+        out = feat._forward_impl(x, additional_features, saved)
+        ctx.feat, ctx.saved = feat, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d = ctx.feat._backward_impl(ctx.saved, grad_out)
+        ctx.saved = None
+        return None, None, d

@@ -425,7 +425,7 @@ class LoftUpUpsampler(BaseUpsampler):
             pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf, N=C, K=D)
             del hn
             dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf, N=C, K=D)
-            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel())
+            _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel(), 0)
             del pre
             dn = tc.gemm(dh, LB["W1T"], out_dtype=torch.float32, N=D, K=C)
             del dh

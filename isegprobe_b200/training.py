@@ -11,7 +11,7 @@ The click embedding (`embed_coords`) is trained THROUGH the frozen backbone and 
 upsamplers, the resize-only ones (`identity` = the "noup" configs, `bilinear`, and torch's `nearest` / `bicubic`) and the
 FeatUp JBU stack (linear in its source: chain of adjoint kernels) and LoftUp (cross-attention backward w.r.t. keys /
 values with recomputed, materialised probabilities) are differentiable, so those configurations train `embed_coords`
-exactly like the reference, as does LiFT (dgrads of its source branch).  Only the MaskCLIP backbone is still forward-only: with them `embed_coords` is kept frozen and the step is head-only."""
+exactly like the reference, as does LiFT (dgrads of its source branch).  Both backbones (DINOv2, MaskCLIP) have their activation backward: with them `embed_coords` is kept frozen and the step is head-only."""
 import torch
 
 from . import dist as idist

@@ -83,8 +83,12 @@ def test_layernorm_gelu_softmax_backward_kernels():
     pr = pre.float().requires_grad_(True)
     F.gelu(pr).backward(dh.float())
     out = torch.empty_like(dh, device=DEV)
-    _call("isp_gelu_bwd_bf16", dh.to(DEV), pre.to(DEV), out, dh.numel())
+    _call("isp_gelu_bwd_bf16", dh.to(DEV), pre.to(DEV), out, dh.numel(), 0)
     assert relerr(out.float(), pr.grad) < 1e-2
+    pq = pre.float().requires_grad_(True)
+    (pq * torch.sigmoid(1.702 * pq)).backward(dh.float())
+    _call("isp_gelu_bwd_bf16", dh.to(DEV), pre.to(DEV), out, dh.numel(), 1)
+    assert relerr(out.float(), pq.grad) < 1e-2
     # softmax rows and its backward
     R, T, Tp = 200, 65, 72
     S = torch.randn(R, Tp, generator=g) * 3
@@ -273,3 +277,30 @@ def test_loftup_source_gradient_vs_oracle_autograd(B, H, W, h, w):
     c = cosine(s.grad, lr_ref.grad)
     assert c > 0.99, c
     assert relerr(s.grad, lr_ref.grad) < 0.2, relerr(s.grad, lr_ref.grad)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 64, 96)])
+def test_maskclip_click_embedding_gradient_vs_oracle_autograd(B, H, W):
+    """models/sbd/maskclip/patch-embed_noup.py trains the click embedding through the frozen CLIP ViT-B/16
+    (core/model/featurizers/MaskCLIP.py:41-92): input gradient against torch autograd through the oracle."""
+    import isegprobe_b200 as isp
+    from oracle import maskclip as omc
+    torch.manual_seed(0)
+    f = isp.MaskCLIPFeaturizer("ViT-B/16", "before_backbone")
+    msd = synth.maskclip_state_dict(seed=0)
+    f.model.visual.load_state_dict(msd)
+    f = f.to(DEV).eval()
+    img = ohead.normalize_image(synth.image_batch(B, H, W, seed=1))
+    n = (H // 16) * (W // 16)
+    emb = torch.randn(B, n, 768, generator=torch.Generator().manual_seed(2)) * 0.5
+    gout = torch.randn(B, 512, H // 16, W // 16, generator=torch.Generator().manual_seed(3))
+    e_ref = emb.clone().requires_grad_(True)
+    omc.maskclip_forward(msd, img, e_ref).backward(gout)
+    e = emb.to(DEV).requires_grad_(True)
+    out = f(img.to(DEV), e)
+    out.backward(gout.to(DEV))
+    c = cosine(e.grad, e_ref.grad)
+    assert c > 0.99, c
+    assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
+    with torch.no_grad():
+        assert torch.equal(out.detach(), f(img.to(DEV), emb.to(DEV)))
