@@ -7,11 +7,10 @@
          core/utils/distributed.py + trainer.py:144-149) -> Adam(lr 5e-5) as models/defaults.py:103-107.
 
 The click embedding (`embed_coords`) is trained THROUGH the frozen backbone and upsampler in the reference
-(DINOv2.py:518-523).  The DINOv2 backbone has its activation backward (featurizers._DinoBackboneFn); of the
-upsamplers, the resize-only ones (`identity` = the "noup" configs, `bilinear`, and torch's `nearest` / `bicubic`) and the
-FeatUp JBU stack (linear in its source: chain of adjoint kernels) and LoftUp (cross-attention backward w.r.t. keys /
-values with recomputed, materialised probabilities) are differentiable, so those configurations train `embed_coords`
-exactly like the reference, as does LiFT (dgrads of its source branch).  Both backbones (DINOv2, MaskCLIP) have their activation backward: with them `embed_coords` is kept frozen and the step is head-only."""
+(DINOv2.py:518-523).  Both backbones (DINOv2, MaskCLIP) and every upsampler (identity = the "noup" configs, bilinear,
+torch's nearest / bicubic, the FeatUp JBU stack, LoftUp, LiFT) have their activation backward on libisp_b200, so the
+step trains `embed_coords` exactly like the reference.  `train_embedding=False` keeps it frozen (features under
+no_grad, head forward / backward only)."""
 import torch
 
 from . import dist as idist
