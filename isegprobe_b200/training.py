@@ -1,6 +1,6 @@
 """Training step of the IS model around the hot path (core/training/trainer.py:377-477, 213-226):
 
-    frozen features (click maps -> embed -> ViT -> upsampler, no_grad)
+    features (click maps -> trainable click embedding -> frozen ViT -> frozen upsampler)
       -> ConvSegHead forward / backward on libisp_b200 (heads._ConvHeadFn)
       -> NormalizedFocalLossSigmoid (core/training/losses.py:42-109; stays torch)
       -> ONE all-reduce of the flat gradient arena (dist.FlatGradArena; DDP semantics: mean over ranks,
