@@ -210,6 +210,17 @@ int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long
                              long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
                              long long d_sb, int out_bf16, int M, int N, int K, int H, int B, float alpha,
                              isp_stream_t stream);
+/* ... and with both operands stored reduction-major (A[b,h] = [K][M], W[b,h] = [K][N]; a_sk / w_sk = stride of a
+ * reduction row): D[b,h] = alpha * A[b,h]^T W[b,h] -- dK = dS^T Q and dV = P^T dO without transposed copies. */
+int isp_gemm_bf16_tc_batched_tn(const void* A, long long a_sk, long long a_sh, long long a_sb, const void* W,
+                                long long w_sk, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
+                                long long d_sb, int out_bf16, int M, int N, int K, int H, int B, float alpha,
+                                isp_stream_t stream);
+/* Mixed: A [M][K] row-major, W stored reduction-major [K][N]: D[b,h] = alpha * A[b,h] W[b,h] (dQ = dS K). */
+int isp_gemm_bf16_tc_batched_nn(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
+                                long long w_sk, long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh,
+                                long long d_sb, int out_bf16, int M, int N, int K, int H, int B, float alpha,
+                                isp_stream_t stream);
 int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, const float* gamma,
                            const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
                            long long M, int C, float eps, isp_stream_t stream);

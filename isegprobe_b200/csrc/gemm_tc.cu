@@ -78,6 +78,9 @@ struct Params {
                       // the ~12 TB/s L2->SM ceiling); the epilogue then does not overlap the next tile's MMAs
   int batched;        // > 0: `batched` independent problems per "head" x `nbatch` "batches" with their own A / W / D
   int nbatch;         // (4-D tensor maps: column, row, head, batch); tiles_m then counts the row tiles of ALL problems
+  int tn;             // batched only, bit 0: A stored reduction-major [K][M] (M contiguous), bit 1: W stored [K][N].
+                      // Such an operand arrives as 64-row x 64-column TMA boxes (128-byte rows, 128B swizzle) and the
+                      // UMMA descriptor walks it "MN-major", as in wgrad_tc.cu; BN is a multiple of 64 with bit 1.
   int cta2;           // 1: launched as clusters of two CTAs that form a CTA pair (tcgen05 cta_group::2).  The pair computes
                       // two vertically adjacent tiles (or tile pairs) of one column tile with ONE 256-row MMA: each CTA
                       // loads its own 128 A rows and only HALF of the weight tile, the tensor cores read both halves.
@@ -130,6 +133,18 @@ __device__ __forceinline__ float act_fn(float v) {
     return fmaf(hv, th, hv);
   }
   return v;
+}
+
+// MN-major operand, 128-byte swizzle: 64 contiguous M (or N) elements per reduction row, 8-row groups 1024 B apart
+// (SBO), the next 64 elements one 8 KB box further (LBO).  Same canonical layout as wgrad_tc.cu.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((8192u >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 struct TileCoord {
@@ -253,8 +268,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           if (p.batched) {
-            tc::tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0, tc_.h0, tc_.img);
-            tc::tma_load_4d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0, tc_.h0, tc_.img);
+            if (p.tn & 1) {  // boxes of 64 reduction rows x 64 columns
+              for (int i = 0; i < BM / 64; ++i)
+                tc::tma_load_4d(sa + i * 8192, &tmA, &full_bar[s], (int)tc_.m0 + i * 64, kb * BK, tc_.h0, tc_.img);
+            } else {
+              tc::tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0, tc_.h0, tc_.img);
+            }
+            if (p.tn & 2) {
+              for (int i = 0; i < p.BN / 64; ++i)
+                tc::tma_load_4d(sb + i * 8192, &tmB, &full_bar[s], tc_.n0 + i * 64, kb * BK, tc_.h0, tc_.img);
+            } else {
+              tc::tma_load_4d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0, tc_.h0, tc_.img);
+            }
             continue;
           }
           if (p.TW) {
@@ -272,7 +297,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer (CTA pair: the leader CTA only)
-    const uint32_t idesc = tc::idesc_bf16_f32(BM << (CTA2 ? 1 : 0), p.BN);
+    // reduction-major operands: both "MN-major" (instruction-descriptor bits 15 / 16)
+    const uint32_t idesc = tc::idesc_bf16_f32(BM << (CTA2 ? 1 : 0), p.BN) | ((p.tn & 1) ? (1u << 15) : 0u) |
+                           ((p.tn & 2) ? (1u << 16) : 0u);
     const int last_in = p.TW ? p.cin_chunks - 1 : kblocks - 1;  // k-block (within a tap / the row) that may be partial
     const int period = p.TW ? p.cin_chunks : kblocks;
     uint32_t it = 0, tl = 0;
@@ -313,6 +340,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc::umma_commit_2sm(&tfull_bar[acc]);
               if (p.pair) tc::umma_commit_2sm(&tfull_bar[1]);
             }
+          } else if (p.tn) {  // reduction-major operand: 16 reduction rows = 2048 B per step inside the 64-row boxes
+            const uint64_t ta = (p.tn & 1) ? smem_desc_mn_sw128(sa) : adesc;
+            const uint64_t tb = (p.tn & 2) ? smem_desc_mn_sw128(sa + a_bytes) : bdesc;
+            const uint64_t ia = (p.tn & 1) ? 128 : 2, ib = (p.tn & 2) ? 128 : 2;
+            tc::umma_bf16(d_tmem, ta, tb, idesc, kb ? 1u : 0u);
+            if (nsteps > 1) tc::umma_bf16(d_tmem, ta + ia, tb + ib, idesc, 1u);
+            if (nsteps > 2) tc::umma_bf16(d_tmem, ta + 2 * ia, tb + 2 * ib, idesc, 1u);
+            if (nsteps > 3) tc::umma_bf16(d_tmem, ta + 3 * ia, tb + 3 * ib, idesc, 1u);
+            tc::umma_commit(&empty_bar[s]);
+            if (kb == kblocks - 1) tc::umma_commit(&tfull_bar[acc]);
           } else {
             tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
             if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -795,10 +832,9 @@ extern "C" int isp_gemm_bf16_tc_ex(const void* A, long long lda, const void* W, 
 // batch; in elements) is explicit, so heads can be column slices of a packed [tokens, 3C] qkv matrix.  Rows /
 // columns beyond M / N / K are zero-filled on load and clipped on store by TMA (no bleed between problems).
 // Used by the attention backward of the frozen ViT (dinov2/layers/attention.py:54-71 under autograd).
-extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
-                                        long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm,
-                                        long long d_sh, long long d_sb, int out_bf16, int M, int N, int K, int H, int B,
-                                        float alpha, isp_stream_t stream) {
+static int gemm_batched_common(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W, long long w_sn,
+                               long long w_sh, long long w_sb, void* D, long long d_sm, long long d_sh, long long d_sb,
+                               int out_bf16, int M, int N, int K, int H, int B, float alpha, int tn, isp_stream_t stream) {
   ISP_REQUIRE(A && W && D, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_batched: null pointer");
   ISP_REQUIRE(M > 0 && N > 0 && K > 0 && H > 0 && B > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc_batched: bad shape");
   const int esz = out_bf16 ? 2 : 4;
@@ -811,6 +847,11 @@ extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long
   p.M = M; p.N = N;
   p.K = (K + gemm::BK - 1) / gemm::BK * gemm::BK;
   p.BN = gemm::pick_bn(N, 256);
+  if (tn & 2) {  // column boxes of W are 64 wide
+    p.BN = (N + 63) / 64 * 64;
+    if (p.BN > 256) p.BN = 256;
+  }
+  p.tn = tn;
   p.last_steps = (K - (p.K - gemm::BK) + 15) / 16;
   p.TW = 0;
   p.batched = H; p.nbatch = B;
@@ -819,13 +860,22 @@ extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long
   p.pair = 0;
   p.bias = nullptr; p.alpha = alpha;
   CUtensorMap tmA, tmB, tmD, tmDt;
-  {
+  const uint32_t box_red[4] = {64, gemm::BK, 1, 1};  // reduction-major operand: 64 columns x 64 reduction rows
+  if (tn & 1) {  // a_sm is the stride of a REDUCTION row; M is the contiguous dimension
+    const uint64_t dims[4] = {(uint64_t)M, (uint64_t)K, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {2, (uint64_t)a_sm * 2, (uint64_t)a_sh * 2, (uint64_t)a_sb * 2};
+    if (int e = make_tmap_bf16(&tmA, A, 4, dims, str, box_red, "gemm_bf16_tc_batched(A, reduction-major)")) return e;
+  } else {
     const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {2, (uint64_t)a_sm * 2, (uint64_t)a_sh * 2, (uint64_t)a_sb * 2};
     const uint32_t box[4] = {gemm::BK, gemm::BM, 1, 1};
     if (int e = make_tmap_bf16(&tmA, A, 4, dims, str, box, "gemm_bf16_tc_batched(A)")) return e;
   }
-  {
+  if (tn & 2) {
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)K, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {2, (uint64_t)w_sn * 2, (uint64_t)w_sh * 2, (uint64_t)w_sb * 2};
+    if (int e = make_tmap_bf16(&tmB, W, 4, dims, str, box_red, "gemm_bf16_tc_batched(W, reduction-major)")) return e;
+  } else {
     const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {2, (uint64_t)w_sn * 2, (uint64_t)w_sh * 2, (uint64_t)w_sb * 2};
     const uint32_t box[4] = {gemm::BK, (uint32_t)p.BN, 1, 1};
@@ -841,6 +891,36 @@ extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long
     if (int e = make_tmap(&tmDt, esz, D, 4, dims, str, boxt, "gemm_bf16_tc_batched(D tail)", false)) return e;
   }
   return gemm::launch(tmA, tmB, tmD, tmDt, tmD, tmDt, tmB, p, out_bf16, 0, false, as_stream(stream));
+}
+
+extern "C" int isp_gemm_bf16_tc_batched(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
+                                        long long w_sn, long long w_sh, long long w_sb, void* D, long long d_sm,
+                                        long long d_sh, long long d_sb, int out_bf16, int M, int N, int K, int H, int B,
+                                        float alpha, isp_stream_t stream) {
+  return gemm_batched_common(A, a_sm, a_sh, a_sb, W, w_sn, w_sh, w_sb, D, d_sm, d_sh, d_sb, out_bf16, M, N, K, H, B, alpha, 0,
+                             stream);
+}
+
+// Same with the operands stored reduction-major: A[b,h] is [K][M] and W[b,h] is [K][N] (a_sk / w_sk = stride of a
+// reduction row, M / N contiguous):  D[b,h] (M x N) = alpha * A[b,h]^T W[b,h].  This is the shape of the attention
+// backward's dK = dS^T Q and dV = P^T dO (reduction over the queries) on the tensors as they are stored -- no
+// transposed copies of the score-sized matrices.
+extern "C" int isp_gemm_bf16_tc_batched_tn(const void* A, long long a_sk, long long a_sh, long long a_sb, const void* W,
+                                           long long w_sk, long long w_sh, long long w_sb, void* D, long long d_sm,
+                                           long long d_sh, long long d_sb, int out_bf16, int M, int N, int K, int H, int B,
+                                           float alpha, isp_stream_t stream) {
+  return gemm_batched_common(A, a_sk, a_sh, a_sb, W, w_sk, w_sh, w_sb, D, d_sm, d_sh, d_sb, out_bf16, M, N, K, H, B, alpha, 3,
+                             stream);
+}
+
+// Mixed form: A row-major [M][K] as in isp_gemm_bf16_tc_batched, W stored reduction-major [K][N]:
+// D[b,h] = alpha * A[b,h] W[b,h]  (dQ = dS K with K as stored, keys x head_dim).
+extern "C" int isp_gemm_bf16_tc_batched_nn(const void* A, long long a_sm, long long a_sh, long long a_sb, const void* W,
+                                           long long w_sk, long long w_sh, long long w_sb, void* D, long long d_sm,
+                                           long long d_sh, long long d_sb, int out_bf16, int M, int N, int K, int H, int B,
+                                           float alpha, isp_stream_t stream) {
+  return gemm_batched_common(A, a_sm, a_sh, a_sb, W, w_sk, w_sh, w_sb, D, d_sm, d_sh, d_sb, out_bf16, M, N, K, H, B, alpha, 2,
+                             stream);
 }
 
 static int conv3x3_common(const void* X, const void* Wp, const float* bias, int act, void* Y, int out_bf16, int Nimg,

@@ -323,7 +323,6 @@ class DINOv2Featurizer(nn.Module):
 
         tok = (3 * C, hd, T * 3 * C)            # (row, head, image) strides of a head slice of qkv
         sq = (Tp, T * Tp, nh * T * Tp)          # ... of the [B, nh, T, Tp] score-shaped tensors
-        tr = (Tp, hd * Tp, nh * hd * Tp)        # ... of the transposed [B, nh, hd, Tp] operands
         bgemm(q0, tok, q0 + 2 * C, tok, _lib.dptr(S), sq, False, T, T, hd)                     # S = Q K^T
         _call("isp_softmax_rows", S, Tp, Pm, Tp, B * nh * T, T, Tp)
         bgemm(_lib.dptr(dO), (C, hd, T * C), q0 + 4 * C, tok, _lib.dptr(dP), sq, False, T, T, hd)  # dP = dO V^T
@@ -331,16 +330,16 @@ class DINOv2Featurizer(nn.Module):
         del S, dP
         dqkv = torch.empty(B * T, 3 * C, dtype=bf, device=dev)
         d0 = _lib.dptr(dqkv)
-        Xt = torch.empty(B, nh, hd, Tp, dtype=bf, device=dev)   # K^T, then Q^T, then dO^T
-        Mt = torch.empty(B, nh, T, Tp, dtype=bf, device=dev)    # dS^T, then P^T
-        _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Xt, B, T, Tp, nh, hd, 1)
-        bgemm(_lib.dptr(dS), sq, _lib.dptr(Xt), tr, d0, tok, True, T, hd, T)                   # dQ = dS K
-        _call("isp_transpose_bf16_batched", dS, Tp, T * Tp, Mt, Tp, T * Tp, B * nh, T, T)
-        _call("isp_repack_heads", qkv, 1, 3 * C, 0, hd, Xt, B, T, Tp, nh, hd, 1)
-        bgemm(_lib.dptr(Mt), sq, _lib.dptr(Xt), tr, d0 + 2 * C, tok, True, T, hd, T)           # dK = dS^T Q
-        _call("isp_transpose_bf16_batched", Pm, Tp, T * Tp, Mt, Tp, T * Tp, B * nh, T, T)
-        _call("isp_repack_heads", dO, 1, C, 0, hd, Xt, B, T, Tp, nh, hd, 1)
-        bgemm(_lib.dptr(Mt), sq, _lib.dptr(Xt), tr, d0 + 4 * C, tok, True, T, hd, T)           # dV = P^T dO
+
+        def bg(name, A, a_str, W, w_str, D, d_str, M, N, K):
+            _lib.call(name, A, *a_str, W, *w_str, D, *d_str, 1, M, N, K, nh, B, 1.0, st)
+
+        do_tok = (C, hd, T * C)
+        # dQ = dS K (K as stored: keys x head_dim); dK = dS^T Q and dV = P^T dO reduce over the queries with both
+        # operands as stored (reduction-major): no transposed copies
+        bg("isp_gemm_bf16_tc_batched_nn", _lib.dptr(dS), sq, q0 + 2 * C, tok, d0, tok, T, hd, T)
+        bg("isp_gemm_bf16_tc_batched_tn", _lib.dptr(dS), sq, q0, tok, d0 + 2 * C, tok, T, hd, T)
+        bg("isp_gemm_bf16_tc_batched_tn", _lib.dptr(Pm), sq, _lib.dptr(dO), do_tok, d0 + 4 * C, tok, T, hd, T)
         return dqkv
 
     def _backward_impl(self, saved, grad_feats):

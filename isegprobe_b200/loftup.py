@@ -349,8 +349,8 @@ class LoftUpUpsampler(BaseUpsampler):
         from .featurizers import DINOv2Featurizer
         return DINOv2Featurizer._ln_bwd(dy, x, gamma, resid, C, eps, ldb)
 
-    def _attention_bwd_image(self, Q, dO, Kp, Vp, Kt, need_dq, HW, T, nh, HP):
-        """One image: Q, dO [HW, nh*HP] bf16; Kp, Vp [nh, T, HP] bf16 (rows = keys), Kt [nh, HP, T8] -> (dQ [HW, nh*HP] bf16
+    def _attention_bwd_image(self, Q, dO, Kp, Vp, need_dq, HW, T, nh, HP):
+        """One image: Q, dO [HW, nh*HP] bf16; Kp, Vp [nh, T, HP] bf16 (rows = keys) -> (dQ [HW, nh*HP] bf16
         or None, dK, dV [nh, T, HP] fp32).  Probabilities are recomputed and materialised per image ([nh, HW, T])."""
         dev, bf = Q.device, torch.bfloat16
         st = _lib.stream_ptr()
@@ -362,7 +362,6 @@ class LoftUpUpsampler(BaseUpsampler):
         key = (HP, T * HP, nh * T * HP)     # ... of Kp / Vp / dK / dV  [nh, T, HP]
         Tp = tc.round_up(T, 8)                # row pitch of the score-shaped tensors (TMA: 16-byte strides)
         sq = (Tp, HW * Tp, nh * HW * Tp)      # ... of the score-shaped [nh, HW, Tp] tensors
-        tr = (Tp, HP * Tp, nh * HP * Tp)      # ... of Kt [nh, HP, Tp]
         S = torch.empty(nh, HW, Tp, dtype=torch.float32, device=dev)
         bgemm(_lib.dptr(Q), row, _lib.dptr(Kp), key, _lib.dptr(S), sq, False, HW, T, HP)           # S = Q K^T
         Pm = torch.empty(nh, HW, Tp, dtype=bf, device=dev)
@@ -374,28 +373,23 @@ class LoftUpUpsampler(BaseUpsampler):
         dQ = None
         if need_dq:
             dQ = torch.empty(HW, nh * HP, dtype=bf, device=dev)
-            bgemm(_lib.dptr(dS), sq, _lib.dptr(Kt), tr, _lib.dptr(dQ), row, True, HW, HP, T)      # dQ = dS K
-        # dK = dS^T Q and dV = P^T dO reduce over the HW queries: only (T / 128) x heads = 32 output tiles, so the
-        # reduction is split nsplit ways over the GEMM's batch dimension (batch stride = a column offset inside the
-        # transposed operands) and the fp32 partial results are summed afterwards.
-        HWp = tc.round_up(HW, 8)
-        nsplit = next((n for n in (14, 16, 8, 7, 4, 2) if HW % n == 0 and (HW // n) % 8 == 0 and HW // n >= 1024), 1)
+            _lib.call("isp_gemm_bf16_tc_batched_nn", _lib.dptr(dS), *sq, _lib.dptr(Kp), *key, _lib.dptr(dQ), *row, 1, HW,
+                      HP, T, nh, 1, 1.0, st)                                                       # dQ = dS K (K as stored)
+        # dK = dS^T Q and dV = P^T dO reduce over the HW queries with both operands as stored (reduction-major GEMM: no
+        # transposed copies of the 1.6 GB score matrices).  Only (T / 128) x heads = 32 output tiles exist, so the
+        # reduction is split nsplit ways over the GEMM's batch dimension (batch stride = a block of query rows) and the
+        # fp32 partial results are summed afterwards.
+        nsplit = next((n for n in (14, 16, 8, 7, 4, 2) if HW % n == 0 and HW // n >= 1024), 1)
         ck = HW // nsplit
-        Mt = torch.empty(nh, T, HWp, dtype=bf, device=dev)
-        Xt = torch.empty(nh, HP, HWp, dtype=bf, device=dev)
         part = torch.empty(nsplit, nh, T, HP, dtype=torch.float32, device=dev)
 
-        def reduce_gemm():
-            _lib.call("isp_gemm_bf16_tc_batched", _lib.dptr(Mt), HWp, T * HWp, ck, _lib.dptr(Xt), HWp, HP * HWp, ck,
-                      _lib.dptr(part), HP, T * HP, nh * T * HP, 0, T, HP, ck, nh, nsplit, 1.0, st)
+        def reduce_gemm(Am, Xm):
+            _lib.call("isp_gemm_bf16_tc_batched_tn", _lib.dptr(Am), Tp, HW * Tp, ck * Tp, _lib.dptr(Xm), nh * HP, HP,
+                      ck * nh * HP, _lib.dptr(part), HP, T * HP, nh * T * HP, 0, T, HP, ck, nh, nsplit, 1.0, st)
             return part.sum(0) if nsplit > 1 else part[0].clone()
 
-        _call("isp_transpose_bf16_batched", dS, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
-        _call("isp_repack_heads", Q, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
-        dK = reduce_gemm()                                                                          # dK = dS^T Q
-        _call("isp_transpose_bf16_batched", Pm, Tp, HW * Tp, Mt, HWp, T * HWp, nh, HW, T)
-        _call("isp_repack_heads", dO, 1, nh * HP, 0, HP, Xt, 1, HW, HWp, nh, HP, 1)
-        dV = reduce_gemm()                                                                          # dV = P^T dO
+        dK = reduce_gemm(dS, Q)                                                                     # dK = dS^T Q
+        dV = reduce_gemm(Pm, dO)                                                                    # dV = P^T dO
         return dQ, dK, dV
 
     def _backward_chunk(self, P, PB, keep, g, H, W, h, w):
@@ -441,17 +435,15 @@ class LoftUpUpsampler(BaseUpsampler):
             Vl = tc.gemm(kvn, L["Wv"], bias=L["bv"], out_dtype=torch.float32, N=D, K=D)
             Kp = torch.empty(B, nh, T, HP, dtype=bf, device=dev)
             Vp = torch.empty(B, nh, T, HP, dtype=bf, device=dev)
-            Kt = torch.empty(B, nh, HP, tc.round_up(T, 8), dtype=bf, device=dev)
             _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, T, nh, HP, 0)
             _call("isp_repack_heads", Vl, 0, D, 0, hd, Vp, B, T, T, nh, HP, 0)
-            _call("isp_repack_heads", Kl, 0, D, 0, hd, Kt, B, T, tc.round_up(T, 8), nh, HP, 1)
             need_dq = li > 0  # the first layer's queries come from the image only
             dQ = torch.empty(M, nh * HP, dtype=bf, device=dev) if need_dq else None
             dK = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
             dV = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
             for b in range(B):
                 dq_b, dK[b], dV[b] = self._attention_bwd_image(Q[b * HW:(b + 1) * HW], dO[b * HW:(b + 1) * HW], Kp[b], Vp[b],
-                                                               Kt[b], need_dq, HW, T, nh, HP)
+                                                               need_dq, HW, T, nh, HP)
                 if need_dq:
                     dQ[b * HW:(b + 1) * HW] = dq_b
             del Q, dO

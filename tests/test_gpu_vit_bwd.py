@@ -47,6 +47,22 @@ def test_batched_gemm_head_slices():
     assert float(out.view(B * T, 3, C)[:, 0].abs().max()) == 0 and float(out.view(B * T, 3, C)[:, 2].abs().max()) == 0
 
 
+def test_batched_gemm_reduction_major_operands():
+    """isp_gemm_bf16_tc_batched_tn: D = A^T W with A [K][M] and W [K][N] as stored (dV = P^T dO, dK = dS^T Q)."""
+    from isegprobe_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    for (B, nh, T, hd) in [(2, 6, 65, 64), (1, 4, 300, 112)]:
+        C = nh * hd
+        Tp = (T + 7) // 8 * 8
+        Pm = (torch.randn(B, nh, T, Tp, generator=g) * 0.2).to(torch.bfloat16).to(DEV)   # [queries][keys]
+        dO = (torch.randn(B * T, C, generator=g) * 0.3).to(torch.bfloat16).to(DEV)       # [queries][heads * hd]
+        out = torch.full((B, nh, T, hd), float("nan"), device=DEV)
+        _lib.call("isp_gemm_bf16_tc_batched_tn", _lib.dptr(Pm), Tp, T * Tp, nh * T * Tp, _lib.dptr(dO), C, hd, T * C,
+                  _lib.dptr(out), hd, T * hd, nh * T * hd, 0, T, hd, T, nh, B, 1.0, _lib.stream_ptr())
+        want = torch.einsum("bhqk,bqhd->bhkd", Pm[..., :T].float(), dO.float().view(B, T, nh, hd))
+        assert relerr(out, want) < 1e-4, (B, nh, T, hd, relerr(out, want))
+
+
 def test_layernorm_gelu_softmax_backward_kernels():
     g = torch.Generator().manual_seed(1)
     M, C = 333, 384
