@@ -22,7 +22,7 @@ UPSAMPLER_REGISTRY["loftup"] = LoftUpUpsampler
 UPSAMPLER_REGISTRY["lift"] = LiFTUpsampler
 
 from .heads import HEAD_REGISTRY, ConvSegHead, SimpleClassifierHead, SimpleConvSegHead  # noqa: E402,F401
-from .featurizers import DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed  # noqa: E402,F401
+from .featurizers import DINOFeaturizer, DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed  # noqa: E402,F401
 from .pipeline import ISegPipeline, install_into_reference  # noqa: E402,F401
 
 __version__ = "0.1.0"

@@ -156,8 +156,18 @@ class DINOv2Featurizer(nn.Module):
         self._packed = None
         self._pos_cache = {}
 
+    feat_type = "token"  # DINOFeaturizer: "key" returns the keys of the last block instead of the normed tokens
+
     def _version(self):
         return sum(p._version for p in self.parameters())
+
+    @staticmethod
+    def _layer_scale(blk):
+        """LayerScale gammas of a block (DINOv2), ones for the plain timm / DINO ViT."""
+        w = blk.norm1.weight
+        if hasattr(blk, "ls1"):
+            return blk.ls1.gamma.detach().float(), blk.ls2.gamma.detach().float()
+        return torch.ones_like(w, dtype=torch.float32), torch.ones_like(w, dtype=torch.float32)
 
     def _pack(self, dev):
         key = (str(dev), self._version())
@@ -176,7 +186,7 @@ class DINOv2Featurizer(nn.Module):
             Wqkv, bqkv = blk.attn.qkv.weight.detach().float().clone(), blk.attn.qkv.bias.detach().float().clone()
             Wqkv[:C] *= sc  # attention.py:66: q * scale
             bqkv[:C] *= sc
-            g1, g2 = blk.ls1.gamma.detach().float(), blk.ls2.gamma.detach().float()
+            g1, g2 = self._layer_scale(blk)
             blocks.append({
                 "n1w": f32(blk.norm1.weight), "n1b": f32(blk.norm1.bias),
                 "Wqkv": tc.pack_linear_weight(Wqkv).to(dev), "bqkv": f32(bqkv),
@@ -246,9 +256,18 @@ class DINOv2Featurizer(nn.Module):
         bf = torch.bfloat16
         if saved is not None:
             saved.update({"B": B, "T": T, "h": h, "w": w, "blocks": []})
-        for L in P["blocks"]:
+        key_feats = None
+        for li, L in enumerate(P["blocks"]):
             x_in = xs
             hn = _ln(xs, L["n1w"], L["n1b"], C, 1e-6, bf)
+            if self.feat_type == "key" and li == len(P["blocks"]) - 1:
+                # DINO.py:591-592: keys of the last block, class token dropped, channels head_dim-major / head-minor
+                # (`permute(0, 2, 3, 1).flatten(-2)`); only the K rows of the qkv projection are needed, in fp32
+                kk = tc.gemm(hn, L["Wqkv"][C:2 * C], bias=L["bqkv"][C:2 * C], out_dtype=torch.float32)
+                key_feats = kk.view(B, T, nh, hd)[:, 1:].permute(0, 1, 3, 2).reshape(B, N, C)
+                if saved is not None:
+                    saved["key_x"] = x_in
+                break
             qkv = tc.gemm(hn, L["Wqkv"], bias=L["bqkv"], out_dtype=bf)
             Kp = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
             Vt = torch.empty(B, nh, 64, Tp, dtype=bf, device=dev)
@@ -264,8 +283,11 @@ class DINOv2Featurizer(nn.Module):
             xs = tc.gemm(h1, L["W2"], bias=L["b2"], resid=xs, out_dtype=torch.float32)
         if saved is not None:
             saved["x_final"] = xs
-        xn = _ln(xs, P["nw"], P["nb"], C, 1e-6, torch.float32)
-        feats = xn.view(B, T, C)[:, 1:]
+        if key_feats is not None:
+            feats = key_feats
+        else:
+            xn = _ln(xs, P["nw"], P["nb"], C, 1e-6, torch.float32)
+            feats = xn.view(B, T, C)[:, 1:]
         if inject and self.feats_injection_mode == "after_backbone":
             feats = feats + additional_features.to(feats.dtype)
         return feats.reshape(B, h, w, C).permute(0, 3, 1, 2)
@@ -282,7 +304,7 @@ class DINOv2Featurizer(nn.Module):
             for blk in m.blocks:
                 Wqkv = blk.attn.qkv.weight.detach().float().clone()
                 Wqkv[:C] *= sc
-                g1, g2 = blk.ls1.gamma.detach().float(), blk.ls2.gamma.detach().float()
+                g1, g2 = self._layer_scale(blk)
                 out.append({
                     "WqkvT": tc.pack_linear_weight(Wqkv.t().contiguous()).to(dev),
                     "WprojT": tc.pack_linear_weight((blk.attn.proj.weight.detach().float() * g1[:, None]).t().contiguous()).to(dev),
@@ -350,10 +372,21 @@ class DINOv2Featurizer(nn.Module):
         B, T, h, w = saved["B"], saved["T"], saved["h"], saved["w"]
         M = B * T
         bf = torch.bfloat16
-        dxn = torch.zeros(B, T, C, dtype=torch.float32, device=dev)  # the CLS token is not part of the features
-        dxn[:, 1:] = grad_feats.detach().float().permute(0, 2, 3, 1).reshape(B, h * w, C)
-        dx, dxb = self._ln_bwd(dxn.view(M, C), saved["x_final"], P["nw"], None, C)
-        for L, LB, (x_in, qkv, x_mid) in zip(reversed(P["blocks"]), reversed(PB), reversed(saved["blocks"])):
+        g = grad_feats.detach().float().permute(0, 2, 3, 1).reshape(B, h * w, C)
+        blocks, blocks_b = P["blocks"], PB
+        if self.feat_type == "key":  # features = K rows of the last block's qkv projection (channel order d * heads + head)
+            hd = C // nh
+            dk = torch.zeros(B, T, C, dtype=bf, device=dev)
+            dk[:, 1:] = g.view(B, h * w, hd, nh).permute(0, 1, 3, 2).reshape(B, h * w, C).to(bf)
+            L, LB = blocks[-1], blocks_b[-1]
+            dn = tc.gemm(dk.view(M, C), LB["WqkvT"][:, C:2 * C], out_dtype=torch.float32, N=C, K=C)
+            dx, dxb = self._ln_bwd(dn, saved["key_x"], L["n1w"], None, C)
+            blocks, blocks_b = blocks[:-1], blocks_b[:-1]
+        else:
+            dxn = torch.zeros(B, T, C, dtype=torch.float32, device=dev)  # the CLS token is not part of the features
+            dxn[:, 1:] = g
+            dx, dxb = self._ln_bwd(dxn.view(M, C), saved["x_final"], P["nw"], None, C)
+        for L, LB, (x_in, qkv, x_mid) in zip(reversed(blocks), reversed(blocks_b), reversed(saved["blocks"])):
             # MLP: x_out = x_mid + fc2(gelu(fc1(LN2 x_mid)))   (LayerScale folded into fc2)
             hn = _ln(x_mid, L["n2w"], L["n2b"], C, 1e-6, bf)
             pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf)
@@ -367,6 +400,65 @@ class DINOv2Featurizer(nn.Module):
             dn = tc.gemm(dqkv, LB["WqkvT"], out_dtype=torch.float32)
             dx, dxb = self._ln_bwd(dn, x_in, L["n1w"], dx, C)
         return dx.view(B, T, C)[:, 1:].contiguous()
+
+
+class _TimmBlock(nn.Module):
+    def __init__(self, dim, mlp_ratio=4):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = nn.Module()
+        self.attn.qkv = nn.Linear(dim, 3 * dim)
+        self.attn.proj = nn.Linear(dim, dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = nn.Module()
+        self.mlp.fc1 = nn.Linear(dim, mlp_ratio * dim)
+        self.mlp.fc2 = nn.Linear(mlp_ratio * dim, dim)
+
+
+class _TimmViT(nn.Module):
+    """Parameter container with the names of DINO.py's VisionTransformer / timm's vit_small_patch16_224 (minus the
+    classifier head, DINO.py:498-504): no LayerScale, no mask token."""
+
+    def __init__(self, dim=384, depth=12, heads=6, patch=16, img_size=224):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.patch_size = dim, heads, patch
+        n = (img_size // patch) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, dim))
+        self.patch_embed = nn.Module()
+        self.patch_embed.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+        self.blocks = nn.ModuleList([_TimmBlock(dim) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+
+
+class DINOFeaturizer(DINOv2Featurizer):
+    """`type="vit"` / `"dino"` backbone (core/model/featurizers/DINO.py:470-611): ViT-S with 16-pixel patches, features =
+    the keys of the last block (`feat_type="key"`, channel order head_dim-major) or the normed tokens ("token").  Same
+    constructor as the reference; the reference copies timm / hub weights into its own ViT (network) -- here the ViT is
+    built locally with those parameter names (a timm `vit_small_patch16_224` state dict without `head.*` loads with
+    `self.model.load_state_dict`) and random-initialised otherwise.  Runs on the DINOv2 code path (same kernels,
+    same activation backward)."""
+
+    def __init__(self, arch: str = "vit_small_patch16_224", patch_size: int = 16, feat_type: str = "key",
+                 feats_injection_mode: str = "no_injection") -> None:
+        nn.Module.__init__(self)
+        if feat_type not in ("key", "token"):
+            raise ValueError("Unknown feat type:{}".format(feat_type))  # DINO.py:606
+        assert feats_injection_mode in ("before_backbone", "after_backbone"), \
+            f"Unknown feats_injection_mode: {feats_injection_mode}"       # DINO.py:517-520
+        self.arch, self.feat_type, self.feats_injection_mode = arch, feat_type, feats_injection_mode
+        self.model = _TimmViT(patch=patch_size)
+        self.patch_size = patch_size
+        self.n_feats = 384 if arch == "vit_small" else 768  # DINO.py:508-511 (kept as is)
+        self._packed = None
+        self._pos_cache = {}
+
+    def _forward_impl(self, x, additional_features, saved):
+        if (x.shape[2] // self.patch_size) % 2:
+            raise NotImplementedError("odd patch-grid heights are cropped by the reference's PatchEmbed (DINO.py:207-208)")
+        return super()._forward_impl(x, additional_features, saved)
 
 
 class _DinoBackboneFn(torch.autograd.Function):

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .featurizers import DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed
+from .featurizers import DINOFeaturizer, DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed
 from .heads import HEAD_REGISTRY
 from .upsamplers import UPSAMPLER_REGISTRY, bilinear_align_corners_nhwc, to_nhwc_f32
 
@@ -47,7 +47,7 @@ class ISegPipeline(nn.Module):
                  patch: int = 14, use_disks: bool = True, norm_radius: int = 5, with_prev_mask: bool = True,
                  with_head: bool = True, backbone: str = "dinov2"):
         super().__init__()
-        if backbone not in ("dinov2", "maskclip"):
+        if backbone not in ("dinov2", "maskclip", "vit"):
             raise ValueError(f"Unknown backbone type: {backbone}")
         if upsampler_type not in UPSAMPLER_REGISTRY:
             raise ValueError(f"Unknown upsampler type: {upsampler_type}")  # model_builder.py:64-65
@@ -56,6 +56,9 @@ class ISegPipeline(nn.Module):
         if backbone == "maskclip":  # models/sbd/maskclip/*.py: ViT-B/16, 768-wide tokens, 512-d features
             self.backbone = MaskCLIPFeaturizer("ViT-B/16", "before_backbone")
             patch, backbone_dim, embed_dim = 16, 512, 768
+        elif backbone == "vit":  # models/sbd/vit/patch-embed_noup.py: timm ViT-S/16, key features
+            self.backbone = DINOFeaturizer("vit_small_patch16_224", 16, "key", "before_backbone")
+            patch, embed_dim = 16, backbone_dim
         else:
             self.backbone = DINOv2Featurizer("dinov2_vits14", "before_backbone")
             embed_dim = backbone_dim

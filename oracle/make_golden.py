@@ -125,6 +125,30 @@ def golden_vit():
     save("vit_56x84", out=f)
 
 
+def golden_dino_vit():
+    """DINO.py imports timm and core.utils.log at module level: timm is stubbed (only used by the hub-loading
+    constructor, which is bypassed) and DINOFeaturizer.forward is called unbound on a stand-in carrying the
+    attributes it reads (model, patch_size, feat_type, feats_injection_mode)."""
+    import types
+    sys.modules.setdefault("timm", types.ModuleType("timm"))
+    log = types.ModuleType("core.utils.log")
+    log.logger = __import__("logging").getLogger("ref")
+    sys.modules.setdefault("core.utils.log", log)
+    from core.model.featurizers import DINO as ref
+    m = ref.vit_small(patch_size=16, num_classes=0)
+    sd = synth.dino_vit_state_dict(seed=0)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 384, 1, seed=7).squeeze(-1) * 0.1  # [2, 24, 384]
+    outs = {}
+    with torch.no_grad():
+        for ft in ("key", "token"):
+            me = types.SimpleNamespace(model=m, patch_size=16, feat_type=ft, feats_injection_mode="before_backbone")
+            outs[ft] = ref.DINOFeaturizer.forward(me, img.clone(), emb.clone())
+    save("dino_vit_64x96", key=outs["key"], token=outs["token"])
+
+
 def golden_maskclip():
     """maskclip/model.py imported BY PATH (the package __init__ pulls the CLIP tokenizer, which needs ftfy)."""
     import importlib.util

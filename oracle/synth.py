@@ -136,6 +136,24 @@ def vit_state_dict(dim=384, depth=12, patch=14, n_pos=37 * 37 + 1, mlp_ratio=4, 
     return sd
 
 
+def dino_vit_state_dict(dim=384, depth=12, patch=16, n_pos=14 * 14 + 1, mlp_ratio=4, seed=0):
+    """Keys/shapes of DINO.py vit_small(patch_size=16, num_classes=0).state_dict() (DINO.py:213-287, 394-405)."""
+    G, sd = _Gen(seed), {}
+    sd["cls_token"] = G.randn(1, 1, dim, std=0.02)
+    sd["pos_embed"] = G.randn(1, n_pos, dim, std=0.02)
+    _conv(sd, G, "patch_embed.proj", dim, 3, patch)
+    for i in range(depth):
+        p = f"blocks.{i}"
+        _ln(sd, G, f"{p}.norm1", dim)
+        _linear(sd, G, f"{p}.attn.qkv", 3 * dim, dim)
+        _linear(sd, G, f"{p}.attn.proj", dim, dim)
+        _ln(sd, G, f"{p}.norm2", dim)
+        _linear(sd, G, f"{p}.mlp.fc1", mlp_ratio * dim, dim)
+        _linear(sd, G, f"{p}.mlp.fc2", dim, mlp_ratio * dim)
+    _ln(sd, G, "norm", dim)
+    return sd
+
+
 def maskclip_state_dict(width=768, layers=12, patch=16, out_dim=512, resolution=224, seed=0):
     """Keys/shapes of maskclip.model.VisionTransformer(224, 16, 768, 12, 12, 512).state_dict()
     (/root/reference/core/model/featurizers/maskclip/model.py:286-319)."""

@@ -320,3 +320,31 @@ def test_maskclip_click_embedding_gradient_vs_oracle_autograd(B, H, W):
     assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
     with torch.no_grad():
         assert torch.equal(out.detach(), f(img.to(DEV), emb.to(DEV)))
+
+
+@pytest.mark.parametrize("feat_type", ["key", "token"])
+def test_dino_vit_backbone_forward_and_gradient(feat_type, golden):
+    """`type="vit"` backbone (core/model/featurizers/DINO.py:470-611, models/sbd/vit/patch-embed_noup.py): forward against
+    the reference's golden vector and the oracle; click-embedding gradient against torch autograd through the oracle."""
+    import isegprobe_b200 as isp
+    from oracle import dino as odino
+    g = golden("dino_vit_64x96")
+    f = isp.DINOFeaturizer("vit_small_patch16_224", 16, feat_type, "before_backbone")
+    sd = synth.dino_vit_state_dict(seed=0)
+    f.model.load_state_dict(sd, strict=True)  # timm / DINO key layout
+    f = f.to(DEV).eval()
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 384, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():
+        out = f(img.to(DEV), emb.to(DEV))
+    want = torch.from_numpy(g[feat_type])
+    assert tuple(out.shape) == (2, 384, 4, 6)
+    assert cosine(out, want) > 0.999 and relerr(out, want) < 5e-2, (cosine(out, want), relerr(out, want))
+    gout = torch.randn(2, 384, 4, 6, generator=torch.Generator().manual_seed(3))
+    e_ref = (emb * 5).clone().requires_grad_(True)
+    odino.dino_vit_forward(sd, img, e_ref, feat_type=feat_type).backward(gout)
+    e = (emb * 5).to(DEV).requires_grad_(True)
+    f(img.to(DEV), e).backward(gout.to(DEV))
+    c = cosine(e.grad, e_ref.grad)
+    assert c > 0.99, c
+    assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)

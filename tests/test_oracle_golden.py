@@ -151,3 +151,18 @@ def test_nfl_loss_matches_reference(golden):
     out.mean().backward()
     assert float((out.detach() - torch.from_numpy(g["out"])).abs().max()) < 1e-6
     assert float((pred.grad - torch.from_numpy(g["grad"])).abs().max()) < 1e-7
+
+
+def test_dino_vit_oracle_matches_reference_golden(golden):
+    """DINO / timm ViT-S/16 adapter (DINO.py:529-611), 'key' and 'token' features, non-square image, click embedding
+    injected before the blocks."""
+    from oracle import dino as odino
+    g = golden("dino_vit_64x96")
+    sd = synth.dino_vit_state_dict(seed=0)
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    emb = synth.lr_features(2, 24, 384, 1, seed=7).squeeze(-1) * 0.1
+    with torch.no_grad():
+        for ft in ("key", "token"):
+            out = odino.dino_vit_forward(sd, img, emb, feat_type=ft)
+            want = torch.from_numpy(g[ft])
+            assert float((out - want).abs().max() / want.abs().max()) < 1e-5, ft
