@@ -224,6 +224,10 @@ int isp_gemm_bf16_tc_batched_nn(const void* A, long long a_sm, long long a_sh, l
 int isp_layernorm_rows_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, const float* gamma,
                            const float* resid, long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
                            long long M, int C, float eps, isp_stream_t stream);
+/* Affine-parameter gradients of a trainable LayerNorm (simple_vit click embedding, simple_ViT.py:31-93):
+ * dgamma[c] += sum_rows dy * xhat, dbeta[c] += sum_rows dy (accumulated; C <= 1024). */
+int isp_layernorm_affine_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx, float* dgamma,
+                             float* dbeta, long long M, int C, float eps, isp_stream_t stream);
 int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, int quick, isp_stream_t stream);
 int isp_softmax_rows(const float* S, long long lds, void* P_bf16, long long ldp, long long R, int ncols, int ncols_pad,
                      isp_stream_t stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "isp_gemm_bf16_tc_batched_tn": [_P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _I, _I, _I, _I, _I, _I, _F, _S],
     "isp_gemm_bf16_tc_batched_nn": [_P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _I, _I, _I, _I, _I, _I, _F, _S],
     "isp_layernorm_rows_bwd": [_P, _LL, _P, _I, _LL, _P, _P, _LL, _P, _LL, _P, _LL, _LL, _I, _F, _S],
+    "isp_layernorm_affine_bwd": [_P, _LL, _P, _I, _LL, _P, _P, _LL, _I, _F, _S],
     "isp_gelu_bwd_bf16": [_P, _P, _P, _LL, _I, _S],
     "isp_softmax_rows": [_P, _LL, _P, _LL, _LL, _I, _I, _S],
     "isp_attn_ds_rows": [_P, _LL, _P, _I, _LL, _P, _LL, _LL, _I, _I, _S],

@@ -165,6 +165,78 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
   }
 }
 
+// Affine-parameter gradients of LayerNorm (trainable LayerNorms of the simple_vit click embedding):
+// dgamma[c] += sum_rows dy[r,c] * xhat[r,c], dbeta[c] += sum_rows dy[r,c].  A block walks a chunk of rows (one warp per
+// row at a time, lane = columns lane, lane+32, ...), keeps per-column partial sums in registers, combines its 8 warps
+// through shared memory and issues one atomicAdd per column.
+template <bool X_BF16>
+__global__ void __launch_bounds__(256) layernorm_affine_bwd_kernel(const float* __restrict__ dy, long long lddy,
+                                                                   const void* __restrict__ xv_, long long ldx,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   long long M, int C, float eps, int rows_per_block) {
+  __shared__ float red[2][8][32 * 8];  // [gamma|beta][warp][column slot] for C <= 1024 handled in 4 passes of 256 columns
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  const int n = (C + 31) / 32;
+  float ga[kMaxPerLane], gb[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) ga[i] = gb[i] = 0.f;
+  for (long long row = r0 + warp; row < r1; row += 8) {
+    const float* xr = reinterpret_cast<const float*>(xv_) + row * ldx;
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv_) + row * ldx;
+    const float* dr = dy + row * lddy;
+    float xv[kMaxPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i)
+      if (i < n) {
+        const int c = lane + 32 * i;
+        xv[i] = c < C ? (X_BF16 ? __bfloat162float(xb[c]) : xr[c]) : 0.f;
+        s += xv[i];
+      }
+    const float mean = warp_sum(s) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i)
+      if (i < n) {
+        const float d = (lane + 32 * i < C) ? xv[i] - mean : 0.f;
+        var += d * d;
+      }
+    const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i)
+      if (i < n) {
+        const int c = lane + 32 * i;
+        if (c < C) {
+          const float d = dr[c];
+          ga[i] = fmaf(d, (xv[i] - mean) * rstd, ga[i]);
+          gb[i] += d;
+        }
+      }
+  }
+  for (int base = 0; base < n; base += 8) {  // 8 column slots (256 columns) per pass through shared memory
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[0][warp][i * 32 + lane] = (base + i < n) ? ga[base + i] : 0.f;
+      red[1][warp][i * 32 + lane] = (base + i < n) ? gb[base + i] : 0.f;
+    }
+    __syncthreads();
+    {
+      const int slot = threadIdx.x;  // 256 threads = 256 column slots
+      const int c = (base + slot / 32) * 32 + (slot & 31);
+      if (c < C) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += red[0][w][slot]; b += red[1][w][slot]; }
+        atomicAdd(dgamma + c, a);
+        atomicAdd(dbeta + c, b);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int KIND>  // 0: nn.GELU (erf form), 1: QuickGELU x * sigmoid(1.702 x) (maskclip/model.py:166-168)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat162* __restrict__ dh,
                                                        const __nv_bfloat162* __restrict__ pre,
@@ -304,6 +376,23 @@ extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const voi
     vb::layernorm_bwd_kernel<false><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
         dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
   ISP_CHECK_LAUNCH("layernorm_bwd_kernel");
+  return ISP_OK;
+}
+
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy for LayerNorm over the last dimension of x [M, C] (fp32 | bf16);
+// both outputs are ACCUMULATED (zero them first).  C <= 1024.
+extern "C" int isp_layernorm_affine_bwd(const float* dy, long long lddy, const void* x, int x_bf16, long long ldx,
+                                        float* dgamma, float* dbeta, long long M, int C, float eps, isp_stream_t stream) {
+  ISP_REQUIRE(dy && x && dgamma && dbeta && M > 0 && C > 0 && C <= 32 * vb::kMaxPerLane, ISP_ERR_BAD_SHAPE,
+              "layernorm_affine_bwd: bad arguments (C <= 1024)");
+  const int rows = 64;
+  if (x_bf16)
+    vb::layernorm_affine_bwd_kernel<true><<<cdiv(M, rows), 256, 0, as_stream(stream)>>>(dy, lddy, x, ldx, dgamma, dbeta, M, C,
+                                                                                      eps, rows);
+  else
+    vb::layernorm_affine_bwd_kernel<false><<<cdiv(M, rows), 256, 0, as_stream(stream)>>>(dy, lddy, x, ldx, dgamma, dbeta, M,
+                                                                                       C, eps, rows);
+  ISP_CHECK_LAUNCH("layernorm_affine_bwd_kernel");
   return ISP_OK;
 }
 

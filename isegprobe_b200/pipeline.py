@@ -14,10 +14,12 @@ import torch.nn as nn
 
 from . import ops
 from .featurizers import DINOFeaturizer, DINOv2Featurizer, MaskCLIPFeaturizer, PatchEmbed
+from .simple_vit import SimpleViTFeaturizer
 from .heads import HEAD_REGISTRY
 from .upsamplers import UPSAMPLER_REGISTRY, bilinear_align_corners_nhwc, to_nhwc_f32
 
-FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "maskclip": MaskCLIPFeaturizer, "patch_embedding": PatchEmbed}
+FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "maskclip": MaskCLIPFeaturizer, "patch_embedding": PatchEmbed,
+                       "simple_vit": SimpleViTFeaturizer}
 
 
 def install_into_reference() -> None:
@@ -45,7 +47,8 @@ class ISegPipeline(nn.Module):
     def __init__(self, upsampler_type: str = "loftup", upsampler_params: Optional[dict] = None,
                  head_type: str = "convhead", head_params: Optional[dict] = None, backbone_dim: int = 384,
                  patch: int = 14, use_disks: bool = True, norm_radius: int = 5, with_prev_mask: bool = True,
-                 with_head: bool = True, backbone: str = "dinov2"):
+                 with_head: bool = True, backbone: str = "dinov2", embed_coords_type: str = "patch_embedding",
+                 embed_coords_params: Optional[dict] = None, feats_injection_mode: str = "before_backbone"):
         super().__init__()
         if backbone not in ("dinov2", "maskclip", "vit"):
             raise ValueError(f"Unknown backbone type: {backbone}")
@@ -53,16 +56,26 @@ class ISegPipeline(nn.Module):
             raise ValueError(f"Unknown upsampler type: {upsampler_type}")  # model_builder.py:64-65
         self.use_disks, self.norm_radius, self.with_prev_mask = use_disks, norm_radius, with_prev_mask
         self.upsampler_type = upsampler_type
+        if embed_coords_type not in ("patch_embedding", "simple_vit"):
+            raise ValueError(f"Unsupported backbone type: {embed_coords_type}")  # model_builder.py:50-51
         if backbone == "maskclip":  # models/sbd/maskclip/*.py: ViT-B/16, 768-wide tokens, 512-d features
-            self.backbone = MaskCLIPFeaturizer("ViT-B/16", "before_backbone")
+            self.backbone = MaskCLIPFeaturizer("ViT-B/16", feats_injection_mode)
             patch, backbone_dim, embed_dim = 16, 512, 768
         elif backbone == "vit":  # models/sbd/vit/patch-embed_noup.py: timm ViT-S/16, key features
-            self.backbone = DINOFeaturizer("vit_small_patch16_224", 16, "key", "before_backbone")
+            self.backbone = DINOFeaturizer("vit_small_patch16_224", 16, "key", feats_injection_mode)
             patch, embed_dim = 16, backbone_dim
         else:
-            self.backbone = DINOv2Featurizer("dinov2_vits14", "before_backbone")
+            self.backbone = DINOv2Featurizer("dinov2_vits14", feats_injection_mode)
             embed_dim = backbone_dim
-        self.embed_coords = PatchEmbed((448, 448), (patch, patch), 3 if with_prev_mask else 2, embed_dim)
+        if embed_coords_type == "simple_vit":  # models/sbd/dinov2/simple-vit_noup.py (late injection: backbone_dim wide)
+            ep = dict(img_size=[448, 448], patch_size=(patch, patch), embed_dim=embed_dim, depth=6, heads=8, mlp_dim=2048,
+                      channels=3 if with_prev_mask else 2, dim_head=64)
+            ep.update(embed_coords_params or {})
+            self.embed_coords = SimpleViTFeaturizer(image_size=ep["img_size"], patch_size=ep["patch_size"], dim=ep["embed_dim"],
+                                                    depth=ep["depth"], heads=ep["heads"], mlp_dim=ep["mlp_dim"],
+                                                    channels=ep["channels"], dim_head=ep["dim_head"])
+        else:
+            self.embed_coords = PatchEmbed((448, 448), (patch, patch), 3 if with_prev_mask else 2, embed_dim)
         self.upsampler = UPSAMPLER_REGISTRY[upsampler_type](**(upsampler_params or {}))
         self.head = None
         if with_head:

@@ -149,6 +149,19 @@ def golden_dino_vit():
     save("dino_vit_64x96", key=outs["key"], token=outs["token"])
 
 
+def golden_simple_vit():
+    from core.model.featurizers.simple_ViT import SimpleViTFeaturizer
+    m = SimpleViTFeaturizer(image_size=[56, 84], patch_size=(14, 14), dim=384, depth=2, heads=8, mlp_dim=2048, channels=3,
+                            dim_head=64)
+    sd = synth.simple_vit_state_dict(depth=2, seed=0)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = synth.image_batch(2, 56, 84, seed=4)
+    with torch.no_grad():
+        out = m(x.clone())
+    save("simple_vit_56x84", out=out)
+
+
 def golden_maskclip():
     """maskclip/model.py imported BY PATH (the package __init__ pulls the CLIP tokenizer, which needs ftfy)."""
     import importlib.util
@@ -266,6 +279,8 @@ if __name__ == "__main__":
     golden_lift()
     golden_head()
     golden_vit()
+    golden_dino_vit()
+    golden_simple_vit()
     golden_maskclip()
     golden_nfl()
     golden_noc_driver()

@@ -154,6 +154,25 @@ def dino_vit_state_dict(dim=384, depth=12, patch=16, n_pos=14 * 14 + 1, mlp_rati
     return sd
 
 
+def simple_vit_state_dict(dim=384, depth=6, heads=8, dim_head=64, mlp_dim=2048, patch=14, channels=3, seed=0):
+    """Keys/shapes of SimpleViTFeaturizer(...).state_dict() (simple_ViT.py:96-138)."""
+    G, sd = _Gen(seed), {}
+    pd, inner = channels * patch * patch, heads * dim_head
+    _ln(sd, G, "to_patch_embedding.1", pd)
+    _linear(sd, G, "to_patch_embedding.2", dim, pd)
+    _ln(sd, G, "to_patch_embedding.3", dim)
+    _ln(sd, G, "transformer.norm", dim)
+    for i in range(depth):
+        p = f"transformer.layers.{i}"
+        _ln(sd, G, f"{p}.0.norm", dim)
+        sd[f"{p}.0.to_qkv.weight"] = G.randn(3 * inner, dim, std=dim ** -0.5)
+        sd[f"{p}.0.to_out.weight"] = G.randn(dim, inner, std=inner ** -0.5)
+        _ln(sd, G, f"{p}.1.net.0", dim)
+        _linear(sd, G, f"{p}.1.net.1", mlp_dim, dim)
+        _linear(sd, G, f"{p}.1.net.3", dim, mlp_dim)
+    return sd
+
+
 def maskclip_state_dict(width=768, layers=12, patch=16, out_dim=512, resolution=224, seed=0):
     """Keys/shapes of maskclip.model.VisionTransformer(224, 16, 768, 12, 12, 512).state_dict()
     (/root/reference/core/model/featurizers/maskclip/model.py:286-319)."""

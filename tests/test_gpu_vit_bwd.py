@@ -348,3 +348,101 @@ def test_dino_vit_backbone_forward_and_gradient(feat_type, golden):
     c = cosine(e.grad, e_ref.grad)
     assert c > 0.99, c
     assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
+
+
+def _simple_vit(depth, hw, seed=0):
+    from isegprobe_b200.simple_vit import SimpleViTFeaturizer
+    sd = synth.simple_vit_state_dict(depth=depth, seed=seed)
+    m = SimpleViTFeaturizer(image_size=list(hw), patch_size=(14, 14), dim=384, depth=depth, heads=8, mlp_dim=2048,
+                            channels=3, dim_head=64)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV), sd
+
+
+def test_simple_vit_forward_matches_reference_golden(golden):
+    """models/sbd/dinov2/simple-vit_noup.py's click embedding (simple_ViT.py:96-146) against the reference's output."""
+    m, _ = _simple_vit(2, (56, 84))
+    x = synth.image_batch(2, 56, 84, seed=4).to(DEV)
+    with torch.no_grad():
+        out = m(x)
+    want = torch.from_numpy(golden("simple_vit_56x84")["out"]).to(DEV)
+    assert out.shape == want.shape
+    assert cosine(out, want) > 0.9995 and relerr(out, want) < 3e-2
+    assert m.reshape_feats_to_patches(out).shape == (2, 384, 4, 6)
+
+
+@pytest.mark.parametrize("hw,depth", [((56, 84), 2), ((224, 224), 2)])
+def test_simple_vit_parameter_gradients_match_oracle_autograd(hw, depth):
+    """Every parameter of the trainable SimpleViT gets its gradient (weight gradients on the reduction-major batched
+    GEMM, LayerNorm affine gradients, bias column sums) -- against torch autograd through the fp32 oracle."""
+    from oracle import simple_vit as osv
+    m, sd = _simple_vit(depth, hw)
+    B = 2
+    x = synth.image_batch(B, hw[0], hw[1], seed=4)
+    gen = torch.Generator().manual_seed(11)
+    N = (hw[0] // 14) * (hw[1] // 14)
+    gout = torch.randn(B, N, 384, generator=gen) * 0.1
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out_ref = osv.simple_vit_forward(ref, x)
+    (out_ref * gout).sum().backward()
+    out = m(x.to(DEV))
+    assert out.requires_grad
+    assert cosine(out, out_ref.detach().to(DEV)) > 0.9995
+    (out * gout.to(DEV)).sum().backward()
+    worst = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        want = ref[k].grad.to(DEV)
+        c = cosine(p.grad, want)
+        worst[k] = c
+        assert c > 0.99, (k, c, float(p.grad.norm()), float(want.norm()))
+        assert abs(float(p.grad.norm() / want.norm()) - 1) < 0.05, k
+    assert len(worst) == 6 + 10 * depth + 2
+
+
+def test_pipeline_simple_vit_late_injection_gradients():
+    """models/sbd/dinov2/simple-vit_noup.py: click maps -> trainable SimpleViT -> added to the frozen DINOv2 features AFTER
+    the backbone (DINOv2.py 'after_backbone') -> identity upsampler -> ConvSegHead -> resize.  Logits and the gradients of
+    the SimpleViT parameters / the head against torch autograd through the fp32 oracle chain."""
+    import isegprobe_b200 as isp
+    from oracle import distmaps as odm
+    from oracle import simple_vit as osv
+    B, H, W, depth = 2, 56, 84, 2
+    pipe = isp.ISegPipeline("identity", {}, embed_coords_type="simple_vit", feats_injection_mode="after_backbone",
+                            embed_coords_params={"img_size": [H, W], "depth": depth}).to(DEV)
+    vsd = synth.vit_state_dict(384, depth=12, seed=0)
+    pipe.backbone.model.load_state_dict(vsd)
+    hsd = synth.convhead_state_dict(384, 2, 1, seed=0)
+    pipe.head.load_state_dict(hsd)
+    ssd = synth.simple_vit_state_dict(depth=depth, seed=0)
+    pipe.embed_coords.load_state_dict(ssd)
+    image = torch.cat([synth.image_batch(B, H, W, seed=1), (synth.image_batch(B, H, W, seed=8)[:, :1] > 0.5).float()], 1)
+    pts = synth.click_points(B, 3, H, W, seed=3)
+    gout = torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(4))
+    sr = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    hr_ = {k: v.clone().requires_grad_(True) for k, v in hsd.items()}
+    nimg = ohead.normalize_image(image[:, :3])
+    maps = torch.from_numpy(odm.distmaps(pts.numpy(), H, W, 5, 1.0, True))
+    emb = osv.simple_vit_forward(sr, torch.cat([image[:, 3:], maps], 1))
+    lr = ovit.dinov2_forward(vsd, nimg, None) + emb.reshape(B, H // 14, W // 14, 384).permute(0, 3, 1, 2)
+    want = ohead.bilinear_align_corners(ohead.convhead_forward(hr_, lr), (H, W))
+    (want * gout).sum().backward()
+    pipe.train()
+    logits = pipe(image.to(DEV), pts.to(DEV))["instances"]
+    (logits * gout.to(DEV)).sum().backward()
+    assert cosine(logits, want) > 0.998
+    for k, p in pipe.embed_coords.named_parameters():
+        assert p.grad is not None, k
+        assert cosine(p.grad, sr[k].grad) > 0.98, (k, cosine(p.grad, sr[k].grad))
+    for k, p in pipe.head.named_parameters():
+        if p.requires_grad:
+            assert cosine(p.grad, hr_[k].grad) > 0.98, k
+    # one optimiser step through the trainer (all SimpleViT parameters are in the optimiser)
+    from isegprobe_b200.training import HeadTrainer
+    tr = HeadTrainer(pipe, lr=1e-3)
+    assert tr.train_embedding and len(tr.params) > 6 + 10 * depth
+    before = pipe.embed_coords.transformer.layers[0][0].to_qkv.weight.detach().clone()
+    gt = (synth.image_batch(B, H, W, seed=9)[:, :1] > 0.5).float()
+    loss = tr.step(image.to(DEV), pts.to(DEV), gt.to(DEV))
+    assert bool(torch.isfinite(loss))
+    assert float((pipe.embed_coords.transformer.layers[0][0].to_qkv.weight.detach() - before).abs().max()) > 0

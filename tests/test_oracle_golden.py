@@ -166,3 +166,15 @@ def test_dino_vit_oracle_matches_reference_golden(golden):
             out = odino.dino_vit_forward(sd, img, emb, feat_type=ft)
             want = torch.from_numpy(g[ft])
             assert float((out - want).abs().max() / want.abs().max()) < 1e-5, ft
+
+
+def test_simple_vit_oracle_matches_reference_golden(golden):
+    """SimpleViTFeaturizer (simple_ViT.py:96-146), the trainable click embedding of dinov2/simple-vit_noup.py."""
+    from oracle import simple_vit as osv
+    g = golden("simple_vit_56x84")
+    sd = synth.simple_vit_state_dict(depth=2, seed=0)
+    x = synth.image_batch(2, 56, 84, seed=4)
+    with torch.no_grad():
+        out = osv.simple_vit_forward(sd, x)
+    want = torch.from_numpy(g["out"])
+    assert float((out - want).abs().max() / want.abs().max()) < 1e-5
