@@ -22,15 +22,25 @@ FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "maskclip": MaskCLIPFeaturize
                        "simple_vit": SimpleViTFeaturizer}
 
 
-def install_into_reference() -> None:
+def install_into_reference(featurizers: bool = False) -> None:
     """Swap the reference's registry entries for the B200-native modules (same keys), so
     `ModelBuilder.load_upsampler/load_head` construct ours.  Call after importing the
-    reference's `core.model` package and before building a model."""
+    reference's `core.model` package and before building a model.
+    featurizers=True also rebinds the featurizer classes `ModelBuilder.load_featurizer` and `iSegProbeModel` look up by
+    name (core/utils/model_builder.py:27-49, core/model/iseg_probe_model.py:93-103): the frozen backbones and the two
+    click encoders.  Ours keep the constructor keywords and the state-dict keys of `.model` but do not download
+    weights: load the torch.hub / CLIP / timm state dict into `backbone.model` afterwards."""
     import core.model.heads as ref_heads
     import core.model.upsamplers as ref_up
 
     ref_up.UPSAMPLER_REGISTRY.update(UPSAMPLER_REGISTRY)
     ref_heads.HEAD_REGISTRY.update(HEAD_REGISTRY)
+    if featurizers:
+        import core.model.iseg_probe_model as ref_model
+        import core.utils.model_builder as ref_mb
+        for cls in (DINOv2Featurizer, MaskCLIPFeaturizer, DINOFeaturizer, SimpleViTFeaturizer):
+            setattr(ref_mb, cls.__name__, cls)
+        ref_model.PatchEmbed = PatchEmbed
     try:
         import core.model.ops as ref_ops
         ref_ops.DistMaps = ops.DistMaps
