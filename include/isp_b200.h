@@ -246,6 +246,23 @@ int isp_transpose_bf16_batched(const void* src, long long lds, long long src_z, 
 int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
                           void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
                           int heads, int nkeys, int variant, isp_stream_t stream);
+/* Same, and also writes lse fp32 [B][heads][rows_per_img]: log2 of sum_k 2^(s_k log2 e) of every score row, the
+ * statistic isp_attention_bwd_bf16_tc recomputes the probabilities from. */
+int isp_attention_bf16_tc_lse(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                              void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                              int heads, int nkeys, int variant, float* lse, isp_stream_t stream);
+/* D[B][heads][rows] = sum_d dO[row, h*HP + d] * O[row, h*HP + d] (bf16 [B*rows, ld] operands). */
+int isp_attention_rowdot_heads(const void* dO, long long lddo, const void* O, long long ldo, float* out, int B,
+                               long long rows, int heads, int HP, isp_stream_t stream);
+/* Flash-style attention backward on tcgen05 (scores, probabilities and their gradients never leave the SM): the autograd of
+ * nn.MultiheadAttention in LoftUp's CrossAttentionLayer (loftup/layers.py:186-202) under the trainer's backward
+ * (core/training/trainer.py:213-221).  Q, dO bf16 [B*rows, ld], head h at columns [h*HP, +HP), Q pre-scaled as in the
+ * forward; K, V bf16 [B, heads, nkeys, HP] (rows = keys); lse, dvec fp32 [B][heads][rows] (+ 64 floats of slack) from
+ * isp_attention_bf16_tc_lse / isp_attention_rowdot_heads.  dK, dV fp32 [B, heads, nkeys, HP] and the optional dQ fp32
+ * [B*rows, lddq] are ACCUMULATED into (zero them first).  HP: multiple of 16, <= 128; rows: multiple of 4. */
+int isp_attention_bwd_bf16_tc(const void* Q, long long ldq, const void* dO, long long lddo, const void* K, const void* V,
+                              const float* lse, const float* dvec, float* dK, float* dV, float* dQ, long long lddq, int B,
+                              long long rows, int heads, int nkeys, int HP, isp_stream_t stream);
 
 /* LayerNorm over the last dim of a row-major matrix (f32 or bf16 in/out, biased variance):
  * nn.LayerNorm in loftup/layers.py:26-35,161-202,222-228 and the channel LayerNorm :38-58.

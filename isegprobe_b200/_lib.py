@@ -54,6 +54,9 @@ SIGNATURES = {
     "isp_attn_ds_rows": [_P, _LL, _P, _I, _LL, _P, _LL, _LL, _I, _I, _S],
     "isp_transpose_bf16_batched": [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _S],
     "isp_attention_bf16_tc": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _S],
+    "isp_attention_bf16_tc_lse": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _P, _S],
+    "isp_attention_rowdot_heads": [_P, _LL, _P, _LL, _P, _I, _LL, _I, _I, _S],
+    "isp_attention_bwd_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _I, _S],
     "isp_layernorm_rows": [_P, _I, _LL, _P, _I, _LL, _P, _P, _LL, _I, _F, _S],
     "isp_minmax_per_channel": [_P, _P, _I, _I, _I, _LL, _LL, _S],
     "isp_loftup_fourier_chnorm": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _S],

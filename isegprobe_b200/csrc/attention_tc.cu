@@ -44,6 +44,7 @@ struct Params {
   void* out;                   // bf16 [B*rows_per_img, ldo] (direct-store epilogue of the wide-head variant)
   long long ldo;
   int stagger_ns;              // split mode: the second half's warps start every tile this much later
+  float* lse;                  // optional [B][heads][rows_per_img]: log2-domain log-sum-exp of every score row (for the backward)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2 (ftz); inputs are <= 8
@@ -323,17 +324,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (PL::kStageO && sw == 0 && lane == 0) tc::tma_store_wait_read<0>();  // previous tile's store has read the staging tile
       asm volatile("bar.sync 9, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
       float inv, f0 = 1.f, f1 = 0.f;  // O = (O_0 f0 + O_1 f1) * inv
+      float m_row = m_ref, l_row;      // row maximum (log2 units) and the row sum relative to it
       if constexpr (kSplit) {
         const float m_o = other_x[0], l_o = other_x[2 * kSlot];
         const float m = fmaxf(m_ref, m_o);
         const float f_me = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m);
         const float f_o = (m_o == -INFINITY) ? 0.f : ex2_approx(m_o - m);
-        inv = 1.f / (l * f_me + l_o * f_o);
+        m_row = m;
+        l_row = l * f_me + l_o * f_o;
         f0 = half ? f_o : f_me;
         f1 = half ? f_me : f_o;
       } else {
-        inv = 1.f / (l + other_x[2 * kSlot]);
+        l_row = l + other_x[2 * kSlot];
       }
+      inv = 1.f / l_row;
+      if (p.lse && half == 0 && (long long)qt * BQ + r < p.rows_per_img)
+        p.lse[((long long)b * p.heads + h) * p.rows_per_img + (long long)qt * BQ + r] = m_row + log2f(l_row);
       tc::mbar_wait(&pv_done, (g - 1) & 1);
       tc::tc_fence_after();
       const long long row_local = (long long)qt * BQ + r;
@@ -394,9 +400,9 @@ using namespace isp;
 // zero padded).  Vt: bf16 [B, heads, DV, nblocks*128].  out: bf16 [B*rows_per_img, ldo], head h
 // writes DV columns at h*o_head_stride.  variant 0: head_dim <= 64 (DV = 64); 1: <= 112 (DV = 112);
 // 2: <= 144 (DV = 144, K padded to 192 columns).
-extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
-                                     void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
-                                     int heads, int nkeys, int variant, isp_stream_t stream) {
+static int attention_fwd(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt, void* out,
+                         long long ldo, int o_head_stride, int B, long long rows_per_img, int heads, int nkeys, int variant,
+                         float* lse, isp_stream_t stream) {
   ISP_REQUIRE(Q && K && Vt && out, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: null pointer");
   ISP_REQUIRE(B > 0 && rows_per_img > 0 && heads > 0 && nkeys > 0, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: bad shape");
   ISP_REQUIRE(variant >= 0 && variant <= 2, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: variant %d", variant);
@@ -417,6 +423,7 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
   p.q_head_stride = q_head_stride;
   p.o_head_stride = o_head_stride;
   p.out = out; p.ldo = ldo;
+  p.lse = lse;
   p.stagger_ns = 400;  // measured 150..800 ns: 1.53 -> 1.48 ms on the LoftUp shape (the two warps of an SM sub-partition
                        // then alternate between their TMEM-load and exponential phases instead of colliding)
   const long long nkp = (long long)p.nblocks * attn::BKEY;
@@ -467,4 +474,21 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
     attn::attention_kernel<1, 4, 64><<<grid, attn::kThreads, sm0, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);
   ISP_CHECK_LAUNCH("attention_kernel");
   return ISP_OK;
+}
+
+extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                                     void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                                     int heads, int nkeys, int variant, isp_stream_t stream) {
+  return attention_fwd(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, variant,
+                       nullptr, stream);
+}
+
+// Same, and also writes lse[B][heads][rows_per_img] (fp32, log2 units: log2 of the sum over keys of 2^(s*log2e)), the
+// row statistic isp_attention_bwd_bf16_tc needs to recompute the probabilities tile by tile.
+extern "C" int isp_attention_bf16_tc_lse(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                                         void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                                         int heads, int nkeys, int variant, float* lse, isp_stream_t stream) {
+  ISP_REQUIRE(lse, ISP_ERR_BAD_SHAPE, "attention_bf16_tc_lse: null lse");
+  return attention_fwd(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, variant, lse,
+                       stream);
 }

@@ -102,6 +102,9 @@ class LoftUpUpsampler(BaseUpsampler):
     # dtype of the returned features; ISegPipeline switches to bf16 when a head consumes them (the head rounds its
     # input to bf16 anyway: same bits, one 1.2 GB/8-image conversion pass less)
     out_dtype = torch.float32
+    # backward of the cross-attention on the flash-style kernel (isp_attention_bwd_bf16_tc); False = the older path that
+    # materialises the probabilities per image (kept for heads wider than 128 columns, and as a cross-check in the tests)
+    flash_backward = True
 
     def __init__(self, upsampler_path: str = None, n_dim: int = 384, lr_pe_type: str = "sine", lr_size: int = 16):
         super().__init__()
@@ -438,14 +441,36 @@ class LoftUpUpsampler(BaseUpsampler):
             _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, T, nh, HP, 0)
             _call("isp_repack_heads", Vl, 0, D, 0, hd, Vp, B, T, T, nh, HP, 0)
             need_dq = li > 0  # the first layer's queries come from the image only
-            dQ = torch.empty(M, nh * HP, dtype=bf, device=dev) if need_dq else None
-            dK = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
-            dV = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
-            for b in range(B):
-                dq_b, dK[b], dV[b] = self._attention_bwd_image(Q[b * HW:(b + 1) * HW], dO[b * HW:(b + 1) * HW], Kp[b], Vp[b],
-                                                               need_dq, HW, T, nh, HP)
-                if need_dq:
-                    dQ[b * HW:(b + 1) * HW] = dq_b
+            if self.flash_backward and HP <= 128 and HW % 4 == 0:
+                # flash-style backward: the forward attention is re-run for O and the rows' log-sum-exp, then ONE kernel
+                # recomputes P / dS tile by tile on chip (isp_attention_bwd_bf16_tc) for the whole chunk
+                Tq, KP = tc.round_up(T, 128), P["KP"]
+                Kf = torch.empty(B, nh, Tq, KP, dtype=bf, device=dev)
+                Vtf = torch.empty(B, nh, HP, Tq, dtype=bf, device=dev)
+                _call("isp_repack_heads", Kl, 0, D, 0, hd, Kf, B, T, Tq, nh, KP, 0)
+                _call("isp_repack_heads", Vl, 0, D, 0, hd, Vtf, B, T, Tq, nh, HP, 1)
+                O = torch.empty(M, nh * HP, dtype=bf, device=dev)
+                lse = torch.empty(B * nh * HW + 64, dtype=torch.float32, device=dev)
+                dvec = torch.empty(B * nh * HW + 64, dtype=torch.float32, device=dev)
+                _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kf, Vtf, O, nh * HP, HP, B, HW, nh, T, P["variant"], lse)
+                _call("isp_attention_rowdot_heads", dO, nh * HP, O, nh * HP, dvec, B, HW, nh, HP)
+                del O, Kf, Vtf
+                dK = torch.zeros(B, nh, T, HP, dtype=torch.float32, device=dev)
+                dV = torch.zeros(B, nh, T, HP, dtype=torch.float32, device=dev)
+                dQf = torch.zeros(M, nh * HP, dtype=torch.float32, device=dev) if need_dq else None
+                _call("isp_attention_bwd_bf16_tc", Q, nh * HP, dO, nh * HP, Kp, Vp, lse, dvec, dK, dV, dQf, nh * HP, B, HW,
+                      nh, T, HP)
+                dQ = dQf.to(bf) if need_dq else None
+                del dQf, lse, dvec
+            else:  # wide heads (n_dim = 512: 133 > 128 columns): probabilities materialised per image
+                dQ = torch.empty(M, nh * HP, dtype=bf, device=dev) if need_dq else None
+                dK = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
+                dV = torch.empty(B, nh, T, HP, dtype=torch.float32, device=dev)
+                for b in range(B):
+                    dq_b, dK[b], dV[b] = self._attention_bwd_image(Q[b * HW:(b + 1) * HW], dO[b * HW:(b + 1) * HW], Kp[b],
+                                                                   Vp[b], need_dq, HW, T, nh, HP)
+                    if need_dq:
+                        dQ[b * HW:(b + 1) * HW] = dq_b
             del Q, dO
             if need_dq:
                 dn = tc.gemm(dQ, LB["WqT"], out_dtype=torch.float32, N=D, K=nh * HP)

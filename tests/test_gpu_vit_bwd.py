@@ -293,6 +293,13 @@ def test_loftup_source_gradient_vs_oracle_autograd(B, H, W, h, w):
     c = cosine(s.grad, lr_ref.grad)
     assert c > 0.99, c
     assert relerr(s.grad, lr_ref.grad) < 0.2, relerr(s.grad, lr_ref.grad)
+    # the flash-style attention backward (default) against the path that materialises the probabilities
+    assert m.flash_backward
+    m.flash_backward = False
+    s2 = lr.to(DEV).requires_grad_(True)
+    m(source=s2, guidance=img.to(DEV)).backward(gout.to(DEV))
+    assert cosine(s.grad, s2.grad) > 0.999, cosine(s.grad, s2.grad)
+    assert cosine(s2.grad, lr_ref.grad) > 0.99
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 64, 96)])
@@ -446,3 +453,59 @@ def test_pipeline_simple_vit_late_injection_gradients():
     loss = tr.step(image.to(DEV), pts.to(DEV), gt.to(DEV))
     assert bool(torch.isfinite(loss))
     assert float((pipe.embed_coords.transformer.layers[0][0].to_qkv.weight.detach() - before).abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,nh,rows,T,hd,need_dq", [(2, 4, 4704, 24, 101, True), (1, 4, 8192, 300, 101, True),
+                                                    (2, 2, 1024, 128, 64, False)])
+def test_flash_attention_backward_kernel(B, nh, rows, T, hd, need_dq):
+    """isp_attention_bwd_bf16_tc (+ the forward's lse output and the dO.O row dots) against torch autograd of
+    softmax(Q K^T) V in fp32 on the same bf16 operands: partial query tiles, partial / multiple key blocks, dQ on / off."""
+    from isegprobe_b200 import _lib
+    HP = 112 if hd > 64 else 64
+    variant, DKC = (1, 128) if hd > 64 else (0, 64)
+    g = torch.Generator().manual_seed(5)
+    def rnd(*shape, s=1.0):
+        t = torch.zeros(*shape[:-1], HP)
+        t[..., :hd] = torch.randn(*shape[:-1], hd, generator=g) * s
+        return t.to(torch.bfloat16)
+    Q = rnd(B, rows, nh, HP, s=0.35).reshape(B * rows, nh * HP).to(DEV)
+    dO = rnd(B, rows, nh, HP, s=0.5).reshape(B * rows, nh * HP).to(DEV)
+    K = rnd(B, nh, T, HP, s=1.0).to(DEV)
+    V = rnd(B, nh, T, HP, s=1.0).to(DEV)
+    Tp = (T + 127) // 128 * 128
+    Kp = torch.zeros(B, nh, Tp, DKC, dtype=torch.bfloat16, device=DEV)
+    Kp[:, :, :T, :HP] = K
+    Vt = torch.zeros(B, nh, HP, Tp, dtype=torch.bfloat16, device=DEV)
+    Vt[:, :, :, :T] = V.transpose(2, 3)
+    O = torch.empty(B * rows, nh * HP, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(B * nh * rows + 64, device=DEV)
+    _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, rows, nh, T, variant, lse)
+    # fp32 reference under autograd
+    q = Q.float().view(B, rows, nh, HP).permute(0, 2, 1, 3).requires_grad_(True)
+    k = K.float().requires_grad_(True)
+    v = V.float().requires_grad_(True)
+    s = q @ k.transpose(-1, -2)
+    o = torch.softmax(s, -1) @ v
+    want_lse = torch.logsumexp(s.detach(), -1) * 1.4426950408889634
+    assert float((lse[:B * nh * rows].view(B, nh, rows) - want_lse).abs().max()) < 2e-2
+    assert cosine(O.float().view(B, rows, nh, HP).permute(0, 2, 1, 3), o.detach()) > 0.9999
+    do = dO.float().view(B, rows, nh, HP).permute(0, 2, 1, 3)
+    (o * do).sum().backward()
+    dvec = torch.zeros(B * nh * rows + 64, device=DEV)
+    _call("isp_attention_rowdot_heads", dO, nh * HP, O, nh * HP, dvec, B, rows, nh, HP)
+    want_d = (do * o.detach()).sum(-1)
+    assert relerr(dvec[:B * nh * rows].view(B, nh, rows), want_d) < 2e-2
+    dK = torch.zeros(B, nh, T, HP, device=DEV)
+    dV = torch.zeros(B, nh, T, HP, device=DEV)
+    dQ = torch.zeros(B * rows, nh * HP, device=DEV) if need_dq else None
+    _lib.call("isp_attention_bwd_bf16_tc", _lib.dptr(Q), nh * HP, _lib.dptr(dO), nh * HP, _lib.dptr(K), _lib.dptr(V),
+              _lib.dptr(lse), _lib.dptr(dvec), _lib.dptr(dK), _lib.dptr(dV), _lib.dptr(dQ), nh * HP, B, rows, nh, T, HP,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert cosine(dV, v.grad) > 0.999 and relerr(dV, v.grad) < 3e-2, (cosine(dV, v.grad), relerr(dV, v.grad))
+    assert cosine(dK, k.grad) > 0.999 and relerr(dK, k.grad) < 3e-2, (cosine(dK, k.grad), relerr(dK, k.grad))
+    if hd < HP:
+        assert float(dK[..., hd:].abs().max()) == 0 and float(dV[..., hd:].abs().max()) == 0
+    if need_dq:
+        got = dQ.view(B, rows, nh, HP).permute(0, 2, 1, 3)
+        assert cosine(got, q.grad) > 0.999 and relerr(got, q.grad) < 3e-2, (cosine(got, q.grad), relerr(got, q.grad))
