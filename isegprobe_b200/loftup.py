@@ -293,7 +293,14 @@ class LoftUpUpsampler(BaseUpsampler):
                 del qn
             O = torch.empty(M, nh * HP, dtype=bf, device=dev)
             with timed_kernel("loftup_attention"):
-                _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
+                if keep is not None and self._flash_ok(HP, H * W):
+                    # training: the attention output and the rows' log-sum-exp are what the flash-style backward needs
+                    lse = torch.empty(B * nh * H * W + 64, dtype=torch.float32, device=dev)
+                    _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"],
+                          lse)
+                    keep.setdefault("attn", []).append((O, lse))
+                else:
+                    _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
             del Q
             x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp, stats_out=st_b)
             del O
@@ -323,6 +330,9 @@ class LoftUpUpsampler(BaseUpsampler):
         _call("isp_layernorm_rows", y, 0, C, out.view(M, C), int(out.dtype == torch.bfloat16), C, P["lnf_w"], P["lnf_b"],
               M, C, 1e-6)
 
+
+    def _flash_ok(self, HP, HW):
+        return self.flash_backward and HP <= 128 and HW % 4 == 0
 
     # ---------------------------------------------------------------- activation backward (d loss / d source)
     def _pack_bwd(self, dev):
@@ -441,20 +451,14 @@ class LoftUpUpsampler(BaseUpsampler):
             _call("isp_repack_heads", Kl, 0, D, 0, hd, Kp, B, T, T, nh, HP, 0)
             _call("isp_repack_heads", Vl, 0, D, 0, hd, Vp, B, T, T, nh, HP, 0)
             need_dq = li > 0  # the first layer's queries come from the image only
-            if self.flash_backward and HP <= 128 and HW % 4 == 0:
-                # flash-style backward: the forward attention is re-run for O and the rows' log-sum-exp, then ONE kernel
-                # recomputes P / dS tile by tile on chip (isp_attention_bwd_bf16_tc) for the whole chunk
-                Tq, KP = tc.round_up(T, 128), P["KP"]
-                Kf = torch.empty(B, nh, Tq, KP, dtype=bf, device=dev)
-                Vtf = torch.empty(B, nh, HP, Tq, dtype=bf, device=dev)
-                _call("isp_repack_heads", Kl, 0, D, 0, hd, Kf, B, T, Tq, nh, KP, 0)
-                _call("isp_repack_heads", Vl, 0, D, 0, hd, Vtf, B, T, Tq, nh, HP, 1)
-                O = torch.empty(M, nh * HP, dtype=bf, device=dev)
-                lse = torch.empty(B * nh * HW + 64, dtype=torch.float32, device=dev)
+            if "attn" in keep and self._flash_ok(HP, HW):
+                # flash-style backward: ONE kernel recomputes P / dS tile by tile on chip (isp_attention_bwd_bf16_tc) for
+                # the whole chunk, from the attention output and the rows' log-sum-exp the forward kept
+                O, lse = keep["attn"][li]
                 dvec = torch.empty(B * nh * HW + 64, dtype=torch.float32, device=dev)
-                _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kf, Vtf, O, nh * HP, HP, B, HW, nh, T, P["variant"], lse)
                 _call("isp_attention_rowdot_heads", dO, nh * HP, O, nh * HP, dvec, B, HW, nh, HP)
-                del O, Kf, Vtf
+                keep["attn"][li] = None
+                del O
                 dK = torch.zeros(B, nh, T, HP, dtype=torch.float32, device=dev)
                 dV = torch.zeros(B, nh, T, HP, dtype=torch.float32, device=dev)
                 dQf = torch.zeros(M, nh * HP, dtype=torch.float32, device=dev) if need_dq else None
