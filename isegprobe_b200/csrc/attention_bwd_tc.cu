@@ -6,13 +6,15 @@
 // One CTA owns (image, head, block of 128 keys, chunk of query rows) and walks its queries 64 at a time.  Everything is
 // computed TRANSPOSED so that the 128 keys are the MMA M dimension (full-rate 128-row MMAs) and the TMEM lanes:
 //
-//   S^T  [128 keys x 64 q] = K  Q^T          A = K tile (K-major),  B = Q tile  (K-major)      -> TMEM
-//   dP^T [128 keys x 64 q] = V dO^T          A = V tile (K-major),  B = dO tile (K-major)      -> TMEM
-//   P^T = 2^(S^T log2e - lse[q]),  dS^T = P^T (dP^T - D[q])      softmax warps: TMEM -> registers -> bf16 -> smem tiles
-//                                                                 [128 keys][64 q], written in the 128B-swizzle layout
-//   dV [128 keys x d] += P^T  dO             A = P^T tile (K-major over q),  B = dO tile walked MN-major (same smem)
-//   dK [128 keys x d] += dS^T Q              A = dS^T tile,                  B = Q tile walked MN-major (same smem)
-//   dQ^T [d x 64 q]    = K^T dS^T  (optional) A = K tile walked MN-major,     B = dS^T tile walked MN-major
+//   S^T  [128 keys x 64 q] = K  Q^T          A = K tile (K-major),  B = Q tile  (K-major)      -> TMEM (double-buffered)
+//   dP^T [128 keys x 64 q] = V dO^T          A = V tile (K-major),  B = dO tile (K-major)      -> TMEM (double-buffered)
+//   P^T = 2^(S^T log2e - lse[q]),  dS^T = P^T (dP^T - D[q])      softmax warps: TMEM -> registers -> bf16 -> back into TMEM
+//                                                                 over the thread's own S^T columns (keys on the lanes is
+//                                                                 exactly the A-operand layout of the next two products)
+//   dV [128 keys x d] += P^T  dO             A = P^T  from TMEM,   B = dO tile walked MN-major (the same smem tile)
+//   dK [128 keys x d] += dS^T Q              A = dS^T from TMEM,   B = Q tile walked MN-major (the same smem tile)
+//   dQ^T [d x 64 q]    = K^T dS^T  (optional) A = K tile walked MN-major, B = dS^T as a 128B-swizzled smem tile written by the
+//                                            softmax warps; accumulator over dP^T's TMEM columns
 //
 // The Q / dO tiles are therefore loaded ONCE per step and used as two different operands; dK / dV stay in TMEM for the
 // whole chunk and are added to the fp32 gradients with red.global.add.v4 at the end (chunks of the same key block
@@ -20,9 +22,10 @@
 // lse is the forward's log-sum-exp in log2 units (isp_attention_bf16_tc_lse), D[q] = sum_d dO[q,d] O[q,d]
 // (isp_attention_rowdot_heads); both are [B][heads][rows].
 //
-// Warps: 0 = TMA producer (3-deep Q/dO ring, lse/D by 1-D bulk copies on the same barrier), 1 = MMA issuer,
-// 2..9 = softmax (TMEM lane = key; the two warps of a lane quarter take 32 queries each).  S^T(i+1) is issued as soon
-// as the softmax warps have S^T(i) / dP^T(i) in registers, so the tensor pipe runs under the exponentials.
+// Warps: 0 = TMA producer (4-deep Q/dO ring, lse/D by 1-D bulk copies on the same barrier), 1 = MMA issuer (S^T / dP^T two
+// steps ahead of the softmax), 2..17 = softmax (TMEM lane = key; the four warps of a lane quarter take 16 queries each).
+// TMEM: buffer b at b*128 (S^T 64 columns, dP^T 64), dV at 256, dK at 384.  tcgen05.mma executes in issue order, which
+// orders the reads of P^T(i) / dS^T(i) before S^T(i+2) overwrites their buffer.
 #include "tc_common.cuh"
 
 namespace isp {
@@ -30,17 +33,21 @@ namespace attnbwd {
 
 constexpr int BK = 128;            // keys per CTA
 constexpr int BQ = 64;             // queries per step
-constexpr int kStages = 3;
-constexpr int kSoftmaxWarps = 8;
+constexpr int kStages = 4;
+constexpr int kSoftmaxWarps = 16;          // four per TMEM lane quarter: each takes 16 of the step's 64 queries
 constexpr int kThreads = 64 + 32 * kSoftmaxWarps;
 constexpr uint32_t kKVBytes = 2 * 16384;          // K (or V) tile: two [128 keys x 64 cols] boxes
 constexpr uint32_t kQBytes = 2 * 8192;            // Q (or dO) tile: two [64 q x 64 cols] boxes
 constexpr uint32_t kStageBytes = 2 * kQBytes;
 constexpr uint32_t kPBytes = 16384;               // P^T (or dS^T) tile [128 keys x 64 q]
-constexpr uint32_t kSmem = 2 * kKVBytes + kStages * kStageBytes + 2 * kPBytes;  // 192 KB
+constexpr uint32_t kSmem = 2 * kKVBytes + kStages * kStageBytes + kPBytes;  // 208 KB
 constexpr float kLog2e = 1.4426950408889634f;
 // TMEM columns
-constexpr uint32_t cS = 0, cDP = 64, cDQ = 128, cDV = 256, cDK = 384;
+// buffer b (step parity) at b*128: S^T @+0 (64 columns), dP^T @+64 (64).  Once a step's S^T / dP^T are in registers the same
+// columns are reused: each softmax thread writes P^T (16 packed bf16 columns) and dS^T (16) over ITS OWN 32 S^T columns, and
+// dQ^T(i) is accumulated over dP^T's columns.  The tensor pipe executes in issue order, which orders the MMAs that read
+// P^T(i) / dS^T(i) before S^T(i+2) overwrites the buffer.
+constexpr uint32_t cBUF = 128, cDP = 64, cDV = 256, cDK = 384;
 
 struct Params {
   int nkeys, heads, nkb;         // real keys per image, heads, key blocks per image
@@ -111,16 +118,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t kv_full, full_bar[kStages], empty_bar[kStages], s_full, s_free, p_full, p_free, dq_full,
-      dq_free, acc_full;
+  __shared__ __align__(8) uint64_t kv_full, full_bar[kStages], empty_bar[kStages], s_full[2], p_full, dq_full, dq_free, acc_full;
   __shared__ __align__(16) float stat[kStages][2][BQ];  // [stage][lse | D][query]
   __shared__ uint32_t tmem_base_s;
 
   uint8_t* sK = smem;
   uint8_t* sV = sK + kKVBytes;
   uint8_t* sQ0 = sV + kKVBytes;                   // stage s: Q at sQ0 + s*kStageBytes, dO right after it
-  uint8_t* sP = sQ0 + kStages * kStageBytes;
-  uint8_t* sDS = sP + kPBytes;
+  uint8_t* sDS = sQ0 + kStages * kStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // work item
@@ -137,8 +142,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmDO); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
     tc::mbar_init(&kv_full, 1);
     for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-    tc::mbar_init(&s_full, 1); tc::mbar_init(&s_free, kSoftmaxWarps);
-    tc::mbar_init(&p_full, kSoftmaxWarps); tc::mbar_init(&p_free, 1);
+    tc::mbar_init(&s_full[0], 1); tc::mbar_init(&s_full[1], 1);
+    tc::mbar_init(&p_full, kSoftmaxWarps);
     tc::mbar_init(&dq_full, 1); tc::mbar_init(&dq_free, kSoftmaxWarps);
     tc::mbar_init(&acc_full, 1);
     tc::fence_barrier_init();
@@ -185,136 +190,169 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t id_s = tc::idesc_bf16_f32(BK, BQ);                 // S^T, dP^T: both operands K-major
     const uint32_t id_g = tc::idesc_bf16_f32(BK, p.HP) | kBmn;        // dV, dK: A K-major (P^T / dS^T), B MN-major
     const uint32_t id_q = tc::idesc_bf16_f32(128, BQ) | kAmn | kBmn;  // dQ^T: K tile and dS^T tile both MN-major
-    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP), aDS = tc::smem_u32(sDS);
-    auto issue_s = [&](int i) {  // S^T(i), dP^T(i)
+    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aDS = tc::smem_u32(sDS);
+    // Descriptors are built once; every MMA only adds a compile-time offset to the 14-bit start-address field (>> 4): the
+    // single issuing warp's instruction stream is ~6 instructions per MMA (it was the bottleneck when each descriptor was
+    // rebuilt from its address: 22-30 MMAs per step).
+    const uint64_t dKk = tc::smem_desc_k_sw128(aK), dVk = tc::smem_desc_k_sw128(aV);
+    const uint64_t dKmn = desc_mn(aK, 16384), dDSmn = desc_mn(aDS, 8192);
+    auto issue_s = [&](int i) {  // S^T(i), dP^T(i) -> TMEM buffer i & 1
       const int s = i % kStages;
+      const uint32_t tb = tmem + (i & 1) * cBUF;
       bwait(&full_bar[s], (i / kStages) & 1, 1);
       tc::tc_fence_after();
-      const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes), aDO = aQ + kQBytes;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32, ob = (k >> 2) * 8192 + (k & 3) * 32;
-        if (leader) tc::umma_bf16(tmem + cS, tc::smem_desc_k_sw128(aK + oa), tc::smem_desc_k_sw128(aQ + ob), id_s, k ? 1u : 0u);
+      const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes);
+      const uint64_t dQk = tc::smem_desc_k_sw128(aQ), dDOk = tc::smem_desc_k_sw128(aQ + kQBytes);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // K step k: 32 bytes further inside the 128-byte rows, second box after four steps
+          if (k < ksteps)
+            tc::umma_bf16(tb, dKk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), dQk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s,
+                          k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < ksteps)
+            tc::umma_bf16(tb + cDP, dVk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                          dDOk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s, k ? 1u : 0u);
+        tc::umma_commit(&s_full[i & 1]);
       }
-      for (int k = 0; k < ksteps; ++k) {
-        const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32, ob = (k >> 2) * 8192 + (k & 3) * 32;
-        if (leader) tc::umma_bf16(tmem + cDP, tc::smem_desc_k_sw128(aV + oa), tc::smem_desc_k_sw128(aDO + ob), id_s, k ? 1u : 0u);
-      }
-      if (leader) tc::umma_commit(&s_full);
     };
     bwait(&kv_full, 0, 2);
     issue_s(0);
+    if (nsteps > 1) issue_s(1);
     for (int i = 0; i < nsteps; ++i) {
       const int s = i % kStages;
-      if (i + 1 < nsteps) {
-        bwait(&s_free, i & 1, 3);  // the softmax warps hold S^T(i) / dP^T(i) in registers
-        tc::tc_fence_after();
-        issue_s(i + 1);
-      }
-      bwait(&p_full, i & 1, 4);    // P^T(i), dS^T(i) are in shared memory
+      const uint32_t tb = tmem + (i & 1) * cBUF;
+      bwait(&p_full, i & 1, 4);    // P^T(i), dS^T(i) are in TMEM (over S^T(i)'s columns)
       tc::tc_fence_after();
-      const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes), aDO = aQ + kQBytes;
-      for (int k = 0; k < BQ / 16; ++k)
-        if (leader) tc::umma_bf16(tmem + cDV, tc::smem_desc_k_sw128(aP + k * 32), desc_mn(aDO + k * 2048, 8192), id_g, (i | k) ? 1u : 0u);
-      for (int k = 0; k < BQ / 16; ++k)
-        if (leader) tc::umma_bf16(tmem + cDK, tc::smem_desc_k_sw128(aDS + k * 32), desc_mn(aQ + k * 2048, 8192), id_g, (i | k) ? 1u : 0u);
-      if constexpr (DQ) {
-        if (i > 0) {
-          bwait(&dq_free, (i - 1) & 1, 5);  // dQ^T(i-1) has been drained
+      const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes);
+      const uint64_t dQmn = desc_mn(aQ, 8192), dDOmn = desc_mn(aQ + kQBytes, 8192);
+      if (leader) {
+        // A operands straight from TMEM: queries [16k, 16k+16) -> P^T at columns 16k (8 packed columns), dS^T at 16k + 8;
+        // B: 16 query rows = 2048 bytes further per K step
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k) tc::umma_bf16_ts(tmem + cDV, tb + k * 16, dDOmn + k * 128, id_g, (i | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k) tc::umma_bf16_ts(tmem + cDK, tb + k * 16 + 8, dQmn + k * 128, id_g, (i | k) ? 1u : 0u);
+        if constexpr (DQ) {  // dQ^T(i) over dP^T(i)'s columns (all of dP^T(i) is in registers since p_full(i))
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(tb + cDP, dKmn + k * 128, dDSmn + k * 128, id_q, k ? 1u : 0u);
+          tc::umma_commit(&dq_full);
+        }
+        tc::umma_commit(&empty_bar[s]);
+      }
+      if (i + 2 < nsteps) {
+        if constexpr (DQ) {
+          bwait(&dq_free, i & 1, 5);  // dQ^T(i) has been drained: the buffer can take S^T(i+2) / dP^T(i+2)
           tc::tc_fence_after();
         }
-        for (int k = 0; k < BK / 16; ++k)
-          if (leader) tc::umma_bf16(tmem + cDQ, desc_mn(aK + k * 2048, 16384), desc_mn(aDS + k * 2048, 8192), id_q, k ? 1u : 0u);
-      }
-      if (leader) {
-        tc::umma_commit(&empty_bar[s]);
-        tc::umma_commit(&p_free);
-        if (DQ) tc::umma_commit(&dq_full);
+        issue_s(i + 2);
       }
     }
     if (leader) tc::umma_commit(&acc_full);
   } else {
     // ------------------------------------------------------------------ softmax warps
+    // 16 warps = 4 per SM sub-partition (the arithmetic is latency-bound with fewer: ex2 / LDS / TMEM-load latencies)
     const int sw = warp - 2;
-    const int hq = sw >> 2;              // which 32 queries of the step
+    const int cq = sw >> 2;              // which 16 queries of the step (== the K step of the dV / dK MMAs that reads them)
     const int qd = warp & 3;             // TMEM lane quarter
     const int key = qd * 32 + lane;      // key inside the block == TMEM lane
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const bool key_ok = kb * BK + key < p.nkeys;
-    uint8_t* prow = sP + key * 128;
+    const bool keys_partial = kb * BK + BK > p.nkeys;  // warp-uniform: this key block has padded keys
     uint8_t* dsrow = sDS + key * 128;
     const int sx = key & 7;
 
-    auto drain_dq = [&](int i) {  // dQ^T(i): lane = head-dim index, columns = this warp's 32 queries
+    auto drain_dq = [&](int i) {  // dQ^T(i): lane = head-dim index, columns = this warp's 16 queries
       bwait(&dq_full, i & 1, 6);
       tc::tc_fence_after();
-      uint32_t v[32];
-      tc::tmem_ld32(tmem + lane_addr + cDQ + hq * 32, v);
+      uint32_t v[16];
+      tc::tmem_ld16(tmem + lane_addr + (i & 1) * cBUF + cDP + cq * 16, v);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&dq_free);
       if (key < p.HP) {
-        const long long q0 = (long long)(step0 + i) * BQ + hq * 32;
+        const long long q0 = (long long)(step0 + i) * BQ + cq * 16;
         float* dst = p.dQ + ((long long)b * p.rows + q0) * p.lddq + h * p.HP + key;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
+        for (int e = 0; e < 16; ++e)
           if (q0 + e < p.rows) red_add(dst + (long long)e * p.lddq, __uint_as_float(v[e]));
       }
     };
 
     for (int i = 0; i < nsteps; ++i) {
       const int s = i % kStages;
-      bwait(&s_full, i & 1, 7);
+      const uint32_t tb = tmem + lane_addr + (i & 1) * cBUF + cq * 16;
+      bwait(&s_full[i & 1], (i >> 1) & 1, 7);
       tc::tc_fence_after();
-      uint32_t sv[32], dp[32];
-      tc::tmem_ld32(tmem + lane_addr + cS + hq * 32, sv);
-      tc::tmem_ld32(tmem + lane_addr + cDP + hq * 32, dp);
+      uint32_t sv[16], dp[16];
+      tc::tmem_ld16(tb, sv);
+      tc::tmem_ld16(tb + cDP, dp);
       tc::tmem_ld_wait();
+      if constexpr (DQ) {
+        // dQ^T(i-1): its MMAs were issued a whole step earlier; draining it here also guarantees that the dS^T smem tile of
+        // step i-1 has been read before this step overwrites it
+        if (i > 0) drain_dq(i - 1);
+      }
+      bwait(&full_bar[s], (i / kStages) & 1, 11);  // long complete (the MMAs read the stage): acquires this stage's lse / D
+      const float4* ls = reinterpret_cast<const float4*>(&stat[s][0][cq * 16]);
+      const float4* dv = reinterpret_cast<const float4*>(&stat[s][1][cq * 16]);
+      const long long q0 = (long long)(step0 + i) * BQ + cq * 16;
+      const int nvalid = (int)min((long long)16, p.rows - q0);  // may be <= 0 in the last step
+      uint32_t pk[8], dk[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 l4 = ls[e >> 2], d4 = dv[e >> 2];
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), kLog2e, -l4.x));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), kLog2e, -l4.y));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e + 2]), kLog2e, -l4.z));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e + 3]), kLog2e, -l4.w));
+        const float g0 = p0 * (__uint_as_float(dp[e]) - d4.x), g1 = p1 * (__uint_as_float(dp[e + 1]) - d4.y);
+        const float g2 = p2 * (__uint_as_float(dp[e + 2]) - d4.z), g3 = p3 * (__uint_as_float(dp[e + 3]) - d4.w);
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(p0, p1), a1 = __floats2bfloat162_rn(p2, p3);
+        __nv_bfloat162 c0 = __floats2bfloat162_rn(g0, g1), c1 = __floats2bfloat162_rn(g2, g3);
+        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&a0);
+        pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&a1);
+        dk[e >> 1] = *reinterpret_cast<uint32_t*>(&c0);
+        dk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&c1);
+      }
+      if (keys_partial || nvalid < 16) {  // warp-uniform, only the last key block / last step: zero what is padding
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t keep = (key_ok && 2 * j < nvalid ? 0x0000FFFFu : 0u) | (key_ok && 2 * j + 1 < nvalid ? 0xFFFF0000u : 0u);
+          pk[j] &= keep;
+          dk[j] &= keep;
+        }
+      }
+      // P^T / dS^T go back into TMEM over this thread's own 16 S^T columns (keys on the lanes = A-operand layout):
+      // P^T in the first 8 (16 packed bf16), dS^T in the last 8
+      tc::tmem_st8(tb, pk);
+      tc::tmem_st8(tb + 8, dk);
+      if constexpr (DQ) {  // dQ^T = K^T dS^T takes dS^T as its B operand: also as a 128B-swizzled smem tile [128 keys][64 q]
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int off = ((cq * 2 + c) ^ sx) * 16;
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        }
+        tc::fence_proxy_async();
+      }
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_free);
-      bwait(&full_bar[s], (i / kStages) & 1, 11);  // long complete (the MMAs read the stage): acquires this stage's lse / D
-      const float* ls = &stat[s][0][hq * 32];
-      const float* dv = &stat[s][1][hq * 32];
-      const long long q0 = (long long)(step0 + i) * BQ + hq * 32;
-      const int nvalid = (int)min((long long)32, p.rows - q0);  // may be <= 0 in the last step
-      uint32_t pk[16], dk[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float2 l2 = *reinterpret_cast<const float2*>(ls + e);
-        const float2 d2 = *reinterpret_cast<const float2*>(dv + e);
-        float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), kLog2e, -l2.x));
-        float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), kLog2e, -l2.y));
-        float g0 = p0 * (__uint_as_float(dp[e]) - d2.x);
-        float g1 = p1 * (__uint_as_float(dp[e + 1]) - d2.y);
-        if (!key_ok || e >= nvalid) { p0 = 0.f; g0 = 0.f; }
-        if (!key_ok || e + 1 >= nvalid) { p1 = 0.f; g1 = 0.f; }
-        __nv_bfloat162 a = __floats2bfloat162_rn(p0, p1), c = __floats2bfloat162_rn(g0, g1);
-        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&a);
-        dk[e >> 1] = *reinterpret_cast<uint32_t*>(&c);
-      }
-      if (i > 0) bwait(&p_free, (i - 1) & 1, 8);  // the MMAs of step i-1 have read the P^T / dS^T tiles
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {  // 16-byte chunk (hq*4 + c) of this key's 128-byte row, 128B swizzle
-        const int off = ((hq * 4 + c) ^ sx) * 16;
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
-      }
-      tc::fence_proxy_async();
-      __syncwarp();
       if (lane == 0) tc::mbar_arrive(&p_full);
-      if constexpr (DQ) {
-        if (i > 0) drain_dq(i - 1);  // complete since p_free(i-1): costs no wait here, and the tensor pipe has work queued
-      }
     }
     if constexpr (DQ) drain_dq(nsteps - 1);
-    // epilogue: dV (warps with hq = 0) and dK (hq = 1) of this chunk -> red.add into the fp32 gradients
+    // epilogue: dV (warps with cq = 0, 1) and dK (cq = 2, 3) of this chunk -> red.add into the fp32 gradients; the two warps
+    // of a matrix split its columns at 64
     bwait(&acc_full, 0, 9);
     tc::tc_fence_after();
     {  // (tcgen05.ld is warp-collective: every lane loads, only valid keys add)
-      float* dst = (hq ? p.dK : p.dV) + (((long long)b * p.heads + h) * p.nkeys + kb * BK + key) * p.HP;
-      const uint32_t tsrc = tmem + lane_addr + (hq ? cDK : cDV);
-      for (int c = 0; c < p.HP; c += 16) {
+      const bool is_dk = cq >= 2;
+      float* dst = (is_dk ? p.dK : p.dV) + (((long long)b * p.heads + h) * p.nkeys + kb * BK + key) * p.HP;
+      const uint32_t tsrc = tmem + lane_addr + (is_dk ? cDK : cDV);
+      const int c_lo = (cq & 1) ? min(64, p.HP) : 0, c_hi = (cq & 1) ? p.HP : min(64, p.HP);
+      for (int c = c_lo; c < c_hi; c += 16) {
         uint32_t v[16];
         tc::tmem_ld16(tsrc + c, v);
         tc::tmem_ld_wait();
