@@ -47,7 +47,14 @@ constexpr float kLog2e = 1.4426950408889634f;
 // columns are reused: each softmax thread writes P^T (16 packed bf16 columns) and dS^T (16) over ITS OWN 32 S^T columns, and
 // dQ^T(i) is accumulated over dP^T's columns.  The tensor pipe executes in issue order, which orders the MMAs that read
 // P^T(i) / dS^T(i) before S^T(i+2) overwrites the buffer.
-constexpr uint32_t cBUF = 128, cDP = 64, cDV = 256, cDK = 384;
+constexpr uint32_t cDV = 256, cDK = 384;
+// S^T(i) / dP^T(i) columns.  Without dQ: buffer i&1 at (i&1)*128 holds both (S^T @+0, dP^T @+64).  With dQ the 64 columns of
+// dQ^T need a home of their own (a dQ^T that lived in the dP^T buffer had to be drained before that buffer's next S^T / dP^T
+// could be issued, which put the tensor pipe and the softmax warps in series): S^T stays double-buffered (@0, @64), dP^T is
+// single-buffered @128 (re-issued as soon as the softmax warps hold it in registers), dQ^T @192.
+template <bool DQ> __device__ __forceinline__ uint32_t col_s(int i) { return DQ ? (i & 1) * 64 : (i & 1) * 128; }
+template <bool DQ> __device__ __forceinline__ uint32_t col_dp(int i) { return DQ ? 128 : (i & 1) * 128 + 64; }
+constexpr uint32_t cDQ = 192;
 
 struct Params {
   int nkeys, heads, nkb;         // real keys per image, heads, key blocks per image
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t kv_full, full_bar[kStages], empty_bar[kStages], s_full[2], p_full, dq_full, dq_free, acc_full;
+  __shared__ __align__(8) uint64_t kv_full, full_bar[kStages], empty_bar[kStages], s_full[2], p_full, dq_full, dq_free, dp_full, dp_free, acc_full;
   __shared__ __align__(16) float stat[kStages][2][BQ];  // [stage][lse | D][query]
   __shared__ uint32_t tmem_base_s;
 
@@ -145,6 +152,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc::mbar_init(&s_full[0], 1); tc::mbar_init(&s_full[1], 1);
     tc::mbar_init(&p_full, kSoftmaxWarps);
     tc::mbar_init(&dq_full, 1); tc::mbar_init(&dq_free, kSoftmaxWarps);
+    tc::mbar_init(&dp_full, 1); tc::mbar_init(&dp_free, kSoftmaxWarps);
     tc::mbar_init(&acc_full, 1);
     tc::fence_barrier_init();
   }
@@ -196,9 +204,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // rebuilt from its address: 22-30 MMAs per step).
     const uint64_t dKk = tc::smem_desc_k_sw128(aK), dVk = tc::smem_desc_k_sw128(aV);
     const uint64_t dKmn = desc_mn(aK, 16384), dDSmn = desc_mn(aDS, 8192);
-    auto issue_s = [&](int i) {  // S^T(i), dP^T(i) -> TMEM buffer i & 1
+    auto issue_s = [&](int i, bool with_dp) {  // S^T(i) (and dP^T(i)) -> TMEM
       const int s = i % kStages;
-      const uint32_t tb = tmem + (i & 1) * cBUF;
       bwait(&full_bar[s], (i / kStages) & 1, 1);
       tc::tc_fence_after();
       const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes);
@@ -207,26 +214,56 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // K step k: 32 bytes further inside the 128-byte rows, second box after four steps
           if (k < ksteps)
-            tc::umma_bf16(tb, dKk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), dQk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s,
-                          k ? 1u : 0u);
+            tc::umma_bf16(tmem + col_s<DQ>(i), dKk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                          dQk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s, k ? 1u : 0u);
+        if (with_dp) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < ksteps)
-            tc::umma_bf16(tb + cDP, dVk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                          dDOk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s, k ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            if (k < ksteps)
+              tc::umma_bf16(tmem + col_dp<DQ>(i), dVk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                            dDOk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s, k ? 1u : 0u);
+        }
         tc::umma_commit(&s_full[i & 1]);
       }
     };
+    auto issue_dp = [&](int i) {  // dQ variant: dP^T(i) into the single dP^T buffer
+      const int s = i % kStages;
+      bwait(&full_bar[s], (i / kStages) & 1, 1);
+      tc::tc_fence_after();
+      const uint64_t dDOk = tc::smem_desc_k_sw128(tc::smem_u32(sQ0 + s * kStageBytes) + kQBytes);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < ksteps)
+            tc::umma_bf16(tmem + col_dp<DQ>(i), dVk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                          dDOk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), id_s, k ? 1u : 0u);
+        tc::umma_commit(&dp_full);
+      }
+    };
     bwait(&kv_full, 0, 2);
-    issue_s(0);
-    if (nsteps > 1) issue_s(1);
+    issue_s(0, !DQ);
+    if (nsteps > 1) issue_s(1, !DQ);
+    if constexpr (DQ) issue_dp(0);
     for (int i = 0; i < nsteps; ++i) {
       const int s = i % kStages;
-      const uint32_t tb = tmem + (i & 1) * cBUF;
+      if constexpr (DQ) {
+        if (i + 1 < nsteps) {
+          bwait(&dp_free, i & 1, 3);  // the softmax warps hold dP^T(i) in registers
+          tc::tc_fence_after();
+          issue_dp(i + 1);
+        }
+      }
       bwait(&p_full, i & 1, 4);    // P^T(i), dS^T(i) are in TMEM (over S^T(i)'s columns)
       tc::tc_fence_after();
+      const uint32_t tb = tmem + col_s<DQ>(i);
       const uint32_t aQ = tc::smem_u32(sQ0 + s * kStageBytes);
       const uint64_t dQmn = desc_mn(aQ, 8192), dDOmn = desc_mn(aQ + kQBytes, 8192);
+      if constexpr (DQ) {
+        if (i > 0) {
+          bwait(&dq_free, (i - 1) & 1, 5);  // dQ^T(i-1) has been drained (the softmax warps do that before p_full(i))
+          tc::tc_fence_after();
+        }
+      }
       if (leader) {
         // A operands straight from TMEM: queries [16k, 16k+16) -> P^T at columns 16k (8 packed columns), dS^T at 16k + 8;
         // B: 16 query rows = 2048 bytes further per K step
@@ -234,20 +271,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int k = 0; k < BQ / 16; ++k) tc::umma_bf16_ts(tmem + cDV, tb + k * 16, dDOmn + k * 128, id_g, (i | k) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k) tc::umma_bf16_ts(tmem + cDK, tb + k * 16 + 8, dQmn + k * 128, id_g, (i | k) ? 1u : 0u);
-        if constexpr (DQ) {  // dQ^T(i) over dP^T(i)'s columns (all of dP^T(i) is in registers since p_full(i))
+        if constexpr (DQ) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(tb + cDP, dKmn + k * 128, dDSmn + k * 128, id_q, k ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(tmem + cDQ, dKmn + k * 128, dDSmn + k * 128, id_q, k ? 1u : 0u);
           tc::umma_commit(&dq_full);
         }
         tc::umma_commit(&empty_bar[s]);
       }
-      if (i + 2 < nsteps) {
-        if constexpr (DQ) {
-          bwait(&dq_free, i & 1, 5);  // dQ^T(i) has been drained: the buffer can take S^T(i+2) / dP^T(i+2)
-          tc::tc_fence_after();
-        }
-        issue_s(i + 2);
-      }
+      if (i + 2 < nsteps) issue_s(i + 2, !DQ);  // the buffer's previous contents are read by MMAs issued above
     }
     if (leader) tc::umma_commit(&acc_full);
   } else {
@@ -267,7 +298,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       bwait(&dq_full, i & 1, 6);
       tc::tc_fence_after();
       uint32_t v[16];
-      tc::tmem_ld16(tmem + lane_addr + (i & 1) * cBUF + cDP + cq * 16, v);
+      tc::tmem_ld16(tmem + lane_addr + cDQ + cq * 16, v);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
@@ -283,17 +314,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     for (int i = 0; i < nsteps; ++i) {
       const int s = i % kStages;
-      const uint32_t tb = tmem + lane_addr + (i & 1) * cBUF + cq * 16;
+      const uint32_t tb = tmem + lane_addr + col_s<DQ>(i) + cq * 16;
       bwait(&s_full[i & 1], (i >> 1) & 1, 7);
+      if constexpr (DQ) bwait(&dp_full, i & 1, 12);
       tc::tc_fence_after();
       uint32_t sv[16], dp[16];
       tc::tmem_ld16(tb, sv);
-      tc::tmem_ld16(tb + cDP, dp);
+      tc::tmem_ld16(tmem + lane_addr + col_dp<DQ>(i) + cq * 16, dp);
       tc::tmem_ld_wait();
       if constexpr (DQ) {
-        // dQ^T(i-1): its MMAs were issued a whole step earlier; draining it here also guarantees that the dS^T smem tile of
-        // step i-1 has been read before this step overwrites it
-        if (i > 0) drain_dq(i - 1);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&dp_free);
       }
       bwait(&full_bar[s], (i / kStages) & 1, 11);  // long complete (the MMAs read the stage): acquires this stage's lse / D
       const float4* ls = reinterpret_cast<const float4*>(&stat[s][0][cq * 16]);
@@ -324,6 +356,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[j] &= keep;
           dk[j] &= keep;
         }
+      }
+      if constexpr (DQ) {
+        // dQ^T(i-1): its MMAs were issued after p_full(i-1), a whole load + arithmetic phase ago.  Waiting for them here also
+        // guarantees that the dS^T smem tile of step i-1 has been read before this step overwrites it.
+        if (i > 0) drain_dq(i - 1);
       }
       // P^T / dS^T go back into TMEM over this thread's own 16 S^T columns (keys on the lanes = A-operand layout):
       // P^T in the first 8 (16 packed bf16), dS^T in the last 8
