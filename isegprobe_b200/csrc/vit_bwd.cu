@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 // Same, C % 4 == 0 and 16-byte aligned rows: a lane moves float4 (8 bytes of bf16 x) per step -- the scalar kernel ran
 // at 1 TB/s on the [802816, 404] query stream of the LoftUp backward.
-template <bool X_BF16>
+template <bool X_BF16, int kIt>  // kIt float4 per lane: C <= 128 * kIt
 __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ dy, long long lddy,
                                                                 const void* __restrict__ xv_, long long ldx,
                                                                 const float* __restrict__ gamma,
@@ -97,20 +97,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
                                                                 float* __restrict__ dx, long long lddx,
                                                                 __nv_bfloat16* __restrict__ dx_bf, long long ldb,
                                                                 long long M, int C, float eps) {
-  constexpr int kIt = 8;  // C <= 1024
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int C4 = C >> 2;
   const float4* d4 = reinterpret_cast<const float4*>(dy + row * lddy);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 xv[kIt], gv[kIt];
+  float4 xv[kIt], gv[kIt], rv[kIt];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kIt; ++i) {
     const int c = lane + 32 * i;
-    xv[i] = gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    xv[i] = gv[i] = rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C4) {
+      // the residual gradient is only needed at the end, but its load goes out with the others: one round trip to HBM
+      // per row instead of two (the kernel is latency-bound otherwise: one warp per row, four dependent warp reductions)
+      if (resid) rv[i] = *reinterpret_cast<const float4*>(resid + row * ldr + 4 * c);
       if (X_BF16) {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xv_) + row * ldx + 4 * c);
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
@@ -149,10 +151,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
     if (c < C4) {
       float4 v = make_float4(rstd * (gv[i].x - sa - xv[i].x * sb), rstd * (gv[i].y - sa - xv[i].y * sb),
                              rstd * (gv[i].z - sa - xv[i].z * sb), rstd * (gv[i].w - sa - xv[i].w * sb));
-      if (resid) {
-        const float4 r = *reinterpret_cast<const float4*>(resid + row * ldr + 4 * c);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
+      v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w;
       *reinterpret_cast<float4*>(dx + row * lddx + 4 * c) = v;
       if (dx_bf) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -360,12 +359,15 @@ extern "C" int isp_layernorm_rows_bwd(const float* dy, long long lddy, const voi
                    aligned16(dx) && aligned16(gamma) && ((uintptr_t)x % 16 == 0) && (!resid || (ldr % 4 == 0 && aligned16(resid))) &&
                    (!dx_bf16 || (ldb % 4 == 0 && (uintptr_t)dx_bf16 % 8 == 0));
   if (vec) {
-    if (x_bf16)
-      vb::layernorm_bwd_vec_kernel<true><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
-          dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
-    else
-      vb::layernorm_bwd_vec_kernel<false><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(
-          dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps);
+#define ISP_LN_BWD_VEC(XB, KIT)                                                                                       \
+  vb::layernorm_bwd_vec_kernel<XB, KIT><<<cdiv(M, 8), 256, 0, as_stream(stream)>>>(                                     \
+      dy, lddy, x, ldx, gamma, resid, ldr, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ldb, M, C, eps)
+    if (C <= 512) {  // half the registers of the general instantiation: more rows in flight per SM
+      if (x_bf16) ISP_LN_BWD_VEC(true, 4); else ISP_LN_BWD_VEC(false, 4);
+    } else {
+      if (x_bf16) ISP_LN_BWD_VEC(true, 8); else ISP_LN_BWD_VEC(false, 8);
+    }
+#undef ISP_LN_BWD_VEC
     ISP_CHECK_LAUNCH("layernorm_bwd_vec_kernel");
     return ISP_OK;
   }
