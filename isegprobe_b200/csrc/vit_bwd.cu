@@ -237,23 +237,45 @@ __global__ void __launch_bounds__(256) layernorm_affine_bwd_kernel(const float* 
 }
 
 template <int KIND>  // 0: nn.GELU (erf form), 1: QuickGELU x * sigmoid(1.702 x) (maskclip/model.py:166-168)
+__device__ __forceinline__ float gelu_grad(float v) {
+  if (KIND == 1) {  // d/dv [ v * s(av) ] = s + a v s (1 - s)
+    const float sg = 1.f / (1.f + __expf(-1.702f * v));
+    return sg * (1.f + 1.702f * v * (1.f - sg));
+  }
+  // d/dv [ v * Phi(v) ] = Phi(v) + v * phi(v)
+  const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat162* __restrict__ dh,
                                                        const __nv_bfloat162* __restrict__ pre,
                                                        __nv_bfloat162* __restrict__ out, long long n2) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2) return;
   const float2 d = __bfloat1622float2(dh[i]), x = __bfloat1622float2(pre[i]);
-  auto g = [](float v) {
-    if (KIND == 1) {  // d/dv [ v * s(av) ] = s + a v s (1 - s)
-      const float sg = 1.f / (1.f + __expf(-1.702f * v));
-      return sg * (1.f + 1.702f * v * (1.f - sg));
+  out[i] = __floats2bfloat162_rn(d.x * gelu_grad<KIND>(x.x), d.y * gelu_grad<KIND>(x.y));
+}
+
+// 16 bytes (8 elements) per thread and step, grid-stride: the 2-element kernel ran at 45 % of the HBM copy rate on the
+// [802816, 384] hidden activations of the LoftUp FeedForward backward
+template <int KIND>
+__global__ void __launch_bounds__(256) gelu_bwd_vec_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ pre,
+                                                           uint4* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = dh[i], b = pre[i];
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 d = __bfloat1622float2(pa[e]), x = __bfloat1622float2(pb[e]);
+      pr[e] = __floats2bfloat162_rn(d.x * gelu_grad<KIND>(x.x), d.y * gelu_grad<KIND>(x.y));
     }
-    // d/dv [ v * Phi(v) ] = Phi(v) + v * phi(v)
-    const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
-    return cdf + v * pdf;
-  };
-  out[i] = __floats2bfloat162_rn(d.x * g(x.x), d.y * g(x.y));
+    out[i] = r;
+  }
 }
 
 // one warp per row of scores; ncols valid entries, row pitch lds / ldp; padded P entries are written as zero
@@ -402,6 +424,16 @@ extern "C" int isp_layernorm_affine_bwd(const float* dy, long long lddy, const v
 // (dinov2/layers/mlp.py:34-40), quick == 1: CLIP's QuickGELU.
 extern "C" int isp_gelu_bwd_bf16(const void* dh, const void* pre, void* out, long long n, int quick, isp_stream_t stream) {
   ISP_REQUIRE(dh && pre && out && n > 0 && n % 2 == 0, ISP_ERR_BAD_SHAPE, "gelu_bwd_bf16: bad arguments");
+  if (n % 8 == 0 && aligned16(dh) && aligned16(pre) && aligned16(out)) {
+    const long long n8 = n / 8;
+    const unsigned grid = (unsigned)(cdiv(n8, 256) < 148 * 16 ? cdiv(n8, 256) : 148 * 16);
+    if (quick)
+      vb::gelu_bwd_vec_kernel<1><<<grid, 256, 0, as_stream(stream)>>>((const uint4*)dh, (const uint4*)pre, (uint4*)out, n8);
+    else
+      vb::gelu_bwd_vec_kernel<0><<<grid, 256, 0, as_stream(stream)>>>((const uint4*)dh, (const uint4*)pre, (uint4*)out, n8);
+    ISP_CHECK_LAUNCH("gelu_bwd_vec_kernel");
+    return ISP_OK;
+  }
   if (quick)
     vb::gelu_bwd_kernel<1><<<cdiv(n / 2, 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat162*>(dh), reinterpret_cast<const __nv_bfloat162*>(pre),
