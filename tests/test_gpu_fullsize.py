@@ -149,3 +149,59 @@ def test_jbu_full_size_vs_oracle():
     assert tuple(out.shape) == (1, 384, 512, 512)
     err = float((out - want).abs().max() / want.abs().max())
     assert err < 1e-3, err
+
+
+def test_flash_attention_backward_full_size_properties():
+    """isp_attention_bwd_bf16_tc at the LoftUp shape (200 704 queries x 1024 keys, 4 heads x 101 in 112 columns), where no
+    reference can hold the 822 M scores per head-set: size-independent identities of the softmax backward.
+      * rows of P sum to one      =>  sum over keys of dV  =  sum over queries of dO          (per head, per channel)
+      * rows of dS sum to zero    =>  sum over keys of dK  =  0   and  dQ . 1-direction: sum_k dS K uses the same dS
+      * linearity in dO           =>  gradients for 2*dO are exactly twice those for dO (powers of two are exact in bf16)
+    and equality with torch autograd on a sampled block of 256 queries (all keys)."""
+    from isegprobe_b200 import _lib
+    B, nh, rows, T, hd, HP = 1, 4, 448 * 448, 1024, 101, 112
+    g = torch.Generator(device=DEV).manual_seed(1)
+
+    def rnd(*shape, s=1.0):
+        t = torch.zeros(*shape, device=DEV)
+        t[..., :hd] = torch.randn(*shape[:-1], hd, generator=g, device=DEV) * s
+        return t.to(torch.bfloat16)
+
+    Q = rnd(B, rows, nh, HP, s=0.3).reshape(B * rows, nh * HP)
+    dO = rnd(B, rows, nh, HP, s=0.5).reshape(B * rows, nh * HP)
+    K, V = rnd(B, nh, T, HP), rnd(B, nh, T, HP)
+    Kp = torch.zeros(B, nh, T, 128, dtype=torch.bfloat16, device=DEV)
+    Kp[..., :HP] = K
+    Vt = V.transpose(2, 3).contiguous()
+    O = torch.empty_like(Q)
+    lse = torch.zeros(B * nh * rows + 64, device=DEV)
+    dvec = torch.zeros(B * nh * rows + 64, device=DEV)
+    _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, rows, nh, T, 1, lse)
+
+    def backward(dOx):
+        _call("isp_attention_rowdot_heads", dOx, nh * HP, O, nh * HP, dvec, B, rows, nh, HP)
+        dK, dV = torch.zeros(B, nh, T, HP, device=DEV), torch.zeros(B, nh, T, HP, device=DEV)
+        dQ = torch.zeros(B * rows, nh * HP, device=DEV)
+        _call("isp_attention_bwd_bf16_tc", Q, nh * HP, dOx, nh * HP, K, V, lse, dvec, dK, dV, dQ, nh * HP, B, rows, nh, T, HP)
+        return dK, dV, dQ
+
+    dK, dV, dQ = backward(dO)
+    want = dO.float().view(B, rows, nh, HP).sum(1)                      # [B, nh, HP]
+    got = dV.sum(2)
+    assert float((got - want).abs().max()) < 2e-3 * float(want.abs().max()) + 0.5, float((got - want).abs().max())
+    # sum_k dK[k] = sum_q (sum_k dS[q,k]) Q[q] = 0 up to the bf16 rounding of dS (independent errors of 1024 keys add up):
+    # the signed sum must vanish against the sum of magnitudes
+    cancel = float((dK.sum(2).abs() / dK.abs().sum(2).clamp(min=1e-6))[..., :hd].max())
+    assert cancel < 3e-3, cancel
+    dK2, dV2, dQ2 = backward((dO.float() * 2).to(torch.bfloat16))
+    # dO doubles exactly; P is identical; dS = P (dP - D) doubles up to the fp32 rounding of D = rowsum(dO.O)
+    assert relerr(dV2, 2 * dV) < 1e-5
+    assert relerr(dK2, 2 * dK) < 1e-2 and relerr(dQ2, 2 * dQ) < 1e-2
+    # sampled query block against autograd (all keys): dQ rows are local to the block
+    r0 = 137 * 128
+    q = Q[r0:r0 + 256].float().view(256, nh, HP).permute(1, 0, 2).requires_grad_(True)
+    s = q @ K[0].float().transpose(-1, -2)
+    o = torch.softmax(s, -1) @ V[0].float()
+    (o * dO[r0:r0 + 256].float().view(256, nh, HP).permute(1, 0, 2)).sum().backward()
+    got_q = dQ[r0:r0 + 256].view(256, nh, HP).permute(1, 0, 2)
+    assert cosine(got_q, q.grad) > 0.999 and relerr(got_q, q.grad) < 3e-2, (cosine(got_q, q.grad), relerr(got_q, q.grad))
