@@ -259,7 +259,7 @@ int isp_attention_rowdot_heads(const void* dO, long long lddo, const void* O, lo
  * (core/training/trainer.py:213-221).  Q, dO bf16 [B*rows, ld], head h at columns [h*HP, +HP), Q pre-scaled as in the
  * forward; K, V bf16 [B, heads, nkeys, HP] (rows = keys); lse, dvec fp32 [B][heads][rows] (+ 64 floats of slack) from
  * isp_attention_bf16_tc_lse / isp_attention_rowdot_heads.  dK, dV fp32 [B, heads, nkeys, HP] and the optional dQ fp32
- * [B*rows, lddq] are ACCUMULATED into (zero them first).  HP: multiple of 16, <= 128; rows: multiple of 4. */
+ * [B*rows, lddq] are ACCUMULATED into (zero them first).  HP: multiple of 16, <= 128. */
 int isp_attention_bwd_bf16_tc(const void* Q, long long ldq, const void* dO, long long lddo, const void* K, const void* V,
                               const float* lse, const float* dvec, float* dK, float* dV, float* dQ, long long lddq, int B,
                               long long rows, int heads, int nkeys, int HP, isp_stream_t stream);

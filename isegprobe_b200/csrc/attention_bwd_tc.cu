@@ -176,19 +176,33 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc::tma_load_2d(sK + c * 16384, &tmK, &kv_full, c * 64, krow);
         tc::tma_load_2d(sV + c * 16384, &tmV, &kv_full, c * 64, krow);
       }
-      for (int i = 0; i < nsteps; ++i) {
-        const int s = i % kStages;
-        bwait(&empty_bar[s], ((i / kStages) & 1) ^ 1, 0);
-        const long long q0 = (long long)(step0 + i) * BQ;
+    }
+    const bool stat_bulk = (p.rows & 3) == 0;  // 16-byte aligned row statistics: 1-D bulk copies; else the warp copies them
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % kStages;
+      bwait(&empty_bar[s], ((i / kStages) & 1) ^ 1, 0);
+      const long long q0 = (long long)(step0 + i) * BQ;
+      if (!stat_bulk) {
+#pragma unroll
+        for (int j = lane; j < BQ; j += 32) {
+          const bool ok = q0 + j < p.rows;
+          stat[s][0][j] = ok ? __ldg(p.lse + stat_base + q0 + j) : 0.f;
+          stat[s][1][j] = ok ? __ldg(p.dvec + stat_base + q0 + j) : 0.f;
+        }
+        __syncwarp();  // orders the other lanes' stores before lane 0's (releasing) arrive below
+      }
+      if (lane == 0) {
         const int qrow = (int)((long long)b * p.rows + q0);
         uint8_t* sq = sQ0 + s * kStageBytes;
-        tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes + 2 * BQ * 4);
+        tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes + (stat_bulk ? 2 * BQ * 4 : 0));
         for (int c = 0; c < 2; ++c) {
           tc::tma_load_2d(sq + c * 8192, &tmQ, &full_bar[s], h * p.HP + c * 64, qrow);
           tc::tma_load_2d(sq + kQBytes + c * 8192, &tmDO, &full_bar[s], h * p.HP + c * 64, qrow);
         }
-        bulk_load(&stat[s][0][0], p.lse + stat_base + q0, BQ * 4, &full_bar[s]);
-        bulk_load(&stat[s][1][0], p.dvec + stat_base + q0, BQ * 4, &full_bar[s]);
+        if (stat_bulk) {
+          bulk_load(&stat[s][0][0], p.lse + stat_base + q0, BQ * 4, &full_bar[s]);
+          bulk_load(&stat[s][1][0], p.dvec + stat_base + q0, BQ * 4, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -460,8 +474,8 @@ extern "C" int isp_attention_bwd_bf16_tc(const void* Q, long long ldq, const voi
   ISP_REQUIRE(Q && dO && K && V && lse && dvec && dK && dV, ISP_ERR_BAD_SHAPE, "attention_bwd_bf16_tc: null pointer");
   ISP_REQUIRE(B > 0 && rows > 0 && heads > 0 && nkeys > 0, ISP_ERR_BAD_SHAPE, "attention_bwd_bf16_tc: bad shape");
   ISP_REQUIRE(HP % 16 == 0 && HP >= 16 && HP <= 128, ISP_ERR_UNSUPPORTED, "attention_bwd_bf16_tc: HP %d (multiple of 16, <= 128)", HP);
-  ISP_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && rows % 4 == 0 && (!dQ || lddq >= (long long)heads * HP), ISP_ERR_MISALIGNED,
-              "attention_bwd_bf16_tc: ldq / lddo multiples of 8, rows a multiple of 4");
+  ISP_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && (!dQ || lddq >= (long long)heads * HP), ISP_ERR_MISALIGNED,
+              "attention_bwd_bf16_tc: ldq / lddo must be multiples of 8");
   ISP_REQUIRE(aligned16(Q) && aligned16(dO) && aligned16(K) && aligned16(V) && aligned16(lse) && aligned16(dvec) &&
                   aligned16(dK) && aligned16(dV),
               ISP_ERR_MISALIGNED, "attention_bwd_bf16_tc: 16-byte alignment");

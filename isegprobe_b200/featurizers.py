@@ -327,7 +327,41 @@ class DINOv2Featurizer(nn.Module):
               0 if resid is None else resid.stride(0), dx, C, dxb, dxb.stride(0), M, C, float(eps))
         return dx, dxb
 
+    flash_backward = True  # False: the materialised-probability path below (kept for head dims != 64 and as a cross-check)
+
     def _attention_bwd(self, qkv, dO, B, T, C, nh):
+        """d(qkv) of O = softmax(Q K^T) V per (image, head) (dinov2/layers/attention.py:54-71; Q already carries the
+        1/sqrt(d) scale) on the flash-style backward kernel: the forward attention is re-run for O and the rows'
+        log-sum-exp (cheap at ViT sizes), then isp_attention_bwd_bf16_tc recomputes P / dS tile by tile on chip."""
+        hd = C // nh
+        if hd != 64 or not DINOv2Featurizer.flash_backward:
+            return DINOv2Featurizer._attention_bwd_materialised(self, qkv, dO, B, T, C, nh)
+        dev, bf, M = qkv.device, torch.bfloat16, B * T
+        Tp = tc.round_up(T, 128)
+        Kf = torch.empty(B, nh, Tp, 64, dtype=bf, device=dev)
+        Vt = torch.empty(B, nh, 64, Tp, dtype=bf, device=dev)
+        _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Kf, B, T, Tp, nh, 64, 0)
+        _call("isp_repack_heads", qkv, 1, 3 * C, 2 * C, hd, Vt, B, T, Tp, nh, 64, 1)
+        O = torch.empty(M, C, dtype=bf, device=dev)
+        lse = torch.empty(B * nh * T + 64, dtype=torch.float32, device=dev)
+        dvec = torch.empty(B * nh * T + 64, dtype=torch.float32, device=dev)
+        _call("isp_attention_bf16_tc_lse", qkv, 3 * C, hd, Kf, Vt, O, C, hd, B, T, nh, T, 0, lse)
+        _call("isp_attention_rowdot_heads", dO, C, O, C, dvec, B, T, nh, 64)
+        Kb = torch.empty(B, nh, T, 64, dtype=bf, device=dev)   # rows = keys, no padding: the backward's K / V operands
+        Vb = torch.empty(B, nh, T, 64, dtype=bf, device=dev)
+        _call("isp_repack_heads", qkv, 1, 3 * C, C, hd, Kb, B, T, T, nh, 64, 0)
+        _call("isp_repack_heads", qkv, 1, 3 * C, 2 * C, hd, Vb, B, T, T, nh, 64, 0)
+        dK = torch.zeros(B, nh, T, 64, dtype=torch.float32, device=dev)
+        dV = torch.zeros(B, nh, T, 64, dtype=torch.float32, device=dev)
+        dQ = torch.zeros(M, C, dtype=torch.float32, device=dev)
+        _call("isp_attention_bwd_bf16_tc", qkv, 3 * C, dO, C, Kb, Vb, lse, dvec, dK, dV, dQ, C, B, T, nh, T, 64)
+        dqkv = torch.empty(M, 3 * C, dtype=bf, device=dev)
+        dqkv[:, :C] = dQ
+        dqkv[:, C:2 * C] = dK.permute(0, 2, 1, 3).reshape(M, C)
+        dqkv[:, 2 * C:] = dV.permute(0, 2, 1, 3).reshape(M, C)
+        return dqkv
+
+    def _attention_bwd_materialised(self, qkv, dO, B, T, C, nh):
         """d(qkv) of O = softmax(Q K^T) V per (image, head), probabilities recomputed from Q and K
         (dinov2/layers/attention.py:54-71; Q already carries the 1/sqrt(d) scale).  All products are batched
         tcgen05 GEMMs over (image, head); P, dP, dS are materialised (T x T per head: 2 MB)."""

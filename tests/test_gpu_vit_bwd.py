@@ -509,3 +509,24 @@ def test_flash_attention_backward_kernel(B, nh, rows, T, hd, need_dq):
     if need_dq:
         got = dQ.view(B, rows, nh, HP).permute(0, 2, 1, 3)
         assert cosine(got, q.grad) > 0.999 and relerr(got, q.grad) < 3e-2, (cosine(got, q.grad), relerr(got, q.grad))
+
+
+@pytest.mark.parametrize("B,T,nh", [(2, 1025, 6), (3, 25, 6), (1, 197, 12)])
+def test_vit_attention_backward_flash_equals_materialised(B, T, nh):
+    """The ViT self-attention backward on the flash kernel (token counts that are not multiples of 4 or 64: the row
+    statistics then go through the producer warp instead of bulk copies) against the materialised-probability path and
+    against torch autograd."""
+    from isegprobe_b200.featurizers import DINOv2Featurizer as F2
+    hd = 64
+    C = nh * hd
+    g = torch.Generator().manual_seed(21)
+    qkv = (torch.randn(B * T, 3 * C, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    dO = (torch.randn(B * T, C, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+    got = F2._attention_bwd(None, qkv, dO, B, T, C, nh).float()
+    old = F2._attention_bwd_materialised(None, qkv, dO, B, T, C, nh).float()
+    x = qkv.float().view(B, T, 3, nh, hd).permute(2, 0, 3, 1, 4).requires_grad_(True)
+    o = torch.softmax(x[0] @ x[1].transpose(-1, -2), -1) @ x[2]
+    (o * dO.float().view(B, T, nh, hd).permute(0, 2, 1, 3)).sum().backward()
+    want = x.grad.permute(1, 3, 0, 2, 4).reshape(B * T, 3 * C)
+    assert cosine(got, want) > 0.999 and relerr(got, want) < 3e-2, (cosine(got, want), relerr(got, want))
+    assert cosine(got, old) > 0.999
