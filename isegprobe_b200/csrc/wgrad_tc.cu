@@ -27,7 +27,7 @@ constexpr int kBudget = 200 * 1024;
 
 struct Params {
   int Nimg, H, W, Cout, Cin;
-  int BN;                 // Cin tile (multiple of 64, <= 256)
+  int BN;                 // Cin tile (multiple of 64, <= 256; 384 = two 192-wide MMAs per step)
   int tiles_m, tiles_n, wchunks, splits, stages;
   long long kblocks;      // Nimg * H * wchunks
   float* dW;              // [Cout][9][Cin] fp32, accumulated into
@@ -71,7 +71,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     tc::mbar_init(&acc_empty, 4);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 256);
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -117,7 +117,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_bf16_f32_mn(BM, p.BN);
+    // Cin tiles wider than one MMA (N <= 256) are issued as two half-width MMAs that share the dY operand: a 384-wide tile
+    // moves 21 operand bytes per kMAC through L2 -> SM instead of the 25 of two 192-wide items
+    const int halves = p.BN > 256 ? 2 : 1;
+    const int bn_mma = p.BN / halves;
+    const uint32_t idesc = idesc_bf16_f32_mn(BM, bn_mma);
     const bool leader = tc::elect_one();
     uint32_t n = 0, item_n = 0;
     for (long long it = blockIdx.x; it < nitems; it += gridDim.x, ++item_n) {
@@ -136,6 +140,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           const uint64_t da = smem_desc_mn_sw128(sa + k * 2048, box_bytes);
           const uint64_t db = smem_desc_mn_sw128(sa + a_bytes + k * 2048, box_bytes);
           if (leader) tc::umma_bf16(tmem, da, db, idesc, (kb > kb0 || k) ? 1u : 0u);
+          if (halves == 2) {
+            const uint64_t db2 = smem_desc_mn_sw128(sa + a_bytes + (bn_mma / 64) * box_bytes + k * 2048, box_bytes);
+            if (leader) tc::umma_bf16(tmem + bn_mma, da, db2, idesc, (kb > kb0 || k) ? 1u : 0u);
+          }
         }
         if (leader) tc::umma_commit(&empty_bar[s]);
       }
@@ -173,7 +181,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace wgrad
@@ -194,6 +202,7 @@ extern "C" int isp_conv3x3_wgrad_bf16_tc(const void* X, int ldx, const void* dY,
   p.Nimg = Nimg; p.H = H; p.W = Wd; p.Cout = Cout; p.Cin = Cin;
   p.BN = Cin % 192 == 0 ? 192 : (Cin % 128 == 0 ? 128 : 64);
   if (Cin % 256 == 0) p.BN = 256;
+  if (Cin % 384 == 0) p.BN = 384;  // two 192-wide MMAs per step on one dY tile (TMEM: 384 of 512 columns)
   p.tiles_m = (Cout + wgrad::BM - 1) / wgrad::BM;
   p.tiles_n = Cin / p.BN;
   p.wchunks = (Wd + wgrad::KPIX - 1) / wgrad::KPIX;
