@@ -100,7 +100,7 @@ __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-// mbarrier wait with a wall-clock bound (2 s): a protocol bug reports which barrier starved and traps instead of
+// mbarrier wait with a wall-clock bound (10 s): a protocol bug reports which barrier starved and traps instead of
 // spinning through the generic 2^24-probe limit
 __device__ __noinline__ void wait_timeout(int tag, uint32_t parity) {
   printf("attention_bwd_kernel: barrier %d (parity %u) starved, block %d warp %d\n", tag, parity, (int)blockIdx.x,
@@ -115,7 +115,7 @@ __device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int tag) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (!t0) t0 = t;
-      else if (t - t0 > 2000000000ull) wait_timeout(tag, parity);
+      else if (t - t0 > 10000000000ull) wait_timeout(tag, parity);
     }
   }
 }
