@@ -52,3 +52,28 @@ def test_maskclip_pipeline_keys():
     assert set(ck) == REF_KEYS
     assert tuple(ck["embed_coords.proj.weight"].shape) == (768, 3, 16, 16)
     assert tuple(ck["head.convs.0.conv.weight"].shape) == (512, 512, 3, 3)
+
+
+def test_simple_vit_click_encoder_checkpoint_keys():
+    """models/sbd/dinov2/simple-vit_noup.py saves `embed_coords.*` of a SimpleViTFeaturizer (save_cfg embed_coords=True):
+    our module must expose the reference's keys and shapes (oracle/synth.simple_vit_state_dict lists them as produced by
+    the reference class, oracle/make_golden.golden_simple_vit loads it strict=True) and the late-injection pipeline must
+    keep the backbone frozen and the encoder trainable."""
+    from oracle import synth
+    ref = synth.simple_vit_state_dict(depth=6, seed=0)
+    pipe = isp.ISegPipeline("identity", {}, embed_coords_type="simple_vit", feats_injection_mode="after_backbone")
+    ours = {k[len("embed_coords."):]: v for k, v in pipe.state_dict().items() if k.startswith("embed_coords.")}
+    assert set(ours) == set(ref)
+    for k, v in ref.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    pipe.embed_coords.load_state_dict(ref, strict=True)
+    assert pipe.backbone.feats_injection_mode == "after_backbone"
+    assert all(p.requires_grad for p in pipe.embed_coords.parameters())
+    assert not any(p.requires_grad for p in pipe.backbone.parameters())
+    assert pipe.embed_coords.reshape_feats_to_patches(torch.zeros(2, 1024, 384)).shape == (2, 384, 32, 32)
+    try:
+        isp.ISegPipeline("identity", {}, embed_coords_type="conv_stem")
+    except ValueError as e:
+        assert "Unsupported backbone type" in str(e)  # core/utils/model_builder.py:50-51
+    else:
+        raise AssertionError("unknown embed_coords type must raise")
