@@ -14,7 +14,7 @@
 //   dV [128 keys x d] += P^T  dO             A = P^T  from TMEM,   B = dO tile walked MN-major (the same smem tile)
 //   dK [128 keys x d] += dS^T Q              A = dS^T from TMEM,   B = Q tile walked MN-major (the same smem tile)
 //   dQ^T [d x 64 q]    = K^T dS^T  (optional) A = K tile walked MN-major, B = dS^T as a 128B-swizzled smem tile written by the
-//                                            softmax warps; accumulator over dP^T's TMEM columns
+//                                            softmax warps; accumulator in its own 64 TMEM columns
 //
 // The Q / dO tiles are therefore loaded ONCE per step and used as two different operands; dK / dV stay in TMEM for the
 // whole chunk and are added to the fp32 gradients with red.global.add.v4 at the end (chunks of the same key block
@@ -22,10 +22,12 @@
 // lse is the forward's log-sum-exp in log2 units (isp_attention_bf16_tc_lse), D[q] = sum_d dO[q,d] O[q,d]
 // (isp_attention_rowdot_heads); both are [B][heads][rows].
 //
-// Warps: 0 = TMA producer (4-deep Q/dO ring, lse/D by 1-D bulk copies on the same barrier), 1 = MMA issuer (S^T / dP^T two
-// steps ahead of the softmax), 2..17 = softmax (TMEM lane = key; the four warps of a lane quarter take 16 queries each).
-// TMEM: buffer b at b*128 (S^T 64 columns, dP^T 64), dV at 256, dK at 384.  tcgen05.mma executes in issue order, which
-// orders the reads of P^T(i) / dS^T(i) before S^T(i+2) overwrites their buffer.
+// Warps: 0 = TMA producer (4-deep Q/dO ring; lse/D by 1-D bulk copies on the same barrier, or copied by the warp when the
+// row count is not a multiple of 4), 1 = MMA issuer (S^T / dP^T two steps ahead of the softmax; descriptors built once and
+// advanced by constants -- the issuing warp's instruction stream was the first bottleneck), 2..17 = softmax (TMEM lane =
+// key; the four warps of a lane quarter take 16 queries each).  TMEM column plan: see col_s / col_dp below; dV at 256, dK
+// at 384.  tcgen05.mma executes in issue order, which orders the reads of P^T(i) / dS^T(i) before S^T(i+2) overwrites
+// their buffer.
 #include "tc_common.cuh"
 
 namespace isp {
@@ -39,14 +41,11 @@ constexpr int kThreads = 64 + 32 * kSoftmaxWarps;
 constexpr uint32_t kKVBytes = 2 * 16384;          // K (or V) tile: two [128 keys x 64 cols] boxes
 constexpr uint32_t kQBytes = 2 * 8192;            // Q (or dO) tile: two [64 q x 64 cols] boxes
 constexpr uint32_t kStageBytes = 2 * kQBytes;
-constexpr uint32_t kPBytes = 16384;               // P^T (or dS^T) tile [128 keys x 64 q]
+constexpr uint32_t kPBytes = 16384;               // dS^T smem tile [128 keys x 64 q] (B operand of the dQ^T product)
 constexpr uint32_t kSmem = 2 * kKVBytes + kStages * kStageBytes + kPBytes;  // 208 KB
 constexpr float kLog2e = 1.4426950408889634f;
-// TMEM columns
-// buffer b (step parity) at b*128: S^T @+0 (64 columns), dP^T @+64 (64).  Once a step's S^T / dP^T are in registers the same
-// columns are reused: each softmax thread writes P^T (16 packed bf16 columns) and dS^T (16) over ITS OWN 32 S^T columns, and
-// dQ^T(i) is accumulated over dP^T's columns.  The tensor pipe executes in issue order, which orders the MMAs that read
-// P^T(i) / dS^T(i) before S^T(i+2) overwrites the buffer.
+// TMEM columns.  Once a step's S^T is in registers its columns are reused: each softmax thread writes P^T (8 packed bf16
+// columns) and dS^T (8) over ITS OWN 16 S^T columns.
 constexpr uint32_t cDV = 256, cDK = 384;
 // S^T(i) / dP^T(i) columns.  Without dQ: buffer i&1 at (i&1)*128 holds both (S^T @+0, dP^T @+64).  With dQ the 64 columns of
 // dQ^T need a home of their own (a dQ^T that lived in the dP^T buffer had to be drained before that buffer's next S^T / dP^T
