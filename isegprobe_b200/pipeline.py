@@ -24,12 +24,14 @@ FEATURIZER_REGISTRY = {"dinov2": DINOv2Featurizer, "maskclip": MaskCLIPFeaturize
 
 def install_into_reference(featurizers: bool = False) -> None:
     """Swap the reference's registry entries for the B200-native modules (same keys), so
-    `ModelBuilder.load_upsampler/load_head` construct ours.  Call after importing the
-    reference's `core.model` package and before building a model.
+    `ModelBuilder.load_upsampler/load_head` construct ours and `iSegBaseModel` builds our `DistMaps`.  Call before
+    building a model (before or after importing the reference's `core.model` package: both orders work).
     featurizers=True also rebinds the featurizer classes `ModelBuilder.load_featurizer` and `iSegProbeModel` look up by
     name (core/utils/model_builder.py:27-49, core/model/iseg_probe_model.py:93-103): the frozen backbones and the two
     click encoders.  Ours keep the constructor keywords and the state-dict keys of `.model` but do not download
     weights: load the torch.hub / CLIP / timm state dict into `backbone.model` afterwards."""
+    import sys
+
     import core.model.heads as ref_heads
     import core.model.upsamplers as ref_up
 
@@ -41,11 +43,28 @@ def install_into_reference(featurizers: bool = False) -> None:
         for cls in (DINOv2Featurizer, MaskCLIPFeaturizer, DINOFeaturizer, SimpleViTFeaturizer):
             setattr(ref_mb, cls.__name__, cls)
         ref_model.PatchEmbed = PatchEmbed
-    try:
-        import core.model.ops as ref_ops
-        ref_ops.DistMaps = ops.DistMaps
-    except ImportError:
-        pass
+    # DistMaps: `iSegBaseModel.__init__` constructs the name it bound with `from core.model.ops import DistMaps` at
+    # import time (core/model/iseg_base_model.py:9,60-65), so rebinding `core.model.ops.DistMaps` alone is not enough:
+    # every already-imported module that holds the reference class under that name is rebound too.
+    import core.model.iseg_base_model  # noqa: F401  (make sure the consumer exists before the scan)
+    import core.model.ops as ref_ops
+    ref_cls = ref_ops.DistMaps
+    ref_ops.DistMaps = ops.DistMaps
+    for name, mod in list(sys.modules.items()):
+        if mod is not None and name.startswith("core.") and getattr(mod, "DistMaps", None) is ref_cls:
+            mod.DistMaps = ops.DistMaps
+
+
+def swap_modules(model: nn.Module) -> nn.Module:
+    """For a reference model that was built BEFORE `install_into_reference()` (e.g. restored by
+    core/utils/serialization.py:61-91): replace its `dist_maps` in place with ours (same constructor arguments,
+    core/model/iseg_base_model.py:60-65).  Registry-built parts (upsampler / head) cannot be converted after the
+    fact -- rebuild the model after installing."""
+    dm = getattr(model, "dist_maps", None)
+    if dm is not None and not isinstance(dm, ops.DistMaps):
+        model.dist_maps = ops.DistMaps(norm_radius=dm.norm_radius, spatial_scale=dm.spatial_scale,
+                                       cpu_mode=dm.cpu_mode, use_disks=dm.use_disks)
+    return model
 
 
 class ISegPipeline(nn.Module):

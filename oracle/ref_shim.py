@@ -1,7 +1,9 @@
 """Import shim that makes the reference's hot-path modules importable in the
 authoring container (no omegaconf / mmcv / timm here).  Used ONLY by
-`oracle/make_golden.py` and by not-gpu tests that skip when /root/reference is
-absent.  Nothing on the GPU box may import this (the reference does not travel).
+`oracle/make_golden.py`, by tests (they skip when no reference tree is found) and by
+bench.py's `--impl reference` / context legs.  The tree is /root/reference in the authoring
+container; on the GPU box it is the UNMODIFIED copy `__graft_entry__.build()` stages under the
+git-ignored `baseline/_ref/` (never committed).  Test infrastructure, not product.
 """
 import os
 import sys
@@ -9,7 +11,20 @@ import types
 
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("ISEGPROBE_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")  # git-ignored copy made by __graft_entry__.build() (travels to the GPU box)
+
+
+def _pick_root() -> str:
+    env = os.environ.get("ISEGPROBE_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/core/model"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
