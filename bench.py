@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the hot path (driver contract: see DESIGN.md "Measurement").
 
-  python bench.py --gpus N --steps K --warmup W [--workload jbu|loftup] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload all|loftup|jbu|train|eval] [--impl reference]
 
 A step = one pass of  click maps -> click embedding -> DINOv2 ViT-S/14 -> upsampler (-> 448^2)
 over one batch of synthetic 448x448 images with random-init weights.
-  jbu    : BASELINE.json configs[1]  (FeatUp JBU stack / AdaptiveConv, batch 16 per GPU)  [default]
-  loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)
-  eval   : BASELINE.json configs[3]  (20-click NoC evaluation loop, MaskCLIP ViT-B/16 + LoftUp(512) + head,
-           eval_mode fixed448 with flip TTA, one synthetic GrabCut-shaped sample per rank and step; clicks/s)
+
+  loftup : BASELINE.json configs[2]  (LoftUp cross-attention to 448^2, bf16, batch 32 per GPU)   <- the headline line
+  jbu    : BASELINE.json configs[1]  (FeatUp JBU stack / AdaptiveConv, batch 16 per GPU; JBU parity is UNPINNED)
   train  : BASELINE.json configs[4]  (IS training step as the reference runs it: click maps -> trainable click
            embedding -> frozen DINOv2-S/14 -> frozen LoftUp -> ConvSegHead, NFL loss, backward through the head AND
-           through the frozen upsampler / backbone down to the click embedding, gradient all-reduce, Adam; GLOBAL
-           batch 64 split over the ranks -- strong scaling, as the reference's batch_size // ngpus).
-           `--train-head-only` freezes the click embedding (features under no_grad, head forward/backward only).
-Multi-GPU: one process per GPU (torchrun), images sharded across ranks, no data-path
-collective (weak scaling); time = max over ranks of the CUDA-event time of the K steps.
-`--impl reference` times the CPU oracle port of the same path on the host cores.
+           through the frozen upsampler / backbone down to the click embedding, gradient all-reduce INSIDE the timed step
+           (its own CUDA-event time is reported), Adam; GLOBAL batch 64 split over the ranks -- strong scaling, as the
+           reference's batch_size // ngpus).  Frozen modules run with eval-mode statistics unless --train-mode-frozen.
+  eval   : BASELINE.json configs[3]  (20-click NoC evaluation loop, MaskCLIP ViT-B/16 + LoftUp(512) + head,
+           eval_mode fixed448 with flip TTA, synthetic GrabCut-shaped samples sharded over the ranks; clicks/s)
+  all    : (default) the loftup line, with the other three as sub-records under "workloads" (fewer steps each).
+
+`value`  : device-timed, inputs resident in HBM, CUDA-graph replay (forward workloads).
+`e2e`    : the same step through the public API with HOST buffers: pinned host image + clicks -> device, the whole
+           model INCLUDING the IS head, and the [B,1,448,448] logits copied back to the host every step.
+Multi-GPU: one process per GPU (torchrun), images sharded across ranks, no data-path collective for the forward
+workloads (weak scaling); time = max over ranks of the CUDA-event time of the K steps.
+`--impl reference` times the reference's own model (`iSegProbeModel.forward`, unmodified, from the staged
+baseline/_ref tree; kind "reference") -- or the CPU oracle port when no tree is staged (kind "port") -- on the host cores.
 """
 import argparse
 import json
@@ -44,14 +51,28 @@ WORKLOADS = {
 }
 H = W = 448
 P_CLICKS = 24
+METRIC_FWD = "images/sec @448^2 DINOv2-S/14 + upsampler forward"
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def workload_config(wl, world):
+    """Definition of the workload -- identical in both arms (the b200 line and `--impl reference`); how an arm executes it
+    (graph replay, sample size) is reported outside `config`."""
+    w = WORKLOADS[wl]
+    train = wl == "train"
+    per_gpu = w["batch"] // world if train else w["batch"]
+    return {"workload": w["name"], "batch_per_gpu": per_gpu, "global_batch": per_gpu * world, "image": "448x448",
+            "clicks_per_polarity": P_CLICKS, "weights": "random init (seed 0)",
+            "result": "features [B,384,448,448] (value); mask logits [B,1,448,448] after the IS head (e2e)",
+            "l2": "no explicit flush: every step streams > 10 GB of intermediates (>> 126 MB L2)",
+            "parallelism": f"dp{world} (images sharded over the ranks"
+                           + (", one gradient all-reduce per step)" if train else ", no data-path collective)")}
 
 
 def synth_inputs(batch, seed):
@@ -82,7 +103,9 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
-    def summary(self):
+    def finish(self):
+        self.stop_flag = True
+        self.join()
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -91,13 +114,60 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_port_step(wl, batch, seed=1):
-    """One pass of the same path with the CPU oracle (torch fp32, all host threads)."""
+class Ctx:
+    """Process placement: one process per GPU."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.dist is None:
+            return ms
+        t = torch.tensor([ms], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def timed(self, fn, steps):
+        """EXACTLY `steps` calls bracketed by barrier + synchronize; CUDA events on the launching stream; max over ranks."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_step(wl, batch, seed=1, with_head=False):
+    """One pass of the same path with the CPU oracle (torch fp32, all host threads): (seconds to the features,
+    seconds to the logits or None)."""
     from oracle import distmaps as odm, head as ohead, jbu as ojbu, loftup as oloft, synth, vit as ovit
     torch.manual_seed(0)
     img, pts = synth_inputs(batch, seed)
     vsd = synth.vit_state_dict(384, 12, seed=0)
     psd = synth.patch_embed_state_dict(384, 14, 3, seed=0)
+    hsd = synth.convhead_state_dict(384, 2, 1, seed=0)
     if wl == "jbu":
         usd = ojbu.init_state_dict(384, seed=0)
     else:
@@ -112,89 +182,397 @@ def cpu_port_step(wl, batch, seed=1):
             hr = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
         else:
             hr = oloft.loftup_forward(usd, lr, nimg, cn["norm.weight"], cn["norm.bias"])
-        chk = float(hr.mean())
-    return time.perf_counter() - t0, chk
+        float(hr.mean())
+        t_feat = time.perf_counter() - t0
+        t_all = None
+        if with_head:
+            float(ohead.convhead_forward(hsd, hr).mean())
+            t_all = time.perf_counter() - t0
+    return t_feat, t_all
+
+
+class ReferenceCPU:
+    """The reference's own assembled model (oracle/ref_model.py: unmodified `iSegProbeModel` built by `ModelBuilder` from
+    the models/sbd/dinov2/patch-embed_loftup.py config) on the host cores, fp32, eval, no_grad -- BASELINE.md section 4.
+    The time to the upsampler output is taken by a forward hook on `model.upsampler` (the LoftUp output already is 448^2,
+    so no resize follows), the time to the logits at the return of `model(image, points)`."""
+
+    def __init__(self, wl):
+        from oracle import ref_model
+        self.model = ref_model.build(WORKLOADS[wl]["upsampler"]).eval()
+        self.t_up = None
+        self.model.upsampler.register_forward_hook(lambda *a: setattr(self, "t_up", time.perf_counter()))
+
+    def step(self, batch, seed=1):
+        img, pts = synth_inputs(batch, seed)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = self.model(img, pts)["instances"]
+            float(out.mean())
+        return self.t_up - t0, time.perf_counter() - t0
+
+
+def reference_available(wl):
+    from oracle import ref_shim
+    return wl in ("loftup", "train") and ref_shim.available()
+
+
+def cpu_baseline_record(wl):
+    """Bounded sample for the b200 line: ONE image of the same workload on all host threads."""
+    torch.set_num_threads(os.cpu_count())
+    if reference_available(wl):
+        ref = ReferenceCPU(wl)
+        ref.step(1)  # warm-up (allocator, thread pool)
+        t_feat, t_all = ref.step(1)
+        kind = "reference"
+        what = "the reference's own iSegProbeModel.forward (unmodified modules staged under baseline/_ref), torch CPU fp32"
+    else:
+        t_feat, t_all = cpu_port_step(wl, 1, with_head=True)
+        kind, what = "port", "torch CPU fp32 oracle port (oracle/*.py)"
+    return {"value": 1.0 / t_feat, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"1 image of the same workload (one step at batch 1), {what}; value = to the upsampler output, "
+                      "to_logits = through the IS head",
+            "to_logits": 1.0 / t_all}
 
 
 def run_reference(args):
-    """Reference arm: the CPU port of the reference path (oracle/) on the host cores.  The
-    reference itself cannot run on this box (no omegaconf/mmcv/timm, hub downloads); see DESIGN.md."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    """Reference arm (rank 0 only): same metric / unit / config as the b200 line; every step is a bounded sample
+    (one image) of the workload on all host threads."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    wl = args.workload
-    sample_b = 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_step(wl, sample_b)
-    ts = [cpu_port_step(wl, sample_b)[0] for _ in range(args.steps)]
-    t = sum(ts) / len(ts)
-    v = sample_b / t
-    line = {"impl": "reference", "metric": "images/sec @448^2 DINOv2-S/14 + upsampler forward", "value": v,
-            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOADS[wl]["name"], "batch_per_step": sample_b},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{sample_b} image per step of the same workload, torch CPU fp32 oracle"},
-            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    wl = "loftup" if args.workload == "all" else args.workload
+    if wl in ("train", "eval"):
+        print(json.dumps({"impl": "reference", "unavailable": f"the reference arm times the forward workloads (loftup, jbu); got {wl}"}))
+        return
+    if reference_available(wl):
+        ref = ReferenceCPU(wl)
+        step = lambda: ref.step(1)
+        kind = "reference"
+        what = "the reference's own iSegProbeModel.forward (unmodified modules, staged baseline/_ref tree), torch CPU fp32"
+    else:
+        step = lambda: cpu_port_step(wl, 1, with_head=True)
+        kind = "port"
+        what = "torch CPU fp32 oracle port (no reference tree staged" + ("; FeatUp's JBU is not in the reference tree)" if wl == "jbu" else ")")
+    for _ in range(args.warmup):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t_feat = sum(t[0] for t in ts) / len(ts)
+    t_all = sum(t[1] for t in ts) / len(ts)
+    v, v_all = 1.0 / t_feat, 1.0 / t_all
+    line = {"impl": "reference", "metric": METRIC_FWD, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_feat * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+                             "sample": f"1 image per step of the same workload (per-image cost does not depend on the batch: "
+                                       f"the only batch-coupled op is MinMaxScaler's min/max), {what}"},
+            # value = to the upsampler output (what the b200 line's `value` times); e2e = through the IS head to the logits
+            # (what the b200 line's `e2e` times) -- both measured in the same passes, so each ratio compares like with like
+            "e2e": {"value": v_all, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "ms_per_step": t_all * 1e3}}
     print(json.dumps(line))
 
 
-def run_eval(args, rank, world, dev, dist):
+def reference_on_b200(dev, batch=2, steps=3):
+    """Context number: the reference's own fp32 eager CUDA path (cuDNN / cuBLAS, TF32 off as in the reference)
+    on the same GPU, through `iSegProbeModel.forward`.  Batch 2 = what the reference's evaluation feeds it (image + flip)."""
+    from oracle import ref_model
+    model = ref_model.build("loftup").to(dev).eval()
+    img, pts = synth_inputs(batch, seed=1)
+    img, pts = img.to(dev), pts.to(dev)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            model(img, pts)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(img, pts)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": batch / (ms / 1e3), "unit": "images/s", "batch": batch, "ms_per_step": ms,
+            "what": "reference iSegProbeModel.forward (DINOv2-S/14 + LoftUp + ConvSegHead -> logits), fp32 eager torch on this "
+                    "B200 (unmodified modules from baseline/_ref); compare with e2e / to_logits, not with value"}
+
+
+# ----------------------------------------------------------------------------------------------- GPU workloads
+def attention_standalone(dev, images, iters=10):
+    """The LoftUp cross-attention kernel alone on chunk-shaped operands (for the roofline against the BURST peak)."""
+    from isegprobe_b200 import _lib
+    nh, HP, KP, T, HW = 4, 112, 128, 1024, H * W
+    bf = torch.bfloat16
+    Q = (torch.randn(images * HW, nh * HP, device=dev) * 0.5).to(bf)
+    Kp = (torch.randn(images, nh, T, KP, device=dev) * 0.5).to(bf)
+    Vt = torch.randn(images, nh, HP, T, device=dev).to(bf)
+    O = torch.empty(images * HW, nh * HP, dtype=bf, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _lib.call("isp_attention_bf16_tc", Q.data_ptr(), nh * HP, HP, Kp.data_ptr(), Vt.data_ptr(), O.data_ptr(),
+                  nh * HP, HP, images, HW, nh, T, 1, st)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_forward(wl_name, args, ctx, steps, warmup, headline):
+    import isegprobe_b200 as isp
+    from isegprobe_b200 import upsamplers
+    wl = WORKLOADS[wl_name]
+    B, dev, world = wl["batch"], ctx.dev, ctx.world
+    torch.manual_seed(0)
+    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=True).to(dev).eval()
+    img_h, pts_h = synth_inputs(B, seed=1 + ctx.rank)
+    img_h, pts_h = img_h.pin_memory(), pts_h.pin_memory()
+    img_d, pts_d = img_h.to(dev), pts_h.to(dev)
+
+    def step_device():  # `value`: inputs resident, one CUDA graph replay (ISegPipeline.features_graphed)
+        return pipe.features_graphed(img_d, pts_d)
+
+    def step_logits():  # device-timed counterpart of the e2e leg
+        return pipe.forward_graphed(img_d, pts_d, slot=2)
+
+    # e2e: requests are pipelined two deep -- the pinned host inputs of step i+1 are copied (copy stream, second set of
+    # static graph buffers) while the graph of step i runs, and the logits of step i are read back (async D2H into pinned
+    # memory) while step i+1 runs; the host waits for result i-1 before issuing i+1.
+    h2d = torch.cuda.Stream()
+    res_h = [torch.empty(B, 1, H, W, dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_i = [0]
+
+    def step_e2e():
+        i = e2e_i[0]
+        slot = i & 1
+        logits = pipe.forward_graphed(img_h, pts_h, slot=slot, h2d_stream=h2d)
+        res_h[slot].copy_(logits, non_blocking=True)  # the step's result: every image's mask logits
+        res_ev[slot].record()
+        if i > 0:
+            res_ev[slot ^ 1].synchronize()  # result of the previous step is on the host now
+        e2e_i[0] = i + 1
+        return res_h[slot]
+
+    def step_eager():
+        with torch.no_grad():
+            return pipe.features(img_d, pts_d)
+
+    for _ in range(max(warmup, 3)):
+        step_device()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = ctx.timed(step_device, steps)
+    launches = pipe.graphed_launches() * steps
+    # events cannot be recorded inside a graph replay: the dominant kernel is timed in eager steps right after
+    upsamplers.KERNEL_TIMERS.clear()
+    upsamplers.KERNEL_TIMING = True
+    for _ in range(2):
+        step_eager()
+    upsamplers.KERNEL_TIMING = False
+    torch.cuda.synchronize()
+    ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
+    clocks = sampler.finish() if sampler else None
+    for _ in range(2):
+        step_logits()
+    ms_logits = ctx.timed(step_logits, steps)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = ctx.timed(step_e2e, steps)
+    if ctx.rank != 0:
+        del pipe
+        torch.cuda.empty_cache()
+        return None
+    pk, pk_kind = peaks()
+    C = 384
+    roofline = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic_tab = json.load(open(tp)) if os.path.exists(tp) else {}
+    if wl_name == "jbu":
+        key = next((k for k in ("jbu_stage_512", "adaptive_conv_512") if ktimes.get(k)), None)
+        if key:
+            t = sum(ktimes[key]) / len(ktimes[key])
+            alg = 4.0 * B * (C * 518 * 518 + 49 * 512 * 512 + C * 512 * 512)  # padded input + filters + output, fp32
+            ach = alg / (t * 1e-3) / 1e9
+            traffic = traffic_tab.get("adaptive_conv_512_bytes_per_image")
+            roofline = {"kernel": "AdaptiveConv, JBU stage 512 (" + key + ")", "bound": "hbm", "achieved": ach,
+                        "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} hbm copy", "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                        "traffic": traffic * B if traffic else None,
+                        "traffic_source": traffic_tab.get("adaptive_conv_512_source"),
+                        "ms_per_launch": t, "algorithmic_bytes_per_launch": alg,
+                        "note": "op-level bytes of the stand-alone AdaptiveConv call (SURVEY 8d): padded input + 7x7 filters + output"}
+    elif ktimes.get("loftup_attention"):
+        ci = pipe.upsampler.chunk_images
+        t = sum(ktimes["loftup_attention"]) / len(ktimes["loftup_attention"])
+        flops = 2.0 * 2 * 4 * 200704 * 1024 * 101 * ci  # QK^T + PV, un-padded head dim, per launch (one layer, one chunk)
+        ach = flops / (t * 1e-3) / 1e12
+        traffic = traffic_tab.get("loftup_attention_bytes_per_image")
+        roofline = {"kernel": "attention_kernel<2,7,112> (LoftUp cross-attention, one layer of one chunk per launch)",
+                    "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                    "peak_kind": f"{pk_kind} cuBLAS bf16 sustained (kernel timed inside the step)", "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic * ci if traffic else None,
+                    "traffic_source": traffic_tab.get("loftup_attention_source"), "ms_per_launch": t,
+                    "algorithmic_flops_per_launch": flops, "images_per_launch": ci}
+        if headline:
+            ts = attention_standalone(dev, ci)
+            roofline["standalone"] = {"ms_per_launch": ts, "achieved": flops / (ts * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
+                                      "peak_kind": f"{pk_kind} cuBLAS bf16 burst (kernel timed alone)",
+                                      "frac": flops / (ts * 1e-3) / 1e12 / pk["bf16_tflops"]}
+    n_img = world * B * steps
+    line = {
+        "metric": METRIC_FWD, "value": n_img / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": steps,
+        "warmup": max(warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32 (JBU SIMT kernels) + bf16 tcgen05 (ViT, 1x1 conv)" if wl_name == "jbu" else "bf16",
+        "data": "synthetic", "config": workload_config(wl_name, world),
+        "launch": "CUDA graph replay (one graph per step)",
+        "to_logits": {"value": n_img / (ms_logits / 1e3), "unit": "images/s", "ms_per_step": ms_logits / steps,
+                      "what": "device-timed like `value`, but through the IS head to the logits (the e2e leg's computation)"},
+        "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s",
+                "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4) * world,
+                "d2h_bytes_per_step": int(B * H * W * 4) * world, "ms_per_step": ms_e2e / steps,
+                "what": "ISegPipeline.forward_graphed: pinned host image + clicks -> device, click maps, ViT, upsampler, "
+                        "ConvSegHead, [B,1,448,448] fp32 logits -> pinned host; requests pipelined two deep"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
+    }
+    if wl_name == "jbu":
+        line["parity"] = "unpinned (FeatUp is not in the reference tree; oracle/jbu.py restates the published algorithm)"
+    del pipe
+    torch.cuda.empty_cache()
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_record(wl_name)
+    return line
+
+
+def run_train(args, ctx, steps, warmup):
+    import isegprobe_b200 as isp
+    from isegprobe_b200 import _lib, upsamplers
+    from isegprobe_b200.training import HeadTrainer
+    wl = WORKLOADS["train"]
+    dev, world = ctx.dev, ctx.world
+    B = wl["batch"] // world  # global batch split over the ranks (trainer.py:66-68)
+    torch.manual_seed(0)
+    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=True).to(dev).eval()
+    img_h, pts_h = synth_inputs(B, seed=1 + ctx.rank)
+    img_h, pts_h = img_h.pin_memory(), pts_h.pin_memory()
+    gt_h = (img_h[:, 3:] > 0.5).float().pin_memory()  # synthetic instance masks (the prev-mask channel's blobs)
+    img_d, pts_d, gt_d = img_h.to(dev), pts_h.to(dev), gt_h.to(dev)
+    trainer = HeadTrainer(pipe, train_embedding=not args.train_head_only,
+                          frozen_train_mode=getattr(args, "train_mode_frozen", False))
+
+    def step_device():
+        return trainer.step(img_d, pts_d, gt_d)
+
+    def step_e2e():
+        return trainer.step(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True),
+                            gt_h.to(dev, non_blocking=True)).cpu()  # loss read back each step
+
+    for _ in range(max(warmup, 3)):
+        step_device()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    upsamplers.KERNEL_TIMERS.clear()
+    upsamplers.KERNEL_TIMING = True
+    trainer.comm_events = []
+    l0 = _lib.launch_count()
+    ms = ctx.timed(step_device, steps)
+    launches = _lib.launch_count() - l0
+    upsamplers.KERNEL_TIMING = False
+    comm = [a.elapsed_time(b) for a, b in trainer.comm_events]
+    trainer.comm_events = None
+    ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
+    clocks = sampler.finish() if sampler else None
+    step_e2e()
+    ms_e2e = ctx.timed(step_e2e, steps)
+    comm_ms = ctx.max_over_ranks(sum(comm) / max(len(comm), 1))
+    n_params = sum(p.numel() for p in trainer.params)
+    del trainer, pipe
+    torch.cuda.empty_cache()
+    if ctx.rank != 0:
+        return None
+    n_img = world * B * steps
+    return {
+        "metric": ("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd"
+                   + (")" if args.train_head_only else " + click-embedding gradient through the frozen path)")),
+        "value": n_img / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 (fp32 parameter gradients, loss and optimizer)", "data": "synthetic",
+        "config": workload_config("train", world), "launch": "eager",
+        "frozen_modules": ("train() semantics as the reference's trainer (BatchNorm batch statistics in LoftUp's first_conv)"
+                           if getattr(args, "train_mode_frozen", False) else
+                           "eval-mode statistics (the reference's net.train() also flips the frozen LoftUp's BatchNorm to batch "
+                           "statistics, trainer.py:214; --train-mode-frozen runs that)"),
+        "allreduce": {"ms_per_step": comm_ms, "bytes": 4 * n_params, "ranks": world, "inside_timed_step": True,
+                      "what": "ONE NCCL all-reduce (sum, then / world) of the flat fp32 gradient arena: head + click embedding "
+                              "(core/training/trainer.py:141-149 DDP semantics); CUDA events around the call, max over ranks"
+                              + ("" if world > 1 else "; world size 1: no collective is issued")},
+        "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s",
+                "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4 + gt_h.numel() * 4) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
+    }
+
+
+def run_eval(args, ctx, steps, warmup):
     """Config 4: every rank runs the 20-click loop on its own samples (no collective in the timed region;
     the IoU curves are gathered once at the end).  value = clicks/s over all ranks; a click = one
-    predictor call = one batch-2 (image + flip) forward of the whole model + the host-side click simulator."""
+    predictor call = one batch-2 (image + flip) forward of the whole model + the click simulator."""
     import numpy as np
     import isegprobe_b200 as isp
     from isegprobe_b200 import _lib, evaluation as ev
     from isegprobe_b200 import dist as idist
     wl = WORKLOADS["eval"]
+    rank, world, dev, dist = ctx.rank, ctx.world, ctx.dev, ctx.dist
     torch.manual_seed(0)
     pipe = isp.ISegPipeline("loftup", wl["params"], backbone="maskclip",
                             head_params={"in_channels": 512, "num_layers": 2, "num_classes": 1}).to(dev).eval()
     pipe.embed_coords = isp.PatchEmbed((448, 448), (16, 16), 3, 768).to(dev).eval()
-    n_w, n_t = max(args.warmup, 3), args.steps
+    n_w, n_t = max(warmup, 3), steps
     samples = ev.synthetic_dataset("grabcut", n=(n_w + n_t) * world, seed=0)
     mine = [samples[i] for i in idist.shard_indices(len(samples), world, rank)]
     pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True, use_graph=True)
     for img, gt in mine[:n_w]:
         ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=3)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
-    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
     if sampler:
         sampler.start()
     e0.record()
     curves = [ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=20)[1] for img, gt in mine[n_w:n_w + n_t]]
     e1.record()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - l0  # eager launches (none when every click replays the graph) ...
-    fwd_graphs = pipe.__dict__.get("_fwd_graphs", {})
-    if fwd_graphs:                         # ... plus the kernels inside each replayed graph
-        launches += list(fwd_graphs.values())[-1][4] * 20 * n_t
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+    ctx.barrier()
+    clocks = sampler.finish() if sampler else None
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0 + pipe.graphed_launches() * 20 * n_t  # eager launches + the replayed graphs' kernels
     rows = torch.tensor(np.stack(curves), device=dev)
     allr = idist.gather_sample_results(rows, n_t * world).cpu().numpy()
+    del pred, pipe
+    torch.cuda.empty_cache()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        return None
     noc, _, over = ev.compute_noc_metric(list(allr), [0.85, 0.90], max_clicks=20)
     clicks = 20 * n_t * world
     v = clicks / (ms / 1e3)
-    line = {"metric": "clicks/sec, 20-click NoC loop @448^2 MaskCLIP ViT-B/16 + LoftUp + head (flip TTA)", "value": v,
+    return {"metric": "clicks/sec, 20-click NoC loop @448^2 MaskCLIP ViT-B/16 + LoftUp + head (flip TTA)", "value": v,
             "unit": "clicks/s", "n_gpus": world, "steps": n_t, "warmup": n_w, "ms_per_step": ms / n_t,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "samples_per_rank": n_t, "clicks_per_sample": 20, "weights": "random init (seed 0)",
@@ -204,12 +582,9 @@ def run_eval(args, rank, world, dev, dist):
                     "d2h_bytes_per_step": int(20 * 448 * 448 * 4) * world, "ms_per_step": ms / n_t,
                     "note": "the loop is end-to-end by construction: image / clicks go host->device and the "
                             "probability map comes back to the host clicker every click"},
-            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None, "roofline": None,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": None,
             "noc": {"NoC@85": float(noc[0]), "NoC@90": float(noc[1]), ">=20@85": int(over[0]), ">=20@90": int(over[1]),
                     "note": "random-init weights: the values only show the metric path runs"}}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 def main():
@@ -217,190 +592,44 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="jbu")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["all"], default="all")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-context", action="store_true", help="skip the reference-on-B200 (fp32 eager CUDA) context leg")
     ap.add_argument("--train-head-only", action="store_true")
+    ap.add_argument("--train-mode-frozen", action="store_true",
+                    help="train workload: frozen upsampler in train() mode like the reference's trainer (BN batch statistics)")
+    ap.add_argument("--sub-steps", type=int, default=None, help="steps of the train / eval sub-records of --workload all")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    import isegprobe_b200 as isp
-    from isegprobe_b200 import _lib, upsamplers
-
-    if args.workload == "eval":
-        return run_eval(args, rank, world, dev, dist)
-    wl = WORKLOADS[args.workload]
-    train = args.workload == "train"
-    B = wl["batch"] // world if train else wl["batch"]  # train: global batch split over ranks (trainer.py:66-68)
-    torch.manual_seed(0)
-    pipe = isp.ISegPipeline(wl["upsampler"], wl["params"], with_head=train).to(dev).eval()
-    img_h, pts_h = synth_inputs(B, seed=1 + rank)
-    img_h, pts_h = img_h.pin_memory(), pts_h.pin_memory()
-    img_d, pts_d = img_h.to(dev), pts_h.to(dev)
-    if train:
-        from isegprobe_b200.training import HeadTrainer
-        trainer = HeadTrainer(pipe, train_embedding=not args.train_head_only)
-        gt_h = (img_h[:, 3:] > 0.5).float().pin_memory()  # synthetic instance masks (the prev-mask channel's blobs)
-        gt_d = gt_h.to(dev)
-
-        def step_device():
-            return trainer.step(img_d, pts_d, gt_d)
-
-        def step_e2e():
-            return trainer.step(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True),
-                                gt_h.to(dev, non_blocking=True)).cpu()  # loss read back each step
-    else:
-        # the step is replayed from a CUDA graph (ISegPipeline.features_graphed); the e2e variant copies the
-        # pinned host inputs straight into the graph's static input buffers
-        def step_device():
-            return pipe.features_graphed(img_d, pts_d)
-
-        # e2e: requests are pipelined two deep -- the pinned host inputs of step i+1 are copied (copy stream, second
-        # set of static graph buffers) while the graph of step i runs, and the centre-pixel feature vectors of step i are read
-        # back (async D2H into pinned memory) while step i+1 runs; the host waits for result i-1 before issuing i+1.
-        h2d = torch.cuda.Stream()
-        res_h = [torch.empty(B, 384, dtype=torch.float32).pin_memory() for _ in range(2)]
-        res_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        e2e_i = [0]
-
-        def step_e2e():
-            i = e2e_i[0]
-            slot = i & 1
-            out = pipe.features_graphed(img_h, pts_h, slot=slot, h2d_stream=h2d)
-            # the features stay on the device for the head; what is read back each step is each image's centre-pixel
-            # feature vector (a full-tensor checksum would add a 4.9 GB reduction pass that is not part of the path)
-            res_h[slot].copy_(out[:, :, H // 2, W // 2], non_blocking=True)
-            res_ev[slot].record()
-            if i > 0:
-                res_ev[slot ^ 1].synchronize()  # result of the previous step is on the host now
-            e2e_i[0] = i + 1
-            return res_h[slot]
-
-        def step_eager():
-            with torch.no_grad():
-                return pipe.features(img_d, pts_d)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    upsamplers.KERNEL_TIMERS.clear()
-    upsamplers.KERNEL_TIMING = train  # events cannot be recorded inside a graph replay: the graphed workloads
-    l0 = _lib.launch_count()          # time their dominant kernel in a few eager steps right after the timed region
-    ms = timed(step_device, args.steps)
-    launches = (_lib.launch_count() - l0) if train else pipe.graphed_launches() * args.steps
-    if not train:
-        upsamplers.KERNEL_TIMING = True
-        for _ in range(2):
-            step_eager()
-    upsamplers.KERNEL_TIMING = False
-    torch.cuda.synchronize()
-    ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join()
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    pk, pk_kind = peaks()
-    value = world * B * args.steps / (ms / 1e3)
-    e2e = world * B * args.steps / (ms_e2e / 1e3)
-    C = 384
-    roofline = None
-    if args.workload == "jbu" and ktimes.get("adaptive_conv_512"):
-        t = sum(ktimes["adaptive_conv_512"]) / len(ktimes["adaptive_conv_512"])
-        alg = 4.0 * B * (C * 518 * 518 + 49 * 512 * 512 + C * 512 * 512)  # padded input + filters + output, fp32
-        ach = alg / (t * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("adaptive_conv_512_bytes_per_image")
-            traffic = traffic * B if traffic else None
-        roofline = {"kernel": "adaptive_conv_v3_kernel (JBU stage 512)", "bound": "hbm", "achieved": ach,
-                    "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} hbm copy", "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": traffic, "ms_per_launch": t, "algorithmic_bytes_per_launch": alg}
-    elif args.workload in ("loftup", "train") and ktimes.get("loftup_attention"):
-        t = sum(ktimes["loftup_attention"]) / len(ktimes["loftup_attention"])
-        imgs = ktimes.get("_loftup_attention_images", [pipe.upsampler.chunk_images])[0]
-        flops = 2.0 * 2 * 4 * 200704 * 1024 * 101 * pipe.upsampler.chunk_images  # QK^T + PV, un-padded head dim
-        ach = flops / (t * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("loftup_attention_bytes_per_image")
-            traffic = traffic * pipe.upsampler.chunk_images if traffic else None
-        roofline = {"kernel": "attention_kernel<2,7,112> (LoftUp cross-attention, per layer call)", "bound": "tensor",
-                    "achieved": ach, "peak": pk["bf16_tflops_sustained"], "peak_kind": f"{pk_kind} cuBLAS bf16 sustained",
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "ms_per_launch": t,
-                    "algorithmic_flops_per_launch": flops}
-    line = {
-        "metric": (("images/sec @448^2 IS training step (frozen DINOv2-S/14 + LoftUp, head fwd/bwd"
-                    + (")" if args.train_head_only else " + click-embedding gradient through the frozen path)")) if train
-                   else "images/sec @448^2 DINOv2-S/14 + upsampler forward"), "value": value, "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong" if train else "weak", "vs_baseline": None,
-        "dtype": "f32 (JBU SIMT kernels) + bf16 tcgen05 (ViT, 1x1 conv)" if args.workload == "jbu" else
-                 ("bf16 (fp32 parameter gradients, loss and optimizer)" if train else "bf16"),
-        "data": "synthetic",
-        "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": B * world, "image": "448x448",
-                   "clicks_per_polarity": P_CLICKS, "weights": "random init (seed 0)",
-                   "launch": "eager" if train else "CUDA graph replay (one graph per step)",
-                   "l2": "no explicit flush: every step streams > 10 GB of intermediates (>> 126 MB L2)",
-                   "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-        "e2e": {"value": e2e, "unit": "images/s",
-                "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4 + (gt_h.numel() * 4 if train else 0)) * world,
-                "d2h_bytes_per_step": (4 if train else 4 * B * 384) * world, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": sampler.summary() if sampler else None,
-        "roofline": roofline,
-        "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
-    }
-    if not args.no_cpu_baseline and world == 1 and not train:
-        torch.set_num_threads(os.cpu_count())
-        t, _ = cpu_port_step(args.workload, 1)
-        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "1 image of the same workload (one step at batch 1), torch CPU fp32 oracle"}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    ctx = Ctx()
+    try:
+        if args.workload == "all":
+            line = run_forward("loftup", args, ctx, args.steps, args.warmup, headline=True)
+            sub = args.sub_steps or min(args.steps, 5)
+            subs = {"jbu": run_forward("jbu", args, ctx, args.steps, args.warmup, headline=False),
+                    "train": run_train(args, ctx, sub, 3),
+                    "eval": run_eval(args, ctx, min(sub, 4), 3)}
+            if line is not None:
+                line["workloads"] = subs
+        elif args.workload == "train":
+            line = run_train(args, ctx, args.steps, args.warmup)
+        elif args.workload == "eval":
+            line = run_eval(args, ctx, args.steps, args.warmup)
+        else:
+            line = run_forward(args.workload, args, ctx, args.steps, args.warmup, headline=True)
+        if line is not None and ctx.world == 1 and not args.no_context and args.workload in ("all", "loftup"):
+            from oracle import ref_shim
+            if ref_shim.available():
+                try:
+                    line["reference_on_b200"] = reference_on_b200(ctx.dev)
+                except Exception as e:  # context only: never lose the bench line over it
+                    line["reference_on_b200"] = {"unavailable": repr(e)[:200]}
+        if line is not None:
+            print(json.dumps(line))
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

@@ -131,37 +131,31 @@ class ISegPipeline(nn.Module):
             hr = bilinear_align_corners_nhwc(to_nhwc_f32(hr), tuple(norm_img.shape[2:])).permute(0, 3, 1, 2)
         return hr
 
-    def features_graphed(self, image: torch.Tensor, points: torch.Tensor, slot: int = 0,
-                         h2d_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
-        """`features` replayed from a CUDA graph (one capture per input shape): the ~700 kernel launches of a
-        step -- most of them tens of microseconds in the ViT -- are issued by the GPU front-end instead of
-        ~700 Python/ctypes calls, which otherwise leave the device waiting between the small kernels.
-        Inference only (no autograd); the result lives in a buffer owned by the graph and is overwritten by
-        the next call with the same shapes and the same `slot`.
-        Pipelined serving: alternate `slot` 0/1 and pass a copy stream -- the host->device copy of the next request then
-        runs on `h2d_stream` while the previous request's graph executes (each slot has its own static input / output
-        buffers; the copy waits for the slot's previous replay, the replay waits for the copy)."""
-        assert not torch.is_grad_enabled() or not any(p.requires_grad for p in self.embed_coords.parameters()) or \
-            not self.training, "features_graphed is an inference path"
-        dev = next(self.backbone.parameters()).device  # inputs may be (pinned) host tensors: copied straight into the static buffers
-        key = (tuple(image.shape), tuple(points.shape), image.dtype, points.dtype, slot)
+    def _graphed(self, kind: str, image: torch.Tensor, points: torch.Tensor, slot: int,
+                 h2d_stream: Optional[torch.cuda.Stream]) -> torch.Tensor:
+        """One CUDA graph per (kind, input shapes / dtypes, slot): static input buffers, replay, result in a buffer the
+        graph owns.  Inputs may be (pinned) host tensors: they are copied straight into the static buffers."""
+        dev = next(self.backbone.parameters()).device
+        key = (kind, tuple(image.shape), tuple(points.shape), image.dtype, points.dtype, slot)
         graphs = self.__dict__.setdefault("_graphs", {})
         entry = graphs.get(key)
         if entry is None:
             from . import _lib
+            fn = self.features if kind == "features" else (lambda i, p: self.forward(i, p)["instances"])
             s_img, s_pts = image.to(dev, copy=True), points.to(dev, copy=True)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():  # warm-up: weight packing, host-scalar caches, kernel attributes
                 for _ in range(2):
-                    self.features(s_img, s_pts)
+                    fn(s_img, s_pts)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
             with torch.cuda.graph(graph), torch.no_grad():
-                out = self.features(s_img, s_pts)
+                out = fn(s_img, s_pts)
             entry = (graph, s_img, s_pts, out, _lib.launch_count() - l0, torch.cuda.Event())
             graphs[key] = entry
+            self.__dict__["_last_graph_launches"] = entry[4]
         graph, s_img, s_pts, out, _, done = entry
         cur = torch.cuda.current_stream()
         if h2d_stream is None:
@@ -179,41 +173,33 @@ class ISegPipeline(nn.Module):
         done.record(cur)
         return out
 
-    def forward_graphed(self, image: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
-        """`forward(image, points)["instances"]` replayed from a CUDA graph (one capture per input shape / dtype).
+    def features_graphed(self, image: torch.Tensor, points: torch.Tensor, slot: int = 0,
+                         h2d_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """`features` replayed from a CUDA graph (one capture per input shape): the ~700 kernel launches of a
+        step -- most of them tens of microseconds in the ViT -- are issued by the GPU front-end instead of
+        ~700 Python/ctypes calls, which otherwise leave the device waiting between the small kernels.
+        Inference only (no autograd); the result lives in a buffer owned by the graph and is overwritten by
+        the next call with the same shapes and the same `slot`.
+        Pipelined serving: alternate `slot` 0/1 and pass a copy stream -- the host->device copy of the next request then
+        runs on `h2d_stream` while the previous request's graph executes (each slot has its own static input / output
+        buffers; the copy waits for the slot's previous replay, the replay waits for the copy)."""
+        assert not torch.is_grad_enabled() or not any(p.requires_grad for p in self.embed_coords.parameters()) or \
+            not self.training, "features_graphed is an inference path"
+        return self._graphed("features", image, points, slot, h2d_stream)
+
+    def forward_graphed(self, image: torch.Tensor, points: torch.Tensor, slot: int = 0,
+                        h2d_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """`forward(image, points)["instances"]` replayed from a CUDA graph (one capture per input shape / dtype / slot).
         Inference only; the logits live in a buffer owned by the graph and are overwritten by the next call with the
-        same shapes.  Used by the NoC evaluation loop (FixedSizePredictor(use_graph=True)): a click is ~430 launches,
-        most of them tens of microseconds."""
+        same shapes and slot.  Used by the NoC evaluation loop (FixedSizePredictor(use_graph=True): a click is ~430
+        launches, most of them tens of microseconds) and by bench.py's end-to-end leg (host buffers in, logits out,
+        requests pipelined two deep exactly like `features_graphed`)."""
         assert self.head is not None
-        dev = next(self.backbone.parameters()).device
-        key = ("fwd", tuple(image.shape), tuple(points.shape), image.dtype, points.dtype)
-        graphs = self.__dict__.setdefault("_fwd_graphs", {})
-        entry = graphs.get(key)
-        if entry is None:
-            from . import _lib
-            s_img, s_pts = image.to(dev, copy=True), points.to(dev, copy=True)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), torch.no_grad():
-                for _ in range(2):
-                    self.forward(s_img, s_pts)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            l0 = _lib.launch_count()
-            with torch.cuda.graph(graph), torch.no_grad():
-                out = self.forward(s_img, s_pts)["instances"]
-            entry = (graph, s_img, s_pts, out, _lib.launch_count() - l0)
-            graphs[key] = entry
-        graph, s_img, s_pts, out, _ = entry
-        s_img.copy_(image, non_blocking=True)
-        s_pts.copy_(points, non_blocking=True)
-        graph.replay()
-        return out
+        return self._graphed("forward", image, points, slot, h2d_stream)
 
     def graphed_launches(self) -> int:
         """Kernel launches inside the most recently captured graph (bench.py's gpu_launches claim)."""
-        graphs = self.__dict__.get("_graphs", {})
-        return list(graphs.values())[-1][4] if graphs else 0
+        return self.__dict__.get("_last_graph_launches", 0)
 
     def forward(self, image: torch.Tensor, points: torch.Tensor) -> Dict:
         hr = self.features(image, points)

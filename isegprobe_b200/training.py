@@ -41,8 +41,10 @@ def normalized_focal_loss(pred: torch.Tensor, label: torch.Tensor, alpha: float 
 class HeadTrainer:
     """One process per GPU; each rank steps on its own shard of the global batch."""
 
-    def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, train_embedding: bool = True):
+    def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, train_embedding: bool = True,
+                 frozen_train_mode: bool = False):
         self.pipe = pipeline
+        self.frozen_train_mode = frozen_train_mode
         assert pipeline.head is not None, "the pipeline was built without a head"
         self.train_embedding = train_embedding and (pipeline.upsampler_type in ("identity", "bilinear", "nearest", "bicubic", "jbu_featup", "loftup", "lift")
                                 and hasattr(pipeline.backbone, "_backward_impl"))
@@ -52,6 +54,7 @@ class HeadTrainer:
         if self.train_embedding:
             self.params += list(pipeline.embed_coords.parameters())
         self.arena = idist.FlatGradArena(self.params)
+        self.comm_events = None  # bench.py: a list here makes every step record CUDA events around the all-reduce
         self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps)
 
     def step(self, image: torch.Tensor, points: torch.Tensor, gt_mask: torch.Tensor) -> torch.Tensor:
@@ -68,6 +71,13 @@ class HeadTrainer:
         loss = normalized_focal_loss(logits, gt_mask).mean()
         self.arena.zero_()
         loss.backward()
-        self.arena.all_reduce_mean()
+        if self.comm_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.arena.all_reduce_mean()
+            e1.record()
+            self.comm_events.append((e0, e1))
+        else:
+            self.arena.all_reduce_mean()
         self.opt.step()
         return loss.detach()

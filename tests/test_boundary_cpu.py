@@ -12,21 +12,6 @@ from oracle import ref_shim
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="no reference tree (run __graft_entry__.build() where /root/reference exists)")
 
 
-def reference_cfgs(upsampler="loftup"):
-    """The config dictionaries of models/sbd/dinov2/patch-embed_{loftup,jbu,lift}.py:27-88 (define_modules_cfg), with
-    the checkpoint paths set to None (= random init, our documented extension; the reference always torch.load()s)."""
-    up = {"loftup": dict(type="loftup", params=dict(upsampler_path=None, n_dim=384)),
-          "jbu_featup": dict(type="jbu_featup", params=dict(backbone_type="dinov2", use_norm=True)),
-          "lift": dict(type="lift", params=dict(lift_path=None, n_dim=384, patch=14))}[upsampler]
-    return dict(
-        backbone_cfg=dict(type="dinov2", params=dict(feats_injection_mode="before_backbone")),
-        embed_coords_cfg=dict(type="patchEmbed", params=dict(img_size=(448, 448), patch_size=(14, 14), embed_dim=384)),
-        head_cfg=dict(type="convhead", params=dict(in_channels=384, num_layers=2, num_classes=1)),
-        upsampler_cfg=up, neck_cfg=None,
-        save_cfg=dict(embed_coords=True, backbone=False, upsampler=False, head=True),
-        architecture="backbone_upsampler_head")
-
-
 def build_reference_model(upsampler="loftup"):
     """models/sbd/dinov2/patch-embed_loftup.py:91-112 (init_model) with the reference's own classes."""
     ref_shim.install()
@@ -34,6 +19,7 @@ def build_reference_model(upsampler="loftup"):
     isp.install_into_reference(featurizers=True)
     from core.model.iseg_probe_model import iSegProbeModel
     from core.utils.model_builder import ModelBuilder
+    from oracle.ref_model import reference_cfgs
     return iSegProbeModel(**reference_cfgs(upsampler), model_builder=ModelBuilder(), use_disks=True, norm_radius=5,
                           with_prev_mask=True)
 
