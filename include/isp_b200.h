@@ -251,6 +251,14 @@ int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_stride, const
 int isp_attention_bf16_tc_lse(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
                               void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
                               int heads, int nkeys, int variant, float* lse, isp_stream_t stream);
+/* Tuned variant-1 entry (LoftUp cross-attention, loftup/layers.py:186-202).  lsum_col >= 0: Vt row `lsum_col` of every head
+ * (one of the head's zero-padding rows, e.g. 101 for head_dim 101 in DV = 112) holds ones, so the softmax denominator
+ * accumulates in that O column on the tensor pipe; poly in {0,2,3,4}: that many of every 8 exponentials are evaluated by an
+ * FMA-pipe polynomial (relative error 1e-4) instead of MUFU.EX2.  lse may be NULL.  out column lsum_col receives 1.0. */
+int isp_attention_bf16_tc_opt(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                              void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                              int heads, int nkeys, int variant, float* lse, int lsum_col, int poly,
+                              isp_stream_t stream);
 /* D[B][heads][rows] = sum_d dO[row, h*HP + d] * O[row, h*HP + d] (bf16 [B*rows, ld] operands). */
 int isp_attention_rowdot_heads(const void* dO, long long lddo, const void* O, long long ldo, float* out, int B,
                                long long rows, int heads, int HP, isp_stream_t stream);

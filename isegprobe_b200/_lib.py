@@ -55,6 +55,7 @@ SIGNATURES = {
     "isp_transpose_bf16_batched": [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _S],
     "isp_attention_bf16_tc": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _S],
     "isp_attention_bf16_tc_lse": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _P, _S],
+    "isp_attention_bf16_tc_opt": [_P, _LL, _I, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _I, _P, _I, _I, _S],
     "isp_attention_rowdot_heads": [_P, _LL, _P, _LL, _P, _I, _LL, _I, _I, _S],
     "isp_attention_bwd_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _I, _S],
     "isp_layernorm_rows": [_P, _I, _LL, _P, _I, _LL, _P, _P, _LL, _I, _F, _S],

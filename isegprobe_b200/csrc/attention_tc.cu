@@ -315,7 +315,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&p_full[kSplit ? half : 0]);
+        if (lane == 0) {
+          // S(j+1) is ready a block ahead, so a warp may finish block j+1 before a sibling has arrived for block j: never
+          // arrive twice in one phase (the previous phase has normally completed long ago -- one poll)
+          if (g > 0) tc::mbar_wait(&p_full[kSplit ? half : 0], (g - 1) & 1);
+          tc::mbar_arrive(&p_full[kSplit ? half : 0]);
+        }
       }
       // epilogue: O / l -> bf16 -> dense smem tile -> one TMA store (clipped at the image's last row);
       // the wide-head variant has no smem left for the tile and stores its rows directly
@@ -395,24 +400,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 using namespace isp;
 
+namespace isp {
+int attention_pair_launch(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt, void* out,
+                          long long ldo, int o_head_stride, int B, long long rows_per_img, int heads, int nkeys, float* lse,
+                          int lsum_col, int poly, isp_stream_t stream);  // attention_pair_tc.cu
+}
+
 // Q: bf16 [B*rows_per_img, ldq]; head h reads columns [h*q_head_stride, +DK) (zero K padding
 // makes any extra columns harmless).  K: bf16 [B, heads, nblocks*128, DKC] (DKC = 64 or 128,
 // zero padded).  Vt: bf16 [B, heads, DV, nblocks*128].  out: bf16 [B*rows_per_img, ldo], head h
-// writes DV columns at h*o_head_stride.  variant 0: head_dim <= 64 (DV = 64); 1: <= 112 (DV = 112);
-// 2: <= 144 (DV = 144, K padded to 192 columns).
+// writes DV columns at h*o_head_stride.  variant 0: head_dim <= 64 (DV = 64); 1: <= 112 (DV = 112) on the two-tile kernel of
+// attention_pair_tc.cu; 2: <= 144 (DV = 144, K padded to 192 columns); 3: the DV = 112 geometry on this file's one-tile
+// kernel (cross-check in the tests, and the "before" of tools/tune_attention.py).
 static int attention_fwd(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt, void* out,
                          long long ldo, int o_head_stride, int B, long long rows_per_img, int heads, int nkeys, int variant,
-                         float* lse, isp_stream_t stream) {
+                         float* lse, int lsum_col, int poly, isp_stream_t stream) {
   ISP_REQUIRE(Q && K && Vt && out, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: null pointer");
   ISP_REQUIRE(B > 0 && rows_per_img > 0 && heads > 0 && nkeys > 0, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: bad shape");
-  ISP_REQUIRE(variant >= 0 && variant <= 2, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: variant %d", variant);
+  ISP_REQUIRE(variant >= 0 && variant <= 3, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: variant %d", variant);
+  const bool pair = variant == 1;
+  if (variant == 3) variant = 1;
   const int DV = variant == 0 ? 64 : variant == 1 ? 112 : 144, DKC = variant == 0 ? 64 : variant == 1 ? 128 : 192;
+  ISP_REQUIRE(lsum_col < DV, ISP_ERR_BAD_SHAPE, "attention_bf16_tc: lsum_col %d outside the %d value columns", lsum_col, DV);
+  ISP_REQUIRE((lsum_col < 0 && poly == 0) || pair, ISP_ERR_UNSUPPORTED,
+              "attention_bf16_tc: the ones-column row sum / polynomial exp2 exist for variant 1 only");
+  ISP_REQUIRE(poly == 0 || (lsum_col >= 0 && (poly == 2 || poly == 3 || poly == 4)), ISP_ERR_UNSUPPORTED,
+              "attention_bf16_tc: poly must be 0, or 2 / 3 / 4 (of every 8 exponentials) together with lsum_col >= 0");
   ISP_REQUIRE(ldq % 8 == 0 && ldo % 8 == 0 && o_head_stride % 8 == 0 && q_head_stride % 8 == 0, ISP_ERR_MISALIGNED,
               "attention_bf16_tc: ldq/ldo/q_head_stride/o_head_stride must be multiples of 8 (TMA box starts and "
               "vector stores need 16-byte alignment)");
   ISP_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(Vt) && aligned16(out), ISP_ERR_MISALIGNED,
               "attention_bf16_tc: 16-byte alignment");
   ISP_REQUIRE((long long)B * rows_per_img < (1ll << 31), ISP_ERR_UNSUPPORTED, "attention_bf16_tc: too many rows");
+  if (pair)
+    return attention_pair_launch(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, lse,
+                                 lsum_col, poly, stream);
   attn::Params p = {};
   p.nkeys = nkeys;
   p.nblocks = (nkeys + attn::BKEY - 1) / attn::BKEY;
@@ -449,13 +471,16 @@ static int attention_fwd(const void* Q, long long ldq, int q_head_stride, const 
     const uint32_t box[2] = {64, (uint32_t)DV};
     if (int e = make_tmap_bf16(&tmV, Vt, 2, dims, str, box, "attention(Vt)")) return e;
   }
-  static int num_sms = 0;
-  static bool attr_set = false;
-  if (!num_sms) {
-    int dev = 0;
-    ISP_CUDA(cudaGetDevice(&dev));
-    ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  // per-device launch state (SM count, dynamic shared-memory opt-in): one process may drive several GPUs
+  constexpr int kMaxDev = 64;
+  static int num_sms_dev[kMaxDev] = {};
+  static bool attr_set_dev[kMaxDev] = {};
+  int dev = 0;
+  ISP_CUDA(cudaGetDevice(&dev));
+  ISP_REQUIRE(dev >= 0 && dev < kMaxDev, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: device ordinal %d", dev);
+  if (!num_sms_dev[dev]) ISP_CUDA(cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = num_sms_dev[dev];
+  bool& attr_set = attr_set_dev[dev];
   auto smem_of = [](uint32_t plan) { return (int)(plan > attn::kSmemMin ? plan : attn::kSmemMin); };
   const int sm0 = smem_of(attn::Plan<1, 64>::kBytes), sm1 = smem_of(attn::Plan<2, 112>::kBytes),
             sm2 = smem_of(attn::Plan<3, 144>::kBytes);
@@ -480,7 +505,7 @@ extern "C" int isp_attention_bf16_tc(const void* Q, long long ldq, int q_head_st
                                      void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
                                      int heads, int nkeys, int variant, isp_stream_t stream) {
   return attention_fwd(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, variant,
-                       nullptr, stream);
+                       nullptr, -1, 0, stream);
 }
 
 // Same, and also writes lse[B][heads][rows_per_img] (fp32, log2 units: log2 of the sum over keys of 2^(s*log2e)), the
@@ -490,5 +515,19 @@ extern "C" int isp_attention_bf16_tc_lse(const void* Q, long long ldq, int q_hea
                                          int heads, int nkeys, int variant, float* lse, isp_stream_t stream) {
   ISP_REQUIRE(lse, ISP_ERR_BAD_SHAPE, "attention_bf16_tc_lse: null lse");
   return attention_fwd(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, variant, lse,
-                       stream);
+                       -1, 0, stream);
+}
+
+// Tuned entry of the two-tile kernel (variant 1, LoftUp cross-attention): `lsum_col` >= 0 names a V^T row the caller filled
+// with ones (a zero-padding row of the head, e.g. 101 for head_dim 101 in 112) -- the row sum of the probabilities then
+// accumulates in that O column on the tensor pipe instead of 128 FADDs per thread and key block; `poly` in {0, 2, 3, 4}
+// moves that many of every 8 exponentials from the MUFU pipe to an FMA-pipe polynomial (max relative error 1e-4, below the
+// bf16 rounding of P).  lse may be NULL.  Column lsum_col of `out` receives 1.0 (callers' next weight matrix has zero rows
+// there).
+extern "C" int isp_attention_bf16_tc_opt(const void* Q, long long ldq, int q_head_stride, const void* K, const void* Vt,
+                                         void* out, long long ldo, int o_head_stride, int B, long long rows_per_img,
+                                         int heads, int nkeys, int variant, float* lse, int lsum_col, int poly,
+                                         isp_stream_t stream) {
+  return attention_fwd(Q, ldq, q_head_stride, K, Vt, out, ldo, o_head_stride, B, rows_per_img, heads, nkeys, variant, lse,
+                       lsum_col, poly, stream);
 }

@@ -292,13 +292,23 @@ class LoftUpUpsampler(BaseUpsampler):
                 Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
                 del qn
             O = torch.empty(M, nh * HP, dtype=bf, device=dev)
+            # variant 1 (head_dim <= 112, the two-tile kernel): a zero-padding row of every V^T head is filled with ones, so
+            # the softmax denominator accumulates in that column of O on the tensor pipe (Wo has zero rows there)
+            lsum = hd if (P["variant"] == 1 and hd < HP) else -1
+            if lsum >= 0:
+                Vt[:, :, hd, :T] = 1.0
             with timed_kernel("loftup_attention"):
+                lse = None
                 if keep is not None and self._flash_ok(HP, H * W):
                     # training: the attention output and the rows' log-sum-exp are what the flash-style backward needs
                     lse = torch.empty(B * nh * H * W + 64, dtype=torch.float32, device=dev)
+                    keep.setdefault("attn", []).append((O, lse))
+                if lsum >= 0:
+                    _call("isp_attention_bf16_tc_opt", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"],
+                          lse, lsum, 0)
+                elif lse is not None:
                     _call("isp_attention_bf16_tc_lse", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"],
                           lse)
-                    keep.setdefault("attn", []).append((O, lse))
                 else:
                     _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
             del Q

@@ -19,11 +19,12 @@ def _call(name, *a):
     _lib.call(name, *[(_lib.dptr(x) if torch.is_tensor(x) else x) for x in a], _lib.stream_ptr())
 
 
-def _attention(Q, K, V, heads, hd, variant, q_head_stride, big_logits=False):
-    """Q [B,T,heads*hd(+pad)], K,V [B,S,heads,hd] float tensors (bf16-representable)."""
+def _attention(Q, K, V, heads, hd, variant, q_head_stride, big_logits=False, lsum=False, poly=0):
+    """Q [B,T,heads*hd(+pad)], K,V [B,S,heads,hd] float tensors (bf16-representable).
+    lsum / poly: the tuned entry isp_attention_bf16_tc_opt (ones row in V^T at index hd, polynomial exp2)."""
     B, T = Q.shape[:2]
     S = K.shape[1]
-    DV, DKC = (112, 128) if variant else (64, 64)
+    DV, DKC = (112, 128) if variant else (64, 64)  # variant 1: two-tile kernel, 3: one-tile kernel, same geometry
     Spad = (S + 127) // 128 * 128
     Kp = torch.zeros(B, heads, Spad, DKC, dtype=torch.bfloat16)
     Kp[:, :, :S, :hd] = K.permute(0, 2, 1, 3).to(torch.bfloat16)
@@ -32,21 +33,31 @@ def _attention(Q, K, V, heads, hd, variant, q_head_stride, big_logits=False):
     ldq = Q.shape[2]
     Qd = Q.reshape(B * T, ldq).to(torch.bfloat16).to(DEV)
     out = torch.zeros(B * T, heads * DV, dtype=torch.bfloat16, device=DEV)
-    _call("isp_attention_bf16_tc", Qd, ldq, q_head_stride, Kp.to(DEV), Vt.to(DEV), out, heads * DV, DV, B, T, heads, S,
-          variant)
+    if lsum:
+        Vt[:, :, hd, :S] = 1.0
+        _call("isp_attention_bf16_tc_opt", Qd, ldq, q_head_stride, Kp.to(DEV), Vt.to(DEV), out, heads * DV, DV, B, T, heads,
+              S, variant, None, hd, poly)
+    else:
+        _call("isp_attention_bf16_tc", Qd, ldq, q_head_stride, Kp.to(DEV), Vt.to(DEV), out, heads * DV, DV, B, T, heads, S,
+              variant)
     torch.cuda.synchronize()
     out = out.float().cpu().reshape(B, T, heads, DV)
     q = torch.stack([Q[:, :, h * q_head_stride:h * q_head_stride + hd] for h in range(heads)], 2)  # B,T,h,hd
     s = torch.einsum("bthd,bshd->bhts", q.float(), K.float())
     want = torch.einsum("bhts,bshd->bthd", torch.softmax(s, -1), V.float())
-    if DV > hd:
+    if lsum:  # the ones-column holds the normalised row sum: 1.0
+        dev1 = float((out[..., hd] - 1.0).abs().max())
+        assert dev1 < 1e-2, dev1
+        assert float(out[..., hd + 1:].abs().max()) == 0.0
+    elif DV > hd:
         assert float(out[..., hd:].abs().max()) == 0.0  # padded head columns stay zero
     return out[..., :hd], want
 
 
 @pytest.mark.parametrize("B,T,S,heads,hd,variant", [(1, 128, 128, 1, 64, 0), (2, 300, 257, 6, 64, 0),
                                                     (1, 256, 1024, 4, 101, 1), (2, 1025, 1025, 6, 64, 0),
-                                                    (1, 1000, 196, 4, 101, 1)])
+                                                    (1, 1000, 196, 4, 101, 1), (2, 1000, 196, 4, 101, 3),
+                                                    (3, 130, 1024, 4, 101, 1), (1, 5000, 1024, 4, 101, 1)])
 def test_attention_vs_torch(B, T, S, heads, hd, variant):
     g = torch.Generator().manual_seed(T + S)
     bf = lambda x: x.to(torch.bfloat16).float()
@@ -57,6 +68,27 @@ def test_attention_vs_torch(B, T, S, heads, hd, variant):
     K = bf(torch.randn(B, S, heads, hd, generator=g) * hd ** -0.25)
     V = bf(torch.randn(B, S, heads, hd, generator=g))
     out, want = _attention(Q, K, V, heads, hd, variant, qs)
+    assert relerr(out, want) < 2e-2 and cosine(out, want) > 0.9995, (relerr(out, want), cosine(out, want))
+
+
+@pytest.mark.parametrize("poly", [0, 2, 3, 4])
+@pytest.mark.parametrize("B,T,S", [(1, 256, 1024), (2, 1000, 196), (1, 300, 1000)])
+def test_attention_tuned_entry_vs_torch(B, T, S, poly):
+    """isp_attention_bf16_tc_opt: row sum accumulated by the tensor pipe in the ones-column, `poly` of every 8 exponentials
+    on the FMA pipe; same tolerance as the plain entry (S = 196 / 1000: masked keys in the last block; big logits exercise the
+    lazy rescale with the ones-column)."""
+    heads, hd = 4, 101
+    g = torch.Generator().manual_seed(T + S + poly)
+    bf = lambda x: x.to(torch.bfloat16).float()
+    qs = 112
+    Q = torch.zeros(B, T, heads * qs)
+    for h in range(heads):
+        Q[:, :, h * qs:h * qs + hd] = bf(torch.randn(B, T, hd, generator=g) * hd ** -0.25)
+    K = bf(torch.randn(B, S, heads, hd, generator=g) * hd ** -0.25)
+    if S == 1000:
+        K[:, 600:] *= 6.0  # later key blocks carry much larger scores: the running max jumps by more than 2^8
+    V = bf(torch.randn(B, S, heads, hd, generator=g))
+    out, want = _attention(Q, K, V, heads, hd, 1, qs, lsum=True, poly=poly)
     assert relerr(out, want) < 2e-2 and cosine(out, want) > 0.9995, (relerr(out, want), cosine(out, want))
 
 
