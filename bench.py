@@ -12,7 +12,8 @@ over one batch of synthetic 448x448 images with random-init weights.
            embedding -> frozen DINOv2-S/14 -> frozen LoftUp -> ConvSegHead, NFL loss, backward through the head AND
            through the frozen upsampler / backbone down to the click embedding, gradient all-reduce INSIDE the timed step
            (its own CUDA-event time is reported), Adam; GLOBAL batch 64 split over the ranks -- strong scaling, as the
-           reference's batch_size // ngpus).  Frozen modules run with eval-mode statistics unless --train-mode-frozen.
+           reference's batch_size // ngpus).  The whole model is in train() like the reference's trainer (the frozen LoftUp's
+           BatchNorm uses batch statistics); --train-eval-mode-frozen keeps the frozen modules in eval().
   eval   : BASELINE.json configs[3]  (20-click NoC evaluation loop, MaskCLIP ViT-B/16 + LoftUp(512) + head,
            eval_mode fixed448 with flip TTA, synthetic GrabCut-shaped samples sharded over the ranks; clicks/s)
   all    : (default) the loftup line, with the other three as sub-records under "workloads" (fewer steps each).
@@ -478,7 +479,7 @@ def run_train(args, ctx, steps, warmup):
     gt_h = (img_h[:, 3:] > 0.5).float().pin_memory()  # synthetic instance masks (the prev-mask channel's blobs)
     img_d, pts_d, gt_d = img_h.to(dev), pts_h.to(dev), gt_h.to(dev)
     trainer = HeadTrainer(pipe, train_embedding=not args.train_head_only,
-                          frozen_train_mode=getattr(args, "train_mode_frozen", False))
+                          frozen_train_mode=not args.train_eval_mode_frozen)
 
     def step_device():
         return trainer.step(img_d, pts_d, gt_d)
@@ -519,10 +520,10 @@ def run_train(args, ctx, steps, warmup):
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16 (fp32 parameter gradients, loss and optimizer)", "data": "synthetic",
         "config": workload_config("train", world), "launch": "eager",
-        "frozen_modules": ("train() semantics as the reference's trainer (BatchNorm batch statistics in LoftUp's first_conv)"
-                           if getattr(args, "train_mode_frozen", False) else
-                           "eval-mode statistics (the reference's net.train() also flips the frozen LoftUp's BatchNorm to batch "
-                           "statistics, trainer.py:214; --train-mode-frozen runs that)"),
+        "frozen_modules": ("eval() (running-statistics BatchNorm) -- NOT the reference trainer's semantics"
+                           if args.train_eval_mode_frozen else
+                           "net.train() on the whole model as the reference's trainer does (trainer.py:213-214): the frozen LoftUp's "
+                           "BatchNorm runs on batch statistics of the rank's local batch and updates its running statistics"),
         "allreduce": {"ms_per_step": comm_ms, "bytes": 4 * n_params, "ranks": world, "inside_timed_step": True,
                       "what": "ONE NCCL all-reduce (sum, then / world) of the flat fp32 gradient arena: head + click embedding "
                               "(core/training/trainer.py:141-149 DDP semantics); CUDA events around the call, max over ranks"
@@ -602,8 +603,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-context", action="store_true", help="skip the reference-on-B200 (fp32 eager CUDA) context leg")
     ap.add_argument("--train-head-only", action="store_true")
-    ap.add_argument("--train-mode-frozen", action="store_true",
-                    help="train workload: frozen upsampler in train() mode like the reference's trainer (BN batch statistics)")
+    ap.add_argument("--train-eval-mode-frozen", action="store_true",
+                    help="train workload: keep the frozen backbone / upsampler in eval() (running-statistics BatchNorm); the default "
+                         "is net.train() on the whole model like the reference's trainer (batch-statistics BatchNorm in LoftUp)")
     ap.add_argument("--sub-steps", type=int, default=None, help="steps of the train / eval sub-records of --workload all")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -192,6 +192,17 @@ int isp_head_classifier_bwd(const void* act_bf16, long long lda, const float* dl
                             isp_stream_t stream);
 int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, int C, isp_stream_t stream);
 
+/* BatchNorm2d in training mode for the frozen LoftUp / LiFT conv stacks (loftup/loftup.py:55-65, LiFT.py:17-24 under the
+ * trainer's net.train(), core/training/trainer.py:213-214): the conv writes its raw bf16 output, then
+ * isp_col_moments_bf16 writes per-channel (sum, sum of squares) partials for slabs of ISP_COL_MOMENTS_SLAB_ROWS rows --
+ * partial fp32 [slabs][2][ldp], no atomics -- and isp_bn_relu_rows_bf16 applies y = max(x*scale[c] + shift[c], 0) in place
+ * and (optionally) writes stats fp32 [M][2], the (sum, sum of squares) of every stored row for a fused LayerNorm with
+ * ln_slots = 1 (isp_gemm_bf16_tc_ex). */
+#define ISP_COL_MOMENTS_SLAB_ROWS 1024
+int isp_col_moments_bf16(const void* x_bf16, long long ld, long long M, int C, float* partial, int ldp, isp_stream_t stream);
+int isp_bn_relu_rows_bf16(void* x_bf16, long long ld, const float* scale, const float* shift, long long M, int C,
+                          float* stats, isp_stream_t stream);
+
 /* Activation backward through the frozen ViT: the reference trains the click embedding THROUGH the frozen
  * backbone (core/model/featurizers/DINOv2.py:518-523 injects it before the blocks; trainer backward
  * core/training/trainer.py:213-221), so d(loss)/d(additional_features) needs every block's input gradient

@@ -158,6 +158,9 @@ class LoftUpUpsampler(BaseUpsampler):
         P["cn203_w"], P["cn203_b"] = f32(fc[0].norm.weight), f32(fc[0].norm.bias)
         P["conv1_w"], P["conv1_b"] = fold_bn(fc[1], fc[2])
         P["conv2_w"], P["conv2_b"] = fold_bn(fc[4], fc[5])
+        # train() mode (BatchNorm batch statistics): the un-folded convs
+        P["conv1_w_raw"], P["conv1_b_raw"] = tc.pack_conv3x3_weight(fc[1].weight.detach().float()).to(dev), f32(fc[1].bias)
+        P["conv2_w_raw"], P["conv2_b_raw"] = tc.pack_conv3x3_weight(fc[4].weight.detach().float()).to(dev), f32(fc[4].bias)
         fb = up.fourier_feat[1].biases.detach().float()
         P["fb_sin"], P["fb_cos"] = f32(fb[0].flatten()), f32(fb[1].flatten())
         lb = up.lr_pe.biases.detach().float()
@@ -243,15 +246,81 @@ class LoftUpUpsampler(BaseUpsampler):
         out = torch.empty(B, H, W, C, dtype=self.out_dtype, device=dev)
         if saved is not None:
             saved.update({"src": src, "chunks": [], "H": H, "W": W, "h": h, "w": w})
-        for b0 in range(0, B, self.chunk_images):
-            b1 = min(B, b0 + self.chunk_images)
+        spans = [(b0, min(B, b0 + self.chunk_images)) for b0 in range(0, B, self.chunk_images)]
+        queries = self._queries_train_mode(P, img, mm, spans, H, W) if self.training else None
+        for i, (b0, b1) in enumerate(spans):
             keep = None if saved is None else {"b0": b0, "b1": b1}
-            self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w, keep)
+            pre = None
+            if queries is not None:
+                pre, queries[i] = queries[i], None  # (x, st_a) of this chunk; released as the loop advances
+            self._forward_chunk(P, img[b0:b1], src[b0:b1], mm, out[b0:b1], H, W, h, w, keep, pre)
             if saved is not None:
                 saved["chunks"].append(keep)
         return out.permute(0, 3, 1, 2)
 
-    def _forward_chunk(self, P, img, src, mm, out, H, W, h, w, keep=None):
+    # ---------------------------------------------------------------- train() mode: BatchNorm with batch statistics
+    def _fourier(self, P, img, mm, H, W):
+        B = img.shape[0]
+        ff = torch.empty(B, H, W, 208, dtype=torch.bfloat16, device=img.device)
+        _call("isp_loftup_fourier_chnorm", img, *img.stride(), mm, self._grid(P, H, img.device), self._grid(P, W, img.device),
+              P["freqs20"], P["fb_sin"], P["fb_cos"], P["cn203_w"], P["cn203_b"], ff, B, H, W, 208, 1e-5)
+        return ff
+
+    @staticmethod
+    def _bn_batch_affine(bn, xs, C, count):
+        """Training-mode BatchNorm2d of the conv outputs `xs` (list of NHWC bf16 chunks): per-channel batch statistics over
+        ALL chunks (torch.nn.BatchNorm2d: biased variance normalises, unbiased variance feeds running_var), the running
+        statistics updated in place exactly as nn.BatchNorm2d does in train() (momentum 0.1, num_batches_tracked += 1).
+        Returns the (scale, shift) of  y = x * scale + shift."""
+        dev = xs[0].device
+        tot = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        for x in xs:
+            M, ld = x.numel() // x.shape[-1], x.shape[-1]
+            slabs = (M + 1023) // 1024  # ISP_COL_MOMENTS_SLAB_ROWS
+            part = torch.empty(slabs, 2, C, dtype=torch.float32, device=dev)
+            _call("isp_col_moments_bf16", x, ld, M, C, part, C)
+            tot += part.sum(0, dtype=torch.float64)
+        mean = tot[0] / count
+        var = (tot[1] / count - mean * mean).clamp_(min=0.0)
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(mean.to(bn.running_mean.dtype), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var * (count / max(count - 1, 1))).to(bn.running_var.dtype), alpha=m)
+            bn.num_batches_tracked += 1
+        scale = bn.weight.detach().double() / torch.sqrt(var + bn.eps)
+        shift = bn.bias.detach().double() - mean * scale
+        return scale.float().contiguous(), shift.float().contiguous()
+
+    def _queries_train_mode(self, P, img, mm, spans, H, W):
+        """first_conv (loftup/loftup.py:55-65) as nn.BatchNorm2d computes it in train(): batch statistics of each conv's
+        output over the whole local batch.  The raw conv outputs of all chunks are kept until their statistics are known
+        (bf16, 167 MB per image and conv), then normalised + ReLU'd in place.  Returns [(x [M,Dp] bf16, row statistics)]."""
+        fc = self.upsampler.upsampler.first_conv
+        D, Dp = P["D"], tc.round_up(P["D"], 16)
+        count = img.shape[0] * H * W
+        y1 = []
+        for b0, b1 in spans:
+            ff = self._fourier(P, img[b0:b1], mm, H, W)
+            y1.append(tc.conv3x3(ff, P["conv1_w_raw"], P["conv1_b_raw"], 203, D, act=None, ldy=Dp))
+            del ff
+        sc1, sh1 = self._bn_batch_affine(fc[2], y1, D, count)
+        y2 = []
+        for i in range(len(spans)):
+            x = y1[i]
+            _call("isp_bn_relu_rows_bf16", x, Dp, sc1, sh1, x.numel() // Dp, D, None)
+            y2.append(tc.conv3x3(x, P["conv2_w_raw"], P["conv2_b_raw"], D, D, act=None, ldy=Dp))
+            y1[i] = x = None
+        sc2, sh2 = self._bn_batch_affine(fc[5], y2, D, count)
+        outs = []
+        for x in y2:
+            M = x.numel() // Dp
+            st = torch.empty(M, 1, 2, dtype=torch.float32, device=x.device)
+            _call("isp_bn_relu_rows_bf16", x, Dp, sc2, sh2, M, D, st)
+            outs.append((x.view(M, Dp), st))
+        self._packed = None  # the running statistics moved: the eval-mode fold is stale
+        return outs
+
+    def _forward_chunk(self, P, img, src, mm, out, H, W, h, w, keep=None, pre=None):
         dev = img.device
         D, hd, C, nh = P["D"], P["hd"], self.n_dim, self.HEADS
         HP, KP = P["HP"], P["KP"]
@@ -259,23 +328,28 @@ class LoftUpUpsampler(BaseUpsampler):
         M, T = B * H * W, h * w
         Dp = tc.round_up(D, 16)  # row stride of the token matrices (404 -> 416)
         bf = torch.bfloat16
-        ff = torch.empty(B, H, W, 208, dtype=bf, device=dev)
-        _call("isp_loftup_fourier_chnorm", img, *img.stride(), mm, self._grid(P, H, dev), self._grid(P, W, dev),
-              P["freqs20"], P["fb_sin"], P["fb_cos"], P["cn203_w"], P["cn203_b"], ff, B, H, W, 208, 1e-5)
-        x = tc.conv3x3(ff, P["conv1_w"], P["conv1_b"], 203, D, act="relu", ldy=Dp)
-        del ff
         fuse = self.fuse_layernorm
         st_a = st_b = None
         if fuse:  # per-row (sum, sum of squares) slots: conv2 / FFN2 write st_a, out-proj writes st_b
             st_a = torch.empty(M, tc.stats_slots(D, bf, False), 2, dtype=torch.float32, device=dev)
             st_b = torch.empty(M, tc.stats_slots(D, bf, True), 2, dtype=torch.float32, device=dev)
-        x = tc.conv3x3(x, P["conv2_w"], P["conv2_b"], D, D, act="relu", ldy=Dp, stats_out=st_a).view(M, Dp)
+        if pre is not None:  # train() mode: the queries were produced with batch-statistics BatchNorm
+            x, st_q = pre
+            if not fuse:
+                st_q = None
+        else:
+            ff = self._fourier(P, img, mm, H, W)
+            x = tc.conv3x3(ff, P["conv1_w"], P["conv1_b"], 203, D, act="relu", ldy=Dp)
+            del ff
+            x = tc.conv3x3(x, P["conv2_w"], P["conv2_b"], D, D, act="relu", ldy=Dp, stats_out=st_a).view(M, Dp)
+            st_q = st_a
         kv = torch.empty(B * T, D, dtype=torch.float32, device=dev)
         _call("isp_loftup_lr_prepare", src, *src.stride(), P["cn_w"], P["cn_b"], self._grid(P, h, dev),
               self._grid(P, w, dev), P["freqs5"], P["lb_sin"], P["lb_cos"], kv, B, C, h, w, 1e-5)
         Tp = tc.round_up(T, 128)
         if keep is not None:  # what the activation backward re-reads: the query stream at every residual point, kv
             keep["kv"], keep["xs"] = kv, [x]
+        st_cur = st_q  # row statistics of the current query stream (first layer: the producer's; later: FFN2's = st_a)
         for L in P["layers"]:
             kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, tc.round_up(D, 8))
             Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
@@ -286,7 +360,7 @@ class LoftUpUpsampler(BaseUpsampler):
             _call("isp_repack_heads", Vl, 0, D, 0, hd, Vt, B, T, Tp, nh, HP, 1)
             if fuse:
                 Wq, gq, bq = L["Wq_ln"]
-                Q = tc.gemm(x, Wq, bias=bq, out_dtype=bf, N=nh * HP, K=D, ln_stats=st_a, ln_g=gq, ln_eps=1e-5)
+                Q = tc.gemm(x, Wq, bias=bq, out_dtype=bf, N=nh * HP, K=D, ln_stats=st_cur, ln_g=gq, ln_eps=1e-5)
             else:
                 qn = self._ln(x, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
                 Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
@@ -325,6 +399,7 @@ class LoftUpUpsampler(BaseUpsampler):
                 h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)
                 del hn
             x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp, stats_out=st_a)
+            st_cur = st_a
             del h1
             if keep is not None:
                 keep["xs"].append(x)

@@ -9,8 +9,15 @@
 The click embedding (`embed_coords`) is trained THROUGH the frozen backbone and upsampler in the reference
 (DINOv2.py:518-523).  Both backbones (DINOv2, MaskCLIP) and every upsampler (identity = the "noup" configs, bilinear,
 torch's nearest / bicubic, the FeatUp JBU stack, LoftUp, LiFT) have their activation backward on libisp_b200, so the
-step trains `embed_coords` exactly like the reference.  `train_embedding=False` keeps it frozen (features under
-no_grad, head forward / backward only)."""
+step trains `embed_coords` like the reference.  `train_embedding=False` keeps it frozen (features under
+no_grad, head forward / backward only).
+
+Module modes.  The reference's trainer calls `self.net.train()` on the WHOLE model (trainer.py:213-214), which also flips
+the frozen upsampler: LoftUp's first_conv BatchNorm then uses batch statistics and updates its running statistics
+(SURVEY Q7).  `frozen_train_mode=True` reproduces that (`pipeline.train()`; LoftUpUpsampler honours `self.training`,
+pinned to the reference module in train() by tests/golden/loftup_train_28x42.npz).  LiFT's BatchNorm and the JBU stack's
+Dropout2d are NOT modelled in train() -- those two upsamplers always run with eval-mode semantics.  With
+`frozen_train_mode=False` every frozen module runs in eval() and only the head (no mode-dependent layers) is in train()."""
 import torch
 
 from . import dist as idist
@@ -42,7 +49,7 @@ class HeadTrainer:
     """One process per GPU; each rank steps on its own shard of the global batch."""
 
     def __init__(self, pipeline, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, train_embedding: bool = True,
-                 frozen_train_mode: bool = False):
+                 frozen_train_mode: bool = True):
         self.pipe = pipeline
         self.frozen_train_mode = frozen_train_mode
         assert pipeline.head is not None, "the pipeline was built without a head"
@@ -61,7 +68,11 @@ class HeadTrainer:
         """image [b,4,H,W] (RGB + previous mask), points [b,2P,3], gt_mask [b,1,H,W] in {0,1,-1}.
         Returns the (detached) mean loss of this rank's shard."""
         pipe = self.pipe
-        pipe.head.train()
+        if self.frozen_train_mode:
+            pipe.train()  # trainer.py:213-214: the whole model, frozen modules included
+        else:
+            pipe.eval()
+            pipe.head.train()
         if self.train_embedding:  # gradients flow head -> resize -> frozen ViT -> click embedding
             logits = pipe(image, points)["instances"]
         else:

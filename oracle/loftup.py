@@ -58,13 +58,32 @@ def batchnorm_eval(x, sd, prefix, eps=1e-5):
     return x * scale[None, :, None, None] + (b - rm * scale)[None, :, None, None]
 
 
-def first_conv(x, sd, p="first_conv"):
-    """loftup.py:55-65 (eval mode: BatchNorm uses running statistics)."""
+def batchnorm_train(x, sd, prefix, eps=1e-5, momentum=0.1, new_stats=None):
+    """nn.BatchNorm2d.forward in train() -- what the reference's trainer runs on the FROZEN upsampler, because
+    `self.net.train()` (core/training/trainer.py:213-214) reaches it: batch statistics over (B, H, W), biased variance for
+    the normalisation; the running statistics move by `momentum` towards the batch mean / UNBIASED variance and
+    num_batches_tracked increments (returned in `new_stats`, keyed like the state dict)."""
+    w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    n = x.numel() // x.shape[1]
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    if new_stats is not None:
+        new_stats[prefix + ".running_mean"] = (1 - momentum) * sd[prefix + ".running_mean"] + momentum * mean
+        new_stats[prefix + ".running_var"] = (1 - momentum) * sd[prefix + ".running_var"] + momentum * var * n / max(n - 1, 1)
+        new_stats[prefix + ".num_batches_tracked"] = sd[prefix + ".num_batches_tracked"] + 1
+    scale = w / torch.sqrt(var + eps)
+    return x * scale[None, :, None, None] + (b - mean * scale)[None, :, None, None]
+
+
+def first_conv(x, sd, p="first_conv", train_stats=None):
+    """loftup.py:55-65.  Eval mode: BatchNorm uses running statistics.  train_stats = {} selects train() mode (batch
+    statistics) and receives the updated running statistics."""
+    bn = batchnorm_eval if train_stats is None else (lambda t, d, k: batchnorm_train(t, d, k, new_stats=train_stats))
     x = channel_layernorm(x, sd[f"{p}.0.norm.weight"], sd[f"{p}.0.norm.bias"], 1e-5)
     x = F.conv2d(x, sd[f"{p}.1.weight"], sd[f"{p}.1.bias"], padding=1)
-    x = torch.relu(batchnorm_eval(x, sd, f"{p}.2"))
+    x = torch.relu(bn(x, sd, f"{p}.2"))
     x = F.conv2d(x, sd[f"{p}.4.weight"], sd[f"{p}.4.bias"], padding=1)
-    return torch.relu(batchnorm_eval(x, sd, f"{p}.5"))
+    return torch.relu(bn(x, sd, f"{p}.5"))
 
 
 def cross_attention(q_in, kv_in, sd, p, heads=4):
@@ -109,11 +128,11 @@ def ca_transformer(q, kv, sd, p="ca_transformer", depth=2):
     return F.layer_norm(q, (D,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
 
 
-def queries(img, sd):
+def queries(img, sd, train_stats=None):
     """loftup.py:102-110: Fourier features of the min-max-scaled image -> first_conv
     -> [B, HW, D]."""
     x = fourier_features(minmax_scale(img), sd["fourier_feat.1.biases"], 20, True)
-    x = first_conv(x, sd)
+    x = first_conv(x, sd, train_stats=train_stats)
     return x.flatten(2).permute(0, 2, 1)
 
 
@@ -123,14 +142,14 @@ def keys_values(lr, sd):
     return torch.cat([lr, pe], 1).flatten(2).permute(0, 2, 1)
 
 
-def loftup_forward(sd, lr_feats, img, cn_weight=None, cn_bias=None):
+def loftup_forward(sd, lr_feats, img, cn_weight=None, cn_bias=None, train_stats=None):
     """LoftUp.forward (loftup.py:100-138), optionally preceded by the wrapper's
     ChannelNorm on the LR features (loftup.py:141-149).  sd keys are those of
-    `LoftUp(dim).state_dict()`."""
+    `LoftUp(dim).state_dict()`.  train_stats = {}: the module in train() mode (see batchnorm_train)."""
     if cn_weight is not None:
         lr_feats = channel_layernorm(lr_feats, cn_weight, cn_bias, 1e-5)
     B, _, H, W = img.shape
-    q = queries(img, sd)
+    q = queries(img, sd, train_stats)
     kv = keys_values(lr_feats, sd)
     x = ca_transformer(q, kv, sd)
     x = x.permute(0, 2, 1).reshape(B, -1, H, W)

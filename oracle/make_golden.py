@@ -72,6 +72,15 @@ def golden_loftup():
         q = up.first_conv(up.fourier_feat(img))
         ff = up.fourier_feat(img)
     save("loftup_28x42", out=out, first_conv=q[:, :, ::3, ::3], fourier=ff[:, :, ::3, ::3])
+    # the same module in train() mode -- how the reference's trainer runs the frozen upsampler (trainer.py:213-214):
+    # BatchNorm batch statistics, running statistics updated.  Three images so that batch statistics differ from a pair.
+    model.train()
+    img3 = (synth.image_batch(3, 28, 42, seed=5) - 0.45) / 0.225
+    lr3 = synth.lr_features(3, 384, 2, 3, seed=6)
+    with torch.no_grad():
+        out_t = model(lr3, img3)
+    stats = {k.replace(".", "_"): v.detach().clone() for k, v in up.state_dict().items() if "running" in k or "num_batches" in k}
+    save("loftup_train_28x42", out=out_t, **stats)
 
 
 def golden_lift():

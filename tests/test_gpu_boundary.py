@@ -108,3 +108,38 @@ def test_reference_model_trains_through_our_modules(models):
     for k in grads[0]:
         c = cosine(grads[1][k], grads[0][k])
         assert c > 0.99, (k, c)
+
+
+def test_reference_model_in_train_mode_matches(models):
+    """`net.train()` as the reference's trainer issues it (trainer.py:213-214) on both models: the frozen LoftUp's
+    BatchNorm switches to batch statistics (and moves its running statistics) in the reference AND in ours; logits,
+    gradients of the trainable parameters and the updated running statistics must agree.  Runs last: it mutates the
+    modules' BatchNorm buffers."""
+    from isegprobe_b200.training import normalized_focal_loss
+    ref_model, our_model, _ = models
+    image, pts = _inputs(B=2)
+    gt = (image[:, 3:] > 0.5).float()
+    res = []
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for m in (ref_model, our_model):
+            m.train()
+            m.zero_grad(set_to_none=True)
+            logits = m(image, pts)["instances"].float()
+            normalized_focal_loss(logits, gt).mean().backward()
+            grads = {k: p.grad.detach().float().cpu() for k, p in m.named_parameters() if p.requires_grad}
+            bn = {k: v.detach().float().cpu() for k, v in m.upsampler.state_dict().items() if "running_" in k}
+            res.append((logits.detach().cpu(), grads, bn))
+            m.eval()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    (l0, g0, b0), (l1, g1, b1) = res
+    assert cosine(l1, l0) > 0.999, cosine(l1, l0)
+    for k in g0:
+        assert cosine(g1[k], g0[k]) > 0.99, (k, cosine(g1[k], g0[k]))
+    # reference keys: upsampler.upsampler.first_conv.N.running_*; ours: upsampler.upsampler.first_conv.N.running_* as well
+    assert len(b0) == 4 and set(b0) == set(b1), (sorted(b0), sorted(b1))
+    for k in b0:
+        err = float((b1[k] - b0[k]).abs().max() / b0[k].abs().max())
+        assert err < 2e-2, (k, err)

@@ -33,6 +33,37 @@ def test_loftup_golden_reference(golden):
     assert relerr(out, want) < 0.15
 
 
+def test_loftup_train_mode_golden_reference(golden):
+    """module.train() (what the reference's trainer does to the frozen upsampler, core/training/trainer.py:213-214):
+    BatchNorm2d of first_conv with batch statistics over the whole batch -- across the internal image chunks -- and the
+    running statistics updated like nn.BatchNorm2d; pinned to the reference module run in train() (golden vectors)."""
+    g = golden("loftup_train_28x42")
+    m, sd, cn = _module()
+    m.chunk_images = 2  # 3 images -> two chunks: the statistics must still be those of the whole batch
+    m.train()
+    img = (synth.image_batch(3, 28, 42, seed=5) - 0.45) / 0.225
+    lr = synth.lr_features(3, 384, 2, 3, seed=6)
+    with torch.no_grad():
+        out = m(source=lr.to(DEV), guidance=img.to(DEV))
+    want = torch.from_numpy(g["out"])
+    c = cosine(out, want)
+    assert c >= 0.999, c
+    new = m.upsampler.upsampler.state_dict()
+    for k in ("first_conv.2.running_mean", "first_conv.2.running_var", "first_conv.5.running_mean", "first_conv.5.running_var"):
+        assert relerr(new[k], torch.from_numpy(g[k.replace(".", "_")])) < 2e-2, (k, relerr(new[k], torch.from_numpy(g[k.replace(".", "_")])))
+        assert relerr(new[k], sd[k]) > 1e-3  # they did move
+    assert int(new["first_conv.2.num_batches_tracked"]) == 1 and int(new["first_conv.5.num_batches_tracked"]) == 1
+    # eval() afterwards folds the UPDATED running statistics (oracle eval forward on the new state dict)
+    m.eval()
+    sd2 = {k: v.detach().cpu().clone() for k, v in new.items()}
+    img2 = (synth.image_batch(2, 28, 42, seed=1) - 0.45) / 0.225
+    lr2 = synth.lr_features(2, 384, 2, 3, seed=2)
+    with torch.no_grad():
+        out2 = m(source=lr2.to(DEV), guidance=img2.to(DEV))
+        want2 = oloft.loftup_forward(sd2, lr2, img2, cn["norm.weight"], cn["norm.bias"])
+    assert cosine(out2, want2) >= 0.999
+
+
 @pytest.mark.parametrize("B,H,W,h,w", [(1, 56, 56, 4, 4), (3, 64, 96, 8, 12), (5, 32, 32, 3, 3)])
 def test_loftup_vs_oracle(B, H, W, h, w):
     m, sd, cn = _module()

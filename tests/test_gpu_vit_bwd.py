@@ -212,7 +212,8 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
         pipe.upsampler.lift.load_state_dict(tsd)
         feats = ohead.bilinear_align_corners(olift.lift_forward(tsd, lr, nimg), (H, W))
     elif up_type == "loftup":
-        feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"])
+        # pipe.train() below is the trainer's net.train(): LoftUp's BatchNorm runs on batch statistics (trainer.py:213-214)
+        feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"], train_stats={})
     elif up_type == "jbu_featup":
         feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
     else:

@@ -63,6 +63,22 @@ def test_loftup_matches_reference(golden):
     assert _relerr(out, g["out"]) < 1e-4
 
 
+def test_loftup_train_mode_matches_reference(golden):
+    """train() semantics of the frozen upsampler (trainer.py:213-214): batch-statistics BatchNorm + running-stat updates."""
+    g = golden("loftup_train_28x42")
+    sd = synth.loftup_state_dict(384, seed=0)
+    cn = synth.channelnorm_state_dict(384, seed=1)
+    img = (synth.image_batch(3, 28, 42, seed=5) - 0.45) / 0.225
+    lr = synth.lr_features(3, 384, 2, 3, seed=6)
+    new = {}
+    with torch.no_grad():
+        out = oloft.loftup_forward(sd, lr, img, cn["norm.weight"], cn["norm.bias"], train_stats=new)
+    assert _relerr(out, g["out"]) < 1e-4
+    assert len(new) == 6
+    for k, v in new.items():
+        assert _relerr(v.float(), g[k.replace(".", "_")]) < 1e-5, k
+
+
 def test_lift_matches_reference(golden):
     g = golden("lift_56x84")
     sd = synth.lift_state_dict(384, seed=0)
