@@ -553,9 +553,15 @@ def run_eval(args, ctx, steps, warmup):
     n_w, n_t = max(warmup, 3), steps
     samples = ev.synthetic_dataset("grabcut", n=(n_w + n_t) * world, seed=0)
     mine = [samples[i] for i in idist.shard_indices(len(samples), world, rank)]
-    pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True, use_graph=True)
-    for img, gt in mine[:n_w]:
-        ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=3)
+    # device-resident loop (ZoomIn / flip / un-zoom / IoU / click simulator on the GPU, two samples interleaved per rank);
+    # --eval-host-driver runs the host driver instead (torch transforms, numpy IoU, cv2 clicker: the reference's structure)
+    if args.eval_host_driver:
+        pred = ev.FixedSizePredictor(pipe, dev, target_size=(448, 448), with_flip=True, use_graph=True)
+        run = lambda ss, nclk: [ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=nclk)[1] for img, gt in ss]
+    else:
+        evl = ev.DeviceNoCEvaluator(pipe, dev, target_size=(448, 448), with_flip=True, lanes=2)
+        run = lambda ss, nclk: [r[1] for r in evl.evaluate(ss, max_iou_thr=1.01, max_clicks=nclk)]
+    run(mine[:n_w], 3)
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
@@ -563,7 +569,7 @@ def run_eval(args, ctx, steps, warmup):
     if sampler:
         sampler.start()
     e0.record()
-    curves = [ev.evaluate_sample(img, gt, pred, max_iou_thr=1.01, max_clicks=20)[1] for img, gt in mine[n_w:n_w + n_t]]
+    curves = run(mine[n_w:n_w + n_t], 20)
     e1.record()
     ctx.barrier()
     clocks = sampler.finish() if sampler else None
@@ -571,7 +577,7 @@ def run_eval(args, ctx, steps, warmup):
     launches = _lib.launch_count() - l0 + pipe.graphed_launches() * 20 * n_t  # eager launches + the replayed graphs' kernels
     rows = torch.tensor(np.stack(curves), device=dev)
     allr = idist.gather_sample_results(rows, n_t * world).cpu().numpy()
-    del pred, pipe
+    del run, pipe
     torch.cuda.empty_cache()
     if rank != 0:
         return None
@@ -582,12 +588,15 @@ def run_eval(args, ctx, steps, warmup):
             "unit": "clicks/s", "n_gpus": world, "steps": n_t, "warmup": n_w, "ms_per_step": ms / n_t,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "samples_per_rank": n_t, "clicks_per_sample": 20, "weights": "random init (seed 0)",
+                       "driver": ("host (torch transforms, numpy IoU, cv2 clicker)" if args.eval_host_driver else
+                                  "device-resident (isp_zoom_in_fwd / isp_unzoom_probs / isp_noc_next_click, 2 samples interleaved)"),
                        "l2": "inputs change every click; every forward streams > 2 GB of intermediates",
                        "parallelism": f"dp{world} (samples sharded round-robin, final IoU gather only)"},
-            "e2e": {"value": v, "unit": "clicks/s", "h2d_bytes_per_step": int(20 * 2 * 4 * 448 * 448 * 4) * world,
-                    "d2h_bytes_per_step": int(20 * 448 * 448 * 4) * world, "ms_per_step": ms / n_t,
-                    "note": "the loop is end-to-end by construction: image / clicks go host->device and the "
-                            "probability map comes back to the host clicker every click"},
+            "e2e": {"value": v, "unit": "clicks/s",
+                    "h2d_bytes_per_step": int((20 * 2 * 4 * 448 * 448 * 4) if args.eval_host_driver else (640 * 640 * 16 + 20 * 2 * 48 * 12)) * world,
+                    "d2h_bytes_per_step": int((20 * 448 * 448 * 4) if args.eval_host_driver else 20 * 48) * world, "ms_per_step": ms / n_t,
+                    "note": "the loop is end-to-end by construction: the sample (image + ground truth) goes host->device once, "
+                            "every click reads the next click / IoU counts / bounding box (48 bytes) back and sends the click list"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": None,
             "noc": {"NoC@85": float(noc[0]), "NoC@90": float(noc[1]), ">=20@85": int(over[0]), ">=20@90": int(over[1]),
                     "note": "random-init weights: the values only show the metric path runs"}}
@@ -603,6 +612,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-context", action="store_true", help="skip the reference-on-B200 (fp32 eager CUDA) context leg")
     ap.add_argument("--train-head-only", action="store_true")
+    ap.add_argument("--eval-host-driver", action="store_true", help="eval workload: the host driver instead of the device-resident loop")
     ap.add_argument("--train-eval-mode-frozen", action="store_true",
                     help="train workload: keep the frozen backbone / upsampler in eval() (running-statistics BatchNorm); the default "
                          "is net.train() on the whole model like the reference's trainer (batch-statistics BatchNorm in LoftUp)")

@@ -192,6 +192,26 @@ int isp_head_classifier_bwd(const void* act_bf16, long long lda, const float* dl
                             isp_stream_t stream);
 int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, int C, isp_stream_t stream);
 
+/* Device side of the NoC evaluation loop, one sample per call, fp32.
+ * isp_zoom_in_fwd: ZoomIn._transform + AddHorizontalFlip.transform (core/inference/transforms/zoom_in.py:51-104,216-240,
+ *   flip.py:13-29): out [with_flip ? 2 : 1][4][S0][S1] = bilinear (align_corners=True) resize of the ROI rows rmin..rmax, columns
+ *   cmin..cmax (inclusive) of image [3,Hs,Ws] || prev [Hs,Ws] (NULL = zeros), and its horizontal flip.
+ * isp_unzoom_probs: the inverse chain (flip.py:31-36, base_transform.py:38-39, zoom_in.py:106-130) -- probabilities
+ *   sigmoid(mean of the logits and the flipped logits) resized back to the ROI, zeros elsewhere -> prob [Hs,Ws]; pred_mask =
+ *   prob > pred_thr (uint8); stats int[8] = {intersection, union with gt (label -1 ignored; core/inference/utils.py:107-120),
+ *   #pixels with prob > box_thr, their first / last row and column (INT_MAX / -1 if none), 0}.  gt may be NULL.
+ * isp_noc_next_click: Clicker._get_next_click (core/inference/clicker.py:58-91): exact Euclidean distance transform of the
+ *   zero-padded false-negative / false-positive masks (cv2.distanceTransform(DIST_L2, 0)), clicked pixels zeroed;
+ *   best[m] = (float bits of the largest distance << 32) | (0xFFFFFFFF - row-major index of its first occurrence), m = 0
+ *   false negatives, 1 false positives.  work: 2*H*W ints. */
+int isp_zoom_in_fwd(const float* image, const float* prev, int Hs, int Ws, int rmin, int rmax, int cmin, int cmax, float* out,
+                    int S0, int S1, int with_flip, isp_stream_t stream);
+int isp_unzoom_probs(const float* logits, int S0, int S1, int with_flip, int Hs, int Ws, int rmin, int rmax, int cmin,
+                     int cmax, float* prob, const int* gt, float pred_thr, float box_thr, unsigned char* pred_mask, int* stats,
+                     isp_stream_t stream);
+int isp_noc_next_click(const int* gt, const unsigned char* pred_mask, const unsigned char* clicked, int H, int W, int* work,
+                       unsigned long long* best, isp_stream_t stream);
+
 /* BatchNorm2d in training mode for the frozen LoftUp / LiFT conv stacks (loftup/loftup.py:55-65, LiFT.py:17-24 under the
  * trainer's net.train(), core/training/trainer.py:213-214): the conv writes its raw bf16 output, then
  * isp_col_moments_bf16 writes per-channel (sum, sum of squares) partials for slabs of ISP_COL_MOMENTS_SLAB_ROWS rows --

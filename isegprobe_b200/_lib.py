@@ -44,6 +44,9 @@ SIGNATURES = {
     "isp_conv3x3_wgrad_bf16_tc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _S],
     "isp_head_classifier_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _LL, _I, _S],
     "isp_colsum_bf16": [_P, _LL, _P, _LL, _I, _S],
+    "isp_zoom_in_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _S],
+    "isp_unzoom_probs": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _F, _F, _P, _P, _S],
+    "isp_noc_next_click": [_P, _P, _P, _I, _I, _P, _P, _S],
     "isp_col_moments_bf16": [_P, _LL, _LL, _I, _P, _I, _S],
     "isp_bn_relu_rows_bf16": [_P, _LL, _P, _P, _LL, _I, _P, _S],
     "isp_gemm_bf16_tc_batched": [_P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _I, _I, _I, _I, _I, _I, _F, _S],

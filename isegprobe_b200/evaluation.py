@@ -14,7 +14,9 @@ on one GPU, core/inference/utils.py:270-274).
 
 The model is any callable `net(image [B,4,H,W], points [B,2P,3]) -> {"instances": logits}` with a
 `with_prev_mask` attribute: `ISegPipeline`, or the reference's own `iSegProbeModel`.  The crop / resize /
-flip glue here is torch on the model's device (plumbing; moving it into the kernels is row f2)."""
+flip glue of FixedSizePredictor is torch on the model's device -- the structure of the reference's driver, kept as the
+pinned host path; `DeviceNoCEvaluator` (below) is the device-resident loop of rows f1 / f2: transforms, IoU and the click
+simulator run in libisp_b200 kernels and two samples are interleaved per rank."""
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -335,7 +337,7 @@ def compute_noc_metric(all_ious: Sequence[np.ndarray], iou_thrs: Sequence[float]
     return noc, noc_std, over
 
 
-def evaluate_dataset_sharded(samples: Sequence[Tuple[np.ndarray, np.ndarray]], predictor: FixedSizePredictor,
+def evaluate_dataset_sharded(samples: Sequence[Tuple[np.ndarray, np.ndarray]], predictor,
                              max_iou_thr: float = 1.01, max_clicks: int = 20, pred_thr: float = 0.49):
     """evaluate_dataset (evaluation.py:23-40) with the samples sharded round-robin over the ranks
     (dist.shard_indices) and the per-sample IoU curves gathered at the end (dist.gather_sample_results):
@@ -344,14 +346,178 @@ def evaluate_dataset_sharded(samples: Sequence[Tuple[np.ndarray, np.ndarray]], p
     n = len(samples)
     mine = idist.shard_indices(n)
     rows = torch.full((len(mine), max_clicks + 1), float("nan"), dtype=torch.float32)
-    for j, i in enumerate(mine):
-        image, gt = samples[i]
-        _, ious, _ = evaluate_sample(image, gt, predictor, max_iou_thr=max_iou_thr, pred_thr=pred_thr, max_clicks=max_clicks)
+    if isinstance(predictor, DeviceNoCEvaluator):  # the device-resident loop: this rank's samples, `lanes` at a time
+        curves = [r[1] for r in predictor.evaluate([samples[i] for i in mine], max_iou_thr=max_iou_thr, pred_thr=pred_thr,
+                                                    max_clicks=max_clicks)]
+    else:
+        curves = [evaluate_sample(samples[i][0], samples[i][1], predictor, max_iou_thr=max_iou_thr, pred_thr=pred_thr,
+                                  max_clicks=max_clicks)[1] for i in mine]
+    for j, ious in enumerate(curves):
         rows[j, 0] = len(ious)
         rows[j, 1:1 + len(ious)] = torch.from_numpy(ious)
     dev = predictor.device if idist.world() > 1 and torch.distributed.get_backend() == "nccl" else "cpu"
     full = idist.gather_sample_results(rows.to(dev), n).cpu()
     return [full[i, 1:1 + int(full[i, 0])].numpy() for i in range(n)]
+
+
+# ------------------------------------------------------------------ device-resident loop
+class _Lane:
+    """One sample in flight: its image / ground truth / probability map / masks live on the device for the whole click loop."""
+
+    def __init__(self, index, image, gt_mask, device):
+        arr = np.asarray(image)
+        t = torch.from_numpy(np.ascontiguousarray(arr.transpose(2, 0, 1)))
+        self.index = index
+        self.image = (t.float().div(255) if arr.dtype == np.uint8 else t.float()).to(device).contiguous()
+        self.H, self.W = int(self.image.shape[1]), int(self.image.shape[2])
+        self.gt = torch.from_numpy(np.ascontiguousarray(gt_mask.astype(np.int32))).to(device)
+        self.prob = None  # previous probability map [H, W] (None = zeros: first click)
+        self.prob_next = torch.empty(self.H, self.W, dtype=torch.float32, device=device)
+        self.pred_mask = torch.zeros(self.H, self.W, dtype=torch.uint8, device=device)
+        self.clicked = torch.zeros(self.H, self.W, dtype=torch.uint8, device=device)
+        self.work = torch.empty(2 * self.H * self.W, dtype=torch.int32, device=device)
+        self.result_d = torch.zeros(6, dtype=torch.int64, device=device)  # [best_fn, best_fp, 4 x packed int32 stats]
+        self.result_h = torch.zeros(6, dtype=torch.int64).pin_memory()
+        self.event = torch.cuda.Event()
+        self.clicks: List[Click] = []
+        self.ious: List[float] = []
+        self.roi = None
+        self.have_stats = False
+        self.done = False
+
+
+class DeviceNoCEvaluator:
+    """evaluate_sample (core/inference/evaluation.py:43-88) for eval_mode "fixedNNN" with flip TTA, with everything between
+    two network calls on the device: ZoomIn crop + resize + flip (`isp_zoom_in_fwd`), flip-average + sigmoid + un-zoom + threshold
+    + IoU counts + bounding box (`isp_unzoom_probs`), and the click simulator (`isp_noc_next_click`).  Per click the host reads
+    back 48 bytes (next click, IoU counts, bounding box) and does the ZoomIn ROI bookkeeping (integer / float scalar logic of
+    zoom_in.py:51-104, kept verbatim); `lanes` samples are interleaved on one stream so that this read-back and the host
+    logic of one sample overlap the forward of another.  Click sequences / IoU curves: identical to the host path
+    (FixedSizePredictor + Clicker), see tests/test_gpu_noc_device.py."""
+
+    def __init__(self, net, device, target_size=(448, 448), with_flip: bool = True, lanes: int = 2, graph_clicks: int = 24,
+                 expansion_ratio: float = 1.4, min_crop_size: int = 200, recompute_thresh_iou: float = 0.5,
+                 prob_thresh: float = 0.5):
+        self.net, self.device = net, torch.device(device)
+        self.S0, self.S1 = int(target_size[0]), int(target_size[1])
+        self.with_flip, self.lanes, self.graph_clicks = with_flip, max(1, lanes), graph_clicks
+        self.expansion_ratio, self.min_crop_size = expansion_ratio, min_crop_size
+        self.recompute_thresh_iou, self.prob_thresh = recompute_thresh_iou, prob_thresh
+        self.use_graph = hasattr(net, "forward_graphed")
+
+    # -- device steps ---------------------------------------------------------------------------------------------
+    def _enqueue_click(self, ln: _Lane):
+        from . import _lib
+        st = _lib.stream_ptr()
+        _lib.call("isp_noc_next_click", _lib.dptr(ln.gt), _lib.dptr(ln.pred_mask), _lib.dptr(ln.clicked), ln.H, ln.W,
+                  _lib.dptr(ln.work), _lib.dptr(ln.result_d), st)
+        ln.result_h.copy_(ln.result_d, non_blocking=True)
+        ln.event.record()
+
+    def _roi_for(self, ln: _Lane, stats) -> Tuple[int, int, int, int]:
+        """ZoomIn._transform's ROI bookkeeping (zoom_in.py:51-104) with skip_clicks = -1."""
+        current = None
+        if ln.have_stats and stats[2] > 0:  # mask = prev_probs > prob_thresh is not empty
+            rmin, rmax, cmin, cmax = stats[3], stats[4], stats[5], stats[6]
+            for c in ln.clicks:  # _object_roi_of: positive clicks join the mask
+                if c.is_positive:
+                    y, x = int(c.coords[0]), int(c.coords[1])
+                    rmin, rmax, cmin, cmax = min(rmin, y), max(rmax, y), min(cmin, x), max(cmax, x)
+            bb = _expand_bbox((rmin, rmax, cmin, cmax), self.expansion_ratio, self.min_crop_size)
+            current = max(0, bb[0]), min(ln.H - 1, bb[1]), max(0, bb[2]), min(ln.W - 1, bb[3])
+        if current is None:
+            current = 0, ln.H - 1, 0, ln.W - 1
+        if (ln.roi is None or not ZoomIn._check_roi(ln.roi, ln.clicks)
+                or _bbox_iou(current, ln.roi) < self.recompute_thresh_iou):
+            ln.roi = current
+        return ln.roi
+
+    def _points(self, ln: _Lane, roi) -> torch.Tensor:
+        rmin, rmax, cmin, cmax = roi
+        tc_ = [c.copy(coords=(self.S0 * (c.coords[0] - rmin) / (rmax - rmin + 1), self.S1 * (c.coords[1] - cmin) / (cmax - cmin + 1)))
+               for c in ln.clicks]
+        lists = [tc_]
+        if self.with_flip:
+            lists.append([c.copy(coords=(c.coords[0], self.S1 - c.coords[1] - 1)) for c in tc_])
+        num_pos = [sum(c.is_positive for c in cl) for cl in lists]
+        num_neg = [len(cl) - p for cl, p in zip(lists, num_pos)]
+        n = max(1, max(num_pos + num_neg))
+        if self.use_graph and n <= self.graph_clicks:
+            n = self.graph_clicks
+        total = []
+        for cl in lists:
+            pos = [c.coords_and_indx for c in cl if c.is_positive]
+            neg = [c.coords_and_indx for c in cl if not c.is_positive]
+            total.append(pos + (n - len(pos)) * [(-1, -1, -1)] + neg + (n - len(neg)) * [(-1, -1, -1)])
+        return torch.tensor(np.asarray(total, dtype=np.float64), dtype=torch.float32).pin_memory().to(self.device, non_blocking=True)
+
+    def _enqueue_prediction(self, ln: _Lane, roi, pred_thr: float):
+        from . import _lib
+        st = _lib.stream_ptr()
+        nb = 2 if self.with_flip else 1
+        net_in = torch.empty(nb, 4, self.S0, self.S1, dtype=torch.float32, device=self.device)
+        _lib.call("isp_zoom_in_fwd", _lib.dptr(ln.image), _lib.dptr(ln.prob), ln.H, ln.W, roi[0], roi[1], roi[2], roi[3],
+                  _lib.dptr(net_in), self.S0, self.S1, int(self.with_flip), st)
+        points = self._points(ln, roi)
+        if self.use_graph and points.shape[1] == 2 * self.graph_clicks:
+            logits = self.net.forward_graphed(net_in, points)
+        else:
+            logits = self.net(net_in, points)["instances"]
+        logits = logits.float()
+        if tuple(logits.shape[2:]) != (self.S0, self.S1):  # base_predictor.py:93-98
+            logits = F.interpolate(logits, mode="bilinear", align_corners=True, size=(self.S0, self.S1))
+        logits = logits.contiguous()
+        stats = ln.result_d[2:].view(torch.int32)
+        _lib.call("isp_unzoom_probs", _lib.dptr(logits), self.S0, self.S1, int(self.with_flip), ln.H, ln.W, roi[0], roi[1],
+                  roi[2], roi[3], _lib.dptr(ln.prob_next), _lib.dptr(ln.gt), float(pred_thr), float(self.prob_thresh),
+                  _lib.dptr(ln.pred_mask), _lib.dptr(stats), st)
+        ln.prob, ln.prob_next = ln.prob_next, (ln.prob if ln.prob is not None else torch.empty_like(ln.prob_next))
+        ln.have_stats = True
+
+    # -- driver ---------------------------------------------------------------------------------------------------
+    def _advance(self, ln: _Lane, max_iou_thr, pred_thr, min_clicks, max_clicks):
+        """Consume the lane's read-back (IoU of the last prediction, next click) and enqueue the next click's work."""
+        ln.event.synchronize()
+        res = ln.result_h
+        stats = res[2:].view(torch.int32).tolist()
+        if ln.have_stats:
+            iou = stats[0] / stats[1] if stats[1] else float("nan")
+            ln.ious.append(iou)
+            n = len(ln.ious)
+            if (iou >= max_iou_thr and n >= min_clicks) or n >= max_clicks:
+                ln.done = True
+                return
+        keys = [int(v) & 0xFFFFFFFFFFFFFFFF for v in res[:2].tolist()]
+        dmax = [np.frombuffer(np.uint32(k >> 32).tobytes(), dtype=np.float32)[0] for k in keys]
+        is_pos = bool(dmax[0] > dmax[1])
+        idx = 0xFFFFFFFF - (keys[0 if is_pos else 1] & 0xFFFFFFFF)
+        y, x = divmod(int(idx), ln.W)
+        ln.clicks.append(Click(is_positive=is_pos, coords=(y, x), indx=len(ln.clicks)))
+        ln.clicked[y, x] = 1
+        roi = self._roi_for(ln, stats)
+        self._enqueue_prediction(ln, roi, pred_thr)
+        self._enqueue_click(ln)
+
+    def evaluate(self, samples: Sequence[Tuple[np.ndarray, np.ndarray]], max_iou_thr: float = 1.01, pred_thr: float = 0.49,
+                 min_clicks: int = 1, max_clicks: int = 20, return_probs: bool = False):
+        """-> [(clicks_list, ious float32 array, final probability map or None)] in sample order."""
+        out = [None] * len(samples)
+        pending = list(range(len(samples)))[::-1]
+        active: List[_Lane] = []
+        with torch.no_grad():
+            while pending or active:
+                while pending and len(active) < self.lanes:
+                    i = pending.pop()
+                    ln = _Lane(i, samples[i][0], samples[i][1], self.device)
+                    self._enqueue_click(ln)
+                    active.append(ln)
+                for ln in list(active):
+                    self._advance(ln, max_iou_thr, pred_thr, min_clicks, max_clicks)
+                    if ln.done:
+                        probs = ln.prob.cpu().numpy() if return_probs else None
+                        out[ln.index] = (ln.clicks, np.array(ln.ious, dtype=np.float32), probs)
+                        active.remove(ln)
+        return out
 
 
 # ------------------------------------------------------------------ synthetic datasets (SURVEY.md 8d, config 4)
