@@ -484,9 +484,15 @@ def run_train(args, ctx, steps, warmup):
     def step_device():
         return trainer.step(img_d, pts_d, gt_d)
 
+    import random
+    sim_rng, sim_rounds = random.Random(1234), []
+
     def step_e2e():
+        # as the reference's batch_forward runs it (trainer.py:399-431): random.randint(0, 3) no-grad click-simulation rounds
+        # (eval() forward, sigmoid, host-side cv2 next-click) in front of the graded forward; loss read back each step
+        sim_rounds.append(sim_rng.randint(0, 3))
         return trainer.step(img_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True),
-                            gt_h.to(dev, non_blocking=True)).cpu()  # loss read back each step
+                            gt_h.to(dev, non_blocking=True), click_sim_rounds=sim_rounds[-1]).cpu()
 
     for _ in range(max(warmup, 3)):
         step_device()
@@ -505,6 +511,7 @@ def run_train(args, ctx, steps, warmup):
     ktimes = {k: [a.elapsed_time(b) for a, b in v] for k, v in upsamplers.KERNEL_TIMERS.items()}
     clocks = sampler.finish() if sampler else None
     step_e2e()
+    del sim_rounds[:]
     ms_e2e = ctx.timed(step_e2e, steps)
     comm_ms = ctx.max_over_ranks(sum(comm) / max(len(comm), 1))
     n_params = sum(p.numel() for p in trainer.params)
@@ -530,7 +537,11 @@ def run_train(args, ctx, steps, warmup):
                               + ("" if world > 1 else "; world size 1: no collective is issued")},
         "e2e": {"value": n_img / (ms_e2e / 1e3), "unit": "images/s",
                 "h2d_bytes_per_step": int(img_h.numel() * 4 + pts_h.numel() * 4 + gt_h.numel() * 4) * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / steps},
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / steps,
+                "click_simulation_rounds": list(sim_rounds),
+                "what": "HeadTrainer.step from pinned host tensors incl. the reference's click-simulation rounds (random.randint(0, 3) "
+                        "per step, seeded: eval() forward + sigmoid + host cv2 next-click each, trainer.py:399-431), loss read back; "
+                        "`value` is the graded step alone (0 rounds)"},
         "gpu_launches": int(launches), "clocks": clocks,
         "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
     }

@@ -45,6 +45,41 @@ def normalized_focal_loss(pred: torch.Tensor, label: torch.Tensor, alpha: float 
     return torch.sum(loss, dim=dims) / (bsum + eps)
 
 
+def get_next_points(pred: torch.Tensor, gt: torch.Tensor, points: torch.Tensor, click_indx: int,
+                    pred_thresh: float = 0.49) -> torch.Tensor:
+    """Click simulation of the training loop (core/training/trainer.py:577-618), host-side like the reference (OUT OF SCOPE
+    to accelerate; in scope to run so that config 5 is measured as the reference runs it): per image, the
+    chamfer distance transform (cv2 DIST_L2, 5x5 mask) of the zero-padded false-negative / false-positive regions of the
+    current prediction, a uniformly random pixel of the inner half of the larger error region, written into the click
+    slot `num_points - click_indx` (positive) or `2 * num_points - click_indx` (negative).  Draws from numpy's global RNG
+    exactly like the reference."""
+    import cv2
+    import numpy as np
+    assert click_indx > 0
+    pred_np = pred.detach().float().cpu().numpy()[:, 0, :, :]
+    gt_np = gt.detach().cpu().numpy()[:, 0, :, :] > 0.5
+    fn_mask = np.logical_and(gt_np, pred_np < pred_thresh)
+    fp_mask = np.logical_and(np.logical_not(gt_np), pred_np > pred_thresh)
+    fn_mask = np.pad(fn_mask, ((0, 0), (1, 1), (1, 1)), "constant").astype(np.uint8)
+    fp_mask = np.pad(fp_mask, ((0, 0), (1, 1), (1, 1)), "constant").astype(np.uint8)
+    num_points = points.size(1) // 2
+    points = points.clone()
+    for b in range(fn_mask.shape[0]):
+        fn_dt = cv2.distanceTransform(fn_mask[b], cv2.DIST_L2, 5)[1:-1, 1:-1]
+        fp_dt = cv2.distanceTransform(fp_mask[b], cv2.DIST_L2, 5)[1:-1, 1:-1]
+        fn_max, fp_max = np.max(fn_dt), np.max(fp_dt)
+        is_positive = fn_max > fp_max
+        dt = fn_dt if is_positive else fp_dt
+        indices = np.argwhere(dt > max(fn_max, fp_max) / 2.0)
+        if len(indices) > 0:
+            coords = indices[np.random.randint(0, len(indices))]
+            slot = (num_points if is_positive else 2 * num_points) - click_indx
+            points[b, slot, 0] = float(coords[0])
+            points[b, slot, 1] = float(coords[1])
+            points[b, slot, 2] = float(click_indx)
+    return points
+
+
 class HeadTrainer:
     """One process per GPU; each rank steps on its own shard of the global batch."""
 
@@ -64,10 +99,28 @@ class HeadTrainer:
         self.comm_events = None  # bench.py: a list here makes every step record CUDA events around the all-reduce
         self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps)
 
-    def step(self, image: torch.Tensor, points: torch.Tensor, gt_mask: torch.Tensor) -> torch.Tensor:
-        """image [b,4,H,W] (RGB + previous mask), points [b,2P,3], gt_mask [b,1,H,W] in {0,1,-1}.
-        Returns the (detached) mean loss of this rank's shard."""
+    def simulate_clicks(self, image: torch.Tensor, points: torch.Tensor, gt_mask: torch.Tensor, rounds: int):
+        """The no-grad click-simulation rounds in front of the graded forward (trainer.py:399-431): the model in eval(),
+        forward on (RGB || previous output), sigmoid, `get_next_points` on the host; returns the 4-channel image with the last
+        prediction as previous mask and the extended click tensor.  `image`: [b,3|4,H,W] (a 4th channel is replaced: the
+        reference starts from an all-zero previous output)."""
         pipe = self.pipe
+        rgb = image[:, :3]
+        prev = torch.zeros_like(rgb[:, :1])
+        with torch.no_grad():
+            for click_indx in range(rounds):
+                pipe.eval()
+                prev = torch.sigmoid(pipe(torch.cat((rgb, prev), dim=1), points)["instances"].float())
+                points = get_next_points(prev, gt_mask, points, click_indx + 1).to(points.device)
+        return torch.cat((rgb, prev), dim=1), points
+
+    def step(self, image: torch.Tensor, points: torch.Tensor, gt_mask: torch.Tensor, click_sim_rounds: int = 0) -> torch.Tensor:
+        """image [b,4,H,W] (RGB + previous mask), points [b,2P,3], gt_mask [b,1,H,W] in {0,1,-1}.
+        click_sim_rounds > 0 runs that many click-simulation rounds first (the reference draws random.randint(0, 3) per batch,
+        trainer.py:400-402).  Returns the (detached) mean loss of this rank's shard."""
+        pipe = self.pipe
+        if click_sim_rounds > 0:
+            image, points = self.simulate_clicks(image, points, gt_mask, click_sim_rounds)
         if self.frozen_train_mode:
             pipe.train()  # trainer.py:213-214: the whole model, frozen modules included
         else:

@@ -223,6 +223,32 @@ def golden_nfl():
     save("nfl_loss", pred=pred, label=label, out=out.detach(), grad=pr.grad)
 
 
+def golden_next_points():
+    """`get_next_points` (core/training/trainer.py:577-618), the click simulation of the training loop.  trainer.py cannot be
+    imported here (core.data needs albumentations), so the UNMODIFIED source of that one function is cut out of the reference
+    file with `ast` and executed with the names it uses (cv2, np, torch)."""
+    import ast
+    import cv2
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "core", "training", "trainer.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_next_points")
+    ns = {"cv2": cv2, "np": np, "torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "trainer.py:get_next_points", "exec"), ns)
+    g = torch.Generator().manual_seed(11)
+    B, H, W, P = 3, 60, 84, 6
+    gt = torch.zeros(B, 1, H, W)
+    gt[0, 0, 10:40, 20:60] = 1
+    gt[1, 0, 5:55, 5:30] = 1
+    gt[2, 0, 30:50, 40:80] = 1
+    pred = torch.rand(B, 1, H, W, generator=g)
+    pred[0, 0, 15:35, 25:50] += 0.6   # partly right: false negatives around it
+    pred[1, 0, 20:50, 40:70] += 0.7   # a false-positive blob
+    points = torch.full((B, 2 * P, 3), -1.0)
+    np.random.seed(123)
+    out1 = ns["get_next_points"](pred, gt, points, 1)
+    out2 = ns["get_next_points"](pred.flip(3), gt, out1, 2)
+    save("next_points", pred=pred, gt=gt, out1=out1, out2=out2)
+
+
 def golden_noc_driver():
     """Click sequences and IoU curves of the reference's evaluate_sample (core/inference/evaluation.py:43-88)
     with BasePredictor + ZoomIn(skip_clicks=-1) + flip (the eval_mode='fixedNNN' stack) around oracle/stubnet.py.
@@ -292,5 +318,6 @@ if __name__ == "__main__":
     golden_simple_vit()
     golden_maskclip()
     golden_nfl()
+    golden_next_points()
     golden_noc_driver()
     golden_jbu_shape()

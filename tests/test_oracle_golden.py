@@ -1,6 +1,7 @@
 """Pin the oracle (CPU restatement) against golden vectors produced by the
 UNMODIFIED reference modules (oracle/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import distmaps as odm
@@ -155,6 +156,22 @@ def test_maskclip_matches_reference(golden):
         want = torch.from_numpy(g[key])
         assert tuple(out.shape) == tuple(want.shape)
         assert float((out - want).abs().max() / want.abs().max()) < 1e-4, key
+
+
+def test_next_points_matches_reference(golden):
+    """Click simulation of the training loop (isegprobe_b200/training.get_next_points) vs the reference function's own
+    source run on the same inputs and numpy RNG state."""
+    import numpy as np
+    pytest.importorskip("cv2")
+    from isegprobe_b200.training import get_next_points
+    g = golden("next_points")
+    pred, gt = torch.from_numpy(g["pred"]), torch.from_numpy(g["gt"])
+    points = torch.full((3, 12, 3), -1.0)
+    np.random.seed(123)
+    out1 = get_next_points(pred, gt, points, 1)
+    out2 = get_next_points(pred.flip(3), gt, out1, 2)
+    assert np.array_equal(out1.numpy(), g["out1"]) and np.array_equal(out2.numpy(), g["out2"])
+    assert (out1[:, :, 2] == 1).sum() == 3 and (out2[:, :, 2] == 2).sum() == 3
 
 
 def test_nfl_loss_matches_reference(golden):
