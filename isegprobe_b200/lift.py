@@ -99,7 +99,15 @@ class LiFTUpsampler(BaseUpsampler):
         self._packed = P
         return P
 
+    _warned_train = False
+
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+        if self.training and not LiFTUpsampler._warned_train:
+            # the reference's trainer puts the frozen LiFT in train() (trainer.py:213-214): its five BatchNorm layers then use
+            # batch statistics.  Not modelled here (LoftUp's and the JBU stack's train() semantics are): eval statistics.
+            import warnings
+            warnings.warn("LiFTUpsampler.train(): BatchNorm batch statistics are not modelled; running statistics are used")
+            LiFTUpsampler._warned_train = True
         if torch.is_grad_enabled() and source.requires_grad:  # frozen weights, but the features' gradient flows through
             return _LiFTFn.apply(self, source, guidance)
         return self._forward_impl(source, guidance, None)

@@ -15,8 +15,9 @@ no_grad, head forward / backward only).
 Module modes.  The reference's trainer calls `self.net.train()` on the WHOLE model (trainer.py:213-214), which also flips
 the frozen upsampler: LoftUp's first_conv BatchNorm then uses batch statistics and updates its running statistics
 (SURVEY Q7).  `frozen_train_mode=True` reproduces that (`pipeline.train()`; LoftUpUpsampler honours `self.training`,
-pinned to the reference module in train() by tests/golden/loftup_train_28x42.npz).  LiFT's BatchNorm and the JBU stack's
-Dropout2d are NOT modelled in train() -- those two upsamplers always run with eval-mode semantics.  With
+pinned to the reference module in train() by tests/golden/loftup_train_28x42.npz; JBUFeatUpUpsampler draws FeatUp's three
+Dropout2d masks and applies them in forward and backward).  LiFT's BatchNorm batch statistics are NOT modelled (a warning is
+issued; running statistics are used).  With
 `frozen_train_mode=False` every frozen module runs in eval() and only the head (no mode-dependent layers) is in train()."""
 import torch
 

@@ -180,9 +180,21 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             cache[key] = hit
         return hit[2]
 
-    def _filters(self, up: _JBULearnedRange, guidance: torch.Tensor, GH: int, GW: int, ld: int) -> torch.Tensor:
+    def _filters(self, up: _JBULearnedRange, guidance: torch.Tensor, GH: int, GW: int, ld: int, masks=None) -> torch.Tensor:
         """Combined per-pixel 7x7 kernels of one stage from the guidance image: [B,GH,GW,ld], ld = 56 (rows padded
-        to 8, the layout isp_adaptive_conv_fwd fetches with one TMA box) or 49 (dense, for the input-gradient kernel)."""
+        to 8, the layout isp_adaptive_conv_fwd fetches with one TMA box) or 49 (dense, for the input-gradient kernel).
+        masks = (range [B,32], fixup [B,49]): train() mode -- the two Dropout2d layers' multiplicative masks.  A mask on the
+        hidden channels of `conv -> GELU -> Dropout2d -> conv` is a per-sample column scaling of the second conv's weight, so
+        the batch is processed one sample at a time with its own folded weights."""
+        if masks is not None:
+            B = guidance.shape[0]
+            filt = torch.empty(B, GH, GW, ld, dtype=torch.float32, device=guidance.device)
+            for b in range(B):
+                filt[b:b + 1] = self._filters_batch(up, guidance[b:b + 1], GH, GW, ld, (masks[0][b], masks[1][b]))
+            return filt
+        return self._filters_batch(up, guidance, GH, GW, ld)
+
+    def _filters_batch(self, up, guidance, GH, GW, ld, fold=None):
         B = guidance.shape[0]
         dev, st = guidance.device, _lib.stream_ptr()
         g = torch.empty(B, GH, GW, 4, dtype=torch.float32, device=dev)
@@ -192,20 +204,24 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         proj = torch.empty(B, GH, GW, 32, dtype=torch.float32, device=dev)
         rp, fp = up.range_proj, up.fixup_proj
         w0, b0, w1, b1 = self._flat(rp[0].weight), rp[0].bias.detach().float(), self._flat(rp[3].weight), rp[3].bias.detach().float()
+        if fold is not None:
+            w1 = (w1 * fold[0].to(w1)[None, :]).contiguous()
         _lib.call("isp_jbu_range_proj", _lib.dptr(g), _lib.dptr(proj), B * GH * GW, _lib.dptr(w0), _lib.dptr(b0),
                   _lib.dptr(w1), _lib.dptr(b1), st)
         filt = torch.empty(B, GH, GW, ld, dtype=torch.float32, device=dev)
         temp = min(max(math.exp(self._scalar(up.range_temp)), 1e-4), 1e4)
         f0, fb0, f1, fb1 = self._flat(fp[0].weight), fp[0].bias.detach().float(), self._flat(fp[3].weight), fp[3].bias.detach().float()
+        if fold is not None:
+            f1 = (f1 * fold[1].to(f1)[None, :]).contiguous()
         _lib.call("isp_jbu_filters", _lib.dptr(proj), _lib.dptr(g), _lib.dptr(filt), B, GH, GW, float(temp),
                   self._scalar(up.sigma_spatial), _lib.dptr(f0), _lib.dptr(fb0), _lib.dptr(f1), _lib.dptr(fb1), ld, st)
         return filt
 
-    def _stage(self, up: _JBULearnedRange, src: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
+    def _stage(self, up: _JBULearnedRange, src: torch.Tensor, guidance: torch.Tensor, masks=None) -> torch.Tensor:
         B, h, w, C = src.shape
         GH, GW = 2 * h, 2 * w
         dev, st = src.device, _lib.stream_ptr()
-        filt = self._filters(up, guidance, GH, GW, 56)
+        filt = self._filters(up, guidance, GH, GW, 56, masks)
         hr = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
         _lib.call("isp_jbu_bicubic2x_reflectpad", _lib.dptr(src), _lib.dptr(hr), B, h, w, C, st)
         out = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
@@ -216,6 +232,25 @@ class JBUFeatUpUpsampler(BaseUpsampler):
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
         return self.forward_resized(source, guidance, None)
 
+    dropout_masks = None  # tests: a dict of explicit masks (keys as oracle.jbu.dropout2d_masks) instead of fresh draws
+
+    def _draw_masks(self, B: int, dev):
+        """train() mode (the reference's trainer puts the frozen stack in train(), core/training/trainer.py:213-214): the
+        multiplicative masks of FeatUp's Dropout2d layers -- range_proj.2 and fixup_proj.2 of every JBULearnedRange (p = 0.1)
+        and JBUStack.fixup_proj.0 (p = 0.2) -- one Bernoulli draw per (sample, channel), kept values scaled by 1 / (1 - p)."""
+        if not self.training:
+            return None
+        if self.dropout_masks is not None:
+            return {k: v.to(dev, torch.float32) for k, v in self.dropout_masks.items()}
+
+        def m(c, p):
+            return torch.bernoulli(torch.full((B, c), 1.0 - p, device=dev)) / (1.0 - p)
+
+        out = {"final": m(self.feat_dim, 0.2)}
+        for k in range(1, 5):
+            out[f"up{k}.range"], out[f"up{k}.fixup"] = m(32, 0.1), m(49, 0.1)
+        return out
+
     def forward_resized(self, source: torch.Tensor, guidance: torch.Tensor, size=None) -> torch.Tensor:
         """`forward` followed by the bilinear (align_corners=True) resize to `size` that the reference
         applies right after the upsampler (core/model/iseg_probe_model.py:120-129).  The final
@@ -223,11 +258,12 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         combination of pixels, so they commute exactly (bias included: the weights sum to 1); doing the
         resize FIRST runs the 1x1 conv on 448^2 instead of 512^2 pixels and writes the bf16 GEMM operand
         in the resize pass.  size=None keeps the reference's 16x output."""
+        masks = self._draw_masks(source.shape[0], source.device)
         if torch.is_grad_enabled() and source.requires_grad:  # frozen stack, but the features' gradient flows through
-            return _JBUFn.apply(self, source, guidance, size)
-        return self._forward_impl(source, guidance, size)
+            return _JBUFn.apply(self, source, guidance, size, masks)
+        return self._forward_impl(source, guidance, size, masks)
 
-    def _backward_impl(self, grad_out: torch.Tensor, guidance: torch.Tensor, src_hw, size):
+    def _backward_impl(self, grad_out: torch.Tensor, guidance: torch.Tensor, src_hw, size, masks=None):
         """d(loss)/d(source) of forward_resized: the stack is linear in `source` (the 7x7 kernels depend on the guidance
         image only), so the backward is the chain of adjoints -- 1x1 conv dgrad (+ identity), resize adjoint, and per
         stage isp_adaptive_conv_grad_input followed by the bicubic / reflect-pad adjoint."""
@@ -245,14 +281,23 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             self._fixT_key = key
         M = B * OH * OW
         gb = g.view(M, C).to(torch.bfloat16)
-        dx = tc.gemm(gb, self._fixT_w, resid=g.view(M, C), alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
+        if masks is None:
+            dx = tc.gemm(gb, self._fixT_w, resid=g.view(M, C), alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
+        else:  # the forward's per-sample dropout masks: d/dx of 0.1 W (m . x) + x  =  0.1 m . (W^T g) + g
+            dx = torch.empty(B, OH, OW, C, dtype=torch.float32, device=dev)
+            WT = self._flat(conv.weight).t()
+            for b in range(B):
+                wb = tc.pack_linear_weight((WT * masks["final"][b][:, None]).contiguous()).to(dev)
+                tc.gemm(gb.view(B, OH * OW, C)[b], wb, resid=g[b].view(OH * OW, C), alpha=0.1, out_dtype=torch.float32, N=C,
+                        K=C, out=dx[b].view(OH * OW, C))
         GH, GW = 16 * src_hw[0], 16 * src_hw[1]
         if (OH, OW) != (GH, GW):
             d = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
             _lib.call("isp_bilinear_ac_nhwc_bwd", _lib.dptr(dx), _lib.dptr(d), B, C, GH, GW, OH, OW, st)
             dx = d
-        for up in (self.upsampler.up4, self.upsampler.up3, self.upsampler.up2, self.upsampler.up1):
-            filt = self._filters(up, guidance, GH, GW, 49)
+        for k, up in zip((4, 3, 2, 1), (self.upsampler.up4, self.upsampler.up3, self.upsampler.up2, self.upsampler.up1)):
+            filt = self._filters(up, guidance, GH, GW, 49,
+                                 None if masks is None else (masks[f"up{k}.range"], masks[f"up{k}.fixup"]))
             dpad = torch.empty(B, GH + 6, GW + 6, C, dtype=torch.float32, device=dev)
             _lib.call("isp_adaptive_conv_grad_input", _lib.dptr(dx), _lib.dptr(filt), _lib.dptr(dpad), B, GH, GW, C, st)
             GH, GW = GH // 2, GW // 2
@@ -260,11 +305,11 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             _lib.call("isp_jbu_bicubic2x_reflectpad_bwd", _lib.dptr(dpad), _lib.dptr(dx), B, GH, GW, C, st)
         return dx.permute(0, 3, 1, 2)
 
-    def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, size=None) -> torch.Tensor:
+    def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, size=None, masks=None) -> torch.Tensor:
         x = to_nhwc_f32(source.detach())
         guidance = guidance.detach().float()
-        for up in (self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4):
-            x = self._stage(up, x, guidance)
+        for k, up in enumerate((self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4), 1):
+            x = self._stage(up, x, guidance, None if masks is None else (masks[f"up{k}.range"], masks[f"up{k}.fixup"]))
         B, H, W, C = x.shape
         OH, OW = (H, W) if size is None else (int(size[0]), int(size[1]))
         conv = self.upsampler.fixup_proj[1]
@@ -285,8 +330,18 @@ class JBUFeatUpUpsampler(BaseUpsampler):
                 _lib.call("isp_bilinear_ac_nhwc_dual", _lib.dptr(x), _lib.dptr(xr), _lib.dptr(xb), B, C, H, W, OH, OW,
                           _lib.stream_ptr())
                 x = xr
-            out = tc.gemm(xb.view(B * OH * OW, C), self._fix_w, bias=self._fix_b, resid=x.view(B * OH * OW, C),
-                          alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
+            if masks is None:
+                out = tc.gemm(xb.view(B * OH * OW, C), self._fix_w, bias=self._fix_b, resid=x.view(B * OH * OW, C),
+                              alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
+            else:  # train(): Dropout2d(0.2) in front of the conv = a per-sample column scaling of its weight
+                out = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
+                Wf = self._flat(conv.weight)
+                for b in range(B):
+                    wb = tc.pack_linear_weight(Wf * masks["final"][b][None, :]).to(x.device)
+                    tc.gemm(xb[b].view(OH * OW, C), wb, bias=self._fix_b, resid=x[b].view(OH * OW, C), alpha=0.1,
+                            out_dtype=torch.float32, N=C, K=C, out=out[b].view(OH * OW, C))
+        elif masks is not None:
+            raise NotImplementedError("JBUFeatUpUpsampler.train() needs a channel count that is a multiple of 8")
         else:  # odd channel counts: fp32 SIMT GEMM
             if (OH, OW) != (H, W):
                 x = bilinear_align_corners_nhwc(x, (OH, OW))
@@ -300,14 +355,14 @@ class _JBUFn(torch.autograd.Function):
     """Frozen JBU stack with an input gradient for `source` (the backbone features)."""
 
     @staticmethod
-    def forward(ctx, mod, source, guidance, size):
-        ctx.mod, ctx.guidance, ctx.size = mod, guidance, size
+    def forward(ctx, mod, source, guidance, size, masks=None):
+        ctx.mod, ctx.guidance, ctx.size, ctx.masks = mod, guidance, size, masks
         ctx.src_hw = (source.shape[2], source.shape[3])
-        return mod._forward_impl(source, guidance, size)
+        return mod._forward_impl(source, guidance, size, masks)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return None, ctx.mod._backward_impl(grad_out, ctx.guidance, ctx.src_hw, ctx.size), None, None
+        return None, ctx.mod._backward_impl(grad_out, ctx.guidance, ctx.src_hw, ctx.size, ctx.masks), None, None, None
 
 
 UPSAMPLER_REGISTRY = {

@@ -69,10 +69,27 @@ def adaptive_conv_grad_input(grad_out, filters):
     return gi
 
 
-def range_kernel(sd, p, g):
+def dropout2d_masks(batch, feat_dim, seed=0):
+    """Multiplicative Dropout2d masks (0 or 1/(1-p) per sample and channel) for the stack in train() mode, keyed like the
+    call sites: up{k}.range (p=0.1, 32 channels), up{k}.fixup (p=0.1, 49 channels), final (p=0.2, feat_dim channels)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def m(c, p):
+        return (torch.rand(batch, c, generator=g) >= p).float() / (1 - p)
+
+    out = {"final": m(feat_dim, 0.2)}
+    for k in range(1, 5):
+        out[f"up{k}.range"] = m(KEY_DIM, 0.1)
+        out[f"up{k}.fixup"] = m(DIAM * DIAM, 0.1)
+    return out
+
+
+def range_kernel(sd, p, g, masks=None):
     """JBULearnedRange.get_range_kernel: softmax_49(temp * <proj(nbr), proj(centre)>)."""
     proj = F.conv2d(g, sd[p + ".range_proj.0.weight"], sd[p + ".range_proj.0.bias"])
-    proj = F.gelu(proj)  # Dropout2d(.1) is identity in eval
+    proj = F.gelu(proj)  # Dropout2d(.1): identity in eval, a per-(sample, channel) mask in train()
+    if masks is not None:
+        proj = proj * masks[p + ".range"][:, :, None, None]
     proj = F.conv2d(proj, sd[p + ".range_proj.3.weight"], sd[p + ".range_proj.3.bias"])
     B, K, H, W = proj.shape
     pp = F.pad(proj, [RADIUS] * 4, mode="reflect")
@@ -91,31 +108,35 @@ def spatial_kernel(sd, p):
     return torch.exp(-d2 / (2 * sd[p + ".sigma_spatial"] ** 2)).reshape(1, DIAM * DIAM, 1, 1)
 
 
-def combined_kernel(sd, p, g):
-    k = range_kernel(sd, p, g) * spatial_kernel(sd, p)
+def combined_kernel(sd, p, g, masks=None):
+    k = range_kernel(sd, p, g, masks) * spatial_kernel(sd, p)
     k = k / k.sum(1, keepdim=True).clamp(1e-7)
     h = F.conv2d(torch.cat([k, g], 1), sd[p + ".fixup_proj.0.weight"], sd[p + ".fixup_proj.0.bias"])
     h = F.gelu(h)
+    if masks is not None:
+        h = h * masks[p + ".fixup"][:, :, None, None]
     h = F.conv2d(h, sd[p + ".fixup_proj.3.weight"], sd[p + ".fixup_proj.3.bias"])
     k = k + 0.1 * h
     B, _, H, W = k.shape
     return k.permute(0, 2, 3, 1).reshape(B, H, W, DIAM, DIAM)
 
 
-def jbu_stage(sd, p, source, guidance):
+def jbu_stage(sd, p, source, guidance, masks=None):
     """JBUStack.upsample + JBULearnedRange.forward for one x2 stage."""
     _, _, h, w = source.shape
     g = F.adaptive_avg_pool2d(guidance, (2 * h, 2 * w))
-    filt = combined_kernel(sd, p, g)
+    filt = combined_kernel(sd, p, g, masks)
     hr = F.interpolate(source, size=(2 * h, 2 * w), mode="bicubic", align_corners=False)
     hr = F.pad(hr, [RADIUS] * 4, mode="reflect")
     return adaptive_conv(hr, filt)
 
 
-def jbu_stack_forward(sd, source, guidance):
-    """JBUStack.forward (eval): 4 stages, then fixup_proj(x)*0.1 + x."""
+def jbu_stack_forward(sd, source, guidance, masks=None):
+    """JBUStack.forward: 4 stages, then fixup_proj(x)*0.1 + x.  masks=None: eval(); masks = dropout2d_masks(...): train()
+    with those Dropout2d draws (what the reference's trainer runs on the frozen stack, trainer.py:213-214)."""
     x = source
     for k in range(1, 5):
-        x = jbu_stage(sd, f"up{k}", x, guidance)
-    y = F.conv2d(x, sd["fixup_proj.1.weight"], sd["fixup_proj.1.bias"])
+        x = jbu_stage(sd, f"up{k}", x, guidance, masks)
+    xd = x if masks is None else x * masks["final"][:, :, None, None]
+    y = F.conv2d(xd, sd["fixup_proj.1.weight"], sd["fixup_proj.1.bias"])
     return y * 0.1 + x

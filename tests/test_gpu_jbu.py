@@ -184,3 +184,38 @@ def test_layout_bilinear_gemm(isp):
     C = torch.empty(300, 50, device=DEV)
     _call("isp_gemm_f32_simt", A.to(DEV), Wt.to(DEV), b.to(DEV), R.to(DEV), 0.1, C, 300, 50, 70)
     assert relerr(C, 0.1 * (A @ Wt.T + b) + R) < 1e-5
+
+
+def test_jbu_train_mode_dropout_fwd_bwd():
+    """train() (the reference's trainer puts the frozen stack in train(), core/training/trainer.py:213-214): FeatUp's three
+    Dropout2d sites with explicit masks, forward and the input gradient vs torch autograd through the oracle with the same
+    masks; and fresh draws differ from eval()."""
+    import isegprobe_b200 as isp
+    from oracle import jbu as ojbu
+    up = isp.JBUFeatUpUpsampler("dinov2").to(DEV)
+    sd = ojbu.init_state_dict(384, seed=0)
+    up.upsampler.load_state_dict(sd)
+    B = 2
+    src = synth.lr_features(B, 384, 4, 6, seed=2)
+    gd = (synth.image_batch(B, 64, 96, seed=1) - 0.45) / 0.225
+    masks = ojbu.dropout2d_masks(B, 384, seed=7)
+    up.train()
+    up.dropout_masks = masks
+    s_d = src.to(DEV).requires_grad_(True)
+    out = up(s_d, gd.to(DEV))
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out * gout.to(DEV)).sum().backward()
+    s_o = src.clone().requires_grad_(True)
+    want = ojbu.jbu_stack_forward(sd, s_o, gd, masks)
+    (want * gout).sum().backward()
+    assert relerr(out, want) < 1e-3, relerr(out, want)
+    assert relerr(s_d.grad, s_o.grad) < 5e-3, relerr(s_d.grad, s_o.grad)
+    # eval() ignores the masks; train() with fresh draws is stochastic
+    up.eval()
+    with torch.no_grad():
+        ev = up(src.to(DEV), gd.to(DEV))
+        assert relerr(ev, ojbu.jbu_stack_forward(sd, src, gd)) < 1e-3
+        up.train()
+        up.dropout_masks = None
+        a, b = up(src.to(DEV), gd.to(DEV)), up(src.to(DEV), gd.to(DEV))
+    assert relerr(a, ev) > 1e-2 and relerr(a, b) > 1e-3

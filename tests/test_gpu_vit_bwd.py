@@ -215,7 +215,10 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
         # pipe.train() below is the trainer's net.train(): LoftUp's BatchNorm runs on batch statistics (trainer.py:213-214)
         feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"], train_stats={})
     elif up_type == "jbu_featup":
-        feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg), (H, W))
+        # pipe.train() below activates FeatUp's Dropout2d layers: the same explicit masks on both sides
+        masks = ojbu.dropout2d_masks(B, 384, seed=7)
+        pipe.upsampler.dropout_masks = masks
+        feats = ohead.bilinear_align_corners(ojbu.jbu_stack_forward(usd, lr, nimg, masks), (H, W))
     else:
         feats = ohead.bilinear_align_corners(lr, (H, W)) if up_type == "bilinear" else lr
     want = ohead.convhead_forward(hr_, feats)
