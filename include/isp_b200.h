@@ -97,10 +97,6 @@ int isp_jbu_range_proj(const float* g, float* proj, long long npix, const float*
 int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W,
                     float temp, float sigma_spatial, const float* fw0, const float* fb0,
                     const float* fw1, const float* fb1, int out_ld, isp_stream_t stream);
-/* first-generation kernel (neighbour projections read from global memory), dense [.,49] output; A/B runs */
-int isp_jbu_filters_v1(const float* proj, const float* g, float* filters, int B, int H, int W,
-                       float temp, float sigma_spatial, const float* fw0, const float* fb0,
-                       const float* fw1, const float* fb1, isp_stream_t stream);
 /* bicubic x2 (align_corners=False, A=-0.75) followed by reflect pad 3:
  * src NHWC [B,h,w,C] -> out NHWC [B,2h+6,2w+6,C] */
 int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,
@@ -113,12 +109,6 @@ int isp_jbu_bicubic2x_reflectpad_bwd(const float* gpad, float* gsrc, int B, int 
  * [B,H,W,49] (FeatUp's layout), 56 = row-padded [B,H,W,7,8] (see isp_jbu_filters). */
 int isp_adaptive_conv_fwd(const float* in_padded, const float* filters, float* out,
                           int B, int H, int W, int C, int filt_ld, isp_stream_t stream);
-/* first-generation NHWC kernel (cp.async fill, per-pixel 7x7 register window), kept for A/B runs */
-int isp_adaptive_conv_fwd_v1(const float* in_padded, const float* filters, float* out,
-                             int B, int H, int W, int C, isp_stream_t stream);
-/* same op, FeatUp's own layout (NCHW in [B,C,H+6,W+6], out [B,C,H,W]); any C */
-int isp_adaptive_conv_fwd_nchw(const float* in_padded, const float* filters, float* out,
-                               int B, int H, int W, int C, isp_stream_t stream);
 /* AdaptiveConv.backward wrt the padded input (NHWC): gi [B,H+6,W+6,C] */
 int isp_adaptive_conv_grad_input(const float* grad_out, const float* filters, float* grad_in,
                                  int B, int H, int W, int C, isp_stream_t stream);
@@ -131,7 +121,8 @@ int isp_gemm_f32_simt(const float* A, const float* W, const float* bias, const f
 /* ---- tcgen05 tensor-core GEMM (TMA -> smem ring -> tcgen05.mma -> TMEM -> epilogue) ----
  * D[M,N] = alpha * act(A[M,K] * W[N,K]^T + bias[N]) + resid[M,N]
  * A, W bf16 row-major (K contiguous; lda, ldw in elements, multiples of 8); D bf16 or f32
- * with row stride ldd >= N (columns N..ldd-1 of a written 8-column group are zeroed);
+ * with row stride N <= ldd <= round_up(N, 16): the padding columns N..ldd-1 are ZERO-FILLED, so D must own them (it cannot
+ * be a column slice of a wider matrix);
  * resid bf16 or f32 with row stride ldr, or NULL; act: 0 none, 1 ReLU, 2 GELU(erf), 3 QuickGELU,
  * 4 GELU in tanh form (one MUFU; differs from the erf form by < 5e-4, used by the bf16 pipelines).
  * Replaces the cuBLAS fp32 GEMMs under nn.Linear / Conv2d(1x1) in LoftUp

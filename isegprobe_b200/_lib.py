@@ -27,12 +27,9 @@ SIGNATURES = {
     "isp_jbu_pool_guidance": [_P, _P, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _S],
     "isp_jbu_range_proj": [_P, _P, _LL, _P, _P, _P, _P, _S],
     "isp_jbu_filters": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _I, _S],
-    "isp_jbu_filters_v1": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _S],
     "isp_jbu_bicubic2x_reflectpad": [_P, _P, _I, _I, _I, _I, _S],
     "isp_jbu_bicubic2x_reflectpad_bwd": [_P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _S],
-    "isp_adaptive_conv_fwd_v1": [_P, _P, _P, _I, _I, _I, _I, _S],
-    "isp_adaptive_conv_fwd_nchw": [_P, _P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_grad_input": [_P, _P, _P, _I, _I, _I, _I, _S],
     "isp_gemm_f32_simt": [_P, _P, _P, _P, _F, _P, _LL, _I, _I, _S],
     "isp_gemm_bf16_tc": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _F, _I, _P, _LL, _I, _LL, _I, _I, _S],

@@ -263,12 +263,7 @@ extern "C" int isp_adaptive_conv_fwd(const float* in_padded, const float* filter
     const uint64_t fstr[4] = {4, 56 * 4, (uint64_t)W * 56 * 4, (uint64_t)H * W * 56 * 4};
     const uint32_t fbox[4] = {56, ac3::TW, ac3::TH, 1};
     if (int e = make_tmap(&tmW, 4, filters, 4, fdims, fstr, fbox, "adaptive_conv_fwd(filters)", false)) return e;
-    static bool attr3 = false;
-    if (!attr3) {
-      ISP_CUDA(cudaFuncSetAttribute(ac3::adaptive_conv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ac3::kSmem));
-      attr3 = true;
-    }
+    if (int e = ensure_dynamic_smem((const void*)ac3::adaptive_conv_v3_kernel, (int)ac3::kSmem)) return e;
     ISP_REQUIRE(cdiv(H, ac3::TH) <= 65535, ISP_ERR_UNSUPPORTED, "adaptive_conv_fwd: grid too large");
     dim3 grid3(cdiv(W, ac3::TW), cdiv(H, ac3::TH), B);
     ac3::adaptive_conv_v3_kernel<<<grid3, ac3::kThreads, ac3::kSmem, as_stream(stream)>>>(tmI, tmW, out, H, W, C);
@@ -290,12 +285,7 @@ extern "C" int isp_adaptive_conv_fwd(const float* in_padded, const float* filter
     const uint32_t box[4] = {56, ac2::TW, ac2::TH, 1};
     if (int e = make_tmap(&tmF, 4, filters, 4, dims, str, box, "adaptive_conv_fwd(filters)", false)) return e;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(ac2::adaptive_conv_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ac2::kSmem));
-    attr_set = true;
-  }
+  if (int e = ensure_dynamic_smem((const void*)ac2::adaptive_conv_v2_kernel, (int)ac2::kSmem)) return e;
   dim3 grid(cdiv(W, ac2::TW), cdiv(H, ac2::TH), B);
   ac2::adaptive_conv_v2_kernel<<<grid, ac2::kThreads, ac2::kSmem, as_stream(stream)>>>(tm, tmF, filters, out, H, W, C, filt_ld);
   ISP_CHECK_LAUNCH("adaptive_conv_v2_kernel");

@@ -480,14 +480,10 @@ extern "C" int isp_attention_bwd_bf16_tc(const void* Q, long long ldq, const voi
               ISP_ERR_MISALIGNED, "attention_bwd_bf16_tc: 16-byte alignment");
   ISP_REQUIRE((long long)B * rows < (1ll << 31) && (long long)B * heads * nkeys < (1ll << 31), ISP_ERR_UNSUPPORTED,
               "attention_bwd_bf16_tc: too many rows");
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    ISP_CUDA(cudaGetDevice(&dev));
-    ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    ISP_CUDA(cudaFuncSetAttribute(attnbwd::attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attnbwd::kSmem));
-    ISP_CUDA(cudaFuncSetAttribute(attnbwd::attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attnbwd::kSmem));
-  }
+  int num_sms = 0;
+  if (int e = device_sm_count(&num_sms)) return e;
+  if (int e = ensure_dynamic_smem((const void*)attnbwd::attention_bwd_kernel<false>, (int)attnbwd::kSmem)) return e;
+  if (int e = ensure_dynamic_smem((const void*)attnbwd::attention_bwd_kernel<true>, (int)attnbwd::kSmem)) return e;
   attnbwd::Params p = {};
   p.nkeys = nkeys; p.heads = heads; p.rows = rows; p.HP = HP;
   p.nkb = (nkeys + attnbwd::BK - 1) / attnbwd::BK;

@@ -417,23 +417,14 @@ int attention_pair_launch(const void* Q, long long ldq, int q_head_stride, const
     const uint32_t box[2] = {64, (uint32_t)DV};
     if (int e = make_tmap_bf16(&tmV, Vt, 2, dims, str, box, "attention_pair(Vt)")) return e;
   }
-  constexpr int kMaxDev = 64;  // per-device launch state: one process may drive several GPUs
-  static int num_sms_dev[kMaxDev] = {};
-  static bool attr_set_dev[kMaxDev] = {};
-  int dev = 0;
-  ISP_CUDA(cudaGetDevice(&dev));
-  ISP_REQUIRE(dev >= 0 && dev < kMaxDev, ISP_ERR_UNSUPPORTED, "attention_pair: device ordinal %d", dev);
-  if (!num_sms_dev[dev]) ISP_CUDA(cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  int num_sms = 0;
+  if (int e = device_sm_count(&num_sms)) return e;
   const int smem = (int)attn2::Plan<2, DV>::kBytes;
-  if (!attr_set_dev[dev]) {
-#define ISP_ATTN2_ATTR(L, P_)                                                                                         \
-  ISP_CUDA(cudaFuncSetAttribute(attn2::attention_pair_kernel<2, 7, DV, L, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                smem))
-    ISP_ATTN2_ATTR(false, 0); ISP_ATTN2_ATTR(true, 0); ISP_ATTN2_ATTR(true, 2); ISP_ATTN2_ATTR(true, 3); ISP_ATTN2_ATTR(true, 4);
+#define ISP_ATTN2_ATTR(L, P_) \
+  if (int e = ensure_dynamic_smem((const void*)attn2::attention_pair_kernel<2, 7, DV, L, P_>, smem)) return e
+  ISP_ATTN2_ATTR(false, 0); ISP_ATTN2_ATTR(true, 0); ISP_ATTN2_ATTR(true, 2); ISP_ATTN2_ATTR(true, 3); ISP_ATTN2_ATTR(true, 4);
 #undef ISP_ATTN2_ATTR
-    attr_set_dev[dev] = true;
-  }
-  const int grid = (int)(p.nitems < num_sms_dev[dev] ? p.nitems : num_sms_dev[dev]);
+  const int grid = (int)(p.nitems < num_sms ? p.nitems : num_sms);
 #define ISP_ATTN2_GO(L, P_) \
   attn2::attention_pair_kernel<2, 7, DV, L, P_><<<grid, attn2::kThreads, smem, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p)
   if (lsum_col < 0) ISP_ATTN2_GO(false, 0);

@@ -471,25 +471,14 @@ static int attention_fwd(const void* Q, long long ldq, int q_head_stride, const 
     const uint32_t box[2] = {64, (uint32_t)DV};
     if (int e = make_tmap_bf16(&tmV, Vt, 2, dims, str, box, "attention(Vt)")) return e;
   }
-  // per-device launch state (SM count, dynamic shared-memory opt-in): one process may drive several GPUs
-  constexpr int kMaxDev = 64;
-  static int num_sms_dev[kMaxDev] = {};
-  static bool attr_set_dev[kMaxDev] = {};
-  int dev = 0;
-  ISP_CUDA(cudaGetDevice(&dev));
-  ISP_REQUIRE(dev >= 0 && dev < kMaxDev, ISP_ERR_UNSUPPORTED, "attention_bf16_tc: device ordinal %d", dev);
-  if (!num_sms_dev[dev]) ISP_CUDA(cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
-  const int num_sms = num_sms_dev[dev];
-  bool& attr_set = attr_set_dev[dev];
+  int num_sms = 0;
+  if (int e = device_sm_count(&num_sms)) return e;
   auto smem_of = [](uint32_t plan) { return (int)(plan > attn::kSmemMin ? plan : attn::kSmemMin); };
   const int sm0 = smem_of(attn::Plan<1, 64>::kBytes), sm1 = smem_of(attn::Plan<2, 112>::kBytes),
             sm2 = smem_of(attn::Plan<3, 144>::kBytes);
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<1, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm0));
-    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<2, 7, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1));
-    ISP_CUDA(cudaFuncSetAttribute(attn::attention_kernel<3, 9, 144>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
-    attr_set = true;
-  }
+  if (int e = ensure_dynamic_smem((const void*)attn::attention_kernel<1, 4, 64>, sm0)) return e;
+  if (int e = ensure_dynamic_smem((const void*)attn::attention_kernel<2, 7, 112>, sm1)) return e;
+  if (int e = ensure_dynamic_smem((const void*)attn::attention_kernel<3, 9, 144>, sm2)) return e;
   const int grid = (int)(p.nitems < num_sms ? p.nitems : num_sms);
   if (variant == 2)
     attn::attention_kernel<3, 9, 144><<<grid, attn::kThreads, sm2, as_stream(stream)>>>(tmQ, tmK, tmV, tmO, p);

@@ -15,6 +15,11 @@ namespace isp {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Per-device launch state (api.cu).  One process may drive several GPUs, so nothing about a device is cached in a
+// process-wide static: the SM count is looked up per current device, and the > 48 KB dynamic shared-memory opt-in of a
+// kernel is applied once per (device, kernel).  Both are thread-safe.  Return 0 / an ISP_ERR_* code (error text set).
+int device_sm_count(int* sms);
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 #define ISP_REQUIRE(cond, code, ...)          \
   do {                                        \

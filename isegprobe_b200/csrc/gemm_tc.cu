@@ -19,6 +19,8 @@
 //               W is [Cout, 9*Cin_pad] with k = (r*3+s)*Cin_pad + c.
 // Replaces: cuDNN/cuBLAS fp32 calls under nn.Conv2d / nn.Linear in LoftUp, ConvSegHead and
 // the ViT blocks.
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace isp {
@@ -650,27 +652,21 @@ static kernel_fn pick_kernel(int out_bf16, int act, bool resid) {
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmDt,
                   const CUtensorMap& tmR, const CUtensorMap& tmRt, const CUtensorMap& tmBh, Params& p, int out_bf16,
                   int act, bool resid, cudaStream_t stream) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    ISP_CUDA(cudaGetDevice(&dev));
-    ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  if (int e = device_sm_count(&num_sms)) return e;
   // pairing halves the number of work units: only when there are at least two waves of pairs
   if (p.pair && (p.batched || (p.tiles_m & 1) || (p.tiles_m / 2) * p.tiles_n < 2LL * num_sms)) p.pair = 0;
-  auto prepare = [](kernel_fn f) -> int {  // opt in to 224 KB of dynamic shared memory, once per instantiation
-    static kernel_fn attr_done[64];
-    static int n_attr = 0;
-    for (int i = 0; i < n_attr; ++i)
-      if (attr_done[i] == f) return ISP_OK;
-    ISP_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    if (n_attr < 64) attr_done[n_attr++] = f;
-    return ISP_OK;
+  auto prepare = [](kernel_fn f) -> int {  // opt in to 224 KB of dynamic shared memory, once per (device, instantiation)
+    return ensure_dynamic_smem((const void*)f, kSmemBytes);
   };
   // CTA-pair mode: tiles per cluster unit divide tiles_m (the weight tile always splits into two swizzle-aligned
   // halves: BN % 16 == 0) and there are at least two waves of cluster units
-  static int max_clusters = -1;  // co-resident 2-CTA clusters of the pair kernel (224 KB smem: one CTA per SM)
-  static const int cta2_env = getenv("ISP_GEMM_CTA2") ? atoi(getenv("ISP_GEMM_CTA2")) : 1;
+  // co-resident 2-CTA clusters of the pair kernel (224 KB smem: one CTA per SM); queried once per device
+  static std::atomic<int> max_clusters_dev[64];  // zero-initialised: 0 = not queried yet, else the count + 1
+  int dev = 0;
+  ISP_CUDA(cudaGetDevice(&dev));
+  ISP_REQUIRE(dev >= 0 && dev < 64, ISP_ERR_UNSUPPORTED, "gemm_tc: device ordinal %d", dev);
+  int max_clusters = max_clusters_dev[dev].load() - 1;
   if (max_clusters < 0) {
     kernel_fn f2 = pick_kernel<true>(out_bf16, act, resid);
     if (int e = prepare(f2)) return e;
@@ -683,9 +679,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, f2, &q) != cudaSuccess) { n = 0; cudaGetLastError(); }
     max_clusters = n;
+    max_clusters_dev[dev].store(n + 1);
   }
   const int G = 2 << p.pair;
-  p.cta2 = (cta2_env && !p.batched && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
+  p.cta2 = (!p.batched && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
             (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters) ? 1 : 0;
   const int stage_bytes = (BM * BK * 2 << p.pair) + (p.BN >> p.cta2) * BK * 2;
   p.epi_bufs = (p.pair && !resid) ? 1 : 2;
@@ -728,6 +725,11 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
   ISP_REQUIRE(A && W && D, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: null pointer");
   ISP_REQUIRE(M > 0 && N > 0 && K > 0, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: bad shape M=%lld N=%d K=%d", M, N, K);
   ISP_REQUIRE(lda >= K && ldw >= K && ldd >= N, ISP_ERR_BAD_SHAPE, "gemm_bf16_tc: leading dimensions too small");
+  // the epilogue stores whole 32 / 64-column chunks, clipped at column ldd by the tensor map, with columns >= N zeroed: a D
+  // that is a column slice of a wider matrix (ldd beyond the padding of N) would have its neighbours overwritten with zeros
+  ISP_REQUIRE(ldd <= (N + 15) / 16 * 16, ISP_ERR_BAD_SHAPE,
+              "gemm_bf16_tc: ldd = %lld exceeds N = %d rounded up to 16: D[:, N:ldd) is zero-filled, so D must own its padding "
+              "columns (not be a column slice of a wider matrix)", ldd, N);
   ISP_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, ISP_ERR_MISALIGNED,
               "gemm_bf16_tc: lda/ldw must be multiples of 8 elements (TMA 16-byte strides), got %lld/%lld", lda, ldw);
   const int esz = out_bf16 ? 2 : 4;

@@ -75,153 +75,6 @@ __global__ void __launch_bounds__(128) range_proj_kernel(const float4* __restric
   for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
 }
 
-// ---------------------------------------------------------------------------
-// Combined 7x7 kernel per pixel.  One thread per pixel (linear over B*H*W so a
-// block's 128 pixels own one contiguous 128*49-float slab of `filters`).
-//   phase 1 (registers): 49 range logits = temp * <proj[nbr], proj[centre]>, softmax,
-//            * spatial Gaussian, renormalise -> k[49]
-//   phase 2 (outer-product MLP): vector in smem [c][tid] (stride 129: conflict-free both
-//            for the per-thread column walk and for the transposed final copy), weights
-//            broadcast from smem as float4, 49 register accumulators.
-constexpr int kFT = 128;        // threads / pixels per block
-constexpr int kVS = kFT + 1;    // smem row stride of the per-thread vectors
-constexpr int kWP = 52;         // padded weight row (49 -> 52 floats = 13 float4)
-
-struct FilterSmem {
-  float v[52 * kVS];            // input vector [k(49), g(3)] then hidden, then output
-  float w0t[52 * kWP];          // fixup_proj.0 transposed: [c][r]
-  float w1t[49 * kWP];          // fixup_proj.3 transposed: [c][r]
-  float b0[kWP], b1[kWP];
-  float spatial[kWP];
-};
-
-__global__ void __launch_bounds__(kFT) jbu_filters_kernel(const float* __restrict__ proj, const float4* __restrict__ g,
-                                                          float* __restrict__ filters, int B, int H, int W, float temp,
-                                                          float inv2s2, const float* __restrict__ fw0,
-                                                          const float* __restrict__ fb0, const float* __restrict__ fw1,
-                                                          const float* __restrict__ fb1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FilterSmem& S = *reinterpret_cast<FilterSmem*>(smem_raw);
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 52 * kWP; i += kFT) {
-    const int c = i / kWP, r = i % kWP;
-    S.w0t[i] = (r < 49) ? fw0[r * 52 + c] : 0.f;
-  }
-  for (int i = tid; i < 49 * kWP; i += kFT) {
-    const int c = i / kWP, r = i % kWP;
-    S.w1t[i] = (r < 49) ? fw1[r * 49 + c] : 0.f;
-  }
-  for (int i = tid; i < kWP; i += kFT) {
-    S.b0[i] = (i < 49) ? fb0[i] : 0.f;
-    S.b1[i] = (i < 49) ? fb1[i] : 0.f;
-    float sp = 0.f;
-    if (i < 49) {  // linspace(-1,1,7): -1 + k/3
-      const float dy = -1.f + (float)(i / 7) * (1.f / 3.f), dx = -1.f + (float)(i % 7) * (1.f / 3.f);
-      sp = expf(-(dy * dy + dx * dx) * inv2s2);
-    }
-    S.spatial[i] = sp;
-  }
-  __syncthreads();
-
-  const long long npix = (long long)B * H * W;
-  const long long pix0 = (long long)blockIdx.x * kFT;
-  const long long pix = pix0 + tid;
-  const bool live = pix < npix;
-  if (live) {
-    const int x = (int)(pix % W), y = (int)((pix / W) % H);
-    const long long img = pix / ((long long)W * H);
-    const float4* pc = reinterpret_cast<const float4*>(proj + pix * 32);
-    float4 ctr[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) ctr[q] = pc[q];
-    float k[49];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int yy = reflect_idx(y + i - 3, H);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int xx = reflect_idx(x + j - 3, W);
-        const float4* pn = reinterpret_cast<const float4*>(proj + ((img * H + yy) * W + xx) * 32);
-        float d = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 n = __ldg(pn + q);
-          d = fmaf(n.x, ctr[q].x, d);
-          d = fmaf(n.y, ctr[q].y, d);
-          d = fmaf(n.z, ctr[q].z, d);
-          d = fmaf(n.w, ctr[q].w, d);
-        }
-        d *= temp;
-        k[i * 7 + j] = d;
-        mx = fmaxf(mx, d);
-      }
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int t = 0; t < 49; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
-    const float inv = 1.f / sum;
-    float sum2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 49; ++t) { k[t] = (k[t] * inv) * S.spatial[t]; sum2 += k[t]; }
-    sum2 = fmaxf(sum2, 1e-7f);
-#pragma unroll
-    for (int t = 0; t < 49; ++t) S.v[t * kVS + tid] = k[t] / sum2;
-    const float4 gv = g[pix];
-    S.v[49 * kVS + tid] = gv.x;
-    S.v[50 * kVS + tid] = gv.y;
-    S.v[51 * kVS + tid] = gv.z;
-  }
-  // layer 0: h = GELU(W0 [k;g] + b0)   (each thread only touches its own column of S.v)
-  float acc[kWP];
-  if (live) {
-#pragma unroll
-    for (int r = 0; r < kWP; ++r) acc[r] = S.b0[r];
-    for (int c = 0; c < 52; ++c) {
-      const float vc = S.v[c * kVS + tid];
-      const float4* wr = reinterpret_cast<const float4*>(&S.w0t[c * kWP]);
-#pragma unroll
-      for (int q = 0; q < 13; ++q) {
-        const float4 w = wr[q];
-        acc[q * 4 + 0] = fmaf(w.x, vc, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(w.y, vc, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(w.z, vc, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(w.w, vc, acc[q * 4 + 3]);
-      }
-    }
-    float kk[49];  // keep k to add the fixup onto; re-read before overwriting with the hidden vector
-#pragma unroll
-    for (int t = 0; t < 49; ++t) kk[t] = S.v[t * kVS + tid];
-#pragma unroll
-    for (int r = 0; r < 49; ++r) S.v[r * kVS + tid] = gelu_erf(acc[r]);
-    // layer 1: o = W1 h + b1 ; out = k + 0.1 * o
-#pragma unroll
-    for (int r = 0; r < kWP; ++r) acc[r] = S.b1[r];
-    for (int c = 0; c < 49; ++c) {
-      const float vc = S.v[c * kVS + tid];
-      const float4* wr = reinterpret_cast<const float4*>(&S.w1t[c * kWP]);
-#pragma unroll
-      for (int q = 0; q < 13; ++q) {
-        const float4 w = wr[q];
-        acc[q * 4 + 0] = fmaf(w.x, vc, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(w.y, vc, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(w.z, vc, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(w.w, vc, acc[q * 4 + 3]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 49; ++t) S.v[t * kVS + tid] = fmaf(0.1f, acc[t], kk[t]);
-  }
-  __syncthreads();
-  // coalesced copy-out: element e of the block's slab = (pixel e/49, tap e%49)
-  const long long nlive = min((long long)kFT, npix - pix0);
-  float* dst = filters + pix0 * 49;
-  for (int e = tid; e < nlive * 49; e += kFT) dst[e] = S.v[(e % 49) * kVS + (e / 49)];
-}
-
-// ---------------------------------------------------------------------------
-// bicubic x2 (align_corners=False, A=-0.75, border clamp) + reflect pad 3, NHWC.
-// thread = (padded pixel, 4 channels).  ATen: src = (dst+0.5)*0.5-0.5, taps floor-1..floor+2.
 __device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
   const float A = -0.75f;
   float x = t + 1.f;
@@ -273,79 +126,7 @@ __global__ void __launch_bounds__(256) bicubic2x_pad_kernel(const float* __restr
   reinterpret_cast<float4*>(out)[idx] = acc;
 }
 
-// Second-generation bicubic x2: one thread produces a 2 (rows) x 4 (cols) block of outputs for
-// 4 channels from a 5 x 6 low-res neighbourhood (3.75 loads per output instead of 16), separable
-// (horizontal then vertical), written straight into the interior of the padded buffer.  The
-// 3-pixel reflect frame is filled afterwards by reflect_border_kernel from that interior.
-__global__ void __launch_bounds__(256, 3) bicubic2x_interior_kernel(const float* __restrict__ src, float* __restrict__ out,
-                                                                 int B, int h, int w, int C) {
-  const int C4 = C / 4, wp = (w + 1) / 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * h * wp * C4;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  long long p = idx / C4;
-  const int lp = (int)(p % wp);
-  p /= wp;
-  const int k = (int)(p % h), b = (int)(p / h);
-  const int l0 = 2 * lp;
-  float cE[4], cO[4];
-  cubic_coeffs(0.75f, cE);  // even outputs: src = k - 0.25 -> floor k-1, t = 0.75
-  cubic_coeffs(0.25f, cO);  // odd outputs:  src = k + 0.25 -> floor k,   t = 0.25
-  const float4* s4 = reinterpret_cast<const float4*>(src) + (long long)b * h * w * C4 + c4;
-  float4 o[2][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[a][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    const int yy = min(max(k - 2 + r, 0), h - 1);
-    float4 v[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int xx = min(max(l0 - 2 + j, 0), w - 1);
-      v[j] = __ldg(s4 + ((long long)yy * w + xx) * C4);
-    }
-    float4 hh[4];  // horizontal results for output cols 2*l0, 2*l0+1, 2*l0+2, 2*l0+3
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float* cc = (q & 1) ? cO : cE;
-      const int o0 = (q >> 1) + (q & 1);  // first tap index into v[]: 0,1,1,2
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a.x = fmaf(v[o0 + j].x, cc[j], a.x);
-        a.y = fmaf(v[o0 + j].y, cc[j], a.y);
-        a.z = fmaf(v[o0 + j].z, cc[j], a.z);
-        a.w = fmaf(v[o0 + j].w, cc[j], a.w);
-      }
-      hh[q] = a;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (r <= 3) {
-        o[0][q].x = fmaf(hh[q].x, cE[r], o[0][q].x); o[0][q].y = fmaf(hh[q].y, cE[r], o[0][q].y);
-        o[0][q].z = fmaf(hh[q].z, cE[r], o[0][q].z); o[0][q].w = fmaf(hh[q].w, cE[r], o[0][q].w);
-      }
-      if (r >= 1) {
-        o[1][q].x = fmaf(hh[q].x, cO[r - 1], o[1][q].x); o[1][q].y = fmaf(hh[q].y, cO[r - 1], o[1][q].y);
-        o[1][q].z = fmaf(hh[q].z, cO[r - 1], o[1][q].z); o[1][q].w = fmaf(hh[q].w, cO[r - 1], o[1][q].w);
-      }
-    }
-  }
-  const int PW = 2 * w + 6, PH = 2 * h + 6;
-  float4* o4 = reinterpret_cast<float4*>(out) + (long long)b * PH * PW * C4 + c4;
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ox = 2 * l0 + q;
-      if (ox < 2 * w) o4[((long long)(2 * k + a + 3) * PW + ox + 3) * C4] = o[a][q];
-    }
-}
-
-// Third generation: the thread marches down a strip of kMarchR low-res rows for its 4 output columns x 4 channels.
+// Interior of the bicubic x2 output: the thread marches down a strip of kMarchR low-res rows for its 4 output columns x 4 channels.
 // Every low-res row is loaded once per strip (6 float4) and filtered horizontally once; the last five horizontal
 // results stay in registers and produce two output rows per step (1.1 loads per output float4 instead of 3.75;
 // ncu on the 2x4-blocked kernel: 44 % of the stalls were the loads).  Same summation order as the blocked kernel.
@@ -547,26 +328,6 @@ extern "C" int isp_jbu_bicubic2x_reflectpad_bwd(const float* gpad, float* gsrc, 
   const long long total = (long long)B * h * w * (C / 4);
   bicubic2x_pad_bwd_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(gpad, gsrc, B, h, w, C);
   ISP_CHECK_LAUNCH("bicubic2x_pad_bwd_kernel");
-  return ISP_OK;
-}
-
-extern "C" int isp_jbu_filters_v1(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
-                               float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
-                               const float* fb1, isp_stream_t stream) {
-  ISP_REQUIRE(proj && g && filters && fw0 && fb0 && fw1 && fb1, ISP_ERR_BAD_SHAPE, "jbu_filters: null pointer");
-  ISP_REQUIRE(B > 0 && H >= 4 && W >= 4, ISP_ERR_BAD_SHAPE, "jbu_filters: need H,W >= 4 (reflect pad 3), got %dx%d", H, W);
-  ISP_REQUIRE(aligned16(proj) && aligned16(g), ISP_ERR_MISALIGNED, "jbu_filters: pointers must be 16-byte aligned");
-  static bool attr_set = false;
-  const int smem = (int)sizeof(FilterSmem);
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(jbu_filters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  const long long npix = (long long)B * H * W;
-  const float inv2s2 = 1.f / (2.f * sigma_spatial * sigma_spatial);
-  jbu_filters_kernel<<<cdiv(npix, kFT), kFT, smem, as_stream(stream)>>>(proj, reinterpret_cast<const float4*>(g),
-                                                                       filters, B, H, W, temp, inv2s2, fw0, fb0, fw1, fb1);
-  ISP_CHECK_LAUNCH("jbu_filters_kernel");
   return ISP_OK;
 }
 

@@ -254,14 +254,10 @@ extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters
   ISP_REQUIRE(out_ld == 49 || out_ld == 56, ISP_ERR_BAD_SHAPE, "jbu_filters: out_ld must be 49 or 56 (got %d)", out_ld);
   ISP_REQUIRE(aligned16(proj) && aligned16(g), ISP_ERR_MISALIGNED, "jbu_filters: pointers must be 16-byte aligned");
   ISP_REQUIRE(B <= 65535 && cdiv(H, jf2::A_TH) <= 65535, ISP_ERR_UNSUPPORTED, "jbu_filters: grid too large");
-  static bool attr_set = false;
   const int smemA = (int)sizeof(jf2::SmemA), smemB = (int)sizeof(jf2::SmemB);
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA));
-    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_fixup_kernel<49>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
-    ISP_CUDA(cudaFuncSetAttribute(jf2::jbu_fixup_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB));
-    attr_set = true;
-  }
+  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_range_kernel, smemA)) return e;
+  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_fixup_kernel<49>, smemB)) return e;
+  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_fixup_kernel<56>, smemB)) return e;
   const float inv2s2 = 1.f / (2.f * sigma_spatial * sigma_spatial);
   dim3 gridA(cdiv(W, jf2::A_TW), cdiv(H, jf2::A_TH), B);
   jf2::jbu_range_kernel<<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2, out_ld);

@@ -208,17 +208,9 @@ extern "C" int isp_conv3x3_wgrad_bf16_tc(const void* X, int ldx, const void* dY,
   p.wchunks = (Wd + wgrad::KPIX - 1) / wgrad::KPIX;
   p.kblocks = (long long)Nimg * H * p.wchunks;
   p.dW = dW;
-  static int num_sms = 0;
-  static bool attr_set = false;
-  if (!num_sms) {
-    int dev = 0;
-    ISP_CUDA(cudaGetDevice(&dev));
-    ISP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  if (!attr_set) {
-    ISP_CUDA(cudaFuncSetAttribute(wgrad::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::kBudget));
-    attr_set = true;
-  }
+  int num_sms = 0;
+  if (int e = device_sm_count(&num_sms)) return e;
+  if (int e = ensure_dynamic_smem((const void*)wgrad::wgrad_tc_kernel, wgrad::kBudget)) return e;
   const int stage_bytes = (2 + p.BN / 64) * wgrad::KPIX * 128;
   p.stages = wgrad::kBudget / stage_bytes;
   if (p.stages > wgrad::kMaxStages) p.stages = wgrad::kMaxStages;
