@@ -183,6 +183,18 @@ int isp_head_classifier_bwd(const void* act_bf16, long long lda, const float* dl
                             isp_stream_t stream);
 int isp_colsum_bf16(const void* x_bf16, long long ld, float* out, long long M, int C, isp_stream_t stream);
 
+/* LoftUp FeedForward block (loftup/layers.py:161-174: x + Linear2(GELU(Linear1(LayerNorm(x))))) in one tcgen05 kernel: the
+ * [128 x NH] hidden tile of a row block stays in shared memory (A operand of the second GEMM), so the hidden activations
+ * never reach HBM.  LayerNorm folded as in isp_gemm_bf16_tc_ex: W1g = W1 * gamma (bf16 [NH, ldw1]), g1[n] = sum_k W1g[n,k],
+ * b1 = W1 beta + bias1; ln_stats fp32 [M][ln_slots][2] = partial (sum, sum of squares) of every x row.  x bf16 [M, ldx]
+ * (K1 real columns, padding zero, ldx <= 448); NH <= 384, multiple of 64; W2 bf16 [N2, ldw2], N2 <= 416; out bf16 [M, ldo]
+ * with N2 <= ldo <= round_up(N2, 16) (padding zero-filled); GELU in tanh form (act 4 of isp_gemm_bf16_tc).
+ * stats_out (or NULL): fp32 [M][4][2] partial (sum, sum of squares) of every stored output row (ln_slots = 4 downstream). */
+int isp_ffn_fused_bf16_tc(const void* x, long long ldx, int K1, const void* W1g, long long ldw1, const float* g1,
+                          const float* b1, int NH, const void* W2, long long ldw2, const float* b2, int N2, void* out,
+                          long long ldo, long long M, const float* ln_stats, int ln_slots, float ln_eps, float* stats_out,
+                          isp_stream_t stream);
+
 /* Device side of the NoC evaluation loop, one sample per call, fp32.
  * isp_zoom_in_fwd: ZoomIn._transform + AddHorizontalFlip.transform (core/inference/transforms/zoom_in.py:51-104,216-240,
  *   flip.py:13-29): out [with_flip ? 2 : 1][4][S0][S1] = bilinear (align_corners=True) resize of the ROI rows rmin..rmax, columns

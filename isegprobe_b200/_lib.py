@@ -41,6 +41,7 @@ SIGNATURES = {
     "isp_conv3x3_wgrad_bf16_tc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _S],
     "isp_head_classifier_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _LL, _I, _S],
     "isp_colsum_bf16": [_P, _LL, _P, _LL, _I, _S],
+    "isp_ffn_fused_bf16_tc": [_P, _LL, _I, _P, _LL, _P, _P, _I, _P, _LL, _P, _I, _P, _LL, _LL, _P, _I, _F, _P, _S],
     "isp_zoom_in_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _S],
     "isp_unzoom_probs": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _F, _F, _P, _P, _S],
     "isp_noc_next_click": [_P, _P, _P, _I, _I, _P, _P, _S],

@@ -98,3 +98,18 @@ def conv3x3(x, w_packed, bias, cin, cout, act="relu", out_dtype=torch.bfloat16, 
                   int(out_dtype == torch.bfloat16), B, H, W, cin, ldx, cout, ldy, _lib.dptr(stats_out),
                   stats_out.shape[1], _lib.stream_ptr())
     return y
+
+
+def ffn_fused(x, W1g, g1, b1, W2, b2, K1, N2, ln_stats, ln_eps=1e-5, ldo=None, want_stats=True):
+    """out = x + Linear2(GELU(Linear1(LayerNorm(x)))) in one kernel (isp_ffn_fused_bf16_tc).  x bf16 [M, ldx]; W1g / g1 / b1
+    from pack_ln_linear; W2 bf16 [N2, K8]; ln_stats [M, slots, 2].  Returns (out bf16 [M, ldo], stats [M, 4, 2] or None)."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    M = x.shape[0]
+    NH = W1g.shape[0]
+    ldo = round_up(N2, 16) if ldo is None else ldo
+    out = torch.empty(M, ldo, dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty(M, 4, 2, dtype=torch.float32, device=x.device) if want_stats else None
+    _lib.call("isp_ffn_fused_bf16_tc", _lib.dptr(x), x.stride(0), int(K1), _lib.dptr(W1g), W1g.stride(0), _lib.dptr(g1),
+              _lib.dptr(b1), int(NH), _lib.dptr(W2), W2.stride(0), _lib.dptr(b2), int(N2), _lib.dptr(out), ldo, M,
+              _lib.dptr(ln_stats), ln_stats.shape[1], float(ln_eps), _lib.dptr(stats), _lib.stream_ptr())
+    return out, stats

@@ -105,6 +105,21 @@ def test_loftup_state_dict_matches_reference_layout():
     m.load_reference_checkpoint(ckpt)
 
 
+def test_loftup_fused_ffn_matches_two_gemm_path():
+    """fuse_ffn (isp_ffn_fused_bf16_tc: the FeedForward block in one kernel) computes the same function as the two GEMM
+    launches; both within the bf16 tolerance of the oracle."""
+    m, sd, cn = _module()
+    img = (synth.image_batch(2, 64, 96, seed=1) - 0.45) / 0.225
+    lr = synth.lr_features(2, 384, 8, 12, seed=2)
+    with torch.no_grad():
+        a = m(source=lr.to(DEV), guidance=img.to(DEV)).float()
+        m.fuse_ffn = True
+        b = m(source=lr.to(DEV), guidance=img.to(DEV)).float()
+        want = oloft.loftup_forward(sd, lr, img, cn["norm.weight"], cn["norm.bias"])
+    assert cosine(a, b) > 0.9999 and relerr(a, b) < 3e-2
+    assert cosine(b, want) >= 0.999
+
+
 def test_loftup_fused_layernorm_matches_unfused():
     """LayerNorm applied in the consuming GEMM's epilogue (default) vs the stand-alone LayerNorm kernel: same
     function, different bf16 rounding points; both must sit within the bf16 tolerance of the oracle."""

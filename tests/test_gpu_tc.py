@@ -146,3 +146,38 @@ def test_conv3x3_paired_tiles(tc, B, H, W, Cin, Cout):
                   _lib.dptr(dx), 1, B, H, W, Cout, Cout, Cin, Cin, _lib.stream_ptr())
         wantd = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1) * (act.float() > 0)
         assert relerr(dx.float(), wantd) < 1e-2 and cosine(dx.float(), wantd) > 0.9999
+
+
+@pytest.mark.parametrize("M", [128, 1000, 4096 + 37])
+def test_ffn_fused_matches_two_gemms_and_fp32(M):
+    """isp_ffn_fused_bf16_tc (LoftUp FeedForward, loftup/layers.py:161-174) vs the two-launch path it replaces (same fused
+    LayerNorm, same tanh-form GELU: identical rounding points except that the hidden tile is rounded to bf16 in both) and vs
+    the fp32 torch expression; row statistics of the output."""
+    import torch.nn.functional as F
+    from isegprobe_b200 import tc
+    D, C, Dp = 404, 384, 416
+    g = torch.Generator().manual_seed(M)
+    x = torch.zeros(M, Dp)
+    x[:, :D] = torch.randn(M, D, generator=g)
+    xb = x.to(torch.bfloat16).to(DEV)
+    gamma, beta = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    W1, b1 = torch.randn(C, D, generator=g) * D ** -0.5, 0.1 * torch.randn(C, generator=g)
+    W2, b2 = torch.randn(D, C, generator=g) * C ** -0.5, 0.1 * torch.randn(D, generator=g)
+    W1g, g1, b1f = [t.to(DEV) for t in tc.pack_ln_linear(W1, b1, gamma, beta)]
+    W2p, b2d = tc.pack_linear_weight(W2).to(DEV), b2.to(DEV)
+    xf = xb.float()[:, :D]
+    st = torch.zeros(M, 3, 2, device=DEV)  # three slots, as a producer GEMM would write them
+    st[:, 0, 0], st[:, 0, 1] = xf.sum(1), (xf * xf).sum(1)
+    out, stats = tc.ffn_fused(xb, W1g, g1, b1f, W2p, b2d, D, D, st)
+    # the two-launch path
+    h1 = tc.gemm(xb, W1g, bias=b1f, act="gelu_tanh", out_dtype=torch.bfloat16, N=C, K=D, ln_stats=st, ln_g=g1, ln_eps=1e-5)
+    st2 = torch.empty(M, tc.stats_slots(D, torch.bfloat16, True), 2, device=DEV)
+    want2 = tc.gemm(h1, W2p, bias=b2d, resid=xb, out_dtype=torch.bfloat16, N=D, K=C, ldd=Dp, stats_out=st2)
+    assert tuple(out.shape) == (M, Dp) and float(out[:, D:].float().abs().max()) == 0.0
+    assert relerr(out[:, :D].float(), want2[:, :D].float()) < 1e-2
+    # fp32 reference of the block
+    ref = xf.cpu() + F.linear(F.gelu(F.linear(F.layer_norm(xf.cpu(), (D,), gamma, beta, 1e-5), W1, b1)), W2, b2)
+    assert relerr(out[:, :D].float(), ref) < 2e-2 and cosine(out[:, :D].float(), ref) > 0.9999
+    # statistics of the stored rows
+    of = out.float()[:, :D]
+    assert relerr(stats.sum(1)[:, 0], of.sum(1)) < 1e-4 and relerr(stats.sum(1)[:, 1], (of * of).sum(1)) < 1e-4

@@ -6,8 +6,9 @@ torch.manual_seed(0)
 pipe = isp.ISegPipeline("loftup", {"upsampler_path": None, "n_dim": 384}, with_head=True).to(dev).eval()
 img, pts = bench.synth_inputs(32, 1)
 img, pts = img.to(dev), pts.to(dev)
-for ci in (4, 8, 16):
+for ci, ff in ((4, False), (4, True)):
     pipe.upsampler.chunk_images = ci
+    pipe.upsampler.fuse_ffn = ff
     pipe.__dict__.pop("_graphs", None)
     for _ in range(3):
         pipe.features_graphed(img, pts)
@@ -18,5 +19,5 @@ for ci in (4, 8, 16):
         pipe.features_graphed(img, pts)
     e1.record()
     torch.cuda.synchronize()
-    print(json.dumps({"chunk_images": ci, "ms_per_step": e0.elapsed_time(e1) / 8, "img_s": 32 * 8 / e0.elapsed_time(e1) * 1e3,
+    print(json.dumps({"chunk_images": ci, "fuse_ffn": ff, "ms_per_step": e0.elapsed_time(e1) / 8, "img_s": 32 * 8 / e0.elapsed_time(e1) * 1e3,
                       "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
