@@ -61,14 +61,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 namespace gemm {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter (they split the chunks)
-constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+#ifndef ISP_GEMM_EPI_WARPS
+#define ISP_GEMM_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = ISP_GEMM_EPI_WARPS;      // kParts warps per TMEM lane quarter (they split the chunks of its 32 rows)
+constexpr int kParts = kEpiWarps / 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kEpiBytesPerWarp = 2 * 4096;         // two staging chunks of 32 rows x 128 B
-constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
-constexpr int kMainBudget = 160 * 1024;
-constexpr int kSmemBytes = kMainBudget + kEpiBytes;  // 224 KB: also forces one CTA per SM (TMEM: 512 columns)
+constexpr int kSmemBytes = 224 * 1024;             // operand ring + epilogue staging (4 KB chunks of 32 rows x 128 B, one or
+                                                   // two per epilogue warp); also forces one CTA per SM (TMEM: 512 columns)
 
 struct Params {
   long long M;        // rows (GEMM) or Nimg*H*W (conv)
@@ -88,6 +90,11 @@ struct Params {
                       // loads its own 128 A rows and only HALF of the weight tile, the tensor cores read both halves.
                       // Per-SM operand fill per MAC x0.67 (x0.78 on top of pair mode) -- the fill rate (~49 B/clk/SM)
                       // is what bounds these kernels -- while every CTA keeps its own accumulators and epilogue.
+  int wres;           // 1 (CTA-pair GEMM with a short reduction): the CTA's share of the weight tile, all k-blocks of it, is loaded
+                      // ONCE and stays in shared memory; every cluster works on one column tile only and streams just the A
+                      // rows.  Per 128 x 208 tile that is 115 KB instead of 208 KB through the ~49 B/clk L2->SM port, which is
+                      // what bounded the K ~ 400 GEMMs of the LoftUp transformer (not HBM, not the tensor pipe)
+  int dbg;            // timing experiments (ISP_GEMM_DBG): 1 no TMA store, 2 no tcgen05.ld, 4 no st.shared, 8 no item body at all
   int epi_bufs;       // staging chunks per epilogue warp: 2, or 1 (pair mode without residual: the 32 KB go to a third
                       // pipeline stage instead)
   int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
@@ -198,13 +205,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t resid_bar[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t wfull_bar;
   __shared__ __align__(16) float bias_s[256], lng_s[256];  // single-buffered: two epilogue barriers per tile
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_half = BM * BK * 2;
   // this CTA's share of the weight tile: all of it, or (CTA pair) its half
-  const uint32_t a_bytes = a_half << p.pair, b_bytes = ((uint32_t)p.BN >> (CTA2 ? 1 : 0)) * BK * 2, stage_bytes = a_bytes + b_bytes;
+  const uint32_t a_bytes = a_half << p.pair, b_bytes = ((uint32_t)p.BN >> (CTA2 ? 1 : 0)) * BK * 2;
+  const uint32_t stage_bytes = a_bytes + (p.wres ? 0u : b_bytes);
   // work unit of a CTA = one tile, or (pair mode) two vertically adjacent tiles; the two CTAs of a CTA pair take
   // adjacent units of the same column tile.  tiles_m is a multiple of the tiles per cluster unit.
   const uint32_t crank = CTA2 ? tc::cluster_ctarank() : 0u;
@@ -216,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
   const int kblocks = p.K / BK;
   uint8_t* epi_smem = smem + kSmemBytes - kEpiWarps * 4096 * p.epi_bufs;
+  uint8_t* wres_smem = epi_smem - (size_t)kblocks * b_bytes;  // resident weights (wres): k-block kb at + kb * b_bytes
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -226,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1u << (CTA2 ? 1 : 0)); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps << (CTA2 ? 1 : 0)); }
     for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&resid_bar[w][0], 1); tc::mbar_init(&resid_bar[w][1], 1); }
+    tc::mbar_init(&wfull_bar, 1u << (CTA2 ? 1 : 0));
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -241,13 +252,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, ps = 0, pph = 0;  // ring position of the producer
+      if (CTA2 && p.wres && u0 < ntiles) {  // every unit of this cluster has the same column tile (host: ustep % tiles_n == 0)
+        const int n0 = tile_coord(p, unit_tile(u0, 0)).n0 + (int)crank * (p.BN >> 1);
+        if (crank == 0) tc::mbar_arrive_expect_tx(&wfull_bar, 2u * kblocks * b_bytes);
+        else tc::mbar_arrive_leader(&wfull_bar);
+        for (int kb = 0; kb < kblocks; ++kb) tc::tma_load_2d_2sm(wres_smem + (size_t)kb * b_bytes, &tmBh, &wfull_bar, kb * BK, n0);
+      }
       for (long long t = u0; t < ntiles; t += ustep) {
         const TileCoord tc_ = tile_coord(p, unit_tile(t, 0));
         const TileCoord tc2 = tile_coord(p, unit_tile(t, 1));
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+          const int s = (int)ps;
+          const uint32_t ph = pph;
+          if (++ps == (uint32_t)p.stages) { ps = 0; pph ^= 1; }
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
@@ -265,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc::tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0);
               if (p.pair) tc::tma_load_2d_2sm(sa + a_half, &tmA, &full_bar[s], kb * BK, (int)tc2.m0);
             }
-            tc::tma_load_2d_2sm(sb, &tmBh, &full_bar[s], kb * BK, tc_.n0 + (int)crank * (p.BN >> 1));
+            if (!p.wres) tc::tma_load_2d_2sm(sb, &tmBh, &full_bar[s], kb * BK, tc_.n0 + (int)crank * (p.BN >> 1));
             continue;
           }
           tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
@@ -299,13 +317,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer (CTA pair: the leader CTA only)
+    // The loop stays warp-converged and everything it computes is warp-uniform (ring position kept as a counter, no
+    // division; descriptors = one add on a constant), with only the tcgen05 instructions themselves predicated on the
+    // elected lane: ptxas then keeps the descriptors in uniform registers.  The earlier form (lane 0 inside a divergent
+    // branch, `it % stages`) cost ~250 instructions = ~1000 cycles per k-block against 416 cycles of MMA work, which is
+    // what bounded every K ~ 400 GEMM (0.35 ms per 802816 x 404 x 448 product with the epilogue switched off).
     // reduction-major operands: both "MN-major" (instruction-descriptor bits 15 / 16)
     const uint32_t idesc = tc::idesc_bf16_f32(BM << (CTA2 ? 1 : 0), p.BN) | ((p.tn & 1) ? (1u << 15) : 0u) |
                            ((p.tn & 2) ? (1u << 16) : 0u);
+    const bool leader = tc::elect_one();
     const int last_in = p.TW ? p.cin_chunks - 1 : kblocks - 1;  // k-block (within a tap / the row) that may be partial
     const int period = p.TW ? p.cin_chunks : kblocks;
-    uint32_t it = 0, tl = 0;
-    for (long long t = u0; t < ntiles && crank == 0; t += ustep, ++tl) {
+    const uint32_t ring_lo = tc::smem_u32(smem), wres_lo = tc::smem_u32(wres_smem);
+    const bool wres = CTA2 && p.wres;
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
+      if (CTA2) tc::umma_bf16_2sm(d, a, b, idesc, accum);
+      else tc::umma_bf16(d, a, b, idesc, accum);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (CTA2) tc::umma_commit_2sm(bar);
+      else tc::umma_commit(bar);
+    };
+    if (wres && crank == 0 && u0 < ntiles) {
+      tc::mbar_wait(&wfull_bar, 0);
+      tc::tc_fence_after();
+    }
+    uint32_t tl = 0, s = 0, ph = 0;
+    if (!p.tn && !p.pair && crank == 0) {
+      // Fast path (K-major operands, one tile per unit: every plain GEMM).  Per k-block: one barrier probe on a precomputed
+      // address, four MMAs whose descriptors differ by a constant in the low word, one commit -- ~30 instructions.  The
+      // generic loop below spends ~85 on the same work, and the uniform datapath runs them at ~6-9 cycles each: more than
+      // the 416 cycles the four MMAs take, so the issuing warp, not the tensor pipe, set the pace of the K ~ 400 GEMMs.
+      const uint32_t full0 = tc::smem_u32(&full_bar[0]), empty0 = tc::smem_u32(&empty_bar[0]);
+      const uint32_t tfull0 = tc::smem_u32(&tfull_bar[0]), tempty0 = tc::smem_u32(&tempty_bar[0]);
+      const uint32_t a_lo0 = ((ring_lo & 0x3FFFFu) >> 4) | (1u << 16);               // descriptor low word of stage 0's A tile
+      const uint32_t b_lo0 = wres ? (((wres_lo & 0x3FFFFu) >> 4) | (1u << 16)) : a_lo0 + (a_bytes >> 4);
+      const uint32_t a_step = stage_bytes >> 4, b_step = wres ? (b_bytes >> 4) : a_step;
+      const int last_steps = p.last_steps;
+      const uint32_t nstages = (uint32_t)p.stages;
+      uint32_t a_lo = a_lo0, b_ring = b_lo0;
+      for (long long t = u0; t < ntiles; t += ustep, ++tl) {
+        const uint32_t acc = tl & 1;
+        tc::mbar_wait_u32(tempty0 + 8u * acc, ((tl >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        uint32_t b_lo = wres ? b_lo0 : b_ring;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait_u32(full0 + 8u * s, ph);
+          tc::tc_fence_after();
+          if (leader) {
+            if (kb + 1 < kblocks || last_steps == 4) {
+              tc::umma_bf16_lo<CTA2>(d_tmem, a_lo, b_lo, idesc, kb ? 1u : 0u);
+              tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+              tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+              tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+            } else {  // the zero-filled K tail of the last k-block is skipped
+              tc::umma_bf16_lo<CTA2>(d_tmem, a_lo, b_lo, idesc, kb ? 1u : 0u);
+              if (last_steps > 1) tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+              if (last_steps > 2) tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+            }
+            tc::umma_commit_u32<CTA2>(empty0 + 8u * s);
+            if (kb + 1 == kblocks) tc::umma_commit_u32<CTA2>(tfull0 + 8u * acc);
+          }
+          __syncwarp();
+          a_lo += a_step;
+          b_ring += a_step;
+          b_lo += b_step;
+          if (++s == nstages) { s = 0; ph ^= 1; a_lo = a_lo0; b_ring = b_lo0; }
+          if (!wres) b_lo = b_ring;
+        }
+      }
+    }
+    for (long long t = u0; t < ntiles && crank == 0 && (p.tn || p.pair); t += ustep, ++tl) {
       // pair mode: the unit owns both accumulators (virtual tiles 2*tl and 2*tl+1 of the epilogue's numbering)
       const uint32_t acc = p.pair ? 0u : (tl & 1), aph = p.pair ? (tl & 1) : ((tl >> 1) & 1);
       tc::mbar_wait(&tempty_bar[acc], aph ^ 1);
@@ -313,174 +396,216 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256u;  // accumulator stages at columns 0 and 256
       int kin = 0;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
+      uint32_t wb = wres_lo;
+      for (int kb = 0; kb < kblocks; ++kb) {
         tc::mbar_wait(&full_bar[s], ph);
         tc::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = tc::smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t adesc = tc::smem_desc_k_sw128(sa), bdesc = tc::smem_desc_k_sw128(sa + a_bytes);
-          // the zero-filled K tail of a row / tap is skipped: those MMAs would add exact zeros
-          const int nsteps = (kin == last_in) ? p.last_steps : BK / 16;
-          // +32 B per 16-element K step inside the 128B swizzle row; fully unrolled so the descriptors
-          // sit in uniform registers (a rolled loop made the issue slower than the MMAs themselves)
-          if (CTA2) {
-            tc::umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
-            if (nsteps > 1) tc::umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-            if (nsteps > 2) tc::umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            if (nsteps > 3) tc::umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-            if (p.pair) {
-              const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
-              tc::umma_bf16_2sm(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
-              if (nsteps > 1) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
-              if (nsteps > 2) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
-              if (nsteps > 3) tc::umma_bf16_2sm(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
+        const uint32_t sa = ring_lo + s * stage_bytes;
+        // the zero-filled K tail of a row / tap is skipped: those MMAs would add exact zeros
+        const int nsteps = (kin == last_in) ? p.last_steps : BK / 16;
+        const uint32_t accum = kb ? 1u : 0u;
+        if (p.tn) {  // reduction-major operand: 16 reduction rows = 2048 B per step inside the 64-row boxes
+          const uint64_t ta = (p.tn & 1) ? smem_desc_mn_sw128(sa) : tc::smem_desc_k_sw128(sa);
+          const uint64_t tb = (p.tn & 2) ? smem_desc_mn_sw128(sa + a_bytes) : tc::smem_desc_k_sw128(sa + a_bytes);
+          const uint64_t ia = (p.tn & 1) ? 128 : 2, ib = (p.tn & 2) ? 128 : 2;
+          if (leader) {
+            mma(d_tmem, ta, tb, accum);
+            if (nsteps > 1) mma(d_tmem, ta + ia, tb + ib, 1u);
+            if (nsteps > 2) mma(d_tmem, ta + 2 * ia, tb + 2 * ib, 1u);
+            if (nsteps > 3) mma(d_tmem, ta + 3 * ia, tb + 3 * ib, 1u);
+          }
+        } else {
+          // K-major, 128B swizzle: +32 B (descriptor + 2) per 16-element K step inside the swizzle row
+          const uint64_t adesc = tc::smem_desc_k_sw128(sa);
+          const uint64_t bdesc = tc::smem_desc_k_sw128(wres ? wb : sa + a_bytes);
+          if (nsteps == BK / 16) {
+            if (leader) {
+              mma(d_tmem, adesc, bdesc, accum);
+              mma(d_tmem, adesc + 2, bdesc + 2, 1u);
+              mma(d_tmem, adesc + 4, bdesc + 4, 1u);
+              mma(d_tmem, adesc + 6, bdesc + 6, 1u);
             }
-            tc::umma_commit_2sm(&empty_bar[s]);                    // both CTAs' smem slots free when these retire
-            if (kb == kblocks - 1) {                                 // accumulators complete in both CTAs
-              tc::umma_commit_2sm(&tfull_bar[acc]);
-              if (p.pair) tc::umma_commit_2sm(&tfull_bar[1]);
+          } else if (leader) {
+            mma(d_tmem, adesc, bdesc, accum);
+            if (nsteps > 1) mma(d_tmem, adesc + 2, bdesc + 2, 1u);
+            if (nsteps > 2) mma(d_tmem, adesc + 4, bdesc + 4, 1u);
+          }
+          if (p.pair) {  // second tile of the pair: A rows 128..255 of the stage (+16 KB), same weight tile
+            const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
+            if (leader) {
+              mma(d_tmem + 256u, adesc2, bdesc, accum);
+              if (nsteps > 1) mma(d_tmem + 256u, adesc2 + 2, bdesc + 2, 1u);
+              if (nsteps > 2) mma(d_tmem + 256u, adesc2 + 4, bdesc + 4, 1u);
+              if (nsteps > 3) mma(d_tmem + 256u, adesc2 + 6, bdesc + 6, 1u);
             }
-          } else if (p.tn) {  // reduction-major operand: 16 reduction rows = 2048 B per step inside the 64-row boxes
-            const uint64_t ta = (p.tn & 1) ? smem_desc_mn_sw128(sa) : adesc;
-            const uint64_t tb = (p.tn & 2) ? smem_desc_mn_sw128(sa + a_bytes) : bdesc;
-            const uint64_t ia = (p.tn & 1) ? 128 : 2, ib = (p.tn & 2) ? 128 : 2;
-            tc::umma_bf16(d_tmem, ta, tb, idesc, kb ? 1u : 0u);
-            if (nsteps > 1) tc::umma_bf16(d_tmem, ta + ia, tb + ib, idesc, 1u);
-            if (nsteps > 2) tc::umma_bf16(d_tmem, ta + 2 * ia, tb + 2 * ib, idesc, 1u);
-            if (nsteps > 3) tc::umma_bf16(d_tmem, ta + 3 * ia, tb + 3 * ib, idesc, 1u);
-            tc::umma_commit(&empty_bar[s]);
-            if (kb == kblocks - 1) tc::umma_commit(&tfull_bar[acc]);
-          } else {
-            tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
-            if (nsteps > 1) tc::umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-            if (nsteps > 2) tc::umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            if (nsteps > 3) tc::umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-            if (p.pair) {  // second tile of the pair: A rows 128..255 of the stage (+16 KB), same weight tile
-              const uint64_t adesc2 = tc::smem_desc_k_sw128(sa + a_half);
-              tc::umma_bf16(d_tmem + 256u, adesc2, bdesc, idesc, kb ? 1u : 0u);
-              if (nsteps > 1) tc::umma_bf16(d_tmem + 256u, adesc2 + 2, bdesc + 2, idesc, 1u);
-              if (nsteps > 2) tc::umma_bf16(d_tmem + 256u, adesc2 + 4, bdesc + 4, idesc, 1u);
-              if (nsteps > 3) tc::umma_bf16(d_tmem + 256u, adesc2 + 6, bdesc + 6, idesc, 1u);
-            }
-            tc::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
-            if (kb == kblocks - 1) {                                 // accumulator(s) complete
-              tc::umma_commit(&tfull_bar[acc]);
-              if (p.pair) tc::umma_commit(&tfull_bar[1]);
-            }
+          }
+        }
+        if (leader) {
+          commit(&empty_bar[s]);          // smem slot free (CTA pair: in both CTAs) when these MMAs retire
+          if (kb == kblocks - 1) {        // accumulator(s) complete (in both CTAs)
+            commit(&tfull_bar[acc]);
+            if (p.pair) commit(&tfull_bar[1]);
           }
         }
         __syncwarp();
         if (++kin == period) kin = 0;
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        wb += b_bytes;
       }
     }
   } else {
-    // ------------------------------------------------------------- epilogue (warps 2..9)
+    // ------------------------------------------------------------- epilogue (warps 2 .. 2 + kEpiWarps)
+    // The warps are independent of each other: each owns the chunks part, part + kParts, ... of its 32 rows of every tile
+    // ("items"), with its own staging buffer(s), residual barriers and TMA store groups; the only CTA-wide step is the
+    // reload of the bias slice when a tile starts at another column than the previous one.
     constexpr int CW = OUT_BF16 ? 64 : 32;    // columns per 128-byte chunk
     constexpr int ESZ = OUT_BF16 ? 2 : 4;
     constexpr int UPS = OUT_BF16 ? 4 : 8;     // 16-byte units per 32 accumulator columns
     constexpr int CPU_ = 16 / ESZ;            // columns per 16-byte unit
     const int ew = warp - 2;
     const int q = warp & 3;      // TMEM lane quarter this warp may access == its 32 rows of the tile
-    const int half = ew >> 2;    // which of the two warps sharing that quarter (takes chunks half, half+2, ...)
+    const int part = ew >> 2;    // which of the kParts warps sharing that quarter
     const int etid = ew * 32 + lane;
     uint8_t* stage = epi_smem + ew * 4096 * p.epi_bufs;
     uint64_t* rbar = resid_bar[ew];
     const int nchunks = (p.BN + CW - 1) / CW;
-    const int n_my = (nchunks - half + 1) / 2;
+    const int n_my = (nchunks - part + kParts - 1) / kParts;  // 0: this warp only takes part in the accumulator hand-over
     const int row = lane, r7 = lane & 7;
+    const uint32_t bmask = (uint32_t)p.epi_bufs - 1u;
     uint32_t tl = 0, st_seq = 0, rph0 = 0, rph1 = 0;
+    int bias_n0 = -1;
     const long long nvirt = ntiles << p.pair;  // virtual tiles of this kernel: accumulator tl & 1, in MMA completion order
-    for (long long vt = u0 << p.pair; vt < nvirt;
-         vt += (vt & p.pair) ? ((ustep << 1) - 1) : (p.pair ? 1 : ustep), ++tl) {
-      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-      const TileCoord tc_ = tile_coord(p, unit_tile(vt >> p.pair, (int)(vt & p.pair)));
-      int c1, c2 = 0, c3 = 0;  // where this warp's 32 rows live in the output tensor
+    auto next_vt = [&](long long vt) -> long long { return vt + ((vt & p.pair) ? ((ustep << 1) - 1) : (p.pair ? 1 : ustep)); };
+    // where this warp's 32 rows of a tile live in the output tensor
+    auto out_coords = [&](const TileCoord& t, int& c1, int& c2, int& c3) {
+      c2 = c3 = 0;
       if (p.TW) {
         const int bw = p.TW < 32 ? p.TW : 32;
         const int pix = q * 32;
-        c1 = tc_.w0 + (p.TW >= 32 ? pix % p.TW : 0);
-        c2 = tc_.h0 + (p.TW >= 32 ? pix / p.TW : q * (32 / bw));
-        c3 = tc_.img;
+        c1 = t.w0 + (p.TW >= 32 ? pix % p.TW : 0);
+        c2 = t.h0 + (p.TW >= 32 ? pix / p.TW : q * (32 / bw));
+        c3 = t.img;
       } else {
-        c1 = (int)tc_.m0 + q * 32;
-        if (p.batched) { c2 = tc_.h0; c3 = tc_.img; }
+        c1 = (int)t.m0 + q * 32;
+        if (p.batched) { c2 = t.h0; c3 = t.img; }
       }
-      // bias slice of this tile -> smem (zeros beyond N, so padded columns come out as exact zeros)
-      epi_bar_sync();  // every epilogue warp is done with the previous tile's bias / g slice
-      if (etid < p.BN) {
-        const int n = tc_.n0 + etid;
-        bias_s[etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-        if (p.ln_stats) lng_s[etid] = n < p.N ? __ldg(p.ln_g + n) : 0.f;
-      }
-      // this thread's row of the tile: global row index (conv mode: linear pixel index) and validity
-      long long grow;
-      bool row_ok;
+    };
+    // this thread's row of a tile: global row index (conv mode: linear pixel index) and validity
+    auto row_of = [&](const TileCoord& t, long long& grow, bool& ok) {
       if (p.TW) {
         const int pix = q * 32 + lane;
-        const int hh = tc_.h0 + pix / p.TW, ww = tc_.w0 + pix % p.TW;
-        row_ok = hh < p.H && ww < p.W;
-        grow = ((long long)tc_.img * p.H + hh) * p.W + ww;
+        const int hh = t.h0 + pix / p.TW, ww = t.w0 + pix % p.TW;
+        ok = hh < p.H && ww < p.W;
+        grow = ((long long)t.img * p.H + hh) * p.W + ww;
       } else {
-        grow = tc_.m0 + q * 32 + lane;
-        row_ok = grow < p.M;
+        grow = t.m0 + q * 32 + lane;
+        ok = grow < p.M;
+      }
+    };
+    // residual chunk i of the tile at t -> staging buffer seq & bmask (one lane)
+    auto issue_resid = [&](const TileCoord& t, int i, uint32_t seq) {
+      int c1, c2, c3;
+      out_coords(t, c1, c2, c3);
+      const int col0 = (part + kParts * i) * CW;
+      const int ncols = min(CW, p.BN - col0);
+      const uint32_t b = seq & bmask;
+      uint8_t* buf = stage + b * 4096;
+      tc::mbar_arrive_expect_tx(&rbar[b], 32u * ncols * ESZ);
+      if (p.TW) tc::tma_load_4d(buf, ncols < CW ? &tmRt : &tmR, &rbar[b], t.n0 + col0, c1, c2, c3);
+      else tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[b], t.n0 + col0, c1);
+    };
+    // LayerNorm statistics of a row are loaded ONE TILE AHEAD (up to kLnPf slots, in registers): issued right after the
+    // previous tile's, they would otherwise cost this warp a full global-memory latency per tile before it can touch the
+    // accumulator (measured: the whole epilogue time of the K ~ 400 GEMMs was this wait plus the residual's)
+    constexpr int kLnPf = 8;
+    const bool ln_on = p.ln_stats != nullptr && n_my > 0;
+    const bool ln_pf = ln_on && p.ln_slots <= kLnPf;
+    float2 sv[kLnPf];
+    auto load_stats = [&](long long grow, bool ok) {
+      const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
+#pragma unroll
+      for (int k = 0; k < kLnPf; ++k) sv[k] = (ok && k < p.ln_slots) ? __ldg(sp2 + k) : make_float2(0.f, 0.f);
+    };
+    long long vt = u0 << p.pair;
+    TileCoord tc_ = tile_coord(p, unit_tile(vt >> p.pair, (int)(vt & p.pair)));  // garbage beyond the last tile, unused
+    long long grow;
+    bool row_ok;
+    row_of(tc_, grow, row_ok);
+    if (vt < nvirt) {
+      if (ln_pf) load_stats(grow, row_ok);
+      if (RESID && p.epi_bufs == 2 && n_my > 0 && lane == 0) issue_resid(tc_, 0, 0);
+    }
+    for (; vt < nvirt; ++tl) {
+      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+      int c1, c2, c3;
+      out_coords(tc_, c1, c2, c3);
+      // bias / g slice of this column tile -> smem (zeros beyond N, so padded columns come out as exact zeros); the tile
+      // sequence is the same for every epilogue warp, so the condition is CTA-uniform
+      if (tc_.n0 != bias_n0) {
+        epi_bar_sync();  // every epilogue warp is done with the previous slice
+        if (etid < p.BN) {
+          const int n = tc_.n0 + etid;
+          bias_s[etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+          if (p.ln_stats) lng_s[etid] = n < p.N ? __ldg(p.ln_g + n) : 0.f;
+        }
+        epi_bar_sync();
+        bias_n0 = tc_.n0;
       }
       float ln_rstd = 1.f, ln_nrm = 0.f;  // x_norm . W = rstd * acc + (-rstd * mean) * g[n]
-      if (p.ln_stats && row_ok) {
+      if (ln_on && row_ok) {
         float su = 0.f, sq = 0.f;
-        const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
-        for (int k = 0; k < p.ln_slots; ++k) {  // fixed order: deterministic
-          const float2 v = __ldg(sp2 + k);
-          su += v.x;
-          sq += v.y;
+        if (ln_pf) {
+#pragma unroll
+          for (int k = 0; k < kLnPf; ++k) { su += sv[k].x; sq += sv[k].y; }  // fixed order: deterministic
+        } else {
+          const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
+          for (int k = 0; k < p.ln_slots; ++k) {
+            const float2 v = __ldg(sp2 + k);
+            su += v.x;
+            sq += v.y;
+          }
         }
         const float mean = su * p.ln_invC;
         ln_rstd = rsqrtf(fmaxf(sq * p.ln_invC - mean * mean, 0.f) + p.ln_eps);
         ln_nrm = -ln_rstd * mean;
       }
-      // residual chunks of this tile: issue the loads now, they land while the tile's MMAs run
-      if (RESID) {
-        if (lane == 0) {
-          tc::tma_store_wait_read<0>();  // both staging buffers have been read by their stores
-          for (int i = 0; i < 2 && i < n_my; ++i) {
-            const int col0 = (half + 2 * i) * CW;
-            const int ncols = min(CW, p.BN - col0);
-            uint8_t* buf = stage + ((st_seq + i) & 1) * 4096;
-            tc::mbar_arrive_expect_tx(&rbar[(st_seq + i) & 1], 32u * ncols * ESZ);
-            if (p.TW) tc::tma_load_4d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1, c2, c3);
-            else tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[(st_seq + i) & 1], tc_.n0 + col0, c1);
-          }
-        }
-        __syncwarp();
-      }
-      epi_bar_sync();  // bias visible to all epilogue warps
+      // the warp's next tile: coordinates, row, and its statistics on their way
+      const long long vt_next = next_vt(vt);
+      const bool has_next = vt_next < nvirt;
+      const TileCoord tc_next = tile_coord(p, unit_tile(vt_next >> p.pair, (int)(vt_next & p.pair)));
+      long long grow_next;
+      bool row_ok_next;
+      row_of(tc_next, grow_next, row_ok_next);
+      if (ln_pf && has_next) load_stats(grow_next, row_ok_next);
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
       const float* bs = bias_s;
       const float* gs = lng_s;
-      const bool ln_on = p.ln_stats != nullptr;
       for (int i = 0; i < n_my; ++i, ++st_seq) {
         float st_sum = 0.f, st_sq = 0.f;
-        const int col0 = (half + 2 * i) * CW;     // column inside the tile
-        const int ncols = min(CW, p.BN - col0);   // multiple of 16
+        const int col0 = (part + kParts * i) * CW;  // column inside the tile
+        const int ncols = min(CW, p.BN - col0);     // multiple of 16
         const bool is_tail = ncols < CW;
-        const int row_bytes = ncols * ESZ;        // dense row pitch of a tail chunk
-        const int nglob = tc_.n0 + col0;          // first global column of the chunk
-        const bool full = nglob + ncols <= p.N;   // no column masking needed
-        const uint32_t b = p.epi_bufs == 2 ? (st_seq & 1) : 0u;
+        const int row_bytes = ncols * ESZ;          // dense row pitch of a tail chunk
+        const int nglob = tc_.n0 + col0;            // first global column of the chunk
+        const bool full = nglob + ncols <= p.N;     // no column masking needed
+        const uint32_t b = st_seq & bmask;
         uint8_t* obuf = stage + b * 4096;
         if (RESID) {
-          if (i >= 2) {  // more than two chunks per warp and tile: reload the buffer once its store has read it
-            if (lane == 0) {
-              tc::tma_store_wait_read<1>();
-              tc::mbar_arrive_expect_tx(&rbar[b], 32u * ncols * ESZ);
-              if (p.TW) tc::tma_load_4d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1, c2, c3);
-              else tc::tma_load_2d(obuf, is_tail ? &tmRt : &tmR, &rbar[b], nglob, c1);
+          if (lane == 0) {
+            // the store that last used the buffer about to be loaded has read it (a few hundred cycles after its issue)
+            tc::tma_store_wait_read<0>();
+            if (p.epi_bufs == 2) {
+              // two buffers: the residual of the NEXT item (of this tile or of the warp's next tile) is requested one
+              // whole item ahead, so its HBM latency is not part of this warp's per-tile time
+              if (i + 1 < n_my) issue_resid(tc_, i + 1, st_seq + 1);
+              else if (has_next) issue_resid(tc_next, 0, st_seq + 1);
+            } else {
+              issue_resid(tc_, i, st_seq);
             }
-            __syncwarp();
           }
+          __syncwarp();
           tc::mbar_wait(&rbar[b], b ? rph1 : rph0);
           if (b) rph1 ^= 1; else rph0 ^= 1;
         } else {
@@ -494,9 +619,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int sb = 0; sb < CW / 32; ++sb) {
           const int scol = sb * 32;
-          if (scol < ncols) {
+          if (scol < ncols && !(p.dbg & 8)) {
             uint32_t vr[32];
-            if (scol + 32 <= ncols) {
+            if (p.dbg & 2) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) vr[e] = 0x3f800000u + e;
+            } else if (scol + 32 <= ncols) {
               tc::tmem_ld32(t_addr + col0 + scol, vr);
             } else {  // 16 live columns
               tc::tmem_ld16(t_addr + col0 + scol, *reinterpret_cast<uint32_t(*)[16]>(&vr[0]));
@@ -581,18 +709,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                   w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
                 }
-                *reinterpret_cast<uint4*>(sp) = w;
+                if (!(p.dbg & 4)) *reinterpret_cast<uint4*>(sp) = w;
+                else if (w.x == 0x12345u) p.stats_out[0] = 1.f;
               }
             }
           }
         }
         if (p.stats_out && row_ok) {
-          const int slot = (tc_.n0 / p.BN) * nchunks + (half + 2 * i);
+          const int slot = (tc_.n0 / p.BN) * nchunks + (part + kParts * i);
           reinterpret_cast<float2*>(p.stats_out)[grow * p.stats_slots + slot] = make_float2(st_sum, st_sq);
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 9)) {
           const CUtensorMap* m = is_tail ? &tmDt : &tmD;
           if (p.TW || p.batched) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
           else tc::tma_store_2d(m, obuf, nglob, c1);
@@ -605,6 +734,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CTA2) tc::mbar_arrive_leader(&tempty_bar[acc]);
         else tc::mbar_arrive(&tempty_bar[acc]);
       }
+      vt = vt_next; tc_ = tc_next; grow = grow_next; row_ok = row_ok_next;
     }
     if (lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA retires
   }
@@ -683,17 +813,29 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   const int G = 2 << p.pair;
   p.cta2 = (!p.batched && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
-            (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters) ? 1 : 0;
-  const int stage_bytes = (BM * BK * 2 << p.pair) + (p.BN >> p.cta2) * BK * 2;
-  p.epi_bufs = (p.pair && !resid) ? 1 : 2;
-  p.stages = (kSmemBytes - kEpiWarps * 4096 * p.epi_bufs) / stage_bytes;
+            (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters && !getenv("ISP_GEMM_NO_CTA2")) ? 1 : 0;
+  // a second staging chunk per epilogue warp only where it hides latency: the residual of the next item is prefetched into it
+  // (pair mode exposes its epilogue anyway and needs the shared memory for the wider operand stages)
+  p.epi_bufs = (resid && !p.pair) ? 2 : 1;
+  // resident weights: plain CTA-pair GEMM without residual (that one needs the shared memory for its second staging chunk,
+  // and its HBM floor is above the operand-fill time anyway) whose share of the weight tile (all k-blocks) fits next to a >= 3-stage ring of A tiles
+  const int a_bytes = BM * BK * 2 << p.pair;
+  const int w_bytes = (p.K / BK) * (p.BN >> 1) * BK * 2;
+  p.wres = (p.cta2 && !p.pair && !p.TW && !resid && max_clusters >= p.tiles_n &&
+            kSmemBytes - kEpiWarps * 4096 - w_bytes >= 3 * a_bytes && !getenv("ISP_GEMM_NO_WRES")) ? 1 : 0;
+  if (p.wres) p.epi_bufs = 1;
+  p.dbg = getenv("ISP_GEMM_DBG") ? atoi(getenv("ISP_GEMM_DBG")) : 0;
+  const int stage_bytes = a_bytes + (p.wres ? 0 : (p.BN >> p.cta2) * BK * 2);
+  p.stages = (kSmemBytes - kEpiWarps * 4096 * p.epi_bufs - (p.wres ? w_bytes : 0)) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (getenv("ISP_GEMM_STAGES")) p.stages = atoi(getenv("ISP_GEMM_STAGES"));  // timing experiments (with ISP_GEMM_DBG=8 only)
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   if (p.cta2) {
     kernel_fn fn = pick_kernel<true>(out_bf16, act, resid);
     if (int e = prepare(fn)) return e;
     const long long nunits = (p.tiles_m / G) * p.tiles_n;
-    const int ncl = (int)(nunits < max_clusters ? nunits : max_clusters);
+    int ncl = (int)(nunits < max_clusters ? nunits : max_clusters);
+    if (p.wres) ncl = ncl / (int)p.tiles_n * (int)p.tiles_n;  // cluster c then only ever sees column tile c % tiles_n
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ncl); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
     cudaLaunchAttribute at[1];

@@ -181,3 +181,35 @@ def test_ffn_fused_matches_two_gemms_and_fp32(M):
     # statistics of the stored rows
     of = out.float()[:, :D]
     assert relerr(stats.sum(1)[:, 0], of.sum(1)) < 1e-4 and relerr(stats.sum(1)[:, 1], (of * of).sum(1)) < 1e-4
+
+
+@pytest.mark.parametrize("N,K,resid,out_dtype", [(404, 448, True, torch.bfloat16), (448, 404, False, torch.bfloat16),
+                                                 (384, 404, False, torch.float32), (384, 384, True, torch.float32),
+                                                 (404, 384, True, torch.bfloat16)])
+def test_gemm_cta_pair_resident_weights(tc, N, K, resid, out_dtype):
+    """Shapes of the LoftUp transformer GEMMs at a row count that selects the CTA-pair kernel with the weight tile resident
+    in shared memory (even number of row tiles, at least two waves of clusters; the last row tile is partial), against
+    fp32 torch on the same bf16 operands, with bias + GELU / residual and the row statistics of the stored output."""
+    M = 152 * 128 - 37
+    g = torch.Generator().manual_seed(N + K)
+    lda, ldd = tc.round_up(K, 16), tc.round_up(N, 16)
+    A = torch.zeros(M, lda, dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    R = None
+    if resid:
+        R = torch.zeros(M, ldd, dtype=out_dtype)
+        R[:, :N] = torch.randn(M, N, generator=g).to(out_dtype)
+    act = None if resid else "gelu"
+    st = torch.full((M, tc.stats_slots(N, out_dtype, resid), 2), float("nan"), device=DEV)
+    out = tc.gemm(A.to(DEV), tc.pack_linear_weight(W).to(DEV), bias=b.to(DEV), resid=None if R is None else R.to(DEV),
+                  act=act, out_dtype=out_dtype, N=N, K=K, ldd=ldd, stats_out=st)
+    want = A[:, :K].float() @ W.float().T + b
+    want = F.gelu(want) if act else want + R[:, :N].float()
+    got = out[:, :N].float().cpu()
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 1e-4
+    assert relerr(got, want) < tol and cosine(got, want) > 0.9999, (relerr(got, want), cosine(got, want))
+    assert ldd == N or float(out[:, N:].float().abs().max()) == 0.0
+    assert torch.allclose(st.sum(1)[:, 0].cpu(), got.sum(1), rtol=1e-4, atol=2e-3)
+    assert torch.allclose(st.sum(1)[:, 1].cpu(), (got * got).sum(1), rtol=1e-4, atol=2e-3)

@@ -1,4 +1,3 @@
-python tools/prof_loftup_gemms.py
-WHICH=out_proj ncu --set full --import-source on --clock-control none -k regex:gemm_tc_kernel --launch-skip 2 --launch-count 1 -o gpurun_out/r02_gemm_outproj -f python tools/prof_loftup_gemms.py > /dev/null 2>&1
-WHICH=ff1 ncu --set full --import-source on --clock-control none -k regex:gemm_tc_kernel --launch-skip 2 --launch-count 1 -o gpurun_out/r02_gemm_ff1 -f python tools/prof_loftup_gemms.py > /dev/null 2>&1
-ls -la gpurun_out/r02_gemm_*.ncu-rep
+ISP_GEMM_DBG=8 WHICH=q_proj ncu --set full --import-source on --clock-control none -k regex:gemm_tc_kernel --launch-skip 2 --launch-count 1 -o gpurun_out/r02_gemm_qproj_dbg8 -f python tools/prof_loftup_gemms.py > /dev/null 2>&1
+WHICH=q_proj ncu --set full --import-source on --clock-control none -k regex:gemm_tc_kernel --launch-skip 2 --launch-count 1 -o gpurun_out/r02_gemm_qproj_v2 -f python tools/prof_loftup_gemms.py > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep

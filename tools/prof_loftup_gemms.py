@@ -4,7 +4,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from isegprobe_b200 import tc
 dev, bf = "cuda", torch.bfloat16
-M = int(os.environ.get("IMAGES", "4")) * 448 * 448
+M = int(float(os.environ.get("IMAGES", "4")) * 448 * 448)
 D, C, Dp, NQ = 404, 384, 416, 448
 torch.manual_seed(0)
 x = torch.randn(M, Dp, device=dev).to(bf); x[:, D:] = 0
