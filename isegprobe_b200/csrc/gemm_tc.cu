@@ -60,6 +60,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 namespace gemm {
 
+#ifdef ISP_GEMM_TRACE
+// developer instrumentation (tools/trace_gemm.py): clock64 stamps of the first 64 tiles of CTA 0
+__device__ long long g_trace[4][64][4];
+#define ISP_TRACE(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_trace[role][tile][slot] = clock64(); } while (0)
+#define ISP_TRACE_ADD(role, tile, slot, v) do { if (blockIdx.x == 0 && (tile) < 64) g_trace[role][tile][slot] += (v); } while (0)
+#else
+#define ISP_TRACE(role, tile, slot) do { } while (0)
+#define ISP_TRACE_ADD(role, tile, slot, v) do { } while (0)
+#endif
+
 constexpr int BM = 128, BK = 64;
 #ifndef ISP_GEMM_EPI_WARPS
 #define ISP_GEMM_EPI_WARPS 16
@@ -94,13 +104,12 @@ struct Params {
                       // ONCE and stays in shared memory; every cluster works on one column tile only and streams just the A
                       // rows.  Per 128 x 208 tile that is 115 KB instead of 208 KB through the ~49 B/clk L2->SM port, which is
                       // what bounded the K ~ 400 GEMMs of the LoftUp transformer (not HBM, not the tensor pipe)
-  int dbg;            // timing experiments (ISP_GEMM_DBG): 1 no TMA store, 2 no tcgen05.ld, 4 no st.shared, 8 no item body at all
   int epi_bufs;       // staging chunks per epilogue warp: 2, or 1 (pair mode without residual: the 32 KB go to a third
                       // pipeline stage instead)
   int last_steps;     // 16-wide MMA steps that hold real data in the last k-block (GEMM) / last chunk of a tap (conv)
   // conv mode (TW == 0 -> plain GEMM)
   int TW, TH, H, W, cin_chunks;
-  long long tiles_m, tiles_n;
+  int tiles_m, tiles_n;  // tiles_m * tiles_n < 2^31 (checked by the host): tile arithmetic is 32-bit unsigned
   int tiles_w, tiles_h;
   // epilogue
   const float* bias;   // [N] or null
@@ -157,20 +166,20 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
 }
 
 struct TileCoord {
-  long long m0;
+  int m0;
   int n0;
   int img, h0, w0;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const Params& p, long long t) {
+__device__ __forceinline__ TileCoord tile_coord(const Params& p, uint32_t t) {
   TileCoord c;
-  const long long tm = t / p.tiles_n;
-  c.n0 = (int)(t % p.tiles_n) * p.BN;
+  const uint32_t tm = t / (uint32_t)p.tiles_n;
+  c.n0 = (int)(t - tm * (uint32_t)p.tiles_n) * p.BN;
   c.m0 = tm * BM;
   c.img = c.h0 = c.w0 = 0;
   if (p.batched) {  // problem z = (batch, head), row tile inside it
-    const long long per = p.tiles_m / ((long long)p.batched * p.nbatch);
-    const long long z = tm / per;
+    const uint32_t per = (uint32_t)p.tiles_m / (uint32_t)(p.batched * p.nbatch);
+    const uint32_t z = tm / per;
     c.m0 = (tm % per) * BM;
     c.h0 = (int)(z % p.batched);
     c.img = (int)(z / p.batched);
@@ -218,9 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // adjacent units of the same column tile.  tiles_m is a multiple of the tiles per cluster unit.
   const uint32_t crank = CTA2 ? tc::cluster_ctarank() : 0u;
   const int gshift = p.pair + (CTA2 ? 1 : 0);
-  const long long ntiles = (p.tiles_m >> gshift) * p.tiles_n;   // units per CTA stream
-  const long long u0 = blockIdx.x >> (CTA2 ? 1 : 0), ustep = gridDim.x >> (CTA2 ? 1 : 0);
-  auto unit_tile = [&](long long u, int sub) -> long long {
+  const uint32_t ntiles = (uint32_t)(p.tiles_m >> gshift) * (uint32_t)p.tiles_n;   // units per CTA stream
+  const uint32_t u0 = blockIdx.x >> (CTA2 ? 1 : 0), ustep = gridDim.x >> (CTA2 ? 1 : 0);
+  auto unit_tile = [&](uint32_t u, int sub) -> uint32_t {
     return gshift ? ((((u / p.tiles_n) << gshift) + (crank << p.pair) + sub) * p.tiles_n + u % p.tiles_n) : u;
   };
   const int kblocks = p.K / BK;
@@ -259,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tc::mbar_arrive_leader(&wfull_bar);
         for (int kb = 0; kb < kblocks; ++kb) tc::tma_load_2d_2sm(wres_smem + (size_t)kb * b_bytes, &tmBh, &wfull_bar, kb * BK, n0);
       }
-      for (long long t = u0; t < ntiles; t += ustep) {
+      for (uint32_t t = u0; t < ntiles; t += ustep) {
         const TileCoord tc_ = tile_coord(p, unit_tile(t, 0));
         const TileCoord tc2 = tile_coord(p, unit_tile(t, 1));
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -356,15 +365,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int last_steps = p.last_steps;
       const uint32_t nstages = (uint32_t)p.stages;
       uint32_t a_lo = a_lo0, b_ring = b_lo0;
-      for (long long t = u0; t < ntiles; t += ustep, ++tl) {
+      for (uint32_t t = u0; t < ntiles; t += ustep, ++tl) {
         const uint32_t acc = tl & 1;
+        if (leader) ISP_TRACE(0, tl, 0);
         tc::mbar_wait_u32(tempty0 + 8u * acc, ((tl >> 1) & 1) ^ 1);
         tc::tc_fence_after();
+        if (leader) ISP_TRACE(0, tl, 1);
         const uint32_t d_tmem = tmem_base + acc * 256u;
         uint32_t b_lo = wres ? b_lo0 : b_ring;
         for (int kb = 0; kb < kblocks; ++kb) {
+#ifdef ISP_GEMM_TRACE
+          const long long w0 = clock64();
+#endif
           tc::mbar_wait_u32(full0 + 8u * s, ph);
           tc::tc_fence_after();
+#ifdef ISP_GEMM_TRACE
+          if (leader) ISP_TRACE_ADD(0, tl, 3, clock64() - w0);
+#endif
           if (leader) {
             if (kb + 1 < kblocks || last_steps == 4) {
               tc::umma_bf16_lo<CTA2>(d_tmem, a_lo, b_lo, idesc, kb ? 1u : 0u);
@@ -377,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (last_steps > 2) tc::umma_bf16_lo<CTA2>(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
             }
             tc::umma_commit_u32<CTA2>(empty0 + 8u * s);
-            if (kb + 1 == kblocks) tc::umma_commit_u32<CTA2>(tfull0 + 8u * acc);
+            if (kb + 1 == kblocks) { tc::umma_commit_u32<CTA2>(tfull0 + 8u * acc); ISP_TRACE(0, tl, 2); }
           }
           __syncwarp();
           a_lo += a_step;
@@ -388,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    for (long long t = u0; t < ntiles && crank == 0 && (p.tn || p.pair); t += ustep, ++tl) {
+    for (uint32_t t = u0; t < ntiles && crank == 0 && (p.tn || p.pair); t += ustep, ++tl) {
       // pair mode: the unit owns both accumulators (virtual tiles 2*tl and 2*tl+1 of the epilogue's numbering)
       const uint32_t acc = p.pair ? 0u : (tl & 1), aph = p.pair ? (tl & 1) : ((tl >> 1) & 1);
       tc::mbar_wait(&tempty_bar[acc], aph ^ 1);
@@ -474,8 +491,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bmask = (uint32_t)p.epi_bufs - 1u;
     uint32_t tl = 0, st_seq = 0, rph0 = 0, rph1 = 0;
     int bias_n0 = -1;
-    const long long nvirt = ntiles << p.pair;  // virtual tiles of this kernel: accumulator tl & 1, in MMA completion order
-    auto next_vt = [&](long long vt) -> long long { return vt + ((vt & p.pair) ? ((ustep << 1) - 1) : (p.pair ? 1 : ustep)); };
     // where this warp's 32 rows of a tile live in the output tensor
     auto out_coords = [&](const TileCoord& t, int& c1, int& c2, int& c3) {
       c2 = c3 = 0;
@@ -514,28 +529,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.TW) tc::tma_load_4d(buf, ncols < CW ? &tmRt : &tmR, &rbar[b], t.n0 + col0, c1, c2, c3);
       else tc::tma_load_2d(buf, ncols < CW ? &tmRt : &tmR, &rbar[b], t.n0 + col0, c1);
     };
-    // LayerNorm statistics of a row are loaded ONE TILE AHEAD (up to kLnPf slots, in registers): issued right after the
-    // previous tile's, they would otherwise cost this warp a full global-memory latency per tile before it can touch the
-    // accumulator (measured: the whole epilogue time of the K ~ 400 GEMMs was this wait plus the residual's)
+    // LayerNorm statistics of a row are loaded ONE TILE AHEAD (an even number of slots <= kLnPf, as float4 pairs kept in
+    // registers): loaded at the start of their own tile they cost the warp a global-memory latency per tile before it
+    // could touch the accumulator
     constexpr int kLnPf = 8;
     const bool ln_on = p.ln_stats != nullptr && n_my > 0;
-    const bool ln_pf = ln_on && p.ln_slots <= kLnPf;
-    float2 sv[kLnPf];
+    const bool ln_pf = ln_on && p.ln_slots <= kLnPf && (p.ln_slots & 1) == 0;
+    const int ln_pairs = p.ln_slots >> 1;
+    const bool has_alpha = p.alpha != 1.f;
+    const float2 alpha2 = make_float2(p.alpha, p.alpha);
+    float4 sv[kLnPf / 2];
     auto load_stats = [&](long long grow, bool ok) {
-      const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
+      const float4* sp4 = reinterpret_cast<const float4*>(p.ln_stats + grow * (2 * p.ln_slots));
 #pragma unroll
-      for (int k = 0; k < kLnPf; ++k) sv[k] = (ok && k < p.ln_slots) ? __ldg(sp2 + k) : make_float2(0.f, 0.f);
+      for (int k = 0; k < kLnPf / 2; ++k) sv[k] = (ok && k < ln_pairs) ? __ldg(sp4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    long long vt = u0 << p.pair;
-    TileCoord tc_ = tile_coord(p, unit_tile(vt >> p.pair, (int)(vt & p.pair)));  // garbage beyond the last tile, unused
+    // The per-tile bookkeeping is on this warp's critical path (one item of 32 x 64 outputs per tile): unit coordinates advance
+    // incrementally (unit u = um * tiles_n + un), no division per tile outside the conv / batched index split
+    const uint32_t tn_u = (uint32_t)p.tiles_n;
+    const uint32_t step_m = ustep / tn_u, step_n = ustep - step_m * tn_u;
+    uint32_t u = u0, um = u0 / tn_u, un = u0 - um * tn_u;
+    int sub = 0;
+    auto coord_of = [&](uint32_t um_, uint32_t un_, int sub_) -> TileCoord {
+      const uint32_t tm = gshift ? ((um_ << gshift) + (crank << p.pair) + (uint32_t)sub_) : um_;
+      TileCoord c;
+      c.n0 = (int)un_ * p.BN;
+      c.m0 = (int)(tm * BM);
+      c.img = c.h0 = c.w0 = 0;
+      if (p.batched) {
+        const uint32_t per = (uint32_t)p.tiles_m / (uint32_t)(p.batched * p.nbatch);
+        const uint32_t z = tm / per;
+        c.m0 = (int)((tm - z * per) * BM);
+        c.img = (int)(z / (uint32_t)p.batched);
+        c.h0 = (int)(z - (uint32_t)c.img * (uint32_t)p.batched);
+      } else if (p.TW) {
+        const uint32_t per_img = (uint32_t)(p.tiles_w * p.tiles_h);
+        c.img = (int)(tm / per_img);
+        const uint32_t r = tm - (uint32_t)c.img * per_img;
+        const uint32_t rh = r / (uint32_t)p.tiles_w;
+        c.h0 = (int)rh * p.TH;
+        c.w0 = (int)(r - rh * (uint32_t)p.tiles_w) * p.TW;
+      }
+      return c;
+    };
+    TileCoord tc_ = coord_of(um, un, 0);  // garbage beyond the last tile, unused
     long long grow;
     bool row_ok;
     row_of(tc_, grow, row_ok);
-    if (vt < nvirt) {
+    if (u < ntiles) {
       if (ln_pf) load_stats(grow, row_ok);
       if (RESID && p.epi_bufs == 2 && n_my > 0 && lane == 0) issue_resid(tc_, 0, 0);
     }
-    for (; vt < nvirt; ++tl) {
+    for (; u < ntiles; ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       int c1, c2, c3;
       out_coords(tc_, c1, c2, c3);
@@ -546,7 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (etid < p.BN) {
           const int n = tc_.n0 + etid;
           bias_s[etid] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-          if (p.ln_stats) lng_s[etid] = n < p.N ? __ldg(p.ln_g + n) : 0.f;
+          lng_s[etid] = (p.ln_stats && n < p.N) ? __ldg(p.ln_g + n) : 0.f;
         }
         epi_bar_sync();
         bias_n0 = tc_.n0;
@@ -556,9 +601,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float su = 0.f, sq = 0.f;
         if (ln_pf) {
 #pragma unroll
-          for (int k = 0; k < kLnPf; ++k) { su += sv[k].x; sq += sv[k].y; }  // fixed order: deterministic
+          for (int k = 0; k < kLnPf / 2; ++k) { su += sv[k].x; sq += sv[k].y; su += sv[k].z; sq += sv[k].w; }  // fixed order
         } else {
           const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_slots;
+#pragma unroll 1
           for (int k = 0; k < p.ln_slots; ++k) {
             const float2 v = __ldg(sp2 + k);
             su += v.x;
@@ -570,20 +616,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_nrm = -ln_rstd * mean;
       }
       // the warp's next tile: coordinates, row, and its statistics on their way
-      const long long vt_next = next_vt(vt);
-      const bool has_next = vt_next < nvirt;
-      const TileCoord tc_next = tile_coord(p, unit_tile(vt_next >> p.pair, (int)(vt_next & p.pair)));
+      uint32_t u_next = u, um_next = um, un_next = un;
+      int sub_next = 0;
+      if (p.pair && sub == 0) {
+        sub_next = 1;
+      } else {
+        u_next = u + ustep;
+        um_next = um + step_m;
+        un_next = un + step_n;
+        if (un_next >= tn_u) { un_next -= tn_u; ++um_next; }
+      }
+      const bool has_next = u_next < ntiles;
+      const TileCoord tc_next = coord_of(um_next, un_next, sub_next);
       long long grow_next;
       bool row_ok_next;
       row_of(tc_next, grow_next, row_ok_next);
       if (ln_pf && has_next) load_stats(grow_next, row_ok_next);
+      if (ew == 0 && lane == 0) ISP_TRACE(1, tl, 0);
+      if (ew == kEpiWarps - 1 && lane == 0) ISP_TRACE(2, tl, 0);
       tc::mbar_wait(&tfull_bar[acc], aph);
       tc::tc_fence_after();
+      if (ew == 0 && lane == 0) ISP_TRACE(1, tl, 1);
+      if (ew == kEpiWarps - 1 && lane == 0) ISP_TRACE(2, tl, 1);
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
       const float* bs = bias_s;
       const float* gs = lng_s;
+      const float2 rstd2 = make_float2(ln_rstd, ln_rstd), nrm2 = make_float2(ln_nrm, ln_nrm);
       for (int i = 0; i < n_my; ++i, ++st_seq) {
-        float st_sum = 0.f, st_sq = 0.f;
+        float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = st_sum2;  // even / odd columns, added at the end
         const int col0 = (part + kParts * i) * CW;  // column inside the tile
         const int ncols = min(CW, p.BN - col0);     // multiple of 16
         const bool is_tail = ncols < CW;
@@ -619,12 +679,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int sb = 0; sb < CW / 32; ++sb) {
           const int scol = sb * 32;
-          if (scol < ncols && !(p.dbg & 8)) {
+          if (scol < ncols) {
             uint32_t vr[32];
-            if (p.dbg & 2) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) vr[e] = 0x3f800000u + e;
-            } else if (scol + 32 <= ncols) {
+            if (scol + 32 <= ncols) {
               tc::tmem_ld32(t_addr + col0 + scol, vr);
             } else {  // 16 live columns
               tc::tmem_ld16(t_addr + col0 + scol, *reinterpret_cast<uint32_t(*)[16]>(&vr[0]));
@@ -637,91 +694,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int u = sb * UPS + uu;          // 16-byte unit inside the chunk row
               if (u * 16 < row_bytes) {
                 uint8_t* sp = orow + (is_tail ? (u << 4) : ((u ^ r7) << 4));
-                float x[CPU_];
+                // packed fp32 pairs (FFMA2 / FADD2 / FMUL2): LayerNorm of the A row folded as a = rstd * acc + (nrm * g[n] + bias[n])
+                // -- with rstd = 1, nrm = 0 and g = 0 when no LayerNorm is fused, so there is one code path
+                float2 x2[CPU_ / 2];
 #pragma unroll
                 for (int e4 = 0; e4 < CPU_; e4 += 4) {
-                  float4 bb = *reinterpret_cast<const float4*>(bs + col0 + scol + uu * CPU_ + e4);
-                  float a0 = __uint_as_float(vr[uu * CPU_ + e4 + 0]), a1 = __uint_as_float(vr[uu * CPU_ + e4 + 1]);
-                  float a2 = __uint_as_float(vr[uu * CPU_ + e4 + 2]), a3 = __uint_as_float(vr[uu * CPU_ + e4 + 3]);
-                  if (ln_on) {  // fused LayerNorm of the A row
-                    const float4 gg = *reinterpret_cast<const float4*>(gs + col0 + scol + uu * CPU_ + e4);
-                    a0 = fmaf(ln_rstd, a0, ln_nrm * gg.x); a1 = fmaf(ln_rstd, a1, ln_nrm * gg.y);
-                    a2 = fmaf(ln_rstd, a2, ln_nrm * gg.z); a3 = fmaf(ln_rstd, a3, ln_nrm * gg.w);
+                  const float4 bb = *reinterpret_cast<const float4*>(bs + col0 + scol + uu * CPU_ + e4);
+                  const float4 gg = *reinterpret_cast<const float4*>(gs + col0 + scol + uu * CPU_ + e4);
+                  const float2 c0 = __ffma2_rn(nrm2, make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+                  const float2 c1v = __ffma2_rn(nrm2, make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+                  float2 a0 = __ffma2_rn(rstd2, make_float2(__uint_as_float(vr[uu * CPU_ + e4 + 0]),
+                                                            __uint_as_float(vr[uu * CPU_ + e4 + 1])), c0);
+                  float2 a1 = __ffma2_rn(rstd2, make_float2(__uint_as_float(vr[uu * CPU_ + e4 + 2]),
+                                                            __uint_as_float(vr[uu * CPU_ + e4 + 3])), c1v);
+                  if constexpr (ACT != 0 && ACT != 5) {
+                    a0.x = act_fn<ACT>(a0.x); a0.y = act_fn<ACT>(a0.y);
+                    a1.x = act_fn<ACT>(a1.x); a1.y = act_fn<ACT>(a1.y);
                   }
-                  x[e4 + 0] = act_fn<ACT>(a0 + bb.x) * p.alpha;
-                  x[e4 + 1] = act_fn<ACT>(a1 + bb.y) * p.alpha;
-                  x[e4 + 2] = act_fn<ACT>(a2 + bb.z) * p.alpha;
-                  x[e4 + 3] = act_fn<ACT>(a3 + bb.w) * p.alpha;
+                  if (has_alpha) { a0 = __fmul2_rn(a0, alpha2); a1 = __fmul2_rn(a1, alpha2); }
+                  x2[e4 / 2] = a0;
+                  x2[e4 / 2 + 1] = a1;
                 }
                 if (RESID) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(sp);
+                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
                   if constexpr (ACT == 5) {
                     // ReLU backward: the "residual" operand is the forward activation; keep the gradient where it is > 0
                     if constexpr (OUT_BF16) {
-                      const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                       for (int k = 0; k < 4; ++k) {
-                        if (!(__uint_as_float(rw[k] << 16) > 0.f)) x[2 * k] = 0.f;
-                        if (!(__uint_as_float(rw[k] & 0xffff0000u) > 0.f)) x[2 * k + 1] = 0.f;
+                        if (!(__uint_as_float(rw[k] << 16) > 0.f)) x2[k].x = 0.f;
+                        if (!(__uint_as_float(rw[k] & 0xffff0000u) > 0.f)) x2[k].y = 0.f;
                       }
                     } else {
-                      if (!(__uint_as_float(rr.x) > 0.f)) x[0] = 0.f;
-                      if (!(__uint_as_float(rr.y) > 0.f)) x[1] = 0.f;
-                      if (!(__uint_as_float(rr.z) > 0.f)) x[2] = 0.f;
-                      if (!(__uint_as_float(rr.w) > 0.f)) x[3] = 0.f;
+                      if (!(__uint_as_float(rr.x) > 0.f)) x2[0].x = 0.f;
+                      if (!(__uint_as_float(rr.y) > 0.f)) x2[0].y = 0.f;
+                      if (!(__uint_as_float(rr.z) > 0.f)) x2[1].x = 0.f;
+                      if (!(__uint_as_float(rr.w) > 0.f)) x2[1].y = 0.f;
                     }
                   } else if constexpr (OUT_BF16) {
-                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // bf16 -> f32 is a shift: the add happens in fp32, one rounding
-                      x[2 * k] += __uint_as_float(rw[k] << 16);
-                      x[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
-                    }
+                    for (int k = 0; k < 4; ++k)  // bf16 -> f32 is a shift: the add happens in fp32, one rounding
+                      x2[k] = __fadd2_rn(x2[k], make_float2(__uint_as_float(rw[k] << 16), __uint_as_float(rw[k] & 0xffff0000u)));
                   } else {
-                    x[0] += __uint_as_float(rr.x); x[1] += __uint_as_float(rr.y);
-                    x[2] += __uint_as_float(rr.z); x[3] += __uint_as_float(rr.w);
+                    x2[0] = __fadd2_rn(x2[0], make_float2(__uint_as_float(rr.x), __uint_as_float(rr.y)));
+                    x2[1] = __fadd2_rn(x2[1], make_float2(__uint_as_float(rr.z), __uint_as_float(rr.w)));
                   }
                 }
                 if (!full) {
 #pragma unroll
-                  for (int e = 0; e < CPU_; ++e)
-                    if (nglob + scol + uu * CPU_ + e >= p.N) x[e] = 0.f;
+                  for (int e = 0; e < CPU_; e += 2) {
+                    if (nglob + scol + uu * CPU_ + e >= p.N) x2[e / 2].x = 0.f;
+                    if (nglob + scol + uu * CPU_ + e + 1 >= p.N) x2[e / 2].y = 0.f;
+                  }
                 }
                 uint4 w;
                 if constexpr (OUT_BF16) {
-                  __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]), b1 = __floats2bfloat162_rn(x[2], x[3]);
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(x2[0].x, x2[0].y), b1 = __floats2bfloat162_rn(x2[1].x, x2[1].y);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(x2[2].x, x2[2].y), b3 = __floats2bfloat162_rn(x2[3].x, x2[3].y);
                   w = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1),
                                  *reinterpret_cast<uint32_t*>(&b2), *reinterpret_cast<uint32_t*>(&b3));
                   if (p.stats_out) {  // statistics of the values the consumer will read (after bf16 rounding)
                     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                      const float lo = __uint_as_float(ww[k] << 16), hi = __uint_as_float(ww[k] & 0xffff0000u);
-                      st_sum += lo + hi;
-                      st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+                      const float2 v = make_float2(__uint_as_float(ww[k] << 16), __uint_as_float(ww[k] & 0xffff0000u));
+                      st_sum2 = __fadd2_rn(st_sum2, v);
+                      st_sq2 = __ffma2_rn(v, v, st_sq2);
                     }
                   }
                 } else {
                   if (p.stats_out) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { st_sum += x[k]; st_sq = fmaf(x[k], x[k], st_sq); }
+                    for (int k = 0; k < 2; ++k) { st_sum2 = __fadd2_rn(st_sum2, x2[k]); st_sq2 = __ffma2_rn(x2[k], x2[k], st_sq2); }
                   }
-                  w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+                  w = make_uint4(__float_as_uint(x2[0].x), __float_as_uint(x2[0].y), __float_as_uint(x2[1].x), __float_as_uint(x2[1].y));
                 }
-                if (!(p.dbg & 4)) *reinterpret_cast<uint4*>(sp) = w;
-                else if (w.x == 0x12345u) p.stats_out[0] = 1.f;
+                *reinterpret_cast<uint4*>(sp) = w;
               }
             }
           }
         }
         if (p.stats_out && row_ok) {
           const int slot = (tc_.n0 / p.BN) * nchunks + (part + kParts * i);
-          reinterpret_cast<float2*>(p.stats_out)[grow * p.stats_slots + slot] = make_float2(st_sum, st_sq);
+          reinterpret_cast<float2*>(p.stats_out)[grow * p.stats_slots + slot] = make_float2(st_sum2.x + st_sum2.y, st_sq2.x + st_sq2.y);
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && !(p.dbg & 9)) {
+        if (lane == 0) {
           const CUtensorMap* m = is_tail ? &tmDt : &tmD;
           if (p.TW || p.batched) tc::tma_store_4d(m, obuf, nglob, c1, c2, c3);
           else tc::tma_store_2d(m, obuf, nglob, c1);
@@ -730,11 +790,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc::tc_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) ISP_TRACE(1, tl, 2);
+      if (ew == kEpiWarps - 1 && lane == 0) ISP_TRACE(2, tl, 2);
       if (lane == 0) {  // accumulator drained (CTA pair: only the leader's MMA warp waits, on the leader's barrier)
         if (CTA2) tc::mbar_arrive_leader(&tempty_bar[acc]);
         else tc::mbar_arrive(&tempty_bar[acc]);
       }
-      vt = vt_next; tc_ = tc_next; grow = grow_next; row_ok = row_ok_next;
+      u = u_next; um = um_next; un = un_next; sub = sub_next;
+      tc_ = tc_next; grow = grow_next; row_ok = row_ok_next;
     }
     if (lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA retires
   }
@@ -813,22 +876,20 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   const int G = 2 << p.pair;
   p.cta2 = (!p.batched && 2 * max_clusters >= num_sms - 4 && p.tiles_m % G == 0 &&
-            (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters && !getenv("ISP_GEMM_NO_CTA2")) ? 1 : 0;
-  // a second staging chunk per epilogue warp only where it hides latency: the residual of the next item is prefetched into it
-  // (pair mode exposes its epilogue anyway and needs the shared memory for the wider operand stages)
+            (p.tiles_m / G) * p.tiles_n >= 2LL * max_clusters) ? 1 : 0;
+  // staging chunks per epilogue warp: one, or two where the second hides latency: the residual of the next item is
+  // prefetched into it (pair mode exposes its epilogue anyway and needs the shared memory for its wider operand stages)
   p.epi_bufs = (resid && !p.pair) ? 2 : 1;
-  // resident weights: plain CTA-pair GEMM without residual (that one needs the shared memory for its second staging chunk,
-  // and its HBM floor is above the operand-fill time anyway) whose share of the weight tile (all k-blocks) fits next to a >= 3-stage ring of A tiles
+  // resident weights: plain CTA-pair GEMM without residual whose share of the weight tile (all k-blocks) fits next to the
+  // staging chunks and a >= 5-stage ring of A tiles (fewer leave the MMA warp waiting for operands: the TMA round trip is
+  // ~3000 cycles; 802816 x 448 x 404 with 3 stages: 4000 cycles of operand wait per 128 x 224 tile, with 5: 1000)
   const int a_bytes = BM * BK * 2 << p.pair;
   const int w_bytes = (p.K / BK) * (p.BN >> 1) * BK * 2;
   p.wres = (p.cta2 && !p.pair && !p.TW && !resid && max_clusters >= p.tiles_n &&
-            kSmemBytes - kEpiWarps * 4096 - w_bytes >= 3 * a_bytes && !getenv("ISP_GEMM_NO_WRES")) ? 1 : 0;
-  if (p.wres) p.epi_bufs = 1;
-  p.dbg = getenv("ISP_GEMM_DBG") ? atoi(getenv("ISP_GEMM_DBG")) : 0;
+            kSmemBytes - kEpiWarps * 4096 - w_bytes >= 5 * a_bytes) ? 1 : 0;
   const int stage_bytes = a_bytes + (p.wres ? 0 : (p.BN >> p.cta2) * BK * 2);
   p.stages = (kSmemBytes - kEpiWarps * 4096 * p.epi_bufs - (p.wres ? w_bytes : 0)) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  if (getenv("ISP_GEMM_STAGES")) p.stages = atoi(getenv("ISP_GEMM_STAGES"));  // timing experiments (with ISP_GEMM_DBG=8 only)
   ISP_REQUIRE(p.stages >= 2, ISP_ERR_UNSUPPORTED, "gemm_tc: tile too large for a 2-stage pipeline");
   if (p.cta2) {
     kernel_fn fn = pick_kernel<true>(out_bf16, act, resid);
@@ -895,7 +956,7 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
   p.BN = gemm::pick_bn(N, (resid && !out_bf16) ? 128 : 256);
   p.last_steps = (K - (p.K - gemm::BK) + 15) / 16;
   p.TW = 0;
-  p.tiles_m = (M + gemm::BM - 1) / gemm::BM;
+  p.tiles_m = (int)((M + gemm::BM - 1) / gemm::BM);
   p.tiles_n = (N + p.BN - 1) / p.BN;
   p.pair = 0;  // K is short here: the exposed epilogue costs more than the shared weight tile saves (measured)
   p.bias = bias; p.alpha = alpha;
@@ -940,6 +1001,18 @@ static int gemm_common(const void* A, long long lda, const void* W, long long ld
   }
   return gemm::launch(tmA, tmB, tmD, tmDt, tmR, tmRt, tmBh, p, out_bf16, act, resid != nullptr, as_stream(stream));
 }
+
+#ifdef ISP_GEMM_TRACE
+extern "C" int isp_gemm_trace_read(long long* host_out, int reset) {
+  ISP_CUDA(cudaDeviceSynchronize());
+  ISP_CUDA(cudaMemcpyFromSymbol(host_out, gemm::g_trace, sizeof(gemm::g_trace)));
+  if (reset) {
+    static long long zeros[4 * 64 * 4];
+    ISP_CUDA(cudaMemcpyToSymbol(gemm::g_trace, zeros, sizeof(zeros)));
+  }
+  return ISP_OK;
+}
+#endif
 
 extern "C" int isp_gemm_bf16_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias,
                                 const void* resid, int resid_bf16, long long ldr, float alpha, int act, void* D,
@@ -999,7 +1072,8 @@ static int gemm_batched_common(const void* A, long long a_sm, long long a_sh, lo
   p.last_steps = (K - (p.K - gemm::BK) + 15) / 16;
   p.TW = 0;
   p.batched = H; p.nbatch = B;
-  p.tiles_m = (long long)((M + gemm::BM - 1) / gemm::BM) * H * B;
+  ISP_REQUIRE((long long)((M + gemm::BM - 1) / gemm::BM) * H * B < (1ll << 24), ISP_ERR_UNSUPPORTED, "gemm_bf16_tc_batched: too many row tiles");
+  p.tiles_m = ((M + gemm::BM - 1) / gemm::BM) * H * B;
   p.tiles_n = (N + p.BN - 1) / p.BN;
   p.pair = 0;
   p.bias = nullptr; p.alpha = alpha;
@@ -1099,7 +1173,8 @@ static int conv3x3_common(const void* X, const void* Wp, const float* bias, int 
   }
   p.TW = TW; p.TH = 128 / TW; p.H = H; p.W = Wd; p.cin_chunks = Cin_pad / 64;
   p.tiles_w = (Wd + p.TW - 1) / p.TW; p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.tiles_m = (long long)Nimg * p.tiles_w * p.tiles_h;
+  ISP_REQUIRE((long long)Nimg * p.tiles_w * p.tiles_h < (1ll << 24), ISP_ERR_UNSUPPORTED, "conv3x3_bf16_tc: too many pixel tiles");
+  p.tiles_m = Nimg * p.tiles_w * p.tiles_h;
   p.tiles_n = (Cout + p.BN - 1) / p.BN;
   p.pair = 1;  // K loop of >= 9 k-blocks: the un-overlapped epilogue is small against the saved operand traffic
   p.bias = bias; p.alpha = 1.f;
