@@ -269,63 +269,84 @@ __device__ __forceinline__ float sincos_turns(float a, bool want_cos) {
   return want_cos ? __cosf(x) : __sinf(x);
 }
 
+constexpr int kFourierPix = 16;  // pixels per warp: the lane's channel constants are loaded once for all of them
 __global__ void __launch_bounds__(256) fourier_chnorm_kernel(
     const float* __restrict__ img, long long sb, long long sc, long long sh, long long sw, const int* __restrict__ mm,
     const float* __restrict__ gridr, const float* __restrict__ gridc, const float* __restrict__ freqs,
     const float* __restrict__ bias_sin, const float* __restrict__ bias_cos, const float* __restrict__ gamma,
     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int B, int H, int W, int ldo, float eps) {
-  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * H * W;
-  if (pix >= total) return;
-  const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-  float u[5];
-  u[0] = gridr[h];
-  u[1] = gridc[w];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float mn = ord_float(mm[c]), mx = ord_float(mm[3 + c]);
-    const float sc_ = fmaxf(__fsub_rn(mx, mn), 1e-4f);
-    const float x = img[b * sb + c * sc + h * sh + w * sw];
-    u[2 + c] = __fsub_rn(__fdiv_rn(__fsub_rn(x, mn), sc_), 0.5f);
-  }
-  // lane owns the channel pairs (2 lane, 2 lane + 1) + 64 i: bf16x2 stores, 128 bytes per warp and instruction
-  float val[8];
-  float s = 0.f;
+  const long long pix0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kFourierPix;
+  if (pix0 >= total) return;
+  // lane owns the channel pairs (2 lane, 2 lane + 1) + 64 i: bf16x2 stores, 128 bytes per warp and instruction.  Per channel:
+  // which of the five inputs it reads (kind 0..4, 5 = raw colour pass-through, 6 = padding), frequency, phase, affine
+  float cf[8], cb[8], cg[8], ce[8];
+  int kind[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = 2 * lane + (i >> 1) * 64 + (i & 1);
-    float v = 0.f;
+    cf[i] = 0.f; cb[i] = 0.f; kind[i] = 6;
     if (c < 200) {
       const int cc = c < 100 ? c : c - 100;
-      const int f = cc / 5, d = cc - f * 5;
-      float ud = u[0];
-      ud = d == 1 ? u[1] : ud; ud = d == 2 ? u[2] : ud; ud = d == 3 ? u[3] : ud; ud = d == 4 ? u[4] : ud;
-      const float arg = __fadd_rn(__fmul_rn(ud, freqs[f]), c < 100 ? bias_sin[cc] : bias_cos[cc]);
-      v = sincos_turns(arg, c >= 100);
+      const int f = cc / 5;
+      kind[i] = cc - f * 5;
+      cf[i] = freqs[f];
+      cb[i] = c < 100 ? bias_sin[cc] : bias_cos[cc];
     } else if (c < 203) {
-      v = c == 200 ? u[2] : (c == 201 ? u[3] : u[4]);
+      kind[i] = 5;
     }
-    val[i] = v;
-    s += v;
+    cg[i] = c < 203 ? gamma[c] : 0.f;
+    ce[i] = c < 203 ? beta[c] : 0.f;
   }
-  const float mean = warp_sum(s) / 203.f;
-  float var = 0.f;
+  float mn[3], sc_[3];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = 2 * lane + (i >> 1) * 64 + (i & 1);
-    const float d = c < 203 ? val[i] - mean : 0.f;
-    var += d * d;
+  for (int c = 0; c < 3; ++c) {
+    mn[c] = ord_float(mm[c]);
+    sc_[c] = fmaxf(__fsub_rn(ord_float(mm[3 + c]), mn[c]), 1e-4f);
   }
-  const float rstd = rsqrtf(warp_sum(var) / 203.f + eps);
-  __nv_bfloat16* o = out + pix * ldo;  // ldo is even and the rows 4-byte aligned (checked by the entry point)
+  const long long pend = pix0 + kFourierPix < total ? pix0 + kFourierPix : total;
+  for (long long pix = pix0; pix < pend; ++pix) {
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    float u[5];
+    u[0] = gridr[h];
+    u[1] = gridc[w];
 #pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    const int c = 2 * lane + (i >> 1) * 64;
-    if (c < ldo) {
-      const float a0 = c < 203 ? (val[i] - mean) * rstd * gamma[c] + beta[c] : 0.f;
-      const float a1 = c + 1 < 203 ? (val[i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1] : 0.f;
-      *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(a0, a1);
+    for (int c = 0; c < 3; ++c) {
+      const float x = img[b * sb + c * sc + h * sh + w * sw];
+      u[2 + c] = __fsub_rn(__fdiv_rn(__fsub_rn(x, mn[c]), sc_[c]), 0.5f);
+    }
+    float val[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 2 * lane + (i >> 1) * 64 + (i & 1);  // compile-time per i except for the lane term
+      const int k = kind[i];
+      float ud = u[0];
+      ud = k == 1 ? u[1] : ud; ud = k == 2 ? u[2] : ud; ud = k == 3 ? u[3] : ud; ud = k == 4 ? u[4] : ud;
+      const float arg = __fadd_rn(__fmul_rn(ud, cf[i]), cb[i]);
+      float v = sincos_turns(arg, c >= 100);
+      if (k >= 5) v = k == 6 ? 0.f : (c == 200 ? u[2] : (c == 201 ? u[3] : u[4]));
+      val[i] = v;
+      s += v;
+    }
+    const float mean = warp_sum(s) / 203.f;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = kind[i] < 6 ? val[i] - mean : 0.f;
+      var += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(var) / 203.f + eps);
+    __nv_bfloat16* o = out + pix * ldo;  // ldo is even and the rows 4-byte aligned (checked by the entry point)
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const int c = 2 * lane + (i >> 1) * 64;
+      if (c < ldo) {
+        const float a0 = kind[i] < 6 ? (val[i] - mean) * rstd * cg[i] + ce[i] : 0.f;
+        const float a1 = kind[i + 1] < 6 ? (val[i + 1] - mean) * rstd * cg[i + 1] + ce[i + 1] : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(a0, a1);
+      }
     }
   }
 }
@@ -377,23 +398,56 @@ constexpr int kRepackT = 64;
 __global__ void __launch_bounds__(256) repack_heads_kernel(const void* __restrict__ src, int src_bf16, long long ld,
                                                            int col0, int hd, __nv_bfloat16* __restrict__ dst, int B,
                                                            int T, int Tpad, int heads, int D, int transpose) {
-  extern __shared__ __nv_bfloat16 rp_tile[];  // [kRepackT][hd | 1] (odd pitch in 16-bit words pairs)
+  extern __shared__ __align__(4) __nv_bfloat16 rp_tile[];  // [kRepackT][pitch], pitch = hd + 2 - (hd & 1): even, 33 (mod 32) words
   const int t0 = blockIdx.x * kRepackT, hh = blockIdx.y, b = blockIdx.z;
-  const int pitch = hd | 1;
+  const int pitch = hd + 2 - (hd & 1);
   const int nt = min(kRepackT, Tpad - t0);
-  for (int e = threadIdx.x; e < kRepackT * hd; e += blockDim.x) {
-    const int tt = e / hd, d = e - tt * hd, t = t0 + tt;
-    float v = 0.f;
-    if (t < T) v = ld_any(src, ((long long)b * T + t) * ld + col0 + hh * hd + d, src_bf16);
-    rp_tile[tt * pitch + d] = __float2bfloat16(v);
+  // pairs of columns where the source allows it (bf16, even head width / offsets): 4-byte loads, stores and smem accesses
+  const bool pairs = src_bf16 && !(hd & 1) && !((col0 + hh * hd) & 1) && !(ld & 1) &&
+                     !(reinterpret_cast<uintptr_t>(src) & 3);
+  if (pairs) {
+    const int hd2 = hd >> 1;
+    const __nv_bfloat16* s16 = static_cast<const __nv_bfloat16*>(src);
+    for (int e = threadIdx.x; e < kRepackT * hd2; e += blockDim.x) {
+      const int tt = e / hd2, d = (e - tt * hd2) * 2, t = t0 + tt;
+      uint32_t v = 0u;
+      if (t < T) v = *reinterpret_cast<const uint32_t*>(s16 + ((long long)b * T + t) * ld + col0 + hh * hd + d);
+      *reinterpret_cast<uint32_t*>(rp_tile + tt * pitch + d) = v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < kRepackT * hd; e += blockDim.x) {
+      const int tt = e / hd, d = e - tt * hd, t = t0 + tt;
+      float v = 0.f;
+      if (t < T) v = ld_any(src, ((long long)b * T + t) * ld + col0 + hh * hd + d, src_bf16);
+      rp_tile[tt * pitch + d] = __float2bfloat16(v);
+    }
   }
   __syncthreads();
   const __nv_bfloat16 zero = __float2bfloat16(0.f);
   __nv_bfloat16* out = dst + ((long long)b * heads + hh) * (long long)Tpad * D;
   if (!transpose) {
-    for (int e = threadIdx.x; e < nt * D; e += blockDim.x) {
-      const int tt = e / D, d = e - tt * D;
-      out[(long long)(t0 + tt) * D + d] = d < hd ? rp_tile[tt * pitch + d] : zero;
+    if (pairs && !(D & 1)) {
+      const int D2 = D >> 1;
+      for (int e = threadIdx.x; e < nt * D2; e += blockDim.x) {
+        const int tt = e / D2, d = (e - tt * D2) * 2;
+        const uint32_t v = d < hd ? *reinterpret_cast<const uint32_t*>(rp_tile + tt * pitch + d) : 0u;
+        *reinterpret_cast<uint32_t*>(out + (long long)(t0 + tt) * D + d) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < nt * D; e += blockDim.x) {
+        const int tt = e / D, d = e - tt * D;
+        out[(long long)(t0 + tt) * D + d] = d < hd ? rp_tile[tt * pitch + d] : zero;
+      }
+    }
+  } else if (!(Tpad & 1)) {  // two tokens per 4-byte store (t0 is a multiple of 64)
+    for (int e = threadIdx.x; e < D * (kRepackT / 2); e += blockDim.x) {
+      const int d = e / (kRepackT / 2), tt = (e - d * (kRepackT / 2)) * 2;
+      if (tt < nt) {  // nt is even here: Tpad and t0 are
+        __nv_bfloat162 v;
+        v.x = d < hd ? rp_tile[tt * pitch + d] : zero;
+        v.y = d < hd ? rp_tile[(tt + 1) * pitch + d] : zero;
+        *reinterpret_cast<__nv_bfloat162*>(out + (long long)d * Tpad + t0 + tt) = v;
+      }
     }
   } else {
     for (int e = threadIdx.x; e < D * kRepackT; e += blockDim.x) {
@@ -530,7 +584,7 @@ extern "C" int isp_loftup_fourier_chnorm(const float* img, long long sb, long lo
   ISP_REQUIRE(ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 3) == 0, ISP_ERR_MISALIGNED,
               "loftup_fourier_chnorm: ldo must be even and the output 4-byte aligned");
   const long long total = (long long)B * H * W;
-  fourier_chnorm_kernel<<<cdiv(total, 8), 256, 0, as_stream(stream)>>>(
+  fourier_chnorm_kernel<<<cdiv(total, 8 * kFourierPix), 256, 0, as_stream(stream)>>>(
       img, sb, sc, sh, sw, mm6, gridr, gridc, freqs20, bias_sin, bias_cos, gamma, beta,
       reinterpret_cast<__nv_bfloat16*>(out_bf16), B, H, W, ldo, eps);
   ISP_CHECK_LAUNCH("fourier_chnorm_kernel");
@@ -558,7 +612,7 @@ extern "C" int isp_repack_heads(const void* src, int src_bf16, long long ld, int
               "repack_heads: bad shape");
   ISP_REQUIRE(B <= 65535 && heads <= 65535 && head_dim <= 512, ISP_ERR_UNSUPPORTED, "repack_heads: grid too large");
   const dim3 grid((unsigned)cdiv(Tpad, kRepackT), (unsigned)heads, (unsigned)B);
-  const size_t smem = (size_t)kRepackT * (head_dim | 1) * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)kRepackT * (head_dim + 2 - (head_dim & 1)) * sizeof(__nv_bfloat16);
   repack_heads_kernel<<<grid, 256, smem, as_stream(stream)>>>(src, src_bf16, ld, col0, head_dim,
                                                               reinterpret_cast<__nv_bfloat16*>(dst_bf16), B, T, Tpad,
                                                               heads, D, transpose);
