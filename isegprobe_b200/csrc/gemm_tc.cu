@@ -76,7 +76,12 @@ constexpr int BM = 128, BK = 64;
 #endif
 constexpr int kEpiWarps = ISP_GEMM_EPI_WARPS;      // kParts warps per TMEM lane quarter (they split the chunks of its 32 rows)
 constexpr int kParts = kEpiWarps / 4;
-constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, the rest epilogue
+constexpr int kFirstEpiWarp = 4;                   // warp group 0 = warp 0 TMA, warp 1 MMA, warps 2-3 idle; the rest epilogue
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+// Registers: the block is compiled for 96 per thread (65536 / 640); warp group 0 gives most of its share back (setmaxnreg)
+// and the epilogue warp groups raise theirs, which removes the spills of the epilogue's per-tile state (their reloads
+// were ~16 % of its stall samples)
+constexpr int kRegsLow = 32, kRegsEpi = 112;  // 128 x (96 - 32) released = 4 x 128 x (112 - 96) acquired: inc draws only on what dec freed
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBytes = 224 * 1024;             // operand ring + epilogue staging (4 KB chunks of 32 rows x 128 B, one or
@@ -258,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  if (warp < kFirstEpiWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -470,8 +476,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wb += b_bytes;
       }
     }
-  } else {
-    // ------------------------------------------------------------- epilogue (warps 2 .. 2 + kEpiWarps)
+  } else if (warp >= kFirstEpiWarp) {
+    // ------------------------------------------------------------- epilogue (warps kFirstEpiWarp ..)
     // The warps are independent of each other: each owns the chunks part, part + kParts, ... of its 32 rows of every tile
     // ("items"), with its own staging buffer(s), residual barriers and TMA store groups; the only CTA-wide step is the
     // reload of the bias slice when a tile starts at another column than the previous one.
@@ -479,7 +485,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int ESZ = OUT_BF16 ? 2 : 4;
     constexpr int UPS = OUT_BF16 ? 4 : 8;     // 16-byte units per 32 accumulator columns
     constexpr int CPU_ = 16 / ESZ;            // columns per 16-byte unit
-    const int ew = warp - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    const int ew = warp - kFirstEpiWarp;
     const int q = warp & 3;      // TMEM lane quarter this warp may access == its 32 rows of the tile
     const int part = ew >> 2;    // which of the kParts warps sharing that quarter
     const int etid = ew * 32 + lane;
