@@ -8,7 +8,23 @@ def relerr(a, b):
 
 def cosine(a, b):
     a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
-    return float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    c = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    _record("cosine", c)
+    return c
+
+
+def _record(kind, value):
+    """ISP_TEST_REPORT=<file>: append every measured cosine with its call site (how the asserted thresholds were chosen;
+    profiles/r02_test_measurements.txt)."""
+    import inspect
+    import os
+    path = os.environ.get("ISP_TEST_REPORT")
+    if not path:
+        return
+    fr = inspect.stack()[2]
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+    with open(path, "a") as f:
+        f.write(f"{test}\t{os.path.basename(fr.filename)}:{fr.lineno}\t{kind}\t{value:.6f}\n")
 
 
 DEV = "cuda:0"

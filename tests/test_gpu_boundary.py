@@ -107,7 +107,7 @@ def test_reference_model_trains_through_our_modules(models):
     assert set(grads[0]) == set(grads[1]) and "embed_coords.proj.weight" in grads[0]
     for k in grads[0]:
         c = cosine(grads[1][k], grads[0][k])
-        assert c > 0.99, (k, c)
+        assert c > 0.999, (k, c)  # measured min 0.99996
 
 
 def test_reference_model_in_train_mode_matches(models):
@@ -137,7 +137,7 @@ def test_reference_model_in_train_mode_matches(models):
     (l0, g0, b0), (l1, g1, b1) = res
     assert cosine(l1, l0) > 0.999, cosine(l1, l0)
     for k in g0:
-        assert cosine(g1[k], g0[k]) > 0.99, (k, cosine(g1[k], g0[k]))
+        assert cosine(g1[k], g0[k]) > 0.999, (k, cosine(g1[k], g0[k]))
     # reference keys: upsampler.upsampler.first_conv.N.running_*; ours: upsampler.upsampler.first_conv.N.running_* as well
     assert len(b0) == 4 and set(b0) == set(b1), (sorted(b0), sorted(b1))
     for k in b0:

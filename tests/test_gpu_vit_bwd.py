@@ -1,6 +1,8 @@
 """GPU parity: activation backward through the frozen ViT (gradient of the injected click embedding) against torch
 autograd through the fp32 oracle (oracle/vit.py; reference: core/model/featurizers/DINOv2.py:500-546 under
-trainer.py:213-221), plus the kernels it is made of.  bf16 tensor-core mode: cosine >= 0.99 on the gradient."""
+trainer.py:213-221), plus the kernels it is made of.  bf16 tensor-core mode: cosine >= 0.999 on the gradient of every single module
+(measured >= 0.99995) and >= 0.99 through the whole bf16 pipeline incl. the head (measured min 0.9929); the measured values of
+every assertion are in profiles/r02_test_measurements.txt (ISP_TEST_REPORT=file pytest ...)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -148,7 +150,7 @@ def test_vit_click_embedding_gradient_vs_oracle_autograd(B, H, W):
     out.backward(gout.to(DEV))
     assert e.grad is not None and tuple(e.grad.shape) == (B, n, 384)
     c = cosine(e.grad, e_ref.grad)
-    assert c > 0.99, c
+    assert c > 0.999, c  # measured >= 0.99995 (profiles/r02_test_measurements.txt)
     assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
     # forward value under autograd equals the inference path bit for bit
     with torch.no_grad():
@@ -236,7 +238,7 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
     assert cosine(gb, pr["proj.bias"].grad) > 0.98, cosine(gb, pr["proj.bias"].grad)
     for k, v in hr_.items():
         got = dict(pipe.head.named_parameters())[k].grad
-        assert cosine(got, v.grad) > 0.99, (k, cosine(got, v.grad))
+        assert cosine(got, v.grad) > 0.99, (k, cosine(got, v.grad))  # whole bf16 pipeline vs fp32 autograd: measured min 0.9929
 
 
 def test_bicubic_reflectpad_adjoint():
@@ -295,7 +297,7 @@ def test_loftup_source_gradient_vs_oracle_autograd(B, H, W, h, w):
     out.backward(gout.to(DEV))
     assert cosine(out, want) >= 0.999
     c = cosine(s.grad, lr_ref.grad)
-    assert c > 0.99, c
+    assert c > 0.999, c  # measured >= 0.99995 (profiles/r02_test_measurements.txt)
     assert relerr(s.grad, lr_ref.grad) < 0.2, relerr(s.grad, lr_ref.grad)
     # the flash-style attention backward (default) against the path that materialises the probabilities
     assert m.flash_backward
@@ -303,7 +305,7 @@ def test_loftup_source_gradient_vs_oracle_autograd(B, H, W, h, w):
     s2 = lr.to(DEV).requires_grad_(True)
     m(source=s2, guidance=img.to(DEV)).backward(gout.to(DEV))
     assert cosine(s.grad, s2.grad) > 0.999, cosine(s.grad, s2.grad)
-    assert cosine(s2.grad, lr_ref.grad) > 0.99
+    assert cosine(s2.grad, lr_ref.grad) > 0.999
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 64, 96)])
@@ -327,7 +329,7 @@ def test_maskclip_click_embedding_gradient_vs_oracle_autograd(B, H, W):
     out = f(img.to(DEV), e)
     out.backward(gout.to(DEV))
     c = cosine(e.grad, e_ref.grad)
-    assert c > 0.99, c
+    assert c > 0.999, c  # measured >= 0.99995 (profiles/r02_test_measurements.txt)
     assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
     with torch.no_grad():
         assert torch.equal(out.detach(), f(img.to(DEV), emb.to(DEV)))
@@ -357,7 +359,7 @@ def test_dino_vit_backbone_forward_and_gradient(feat_type, golden):
     e = (emb * 5).to(DEV).requires_grad_(True)
     f(img.to(DEV), e).backward(gout.to(DEV))
     c = cosine(e.grad, e_ref.grad)
-    assert c > 0.99, c
+    assert c > 0.999, c  # measured >= 0.99995 (profiles/r02_test_measurements.txt)
     assert relerr(e.grad, e_ref.grad) < 0.15, relerr(e.grad, e_ref.grad)
 
 
@@ -406,7 +408,7 @@ def test_simple_vit_parameter_gradients_match_oracle_autograd(hw, depth):
         want = ref[k].grad.to(DEV)
         c = cosine(p.grad, want)
         worst[k] = c
-        assert c > 0.99, (k, c, float(p.grad.norm()), float(want.norm()))
+        assert c > 0.999, (k, c, float(p.grad.norm()), float(want.norm()))
         assert abs(float(p.grad.norm() / want.norm()) - 1) < 0.05, k
     assert len(worst) == 6 + 10 * depth + 2
 
