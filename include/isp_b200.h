@@ -349,6 +349,11 @@ int isp_repack_heads(const void* src, int src_bf16, long long ld, int col0, int 
 int isp_conv3x3_s2_c32(const float* in, long long sb, long long sc, long long sh, long long sw,
                        const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
                        isp_stream_t stream);
+/* isp_conv3x3_s2_c32 without the ReLU (bias = the conv's own bias): the raw output whose batch statistics a BatchNorm2d in
+ * train() normalises with (LiFT.py:69-90 under core/training/trainer.py:213-214). */
+int isp_conv3x3_s2_c32_raw(const float* in, long long sb, long long sc, long long sh, long long sw,
+                       const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
+                       isp_stream_t stream);
 /* F.adaptive_max_pool2d on NHWC f32 (LiFT.py:110) */
 int isp_adaptive_maxpool_nhwc(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,
                               isp_stream_t stream);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "isp_loftup_lr_prepare": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _S],
     "isp_repack_heads": [_P, _I, _LL, _I, _I, _P, _I, _I, _I, _I, _I, _I, _S],
     "isp_conv3x3_s2_c32": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _I, _I, _I, _I, _S],
+    "isp_conv3x3_s2_c32_raw": [_P, _LL, _LL, _LL, _LL, _P, _P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_maxpool_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _S],
     "isp_copy_channels": [_P, _I, _LL, _LL, _LL, _LL, _P, _I, _LL, _LL, _LL, _I, _I, _I, _I, _S],
     "isp_rowdot": [_P, _I, _LL, _P, _P, _P, _LL, _I, _I, _S],

@@ -11,6 +11,7 @@ namespace isp {
 // in: f32, element strides (sb,sc,sh,sw) -> out NHWC f32 [B,Ho,Wo,32].
 // weights [32][Cin][3][3] (torch layout) are staged to smem as [ (ky*3+kx)*Cin + ci ][ co ].
 // thread = (output pixel, co): the warp's 32 lanes share the pixel (broadcast input reads).
+template <bool RELU>
 __global__ void __launch_bounds__(256) conv3x3_s2_c32_kernel(const float* __restrict__ in, long long sb, long long sc,
                                                              long long sh, long long sw, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) conv3x3_s2_c32_kernel(const float* __rest
       for (int ci = 0; ci < Cin; ++ci) acc = fmaf(p[ci * sc], wk[ci * 32], acc);
     }
   }
-  out[pix * 32 + co] = fmaxf(acc, 0.f);
+  out[pix * 32 + co] = RELU ? fmaxf(acc, 0.f) : acc;
 }
 
 // F.adaptive_max_pool2d on NHWC f32: window [floor(o*I/O), ceil((o+1)*I/O))
@@ -82,17 +83,34 @@ __global__ void __launch_bounds__(256) copy_channels_kernel(const void* __restri
 
 using namespace isp;
 
-extern "C" int isp_conv3x3_s2_c32(const float* in, long long sb, long long sc, long long sh, long long sw,
-                                  const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
-                                  isp_stream_t stream) {
+static int conv3x3_s2_c32_common(const float* in, long long sb, long long sc, long long sh, long long sw, const float* w,
+                                 const float* bias, float* out, int B, int Cin, int Hi, int Wi, bool relu,
+                                 isp_stream_t stream) {
   ISP_REQUIRE(in && w && bias && out, ISP_ERR_BAD_SHAPE, "conv3x3_s2_c32: null pointer");
   ISP_REQUIRE(B > 0 && Cin > 0 && Cin <= 32 && Hi > 0 && Wi > 0, ISP_ERR_BAD_SHAPE, "conv3x3_s2_c32: bad shape (Cin <= 32)");
   const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
   const long long npix = (long long)B * Ho * Wo;
-  conv3x3_s2_c32_kernel<<<cdiv(npix, 8), 256, 0, as_stream(stream)>>>(in, sb, sc, sh, sw, w, bias, out, B, Cin, Hi, Wi,
-                                                                    Ho, Wo);
+  if (relu)
+    conv3x3_s2_c32_kernel<true><<<cdiv(npix, 8), 256, 0, as_stream(stream)>>>(in, sb, sc, sh, sw, w, bias, out, B, Cin, Hi,
+                                                                            Wi, Ho, Wo);
+  else
+    conv3x3_s2_c32_kernel<false><<<cdiv(npix, 8), 256, 0, as_stream(stream)>>>(in, sb, sc, sh, sw, w, bias, out, B, Cin, Hi,
+                                                                             Wi, Ho, Wo);
   ISP_CHECK_LAUNCH("conv3x3_s2_c32_kernel");
   return ISP_OK;
+}
+
+extern "C" int isp_conv3x3_s2_c32(const float* in, long long sb, long long sc, long long sh, long long sw,
+                                  const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
+                                  isp_stream_t stream) {
+  return conv3x3_s2_c32_common(in, sb, sc, sh, sw, w, bias, out, B, Cin, Hi, Wi, true, stream);
+}
+
+// the same convolution without the ReLU: the raw output a training-mode BatchNorm takes its batch statistics from
+extern "C" int isp_conv3x3_s2_c32_raw(const float* in, long long sb, long long sc, long long sh, long long sw,
+                                      const float* w, const float* bias, float* out, int B, int Cin, int Hi, int Wi,
+                                      isp_stream_t stream) {
+  return conv3x3_s2_c32_common(in, sb, sc, sh, sw, w, bias, out, B, Cin, Hi, Wi, false, stream);
 }
 
 extern "C" int isp_adaptive_maxpool_nhwc(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,

@@ -94,6 +94,16 @@ def golden_lift():
     with torch.no_grad():
         out = m(img, lr)
     save("lift_56x84", out=out)
+    # the same module in train() (core/training/trainer.py:213-214): its five BatchNorm layers use batch statistics and move
+    # their running statistics; the gradient w.r.t. the LR features (what the click embedding is trained through) included
+    m.train()
+    img3 = (synth.image_batch(3, 56, 84, seed=5) - 0.45) / 0.225
+    lr3 = synth.lr_features(3, 384, 4, 6, seed=6).requires_grad_(True)
+    out_t = m(img3, lr3)
+    gout = synth.lr_features(3, 384, 8, 12, seed=7)
+    (out_t * gout).sum().backward()
+    stats = {k.replace(".", "_"): v.detach().clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+    save("lift_train_56x84", out=out_t.detach(), dsource=lr3.grad.detach(), **stats)
 
 
 def golden_head():

@@ -121,6 +121,42 @@ def test_lift_golden(isp, golden):
     assert cosine(out, want) > 0.999 and relerr(out, want) < 5e-2, (cosine(out, want), relerr(out, want))
 
 
+def test_lift_train_mode_golden_reference(isp, golden):
+    """LiFTUpsampler.train() (what the reference's trainer does to the frozen upsampler, core/training/trainer.py:213-214):
+    the five BatchNorm layers use batch statistics and move their running statistics, and the gradient w.r.t. the LR
+    features goes through the BatchNorm backward of the two double-conv layers; pinned to the reference module in train()."""
+    g = golden("lift_train_56x84")
+    m = isp.LiFTUpsampler(None, 384, 14)
+    sd = synth.lift_state_dict(384, seed=0)
+    m.lift.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    img = (synth.image_batch(3, 56, 84, seed=5) - 0.45) / 0.225
+    lr = synth.lr_features(3, 384, 4, 6, seed=6).to(DEV).requires_grad_(True)
+    out = m(source=lr, guidance=img.to(DEV))
+    out.backward(synth.lr_features(3, 384, 8, 12, seed=7).to(DEV))
+    want = torch.from_numpy(g["out"])
+    assert cosine(out, want) > 0.999 and relerr(out, want) < 5e-2, (cosine(out, want), relerr(out, want))
+    c = cosine(lr.grad, torch.from_numpy(g["dsource"]))
+    assert c > 0.995, c  # measured 0.9973: two batch-statistics BatchNorm backwards over 288 pixels per channel on bf16 tensors
+    new = m.lift.state_dict()
+    for k in g.files:
+        key = [n for n in new if n.replace(".", "_") == k]
+        if "running" in k:
+            assert relerr(new[key[0]], torch.from_numpy(g[k])) < 2e-2, (k, relerr(new[key[0]], torch.from_numpy(g[k])))
+            assert relerr(new[key[0]], sd[key[0]]) > 1e-3  # they did move
+        elif "num_batches" in k:
+            assert int(new[key[0]]) == 1
+    # eval() afterwards folds the UPDATED running statistics
+    m.eval()
+    from oracle import lift as olift
+    sd2 = {k: v.detach().cpu().clone() for k, v in new.items()}
+    img2 = (synth.image_batch(2, 56, 84, seed=1) - 0.45) / 0.225
+    lr2 = synth.lr_features(2, 384, 4, 6, seed=2)
+    with torch.no_grad():
+        out2 = m(source=lr2.to(DEV), guidance=img2.to(DEV))
+    assert cosine(out2, olift.lift_forward(sd2, lr2, img2)) > 0.999
+
+
 def _pipeline_vs_oracle(isp, up_type, params, H, W, B, n_clicks):
     """Logits of ISegPipeline and of the oracle chain (iseg_base_model.py:67-110, iseg_probe_model.py:110-134) on the same
     seeded weights / inputs."""

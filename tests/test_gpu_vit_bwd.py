@@ -212,7 +212,8 @@ def test_pipeline_gradients_vs_oracle_autograd(up_type):
         from oracle import lift as olift
         tsd = synth.lift_state_dict(384, seed=0)
         pipe.upsampler.lift.load_state_dict(tsd)
-        feats = ohead.bilinear_align_corners(olift.lift_forward(tsd, lr, nimg), (H, W))
+        # pipe.train() below is the trainer's net.train(): LiFT's BatchNorm layers run on batch statistics (trainer.py:213-214)
+        feats = ohead.bilinear_align_corners(olift.lift_forward({k: v.clone() for k, v in tsd.items()}, lr, nimg, train=True), (H, W))
     elif up_type == "loftup":
         # pipe.train() below is the trainer's net.train(): LoftUp's BatchNorm runs on batch statistics (trainer.py:213-214)
         feats = oloft.loftup_forward(lsd, lr, nimg, lcn["norm.weight"], lcn["norm.bias"], train_stats={})

@@ -90,6 +90,25 @@ def test_lift_matches_reference(golden):
     assert _relerr(out, g["out"]) < 1e-5
 
 
+def test_lift_train_mode_matches_reference(golden):
+    """oracle.lift.lift_forward(train=True) == the reference LiFT module in train() (core/training/trainer.py:213-214 puts the
+    frozen upsampler there): output, every running statistic / batch counter, and the gradient w.r.t. the LR features."""
+    g = golden("lift_train_56x84")
+    sd = {k: v.clone() for k, v in synth.lift_state_dict(384, seed=0).items()}
+    img = (synth.image_batch(3, 56, 84, seed=5) - 0.45) / 0.225
+    lr = synth.lr_features(3, 384, 4, 6, seed=6).requires_grad_(True)
+    out = olift.lift_forward(sd, lr, img, train=True)
+    (out * synth.lr_features(3, 384, 8, 12, seed=7)).sum().backward()
+    assert _relerr(out.detach().numpy(), g["out"]) < 1e-4
+    assert _relerr(lr.grad.numpy(), g["dsource"]) < 1e-4
+    for k in g.files:
+        if "running" in k:
+            key = [n for n in sd if n.replace(".", "_") == k][0]
+            assert _relerr(sd[key].numpy(), g[k]) < 1e-5, k
+        elif "num_batches" in k:
+            assert int(g[k]) == 1
+
+
 def test_head_and_patch_embed_match_reference(golden):
     g = golden("head_20x28")
     sd = synth.convhead_state_dict(384, 2, 1, seed=0)
