@@ -77,3 +77,25 @@ def test_simple_vit_click_encoder_checkpoint_keys():
         assert "Unsupported backbone type" in str(e)  # core/utils/model_builder.py:50-51
     else:
         raise AssertionError("unknown embed_coords type must raise")
+
+
+def test_checkpoint_cli_verify_and_load(tmp_path):
+    """isegprobe_b200.checkpoint: a reference-style IS checkpoint ({'state_dict': head.* + embed_coords.*}, DataParallel
+    'module.' prefix tolerated) verifies against the matching configuration, loads the way the reference restores it
+    (inference/utils.py:71-74), and a checkpoint of another head width is rejected."""
+    from isegprobe_b200 import checkpoint
+    torch.manual_seed(0)
+    a = isp.ISegPipeline("loftup", {"upsampler_path": None, "n_dim": 384})
+    path = str(tmp_path / "is.pth")
+    torch.save({"state_dict": {"module." + k: v for k, v in _trainable_part(a).items()}, "config": {}}, path)
+    assert checkpoint.main(["verify", path, "--upsampler", "loftup", "--n-dim", "384"]) == 0
+    assert checkpoint.main(["inspect", path]) == 0
+    torch.manual_seed(1)
+    b = isp.ISegPipeline("loftup", {"upsampler_path": None, "n_dim": 384})
+    assert checkpoint.load_into(b, path) == []
+    for k, v in _trainable_part(a).items():
+        assert torch.equal(b.state_dict()[k], v), k
+    bad = {k: (v[:, :100] if k == "head.convs.0.conv.weight" else v) for k, v in _trainable_part(a).items()}
+    import pytest
+    with pytest.raises(ValueError):
+        checkpoint.load_into(b, bad)
