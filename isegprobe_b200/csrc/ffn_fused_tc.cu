@@ -19,6 +19,11 @@
 // b1' = W1 beta + b1, and (sum, sum of squares) of every x row come from the producer's statistics slots.
 // TMEM: one 416-column accumulator region reused by both phases (512 columns would not hold both), so the two epilogues
 // are not overlapped with MMAs of the same tile; the TMA warp keeps prefetching the next phase's weight chunks meanwhile.
+// Measured at 802816 rows (4 images), with parts switched off: MMAs + TMA alone 0.445 ms (bound by the L2->SM fill of the
+// weights, 779 KB per 128-row tile), + epilogue 1 0.58 ms, + epilogue 2 1.02 ms.  Epilogue 2 is the weak part: it reads the
+// residual and writes the output straight from registers, one row per lane -- 32 different lines per memory instruction,
+// which the LSU serves at a fraction of the coalesced rate (the GEMM kernel's staged TMA stores do not fit next to the
+// 96 KB hidden tile).  Equal to the two GEMM launches in time, so it stays opt-in (LoftUpUpsampler.fuse_ffn).
 #include "tc_common.cuh"
 
 namespace isp {
@@ -53,7 +58,6 @@ struct Params {
   const float* b2;          // [N2]
   float* stats_out;         // [M][4][2] or null
   long long ntiles;
-  int dbg;
 };
 
 __device__ __forceinline__ float gelu_tanh(float v) {  // act == 4 of isp_gemm_bf16_tc
@@ -195,7 +199,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc::mbar_wait(&acc1_full, it & 1);
       tc::tc_fence_after();
       const int nh4 = p.NH / 4;  // columns per part (multiple of 16)
-      for (int c0 = part * nh4; c0 < (part + 1) * nh4 && !(p.dbg & 1); c0 += 16) {
+      for (int c0 = part * nh4; c0 < (part + 1) * nh4; c0 += 16) {
         uint32_t vr[16];
         tc::tmem_ld16(t_addr + c0, vr);
         tc::tmem_ld_wait();
@@ -243,10 +247,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int k = 0; k < 4; ++k)  // b2 is padded to a multiple of 16 floats by the caller's packer
           nb[k] = c0 + 4 * k < p.N2 ? __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      if (cb < ce && !(p.dbg & 2)) prefetch(cb);
+      if (cb < ce) prefetch(cb);
       tc::mbar_wait(&acc2_full, it & 1);
       tc::tc_fence_after();
-      for (int c0 = cb; c0 < ce && !(p.dbg & 2); c0 += 16) {
+      for (int c0 = cb; c0 < ce; c0 += 16) {
         uint32_t vr[16];
         tc::tmem_ld16(t_addr + c0, vr);
         const uint32_t rw[8] = {nr0.x, nr0.y, nr0.z, nr0.w, nr1.x, nr1.y, nr1.z, nr1.w};
@@ -318,7 +322,6 @@ extern "C" int isp_ffn_fused_bf16_tc(const void* x, long long ldx, int K1, const
   p.ln_stats = ln_stats; p.ln_slots = ln_slots; p.ln_invC = 1.f / (float)K1; p.ln_eps = ln_eps;
   p.g1 = g1; p.b1 = b1; p.b2 = b2; p.stats_out = stats_out;
   p.ntiles = (M + ffn::BM - 1) / ffn::BM;
-  p.dbg = getenv("ISP_FFN_DBG") ? atoi(getenv("ISP_FFN_DBG")) : 0;
   ISP_REQUIRE(2 * p.n2half <= 416 && (uint32_t)(2 * p.n2half * 128) <= ffn::kStageBytes &&
                   ffn::kXBytes + (uint32_t)NH * 128 <= ffn::kStageBytes,
               ISP_ERR_UNSUPPORTED, "ffn_fused_bf16_tc: tile does not fit the shared-memory ring");
