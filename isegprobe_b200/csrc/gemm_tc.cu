@@ -76,7 +76,7 @@ constexpr int BM = 128, BK = 64;
 #endif
 constexpr int kEpiWarps = ISP_GEMM_EPI_WARPS;      // kParts warps per TMEM lane quarter (they split the chunks of its 32 rows)
 constexpr int kParts = kEpiWarps / 4;
-constexpr int kFirstEpiWarp = 4;                   // warp group 0 = warp 0 TMA, warp 1 MMA, warps 2-3 idle; the rest epilogue
+constexpr int kFirstEpiWarp = 4;                   // warp group 0 = warps 0, 2, 3 TMA producers, warp 1 MMA; the rest epilogue
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 // Registers: the block is compiled for 96 per thread (65536 / 640); warp group 0 gives most of its share back (setmaxnreg)
 // and the epilogue warp groups raise theirs, which removes the spills of the epilogue's per-tile state (their reloads
@@ -247,7 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::prefetch_tmap(&tmD);
     if (RESID) tc::prefetch_tmap(&tmR);
     // CTA pair: the leader's full barrier also counts the peer's producer, its tempty barrier the peer's epilogue warps
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1u << (CTA2 ? 1 : 0)); tc::mbar_init(&empty_bar[s], 1); }
+    const uint32_t nroles = 1u + (p.wres ? 0u : 1u) + (uint32_t)p.pair;  // producer threads arriving on a full barrier (per CTA)
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], nroles << (CTA2 ? 1 : 0)); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull_bar[a], 1); tc::mbar_init(&tempty_bar[a], kEpiWarps << (CTA2 ? 1 : 0)); }
     for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&resid_bar[w][0], 1); tc::mbar_init(&resid_bar[w][1], 1); }
     tc::mbar_init(&wfull_bar, 1u << (CTA2 ? 1 : 0));
@@ -264,52 +265,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp < kFirstEpiWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
-  if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, ps = 0, pph = 0;  // ring position of the producer
-      if (CTA2 && p.wres && u0 < ntiles) {  // every unit of this cluster has the same column tile (host: ustep % tiles_n == 0)
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ------------------------------------------------------------- TMA producers
+    // THREE issuing threads, one per operand stream (role 0 on warp 0: the A tile; role 1 on warp 2: the weight tile; role 2
+    // on warp 3: the second A tile of pair mode).  One thread gets a tensor load accepted only every ~400 cycles whatever
+    // the box size (tools/micro/tma_row_rate.cu: 407 cycles per `cp.async.bulk.tensor` from one thread for 2 KB .. 16 KB
+    // boxes, 204 with two issuing warps, 103 with four), so a single producer thread paced a k-block at 2 x 407 cycles
+    // (GEMM) or 3 x 407 (conv pair) against 416 / 832 cycles of MMA work -- the "operand-stream" bound of round 1.
+    // Every role arrives on the stage's full barrier with its own byte count (barrier count = number of roles).
+    const int role = warp == 0 ? 0 : warp - 1;
+    const bool active = role == 0 || (role == 1 && !p.wres) || (role == 2 && p.pair);
+    if (lane == 0 && active) {
+      uint32_t ps = 0, pph = 0;  // ring position of the producer
+      if (role == 0 && CTA2 && p.wres && u0 < ntiles) {  // every unit of this cluster has the same column tile
         const int n0 = tile_coord(p, unit_tile(u0, 0)).n0 + (int)crank * (p.BN >> 1);
         if (crank == 0) tc::mbar_arrive_expect_tx(&wfull_bar, 2u * kblocks * b_bytes);
         else tc::mbar_arrive_leader(&wfull_bar);
         for (int kb = 0; kb < kblocks; ++kb) tc::tma_load_2d_2sm(wres_smem + (size_t)kb * b_bytes, &tmBh, &wfull_bar, kb * BK, n0);
       }
+      const uint32_t my_bytes = role == 1 ? b_bytes : a_half;
       for (uint32_t t = u0; t < ntiles; t += ustep) {
-        const TileCoord tc_ = tile_coord(p, unit_tile(t, 0));
-        const TileCoord tc2 = tile_coord(p, unit_tile(t, 1));
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const TileCoord tc_ = tile_coord(p, unit_tile(t, role == 2 ? 1 : 0));
+        for (int kb = 0; kb < kblocks; ++kb) {
           const int s = (int)ps;
           const uint32_t ph = pph;
           if (++ps == (uint32_t)p.stages) { ps = 0; pph ^= 1; }
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
+          uint8_t* sa = smem + (size_t)s * stage_bytes + (role == 2 ? a_half : 0u);
+          uint8_t* sb = smem + (size_t)s * stage_bytes + a_bytes;
           if (CTA2) {
             // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-            if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * my_bytes);
             else tc::mbar_arrive_leader(&full_bar[s]);
-            if (p.TW) {
+            if (role == 1) {
+              tc::tma_load_2d_2sm(sb, &tmBh, &full_bar[s], kb * BK, tc_.n0 + (int)crank * (p.BN >> 1));
+            } else if (p.TW) {
               const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
               const int r = tap / 3, q = tap - r * 3;
               tc::tma_load_4d_2sm(sa, &tmA, &full_bar[s], cc * BK, tc_.w0 + q - 1, tc_.h0 + r - 1, tc_.img);
-              if (p.pair)
-                tc::tma_load_4d_2sm(sa + a_half, &tmA, &full_bar[s], cc * BK, tc2.w0 + q - 1, tc2.h0 + r - 1, tc2.img);
             } else {
               tc::tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0);
-              if (p.pair) tc::tma_load_2d_2sm(sa + a_half, &tmA, &full_bar[s], kb * BK, (int)tc2.m0);
             }
-            if (!p.wres) tc::tma_load_2d_2sm(sb, &tmBh, &full_bar[s], kb * BK, tc_.n0 + (int)crank * (p.BN >> 1));
             continue;
           }
-          tc::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          tc::mbar_arrive_expect_tx(&full_bar[s], my_bytes);
           if (p.batched) {
-            if (p.tn & 1) {  // boxes of 64 reduction rows x 64 columns
-              for (int i = 0; i < BM / 64; ++i)
-                tc::tma_load_4d(sa + i * 8192, &tmA, &full_bar[s], (int)tc_.m0 + i * 64, kb * BK, tc_.h0, tc_.img);
-            } else {
-              tc::tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0, tc_.h0, tc_.img);
-            }
-            if (p.tn & 2) {
+            if (role == 0) {
+              if (p.tn & 1) {  // boxes of 64 reduction rows x 64 columns
+                for (int i = 0; i < BM / 64; ++i)
+                  tc::tma_load_4d(sa + i * 8192, &tmA, &full_bar[s], (int)tc_.m0 + i * 64, kb * BK, tc_.h0, tc_.img);
+              } else {
+                tc::tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0, tc_.h0, tc_.img);
+              }
+            } else if (p.tn & 2) {
               for (int i = 0; i < p.BN / 64; ++i)
                 tc::tma_load_4d(sb + i * 8192, &tmB, &full_bar[s], tc_.n0 + i * 64, kb * BK, tc_.h0, tc_.img);
             } else {
@@ -317,16 +325,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             continue;
           }
-          if (p.TW) {
+          if (role == 1) {
+            tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0);
+          } else if (p.TW) {
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
             const int r = tap / 3, q = tap - r * 3;
             tc::tma_load_4d(sa, &tmA, &full_bar[s], cc * BK, tc_.w0 + q - 1, tc_.h0 + r - 1, tc_.img);
-            if (p.pair) tc::tma_load_4d(sa + a_half, &tmA, &full_bar[s], cc * BK, tc2.w0 + q - 1, tc2.h0 + r - 1, tc2.img);
           } else {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, (int)tc_.m0);
-            if (p.pair) tc::tma_load_2d(sa + a_half, &tmA, &full_bar[s], kb * BK, (int)tc2.m0);
           }
-          tc::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tc_.n0);
         }
       }
     }
