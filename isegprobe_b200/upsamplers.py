@@ -251,13 +251,64 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             out[f"up{k}.range"], out[f"up{k}.fixup"] = m(32, 0.1), m(49, 0.1)
         return out
 
+    @staticmethod
+    def _split_rows(x2d: torch.Tensor) -> torch.Tensor:
+        """fp32 [M,C] -> bf16 [M,3C] = [hi | lo | hi] with x = hi + lo to 2^-17."""
+        hi = x2d.to(torch.bfloat16)
+        lo = (x2d - hi.float()).to(torch.bfloat16)
+        return torch.cat((hi, lo, hi), 1)
+
+    @staticmethod
+    def _split_weight(Wm: torch.Tensor) -> torch.Tensor:
+        """fp32 [N,K] -> bf16 [N,3K] = [hi | hi | lo]: with _split_rows the products hi*hi + lo*hi + hi*lo."""
+        hi = Wm.to(torch.bfloat16)
+        lo = (Wm - hi.float()).to(torch.bfloat16)
+        return torch.cat((hi, hi, lo), 1).contiguous()
+
+    def _mix_channels(self, x: torch.Tensor, transpose: bool, mask=None) -> torch.Tensor:
+        """y = x + 0.1 (x . m) W^T  (forward, m = the Dropout2d(0.2) mask of JBUStack.fixup_proj under train(), else 1) or its
+        adjoint  g + 0.1 m . (g W)  (transpose=True), on fp32 NHWC [B,h,w,C] at SOURCE resolution.  tcgen05 GEMM on
+        split-bf16 operands (three products per element, fp32 accumulate, fp32 residual): error ~1e-5 of the 0.1-scaled
+        term.  Channel counts that are not a multiple of 8: the fp32 SIMT GEMM."""
+        from . import tc
+        B, h, w, C = x.shape
+        conv = self.upsampler.fixup_proj[1]
+        Wf = self._flat(conv.weight).to(x.device)
+        x2 = x.reshape(B * h * w, C)
+        if C % 8:
+            if mask is not None:
+                raise NotImplementedError("JBUFeatUpUpsampler.train() needs a channel count that is a multiple of 8")
+            out = torch.empty_like(x2)
+            Wm = Wf.t().contiguous() if transpose else Wf
+            _lib.call("isp_gemm_f32_simt", _lib.dptr(x2), _lib.dptr(Wm), _lib.dptr(None), _lib.dptr(x2), 0.1, _lib.dptr(out), B * h * w,
+                      C, C, _lib.stream_ptr())
+            return out.view(B, h, w, C)
+        if mask is None:
+            key = (conv.weight._version, str(x.device), transpose)
+            cache = self.__dict__.setdefault("_mix_w", {})
+            if cache.get("key" + str(transpose)) != key:
+                cache["key" + str(transpose)] = key
+                cache[transpose] = self._split_weight(Wf.t().contiguous() if transpose else Wf)
+            return tc.gemm(self._split_rows(x2), cache[transpose], resid=x2, alpha=0.1, out_dtype=torch.float32, N=C,
+                           K=3 * C).view(B, h, w, C)
+        out = torch.empty_like(x)
+        for b in range(B):  # per-sample column (forward) / row (adjoint) scaling of the weight
+            Wb = (Wf.t() * mask[b][:, None]) if transpose else (Wf * mask[b][None, :])
+            xb = x[b].reshape(h * w, C)
+            tc.gemm(self._split_rows(xb), self._split_weight(Wb.contiguous()), resid=xb, alpha=0.1, out_dtype=torch.float32,
+                    N=C, K=3 * C, out=out[b].view(h * w, C))
+        return out
+
     def forward_resized(self, source: torch.Tensor, guidance: torch.Tensor, size=None) -> torch.Tensor:
         """`forward` followed by the bilinear (align_corners=True) resize to `size` that the reference
         applies right after the upsampler (core/model/iseg_probe_model.py:120-129).  The final
-        `fixup_proj(x) * 0.1 + x` is a per-pixel linear map and the resize a per-channel convex
-        combination of pixels, so they commute exactly (bias included: the weights sum to 1); doing the
-        resize FIRST runs the 1x1 conv on 448^2 instead of 512^2 pixels and writes the bf16 GEMM operand
-        in the resize pass.  size=None keeps the reference's 16x output."""
+        `fixup_proj(x) * 0.1 + x` of JBUStack.forward is the per-pixel channel map  x -> (I + 0.1 W) x + 0.1 b.  Every
+        other step of the stack -- bicubic x2, reflect pad, AdaptiveConv with its guidance-only 7x7 kernels, the resize --
+        is a spatial linear map applied to each channel alike, so the channel map commutes with all of them (the bias
+        because the resize weights sum to 1).  It is therefore applied ONCE TO THE 32x32 SOURCE (`_mix_channels`:
+        16 384 instead of 3.2 M pixels at B = 16, in split-bf16 arithmetic that is exact to ~2^-17), and 0.1 b is added by
+        the resize pass: the 448^2 1x1-conv GEMM and its bf16 operand copy (2.7 ms of a 19.7 ms step) do not exist.
+        size=None keeps the reference's 16x output."""
         masks = self._draw_masks(source.shape[0], source.device)
         if torch.is_grad_enabled() and source.requires_grad:  # frozen stack, but the features' gradient flows through
             return _JBUFn.apply(self, source, guidance, size, masks)
@@ -267,29 +318,10 @@ class JBUFeatUpUpsampler(BaseUpsampler):
         """d(loss)/d(source) of forward_resized: the stack is linear in `source` (the 7x7 kernels depend on the guidance
         image only), so the backward is the chain of adjoints -- 1x1 conv dgrad (+ identity), resize adjoint, and per
         stage isp_adaptive_conv_grad_input followed by the bicubic / reflect-pad adjoint."""
-        from . import tc
-        g = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()  # [B,OH,OW,C]
-        B, OH, OW, C = g.shape
-        if C % 8:
-            raise NotImplementedError("JBUFeatUpUpsampler backward needs a channel count that is a multiple of 8")
-        dev, st = g.device, _lib.stream_ptr()
+        dx = grad_out.detach().float().permute(0, 2, 3, 1).contiguous()  # [B,OH,OW,C]
+        B, OH, OW, C = dx.shape
+        dev, st = dx.device, _lib.stream_ptr()
         guidance = guidance.detach().float()
-        conv = self.upsampler.fixup_proj[1]
-        key = (conv.weight._version, str(dev))
-        if getattr(self, "_fixT_key", None) != key:
-            self._fixT_w = tc.pack_linear_weight(self._flat(conv.weight).t().contiguous()).to(dev)
-            self._fixT_key = key
-        M = B * OH * OW
-        gb = g.view(M, C).to(torch.bfloat16)
-        if masks is None:
-            dx = tc.gemm(gb, self._fixT_w, resid=g.view(M, C), alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
-        else:  # the forward's per-sample dropout masks: d/dx of 0.1 W (m . x) + x  =  0.1 m . (W^T g) + g
-            dx = torch.empty(B, OH, OW, C, dtype=torch.float32, device=dev)
-            WT = self._flat(conv.weight).t()
-            for b in range(B):
-                wb = tc.pack_linear_weight((WT * masks["final"][b][:, None]).contiguous()).to(dev)
-                tc.gemm(gb.view(B, OH * OW, C)[b], wb, resid=g[b].view(OH * OW, C), alpha=0.1, out_dtype=torch.float32, N=C,
-                        K=C, out=dx[b].view(OH * OW, C))
         GH, GW = 16 * src_hw[0], 16 * src_hw[1]
         if (OH, OW) != (GH, GW):
             d = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
@@ -303,51 +335,31 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             GH, GW = GH // 2, GW // 2
             dx = torch.empty(B, GH, GW, C, dtype=torch.float32, device=dev)
             _lib.call("isp_jbu_bicubic2x_reflectpad_bwd", _lib.dptr(dpad), _lib.dptr(dx), B, GH, GW, C, st)
+        dx = self._mix_channels(dx, True, None if masks is None else masks["final"])  # adjoint of the channel map
         return dx.permute(0, 3, 1, 2)
 
     def _forward_impl(self, source: torch.Tensor, guidance: torch.Tensor, size=None, masks=None) -> torch.Tensor:
         x = to_nhwc_f32(source.detach())
         guidance = guidance.detach().float()
+        # fixup_proj(x) * 0.1 + x of JBUStack.forward, commuted to the source (see forward_resized)
+        x = self._mix_channels(x, False, None if masks is None else masks["final"])
         for k, up in enumerate((self.upsampler.up1, self.upsampler.up2, self.upsampler.up3, self.upsampler.up4), 1):
             x = self._stage(up, x, guidance, None if masks is None else (masks[f"up{k}.range"], masks[f"up{k}.fixup"]))
         B, H, W, C = x.shape
         OH, OW = (H, W) if size is None else (int(size[0]), int(size[1]))
         conv = self.upsampler.fixup_proj[1]
-        # fixup_proj(x) * 0.1 + x  (JBUStack.forward): 1x1 conv on the tcgen05 GEMM (bf16 operands, fp32
-        # accumulate, fp32 residual and output; the 0.1 factor keeps the bf16 rounding below 1e-3 of x)
-        from . import tc
-        key = (conv.weight._version, conv.bias._version, str(x.device))
+        key = (conv.bias._version, str(x.device))
         if getattr(self, "_fix_key", None) != key:
-            self._fix_w = tc.pack_linear_weight(self._flat(conv.weight)).to(x.device)
-            self._fix_b = conv.bias.detach().float().contiguous().to(x.device)
+            self._fix_b = (0.1 * conv.bias.detach().float()).contiguous().to(x.device)
             self._fix_key = key
-        if C % 8 == 0:
-            xb = torch.empty(B, OH, OW, C, dtype=torch.bfloat16, device=x.device)
-            if (OH, OW) == (H, W):
-                _lib.call("isp_bilinear_ac_nhwc", _lib.dptr(x), _lib.dptr(xb), B, C, H, W, H, W, 1, C, _lib.stream_ptr())
-            else:
-                xr = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
-                _lib.call("isp_bilinear_ac_nhwc_dual", _lib.dptr(x), _lib.dptr(xr), _lib.dptr(xb), B, C, H, W, OH, OW,
-                          _lib.stream_ptr())
-                x = xr
-            if masks is None:
-                out = tc.gemm(xb.view(B * OH * OW, C), self._fix_w, bias=self._fix_b, resid=x.view(B * OH * OW, C),
-                              alpha=0.1, out_dtype=torch.float32, N=C, K=C).view(B, OH, OW, C)
-            else:  # train(): Dropout2d(0.2) in front of the conv = a per-sample column scaling of its weight
-                out = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
-                Wf = self._flat(conv.weight)
-                for b in range(B):
-                    wb = tc.pack_linear_weight(Wf * masks["final"][b][None, :]).to(x.device)
-                    tc.gemm(xb[b].view(OH * OW, C), wb, bias=self._fix_b, resid=x[b].view(OH * OW, C), alpha=0.1,
-                            out_dtype=torch.float32, N=C, K=C, out=out[b].view(OH * OW, C))
-        elif masks is not None:
-            raise NotImplementedError("JBUFeatUpUpsampler.train() needs a channel count that is a multiple of 8")
-        else:  # odd channel counts: fp32 SIMT GEMM
+        if C % 4:
             if (OH, OW) != (H, W):
                 x = bilinear_align_corners_nhwc(x, (OH, OW))
-            out = torch.empty_like(x)
-            _lib.call("isp_gemm_f32_simt", _lib.dptr(x), _lib.dptr(self._flat(conv.weight)), _lib.dptr(self._fix_b),
-                      _lib.dptr(x), 0.1, _lib.dptr(out), B * OH * OW, C, C, _lib.stream_ptr())
+            return (x + self._fix_b).permute(0, 3, 1, 2)
+        out = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
+        with timed_kernel(f"resize_bias_{OH}"):
+            _lib.call("isp_bilinear_ac_nhwc_bias", _lib.dptr(x), _lib.dptr(out), _lib.dptr(self._fix_b), B, C, H, W, OH, OW,
+                      _lib.stream_ptr())
         return out.permute(0, 3, 1, 2)
 
 

@@ -134,8 +134,8 @@ def test_jbu_stack_module(isp, B, h, w, H, W):
 
 
 def test_jbu_forward_resized(isp):
-    """Resize-then-1x1 (what the pipeline runs) equals the reference order, stack then
-    bilinear align_corners resize (iseg_probe_model.py:120-129), to fp32-mode tolerance."""
+    """What the pipeline runs (channel map on the source, stack, resize + bias) equals the reference order, stack with its
+    final 1x1 then bilinear align_corners resize (iseg_probe_model.py:120-129), to fp32-mode tolerance."""
     sd = ojbu.init_state_dict(384, seed=0)
     up = isp.JBUFeatUpUpsampler("dinov2").to(DEV).eval()
     up.upsampler.load_state_dict(sd)
@@ -146,6 +146,37 @@ def test_jbu_forward_resized(isp):
         want = F.interpolate(ojbu.jbu_stack_forward(sd, src, gd), size=(112, 112), mode="bilinear", align_corners=True)
     assert tuple(out.shape) == (2, 384, 112, 112)
     assert relerr(out, want) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,OH,OW,with_bias", [(2, 128, 40, 56, 35, 49, True), (1, 384, 64, 64, 56, 56, True),
+                                                       (2, 256, 20, 24, 33, 37, False), (1, 128, 16, 16, 16, 16, True),
+                                                       (1, 96, 12, 12, 9, 30, True)])
+def test_bilinear_resize_with_bias(isp, B, C, H, W, OH, OW, with_bias):
+    """isp_bilinear_ac_nhwc_bias (the JBU stack's last pass: strip-marching kernel for C % 128 == 0, the per-pixel kernel
+    otherwise) against ATen's align_corners=True resize plus a per-channel constant."""
+    g = torch.Generator().manual_seed(C + OH)
+    x, bias = torch.randn(B, C, H, W, generator=g), torch.randn(C, generator=g)
+    want = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=True) + (bias.view(1, C, 1, 1) if with_bias else 0.0)
+    out = torch.empty(B, OH, OW, C, device=DEV)
+    _call("isp_bilinear_ac_nhwc_bias", x.permute(0, 2, 3, 1).contiguous().to(DEV), out, bias.to(DEV) if with_bias else None,
+          B, C, H, W, OH, OW)
+    assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+
+
+def test_jbu_channel_map_commutes(isp):
+    """The stack's final `fixup_proj(x) * 0.1 + x` applied to the SOURCE (upsamplers._mix_channels) instead of the 16x
+    output: forward and adjoint against plain fp32 matrix arithmetic (split-bf16 products: ~1e-5 of the 0.1-scaled term)."""
+    up = isp.JBUFeatUpUpsampler("dinov2").to(DEV).eval()
+    up.upsampler.load_state_dict(ojbu.init_state_dict(384, seed=0))
+    Wm = up.upsampler.fixup_proj[1].weight.detach().view(384, 384).double()
+    x = torch.randn(2, 5, 7, 384, generator=torch.Generator().manual_seed(4)).to(DEV)
+    m = (torch.rand(2, 384, generator=torch.Generator().manual_seed(5)) > 0.2).float().to(DEV) / 0.8
+    for mask in (None, m):
+        xm = x.double() if mask is None else x.double() * mask[:, None, None, :].double()
+        assert relerr(up._mix_channels(x, False, mask), x.double() + 0.1 * xm @ Wm.T) < 1e-5
+        gW = x.double() @ Wm
+        want_t = x.double() + 0.1 * (gW if mask is None else gW * mask[:, None, None, :].double())
+        assert relerr(up._mix_channels(x, True, mask), want_t) < 1e-5
 
 
 def test_jbu_reference_shape_contract(isp):
