@@ -260,13 +260,12 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ i
 // [-1, 1]): reduce in turns with an FMA pair on a two-word 1 / 2pi (error ~1e-7 turns), then one MUFU on |r| <= pi.
 // ~8 instructions instead of sinf's ~25; the result is within 2e-6 of the correctly rounded value of the SAME fp32 argument
 // (the argument itself is formed with the reference's operation order), far below the bf16 rounding of the output.
-__device__ __forceinline__ float sincos_turns(float a, bool want_cos) {
+__device__ __forceinline__ float sincos_turns(float a, float quarter) {  // quarter = 0.25 for cos (cos x = sin(x + pi/2)), 0 for sin
   const float kInv2PiHi = 0.15915494f, kInv2PiLo = 6.4206383e-9f;
   const float k = rintf(a * kInv2PiHi);
   float r = fmaf(a, kInv2PiHi, -k);
   r = fmaf(a, kInv2PiLo, r);
-  const float x = r * 6.28318530717958647692f;
-  return want_cos ? __cosf(x) : __sinf(x);
+  return __sinf((r + quarter) * 6.28318530717958647692f);  // |r| <= 0.5 turns: the MUFU argument stays inside [-pi/2, 3pi/2]
 }
 
 constexpr int kFourierPix = 16;  // pixels per warp: the lane's channel constants are loaded once for all of them
@@ -306,38 +305,45 @@ __global__ void __launch_bounds__(256) fourier_chnorm_kernel(
     sc_[c] = fmaxf(__fsub_rn(ord_float(mm[3 + c]), mn[c]), 1e-4f);
   }
   const long long pend = pix0 + kFourierPix < total ? pix0 + kFourierPix : total;
-  for (long long pix = pix0; pix < pend; ++pix) {
-    const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float u[5];
-    u[0] = gridr[h];
-    u[1] = gridc[w];
+  // (b, h, w) of the first pixel by division once, then carried along (64-bit div / mod per pixel was a third of the kernel)
+  int w = (int)(pix0 % W), h = (int)((pix0 / W) % H), b = (int)(pix0 / ((long long)W * H));
+  float quarter[8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = img[b * sb + c * sc + h * sh + w * sw];
-      u[2 + c] = __fsub_rn(__fdiv_rn(__fsub_rn(x, mn[c]), sc_[c]), 0.5f);
-    }
+  for (int i = 0; i < 8; ++i) quarter[i] = (2 * lane + (i >> 1) * 64 + (i & 1)) >= 100 ? 0.25f : 0.f;
+  // lane j < 5 holds input j of the pixel (row coordinate, column coordinate, three scaled colours); channel i of a lane
+  // fetches its input with one shuffle from lane src[i] (pass-through channels 200..202: inputs 2..4)
+  int src[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = 2 * lane + (i >> 1) * 64 + (i & 1);
+    src[i] = kind[i] < 5 ? kind[i] : (kind[i] == 5 ? c - 198 : 0);
+  }
+  const int cl = (lane >= 2 && lane < 5) ? lane - 2 : 0;
+  const float my_mn = cl == 0 ? mn[0] : (cl == 1 ? mn[1] : mn[2]), my_sc = cl == 0 ? sc_[0] : (cl == 1 ? sc_[1] : sc_[2]);
+  for (long long pix = pix0; pix < pend; ++pix) {
+    const float x = img[b * sb + cl * sc + h * sh + w * sw];
+    float uval = __fsub_rn(__fdiv_rn(__fsub_rn(x, my_mn), my_sc), 0.5f);
+    uval = lane == 0 ? gridr[h] : (lane == 1 ? gridc[w] : uval);
+    if (++w == W) { w = 0; if (++h == H) { h = 0; ++b; } }
     float val[8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = 2 * lane + (i >> 1) * 64 + (i & 1);  // compile-time per i except for the lane term
-      const int k = kind[i];
-      float ud = u[0];
-      ud = k == 1 ? u[1] : ud; ud = k == 2 ? u[2] : ud; ud = k == 3 ? u[3] : ud; ud = k == 4 ? u[4] : ud;
+      const float ud = __shfl_sync(0xffffffffu, uval, src[i]);
       const float arg = __fadd_rn(__fmul_rn(ud, cf[i]), cb[i]);
-      float v = sincos_turns(arg, c >= 100);
-      if (k >= 5) v = k == 6 ? 0.f : (c == 200 ? u[2] : (c == 201 ? u[3] : u[4]));
+      float v = sincos_turns(arg, quarter[i]);
+      if (i >= 6) v = kind[i] >= 5 ? (kind[i] == 6 ? 0.f : ud) : v;  // only channels >= 192 can be pass-through / padding
       val[i] = v;
       s += v;
     }
-    const float mean = warp_sum(s) / 203.f;
+    const float mean = warp_sum(s) * (1.f / 203.f);
     float var = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float d = kind[i] < 6 ? val[i] - mean : 0.f;
       var += d * d;
     }
-    const float rstd = rsqrtf(warp_sum(var) / 203.f + eps);
+    const float rstd = rsqrtf(warp_sum(var) * (1.f / 203.f) + eps);
     __nv_bfloat16* o = out + pix * ldo;  // ldo is even and the rows 4-byte aligned (checked by the entry point)
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {

@@ -91,6 +91,59 @@ def test_reference_model_with_our_modules_matches_the_reference(models):
     assert float(((fused > 0) == (got > 0)).float().mean()) >= 0.999
 
 
+def test_checkpoint_written_by_the_reference_reproduces_its_masks(models, tmp_path):
+    """Row f4: the reference's own model, with "trained" (perturbed) head / click-embedding weights, writes a checkpoint the
+    way its trainer does (core/utils/misc.py:36-68: {'state_dict': net.get_state_dict_to_save(), 'config': ...}, with the
+    save_cfg filter of iseg_probe_model.py:199-258); a FRESH ISegPipeline with differently initialised trainable parts loads
+    it through isegprobe_b200.checkpoint (the reference's restore, inference/utils.py:71-74) and reproduces the reference
+    model's logits / masks."""
+    import isegprobe_b200 as isp
+    from isegprobe_b200 import checkpoint
+    from oracle import ref_model as rm
+    ref, _, _ = models
+    trainable = [p for p in ref.parameters() if p.requires_grad]
+    keep = [p.detach().clone() for p in trainable]
+    g = torch.Generator().manual_seed(11)
+    try:
+        with torch.no_grad():
+            for p in trainable:  # a stand-in for training: every trainable tensor moves by ~20 % of its scale
+                p.add_((torch.randn(p.shape, generator=g) * 0.2 * max(float(p.abs().mean()), 1e-3)).to(p.device))
+        sd = ref.get_state_dict_to_save()
+        assert sd and all(k.startswith(checkpoint.TRAINABLE_PREFIXES) for k in sd), sorted(sd)[:5]  # frozen parts are not stored
+        path = str(tmp_path / "last_checkpoint.pth")
+        torch.save({"state_dict": {k: v.detach().cpu() for k, v in sd.items()}, "config": getattr(ref, "_config", {})}, path)
+        image, pts = _inputs()
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                want = ref(image, pts)["instances"].float().cpu()
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+    finally:
+        with torch.no_grad():
+            for p, k in zip(trainable, keep):
+                p.copy_(k)
+    assert checkpoint.main(["verify", path, "--upsampler", "loftup", "--n-dim", "384"]) == 0
+    torch.manual_seed(5)
+    pipe = isp.ISegPipeline("loftup", {"upsampler_path": rm.write_checkpoint("loftup", str(tmp_path)), "n_dim": 384})
+    pipe.backbone.model.load_state_dict(synth.vit_state_dict(384, depth=12, seed=0))  # frozen parts: their own files
+    pipe.to(DEV).eval()
+    with torch.no_grad():
+        before = pipe(image, pts)["instances"].float().cpu()
+    assert cosine(before, want) < 0.9  # a random head does not reproduce the masks
+    assert checkpoint.load_into(pipe, path) == []
+    with torch.no_grad():
+        got = pipe(image, pts)["instances"].float().cpu()
+    wrong = (got > 0) != (want > 0)
+    agree = 1.0 - float(wrong.float().mean())
+    band = float(want.abs()[wrong].max() / want.abs().max()) if wrong.any() else 0.0
+    print(f"reference-written checkpoint -> ISegPipeline: cosine {cosine(got, want):.6f}, RAW mask agreement {agree:.6f}, "
+          f"disagreeing pixels within {band:.4f} of the logit range of the boundary")
+    assert cosine(got, want) > 0.999
+    assert agree >= 0.99 and band <= 0.03, (agree, band)
+
+
 def test_reference_model_trains_through_our_modules(models):
     """trainer.py:451-459 with the reference's own model object: loss.backward() reaches the trainable parameters
     (head + click embedding through the frozen upsampler and backbone) and matches the reference's gradients."""
