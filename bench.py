@@ -461,6 +461,9 @@ def run_forward(wl_name, args, ctx, steps, warmup, headline):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "kernel_ms": {k: round(sum(v) / len(v), 4) for k, v in ktimes.items() if v},
     }
+    line["features_dtype"] = (str(getattr(pipe.upsampler, "out_dtype", torch.float32)).replace("torch.", "")
+                              + " NHWC (`value` ends at the upsampled features in the format the pipeline's head consumes; "
+                              "arithmetic dtype of the path: `dtype`)")
     if wl_name == "jbu":
         line["parity"] = "unpinned (FeatUp is not in the reference tree; oracle/jbu.py restates the published algorithm)"
     del pipe

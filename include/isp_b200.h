@@ -80,12 +80,12 @@ int isp_bilinear_ac_nhwc_bwd(const float* gout, float* gin, int B, int C, int Hi
  * conv that follows) in one pass over the input.  C % 4 == 0. */
 int isp_bilinear_ac_nhwc_dual(const float* in, float* out_f32, void* out_bf16, int B, int C, int Hin, int Win,
                               int Hout, int Wout, isp_stream_t stream);
-/* out = resize(in) + bias[c] (fp32 NHWC -> fp32 NHWC, align_corners=True, bias NULL or C floats): the resize the reference
+/* out = resize(in) + bias[c] (fp32 NHWC -> fp32 or bf16 NHWC, align_corners=True, bias NULL or C floats): the resize the reference
  * applies after the upsampler (core/model/iseg_probe_model.py:120-129) with the bias of JBUStack's final
  * `fixup_proj(x) * 0.1 + x` (FeatUp, via core/model/upsamplers/JBUFeatUp.py:30-32) folded in; the conv's matrix part
  * is applied at source resolution (isegprobe_b200/upsamplers.py `_mix_channels`). */
-int isp_bilinear_ac_nhwc_bias(const float* in, float* out, const float* bias, int B, int C, int Hin, int Win, int Hout,
-                              int Wout, isp_stream_t stream);
+int isp_bilinear_ac_nhwc_bias(const float* in, void* out, int out_bf16, const float* bias, int B, int C, int Hin, int Win,
+                              int Hout, int Wout, isp_stream_t stream);
 
 /* ---- FeatUp JBU stack (external to the reference tree: JBUFeatUp.py:30-32) --- */
 /* F.adaptive_avg_pool2d(guidance, (OH,OW)): NCHW f32 [B,3,H,W] -> NHWC4 f32 [B,OH,OW,4] (4th = 0) */

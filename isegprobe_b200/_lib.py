@@ -24,7 +24,7 @@ SIGNATURES = {
     "isp_bilinear_ac_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S],
     "isp_bilinear_ac_nhwc_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _S],
     "isp_bilinear_ac_nhwc_dual": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S],
-    "isp_bilinear_ac_nhwc_bias": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S],
+    "isp_bilinear_ac_nhwc_bias": [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _S],
     "isp_jbu_pool_guidance": [_P, _P, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _S],
     "isp_jbu_range_proj": [_P, _P, _LL, _P, _P, _P, _P, _S],
     "isp_jbu_filters": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _I, _S],

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(const float* __restric
 // columns of neighbouring output columns are fetched by the block at the same time (L1 hits): ~1.5 source reads per
 // output from L2 instead of 4.  Same expression tree as bilinear_ac_kernel.
 constexpr int RS = 16;
-__global__ void __launch_bounds__(256) bilinear_ac_march_kernel(const float* __restrict__ in, float* __restrict__ out,
+template <typename OutT>
+__global__ void __launch_bounds__(256) bilinear_ac_march_kernel(const float* __restrict__ in, OutT* __restrict__ out,
                                                                 const float* __restrict__ bias, int C, int Hin, int Win,
                                                                 int Hout, int Wout, float sy, float sx) {
   const int C4 = C / 4;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) bilinear_ac_march_kernel(const float* __r
   int have = -1;
   float4 hc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int oy_end = min(Hout, (int)(blockIdx.y + 1) * RS);
-  float4* o = reinterpret_cast<float4*>(out) + ((size_t)b * Hout * Wout + ox) * C4 + c4;
+  const size_t o0 = ((size_t)b * Hout * Wout + ox) * C4 + c4;  // in 4-channel units
 #pragma unroll 2
   for (int oy = blockIdx.y * RS; oy < oy_end; ++oy) {
     const float fy = sy * (float)oy;
@@ -124,7 +125,13 @@ __global__ void __launch_bounds__(256) bilinear_ac_march_kernel(const float* __r
     r.y = ly0 * h0.y + ly1 * h1.y + bb.y;
     r.z = ly0 * h0.z + ly1 * h1.z + bb.z;
     r.w = ly0 * h0.w + ly1 * h1.w + bb.w;
-    __stcs(o + (size_t)oy * Wout * C4, r);
+    const size_t oi = o0 + (size_t)oy * Wout * C4;
+    if constexpr (sizeof(OutT) == 2) {  // bf16 features for a head that rounds its input to bf16 anyway
+      __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+      __stcs(reinterpret_cast<uint2*>(out) + oi, make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi)));
+    } else {
+      __stcs(reinterpret_cast<float4*>(out) + oi, r);
+    }
   }
 }
 
@@ -300,8 +307,8 @@ extern "C" int isp_bilinear_ac_nhwc_dual(const float* in, float* out_f32, void* 
 
 // out[b,y,x,c] = resize(in)[b,y,x,c] + bias[c]  (fp32 NHWC; bias may be NULL): the last pass of the JBU stack, whose
 // final 1x1 conv has been commuted to the source -- only its bias is left to add here.
-extern "C" int isp_bilinear_ac_nhwc_bias(const float* in, float* out, const float* bias, int B, int C, int Hin, int Win,
-                                         int Hout, int Wout, isp_stream_t stream) {
+extern "C" int isp_bilinear_ac_nhwc_bias(const float* in, void* out, int out_bf16, const float* bias, int B, int C, int Hin,
+                                         int Win, int Hout, int Wout, isp_stream_t stream) {
   ISP_REQUIRE(in && out && B > 0 && C > 0 && C % 4 == 0, ISP_ERR_BAD_SHAPE,
               "bilinear_ac_nhwc_bias: bad arguments (C must be a multiple of 4)");
   ISP_REQUIRE(Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, ISP_ERR_BAD_SHAPE, "bilinear_ac_nhwc_bias: bad size");
@@ -310,13 +317,22 @@ extern "C" int isp_bilinear_ac_nhwc_bias(const float* in, float* out, const floa
   const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
   if (C % 128 == 0 && (long long)B * (C / 128) <= 65535 && cdiv(Hout, RS) <= 65535) {
     dim3 grid(cdiv(Wout, 8), cdiv(Hout, RS), B * (C / 128));
-    bilinear_ac_march_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, out, bias, C, Hin, Win, Hout, Wout, sy, sx);
+    if (out_bf16)
+      bilinear_ac_march_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
+          in, reinterpret_cast<__nv_bfloat16*>(out), bias, C, Hin, Win, Hout, Wout, sy, sx);
+    else
+      bilinear_ac_march_kernel<float><<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), bias, C,
+                                                                                   Hin, Win, Hout, Wout, sy, sx);
     ISP_CHECK_LAUNCH("bilinear_ac_march_kernel");
     return ISP_OK;
   }
   const long long total = (long long)B * Hout * Wout * (C / 4);
-  bilinear_ac_kernel<float><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, out, B, C, Hin, Win, Hout, Wout, C, sy, sx,
-                                                                             nullptr, bias);
+  if (out_bf16)
+    bilinear_ac_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
+        in, reinterpret_cast<__nv_bfloat16*>(out), B, C, Hin, Win, Hout, Wout, C, sy, sx, nullptr, bias);
+  else
+    bilinear_ac_kernel<float><<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<float*>(out), B, C, Hin, Win,
+                                                                               Hout, Wout, C, sy, sx, nullptr, bias);
   ISP_CHECK_LAUNCH("bilinear_ac_kernel(bias)");
   return ISP_OK;
 }

@@ -232,6 +232,9 @@ class JBUFeatUpUpsampler(BaseUpsampler):
     def forward(self, source: torch.Tensor, guidance: torch.Tensor) -> torch.Tensor:
         return self.forward_resized(source, guidance, None)
 
+    # dtype of the returned features; ISegPipeline switches to bf16 when a head consumes them (the head rounds its input to
+    # bf16 anyway: same bits, one 7.4 GB / 16-image conversion pass less)
+    out_dtype = torch.float32
     dropout_masks = None  # tests: a dict of explicit masks (keys as oracle.jbu.dropout2d_masks) instead of fresh draws
 
     def _draw_masks(self, B: int, dev):
@@ -356,10 +359,11 @@ class JBUFeatUpUpsampler(BaseUpsampler):
             if (OH, OW) != (H, W):
                 x = bilinear_align_corners_nhwc(x, (OH, OW))
             return (x + self._fix_b).permute(0, 3, 1, 2)
-        out = torch.empty(B, OH, OW, C, dtype=torch.float32, device=x.device)
+        bf = self.out_dtype == torch.bfloat16 and C % 8 == 0
+        out = torch.empty(B, OH, OW, C, dtype=torch.bfloat16 if bf else torch.float32, device=x.device)
         with timed_kernel(f"resize_bias_{OH}"):
-            _lib.call("isp_bilinear_ac_nhwc_bias", _lib.dptr(x), _lib.dptr(out), _lib.dptr(self._fix_b), B, C, H, W, OH, OW,
-                      _lib.stream_ptr())
+            _lib.call("isp_bilinear_ac_nhwc_bias", _lib.dptr(x), _lib.dptr(out), int(bf), _lib.dptr(self._fix_b), B, C, H, W,
+                      OH, OW, _lib.stream_ptr())
         return out.permute(0, 3, 1, 2)
 
 

@@ -158,9 +158,12 @@ def test_bilinear_resize_with_bias(isp, B, C, H, W, OH, OW, with_bias):
     x, bias = torch.randn(B, C, H, W, generator=g), torch.randn(C, generator=g)
     want = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=True) + (bias.view(1, C, 1, 1) if with_bias else 0.0)
     out = torch.empty(B, OH, OW, C, device=DEV)
-    _call("isp_bilinear_ac_nhwc_bias", x.permute(0, 2, 3, 1).contiguous().to(DEV), out, bias.to(DEV) if with_bias else None,
-          B, C, H, W, OH, OW)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    _call("isp_bilinear_ac_nhwc_bias", xin, out, 0, bias.to(DEV) if with_bias else None, B, C, H, W, OH, OW)
     assert relerr(out.permute(0, 3, 1, 2), want) < 1e-5
+    out_bf = torch.empty(B, OH, OW, C, device=DEV, dtype=torch.bfloat16)  # the head's input format: the same values, rounded
+    _call("isp_bilinear_ac_nhwc_bias", xin, out_bf, 1, bias.to(DEV) if with_bias else None, B, C, H, W, OH, OW)
+    assert torch.equal(out_bf, out.to(torch.bfloat16))
 
 
 def test_jbu_channel_map_commutes(isp):
