@@ -354,6 +354,9 @@ class LoftUpUpsampler(BaseUpsampler):
         Tp = tc.round_up(T, 128)
         if keep is not None:  # what the activation backward re-reads: the query stream at every residual point, kv
             keep["kv"], keep["xs"] = kv, [x]
+            # ... and the row statistics of each of those tensors, so the backward recomputes Q / the FeedForward
+            # pre-activations / the final 1x1 with the SAME fused-LayerNorm GEMMs as the forward (no materialised LayerNorm)
+            keep["st"] = [st_q] if fuse else None
         st_cur = st_q  # row statistics of the current query stream (first layer: the producer's; later: FFN2's = st_a)
         for L in P["layers"]:
             kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, tc.round_up(D, 8))
@@ -391,10 +394,14 @@ class LoftUpUpsampler(BaseUpsampler):
                 else:
                     _call("isp_attention_bf16_tc", Q, nh * HP, HP, Kp, Vt, O, nh * HP, HP, B, H * W, nh, T, P["variant"])
             del Q
+            if keep is not None and fuse:
+                st_b = torch.empty_like(st_b)  # kept: one statistics tensor per saved residual point
             x = tc.gemm(O, L["Wo"], bias=L["bo"], resid=x, out_dtype=bf, N=D, K=nh * HP, ldd=Dp, stats_out=st_b)
             del O
             if keep is not None:
                 keep["xs"].append(x)
+                if fuse:
+                    keep["st"].append(st_b)
             if fuse and self.fuse_ffn and keep is None and C <= 384 and C % 64 == 0 and Dp <= 416:
                 W1, g1, b1 = L["W1_ln"]
                 x, st_a = tc.ffn_fused(x, W1, g1, b1, L["W2"], L["b2"], D, D, st_b, ldo=Dp)
@@ -408,11 +415,15 @@ class LoftUpUpsampler(BaseUpsampler):
                 hn = self._ln(x, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
                 h1 = tc.gemm(hn, L["W1"], bias=L["b1"], act="gelu_tanh", out_dtype=bf, N=C, K=D)
                 del hn
+            if keep is not None and fuse:
+                st_a = torch.empty_like(st_a)
             x = tc.gemm(h1, L["W2"], bias=L["b2"], resid=x, out_dtype=bf, N=D, K=C, ldd=Dp, stats_out=st_a)
             st_cur = st_a
             del h1
             if keep is not None:
                 keep["xs"].append(x)
+                if fuse:
+                    keep["st"].append(st_a)
         if fuse:
             Wf, gf, bfin = P["Wf_ln"]
             y = tc.gemm(x, Wf, bias=bfin, out_dtype=torch.float32, N=C, K=D, ln_stats=st_a, ln_g=gf, ln_eps=1e-5)
@@ -509,10 +520,15 @@ class LoftUpUpsampler(BaseUpsampler):
         HW, T = H * W, h * w
         M = B * HW
         xs, kv = keep["xs"], keep["kv"]
+        sts = keep.get("st")  # row statistics of xs[i] (forward with fuse_layernorm): LayerNorm folded into the recomputing GEMMs
         # out = LN2d(y), y = conv1x1(LN_n(x_last))
-        xn = self._ln(xs[-1], P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
-        y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
-        del xn
+        if sts is not None:
+            Wf, gf, bfin = P["Wf_ln"]
+            y = tc.gemm(xs[-1], Wf, bias=bfin, out_dtype=torch.float32, N=C, K=D, ln_stats=sts[-1], ln_g=gf, ln_eps=1e-5)
+        else:
+            xn = self._ln(xs[-1], P["n_w"], P["n_b"], D, 1e-5, bf, Dp)
+            y = tc.gemm(xn, P["Wf"], bias=P["bf"], out_dtype=torch.float32, N=C, K=D)
+            del xn
         dy, dyb = self._ln_bwd(g.reshape(M, C), y, P["lnf_w"], None, C, 1e-6, C)
         del y, dy
         dn = tc.gemm(dyb, P["WfT"], out_dtype=torch.float32, N=D, K=C)
@@ -523,9 +539,13 @@ class LoftUpUpsampler(BaseUpsampler):
             L, LB = P["layers"][li], PB[li]
             x_in, x_a = xs[2 * li], xs[2 * li + 1]
             # FeedForward: x_f = x_a + W2 gelu(W1 LN_f(x_a) + b1) + b2
-            hn = self._ln(x_a, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
-            pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf, N=C, K=D)
-            del hn
+            if sts is not None:
+                W1, g1, b1 = L["W1_ln"]
+                pre = tc.gemm(x_a, W1, bias=b1, out_dtype=bf, N=C, K=D, ln_stats=sts[2 * li + 1], ln_g=g1, ln_eps=1e-5)
+            else:
+                hn = self._ln(x_a, L["nf_w"], L["nf_b"], D, 1e-5, bf, Dp)
+                pre = tc.gemm(hn, L["W1"], bias=L["b1"], out_dtype=bf, N=C, K=D)
+                del hn
             dh = tc.gemm(dxb, LB["W2T"], out_dtype=bf, N=C, K=D)
             _call("isp_gelu_bwd_bf16", dh, pre, dh, dh.numel(), 0)
             del pre
@@ -535,9 +555,13 @@ class LoftUpUpsampler(BaseUpsampler):
             del dn
             # cross-attention: x_a = x_in + Wo attn(Wq LN_q(x_in), K, V) + bo
             dO = tc.gemm(dxb, LB["WoT"], out_dtype=bf, N=nh * HP, K=D)
-            qn = self._ln(x_in, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
-            Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
-            del qn
+            if sts is not None:
+                Wq, gq, bq = L["Wq_ln"]
+                Q = tc.gemm(x_in, Wq, bias=bq, out_dtype=bf, N=nh * HP, K=D, ln_stats=sts[2 * li], ln_g=gq, ln_eps=1e-5)
+            else:
+                qn = self._ln(x_in, L["nq_w"], L["nq_b"], D, 1e-5, bf, Dp)
+                Q = tc.gemm(qn, L["Wq"], bias=L["bq"], out_dtype=bf, N=nh * HP, K=D)
+                del qn
             kvn = self._ln(kv, L["nkv_w"], L["nkv_b"], D, 1e-5, bf, D8)
             Kl = tc.gemm(kvn, L["Wk"], bias=L["bk"], out_dtype=torch.float32, N=D, K=D)
             Vl = tc.gemm(kvn, L["Wv"], bias=L["bv"], out_dtype=torch.float32, N=D, K=D)
