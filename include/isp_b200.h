@@ -103,6 +103,11 @@ int isp_jbu_range_proj(const float* g, float* proj, long long npix, const float*
 int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W,
                     float temp, float sigma_spatial, const float* fw0, const float* fb0,
                     const float* fw1, const float* fb1, int out_ld, isp_stream_t stream);
+/* Same result with the 52 -> 49 -> 49 fix-up MLP on the fp32 pipe for both layouts (isp_jbu_filters runs it on the tensor
+ * cores, tcgen05 kind::tf32 with hi / lo split activations, for the padded layout): cross-check and A/B timing. */
+int isp_jbu_filters_simt(const float* proj, const float* guidance4, float* filters, int B, int H, int W, float temp,
+                         float sigma_spatial, const float* fw0, const float* fb0, const float* fw1, const float* fb1,
+                         int out_ld, isp_stream_t stream);
 /* bicubic x2 (align_corners=False, A=-0.75) followed by reflect pad 3:
  * src NHWC [B,h,w,C] -> out NHWC [B,2h+6,2w+6,C] */
 int isp_jbu_bicubic2x_reflectpad(const float* src, float* out, int B, int h, int w, int C,

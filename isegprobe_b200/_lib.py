@@ -28,6 +28,7 @@ SIGNATURES = {
     "isp_jbu_pool_guidance": [_P, _P, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _S],
     "isp_jbu_range_proj": [_P, _P, _LL, _P, _P, _P, _P, _S],
     "isp_jbu_filters": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _I, _S],
+    "isp_jbu_filters_simt": [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _I, _S],
     "isp_jbu_bicubic2x_reflectpad": [_P, _P, _I, _I, _I, _I, _S],
     "isp_jbu_bicubic2x_reflectpad_bwd": [_P, _P, _I, _I, _I, _I, _S],
     "isp_adaptive_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _S],

@@ -243,12 +243,18 @@ jbu_fixup_kernel(const float4* __restrict__ g, float* __restrict__ filters, long
 }  // namespace jf2
 }  // namespace isp
 
+namespace isp {
+int jbu_fixup_tc_launch(const float* g, float* filters, long long npix, const float* fw0, const float* fb0, const float* fw1,
+                        const float* fb1, cudaStream_t stream);  // jbu_fixup_tc.cu
+}
 using namespace isp;
 
 // filters layout: out_ld == 49 -> dense [B,H,W,49]; out_ld == 56 -> row-padded [B,H,W,7,8]
-extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
-                               float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
-                               const float* fb1, int out_ld, isp_stream_t stream) {
+// simt != 0: the fix-up MLP on the fp32 pipe (jbu_fixup_kernel) also for the padded layout, which otherwise runs on the
+// tensor cores (jbu_fixup_tc.cu)
+static int jbu_filters_impl(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
+                            float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
+                            const float* fb1, int out_ld, int simt, isp_stream_t stream) {
   ISP_REQUIRE(proj && g && filters && fw0 && fb0 && fw1 && fb1, ISP_ERR_BAD_SHAPE, "jbu_filters: null pointer");
   ISP_REQUIRE(B > 0 && H >= 4 && W >= 4, ISP_ERR_BAD_SHAPE, "jbu_filters: need H,W >= 4 (reflect pad 3), got %dx%d", H, W);
   ISP_REQUIRE(out_ld == 49 || out_ld == 56, ISP_ERR_BAD_SHAPE, "jbu_filters: out_ld must be 49 or 56 (got %d)", out_ld);
@@ -263,6 +269,10 @@ extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters
   jf2::jbu_range_kernel<<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2, out_ld);
   ISP_CHECK_LAUNCH("jbu_range_kernel");
   const long long npix = (long long)B * H * W;
+  if (out_ld == 56 && !simt) {
+    ISP_REQUIRE(aligned16(filters), ISP_ERR_MISALIGNED, "jbu_filters: padded filters must be 16-byte aligned");
+    return jbu_fixup_tc_launch(g, filters, npix, fw0, fb0, fw1, fb1, as_stream(stream));
+  }
   if (out_ld == 56) {
     ISP_REQUIRE(aligned16(filters), ISP_ERR_MISALIGNED, "jbu_filters: padded filters must be 16-byte aligned");
     jf2::jbu_fixup_kernel<56><<<cdiv(npix, jf2::B_PIX), jf2::B_THREADS, smemB, as_stream(stream)>>>(
@@ -273,4 +283,16 @@ extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters
   }
   ISP_CHECK_LAUNCH("jbu_fixup_kernel");
   return ISP_OK;
+}
+
+extern "C" int isp_jbu_filters(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
+                               float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
+                               const float* fb1, int out_ld, isp_stream_t stream) {
+  return jbu_filters_impl(proj, g, filters, B, H, W, temp, sigma_spatial, fw0, fb0, fw1, fb1, out_ld, 0, stream);
+}
+// the same with the fix-up MLP on the fp32 pipe for every layout (cross-check of the tensor-core kernel, A/B timing)
+extern "C" int isp_jbu_filters_simt(const float* proj, const float* g, float* filters, int B, int H, int W, float temp,
+                                    float sigma_spatial, const float* fw0, const float* fb0, const float* fw1,
+                                    const float* fb1, int out_ld, isp_stream_t stream) {
+  return jbu_filters_impl(proj, g, filters, B, H, W, temp, sigma_spatial, fw0, fb0, fw1, fb1, out_ld, 1, stream);
 }

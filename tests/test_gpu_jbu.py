@@ -114,9 +114,17 @@ def test_filters_and_range_proj(isp):
           w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"], 49)
     assert relerr(filt, want) < 1e-4
     filt56 = torch.empty(2, 30, 22, 7, 8, device=DEV)
-    _call("isp_jbu_filters", proj, g4, filt56, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
+    _call("isp_jbu_filters_simt", proj, g4, filt56, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
           w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"], 56)
     assert torch.equal(filt56[..., :7].reshape(2, 30, 22, 49), filt) and float(filt56[..., 7].abs().max()) == 0
+    # padded layout, fix-up MLP on the tensor cores (kind::tf32, hi / lo split activations, weights rounded to tf32): 1320 pixels
+    # = ten 128-pixel tiles and a ragged one; the pad slots carry the guidance values inside the kernel and must come out zero
+    tc56 = torch.full((2, 30, 22, 7, 8), float("nan"), device=DEV)
+    _call("isp_jbu_filters", proj, g4, tc56, 2, 30, 22, math.exp(0.7), 0.8, w["fixup_proj.0.weight"],
+          w["fixup_proj.0.bias"], w["fixup_proj.3.weight"], w["fixup_proj.3.bias"], 56)
+    assert float(tc56[..., 7].abs().max()) == 0
+    assert relerr(tc56[..., :7].reshape(2, 30, 22, 49), want) < 1e-4
+    assert relerr(tc56[..., :7].reshape(2, 30, 22, 49), filt) < 3e-5, relerr(tc56[..., :7].reshape(2, 30, 22, 49), filt)
 
 
 @pytest.mark.parametrize("B,h,w,H,W", [(2, 4, 4, 64, 64), (1, 6, 9, 96, 144), (1, 8, 8, 112, 112)])
