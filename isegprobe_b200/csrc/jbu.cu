@@ -37,42 +37,57 @@ __global__ void __launch_bounds__(256) pool_guidance_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------
-// range_proj: per-pixel MLP 3 -> 32 (GELU) -> 32.  One thread per pixel; weights in smem.
+// range_proj: per-pixel MLP 3 -> 32 (GELU) -> 32.  A thread owns TWO pixels (lane and lane + 32 of its warp's 64), so every
+// broadcast weight load feeds a packed FFMA2; weights in smem.  The 32 outputs of a pixel are 128 contiguous bytes: written
+// straight from the registers a warp store would touch 32 different lines, so each warp transposes its 64 x 32 block
+// through shared memory and stores 512 contiguous bytes per instruction.
 __global__ void __launch_bounds__(128) range_proj_kernel(const float4* __restrict__ g, float4* __restrict__ proj,
                                                          long long npix, const float* __restrict__ w0,
                                                          const float* __restrict__ b0, const float* __restrict__ w1,
                                                          const float* __restrict__ b1) {
   __shared__ float s_w0[32 * 3], s_b0[32], s_w1t[32 * 32], s_b1[32];  // s_w1t[k][o]
+  __shared__ float s_out[4][64][33];
   for (int i = threadIdx.x; i < 96; i += blockDim.x) s_w0[i] = w0[i];
   for (int i = threadIdx.x; i < 32; i += blockDim.x) { s_b0[i] = b0[i]; s_b1[i] = b1[i]; }
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_w1t[(i % 32) * 32 + i / 32] = w1[i];
   __syncthreads();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= npix) return;
-  const float4 gv = g[idx];
-  float o[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wpix0 = ((long long)blockIdx.x * 4 + warp) * 64;  // first pixel of this warp
+  const long long pa = wpix0 + lane, pb = pa + 32;
+  const float4 ga = pa < npix ? g[pa] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 gb = pb < npix ? g[pb] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 o[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) o[j] = s_b1[j];
+  for (int j = 0; j < 32; ++j) o[j] = make_float2(s_b1[j], s_b1[j]);
 #pragma unroll 4
   for (int k = 0; k < 32; ++k) {
-    float h = s_b0[k];
-    h = fmaf(s_w0[k * 3 + 0], gv.x, h);
-    h = fmaf(s_w0[k * 3 + 1], gv.y, h);
-    h = fmaf(s_w0[k * 3 + 2], gv.z, h);
-    h = gelu_erf(h);
+    const float wx = s_w0[k * 3 + 0], wy = s_w0[k * 3 + 1], wz = s_w0[k * 3 + 2], bk = s_b0[k];
+    const float ha = gelu_erf_fast(fmaf(wz, ga.z, fmaf(wy, ga.y, fmaf(wx, ga.x, bk))));
+    const float hb = gelu_erf_fast(fmaf(wz, gb.z, fmaf(wy, gb.y, fmaf(wx, gb.x, bk))));
+    const float2 h2 = make_float2(ha, hb);
     const float4* wr = reinterpret_cast<const float4*>(&s_w1t[k * 32]);
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
       const float4 w = wr[j4];
-      o[j4 * 4 + 0] = fmaf(w.x, h, o[j4 * 4 + 0]);
-      o[j4 * 4 + 1] = fmaf(w.y, h, o[j4 * 4 + 1]);
-      o[j4 * 4 + 2] = fmaf(w.z, h, o[j4 * 4 + 2]);
-      o[j4 * 4 + 3] = fmaf(w.w, h, o[j4 * 4 + 3]);
+      o[j4 * 4 + 0] = __ffma2_rn(make_float2(w.x, w.x), h2, o[j4 * 4 + 0]);
+      o[j4 * 4 + 1] = __ffma2_rn(make_float2(w.y, w.y), h2, o[j4 * 4 + 1]);
+      o[j4 * 4 + 2] = __ffma2_rn(make_float2(w.z, w.z), h2, o[j4 * 4 + 2]);
+      o[j4 * 4 + 3] = __ffma2_rn(make_float2(w.w, w.w), h2, o[j4 * 4 + 3]);
     }
   }
-  float4* dst = proj + idx * 8;
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+  for (int j = 0; j < 32; ++j) {
+    s_out[warp][lane][j] = o[j].x;
+    s_out[warp][lane + 32][j] = o[j].y;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {  // 4 pixels x 8 float4 per instruction
+    const int px = r * 4 + (lane >> 3), u = lane & 7;
+    if (wpix0 + px < npix)
+      proj[(wpix0 + px) * 8 + u] = make_float4(s_out[warp][px][4 * u], s_out[warp][px][4 * u + 1], s_out[warp][px][4 * u + 2],
+                                               s_out[warp][px][4 * u + 3]);
+  }
 }
 
 __device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
@@ -313,7 +328,7 @@ extern "C" int isp_jbu_range_proj(const float* g, float* proj, long long npix, c
   ISP_REQUIRE(g && proj && w0 && b0 && w1 && b1, ISP_ERR_BAD_SHAPE, "jbu_range_proj: null pointer");
   ISP_REQUIRE(npix > 0, ISP_ERR_BAD_SHAPE, "jbu_range_proj: npix=%lld", npix);
   ISP_REQUIRE(aligned16(g) && aligned16(proj), ISP_ERR_MISALIGNED, "jbu_range_proj: pointers must be 16-byte aligned");
-  range_proj_kernel<<<cdiv(npix, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g),
+  range_proj_kernel<<<cdiv(npix, 256), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g),
                                                                     reinterpret_cast<float4*>(proj), npix, w0, b0, w1, b1);
   ISP_CHECK_LAUNCH("range_proj_kernel");
   return ISP_OK;

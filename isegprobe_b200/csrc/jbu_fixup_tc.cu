@@ -49,21 +49,6 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26; the same form as the GEMM epilogue's): 1 RCP + 1 EX2 + 7 FMA per value
-// instead of erff's ~40 instructions -- the GELU between the two layers was the longest phase of a tile
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = x * 0.70710678118654752440f, az = fabsf(z);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-az * az * 1.4426950408889634f));
-  const float erfz = copysignf(fmaf(-poly * t, e, 1.f), z);
-  return 0.5f * x * (1.f + erfz);
-}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
 }

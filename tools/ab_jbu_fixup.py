@@ -20,3 +20,14 @@ for name, out in (("isp_jbu_filters_simt", a), ("isp_jbu_filters", b)):
     e1.record(); torch.cuda.synchronize()
     print(name, e0.elapsed_time(e1) / 5, "ms (range + fixup)")
 print("max abs diff", float((a - b).abs().max()), "rel", float((a - b).abs().max() / a.abs().max()))
+# range_proj (3 -> 32 -> 32 per pixel) alone
+w0 = torch.randn(32, 3, device=dev).contiguous(); b0 = torch.randn(32, device=dev); w1 = (torch.randn(32, 32, device=dev) * 0.2).contiguous(); b1 = torch.randn(32, device=dev)
+def rp():
+    _lib.call("isp_jbu_range_proj", _lib.dptr(g4), _lib.dptr(proj), B * H * W, _lib.dptr(w0), _lib.dptr(b0), _lib.dptr(w1), _lib.dptr(b1), _lib.stream_ptr())
+for _ in range(2): rp()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): rp()
+e1.record(); torch.cuda.synchronize()
+print("isp_jbu_range_proj", e0.elapsed_time(e1) / 5, "ms")
