@@ -42,9 +42,10 @@ struct SmemA {
   float spatial[52];
 };
 
+template <int OUT_LD>  // 49 (dense) or 56 (row-padded): compile-time, so the write-out's index arithmetic has no divisions
 __global__ void __launch_bounds__(A_THREADS, 4)
-jbu_range_kernel(const float* __restrict__ proj, float* __restrict__ filters, int H, int W, float temp, float inv2s2,
-                 int out_ld) {
+jbu_range_kernel(const float* __restrict__ proj, float* __restrict__ filters, int H, int W, float temp, float inv2s2) {
+  constexpr int out_ld = OUT_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemA& S = *reinterpret_cast<SmemA*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,14 +93,14 @@ jbu_range_kernel(const float* __restrict__ proj, float* __restrict__ filters, in
     }
     float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < 49; ++t) { k[t] = expf(k[t] - mx); sum += k[t]; }
+    for (int t = 0; t < 49; ++t) { k[t] = __expf(k[t] - mx); sum += k[t]; }  // MUFU.EX2: 2 instructions instead of expf's ~10
     const float inv = 1.f / sum;
     float sum2 = 0.f;
 #pragma unroll
     for (int t = 0; t < 49; ++t) { k[t] = (k[t] * inv) * S.spatial[t]; sum2 += k[t]; }
-    sum2 = fmaxf(sum2, 1e-7f);
+    const float inv2 = 1.f / fmaxf(sum2, 1e-7f);  // one division per pixel instead of 49
 #pragma unroll
-    for (int t = 0; t < 49; ++t) k[t] = k[t] / sum2;
+    for (int t = 0; t < 49; ++t) k[t] = k[t] * inv2;
   }
   __syncthreads();  // projection tile dead; its storage becomes the k staging buffer [tap][pixel]
 #pragma unroll
@@ -110,9 +111,18 @@ jbu_range_kernel(const float* __restrict__ proj, float* __restrict__ filters, in
     if (y >= H) break;
     const int npx = min(A_TW, W - tx0);
     float* dst = filters + (((size_t)b * H + y) * W + tx0) * out_ld;
-    for (int e = tid; e < npx * out_ld; e += A_THREADS) {
-      const int px = e / out_ld, tap = slot_to_tap(e - px * out_ld, out_ld);
-      dst[e] = tap >= 0 ? S.u.k[tap * A_KS + rr * 32 + px] : 0.f;
+    if (OUT_LD == 56) {  // 14 float4 per pixel: taps 7i .. 7i+3, then 7i+4 .. 7i+6 and the zero pad
+      float4* dst4 = reinterpret_cast<float4*>(dst);
+      for (int e4 = tid; e4 < npx * 14; e4 += A_THREADS) {
+        const int px = e4 / 14, s14 = e4 - px * 14;
+        const float* kp = &S.u.k[((s14 >> 1) * 7 + (s14 & 1) * 4) * A_KS + rr * 32 + px];
+        dst4[e4] = make_float4(kp[0], kp[A_KS], kp[2 * A_KS], (s14 & 1) ? 0.f : kp[3 * A_KS]);
+      }
+    } else {
+      for (int e = tid; e < npx * out_ld; e += A_THREADS) {
+        const int px = e / out_ld, tap = e - px * out_ld;
+        dst[e] = S.u.k[tap * A_KS + rr * 32 + px];
+      }
     }
   }
 }
@@ -259,14 +269,19 @@ static int jbu_filters_impl(const float* proj, const float* g, float* filters, i
   ISP_REQUIRE(B > 0 && H >= 4 && W >= 4, ISP_ERR_BAD_SHAPE, "jbu_filters: need H,W >= 4 (reflect pad 3), got %dx%d", H, W);
   ISP_REQUIRE(out_ld == 49 || out_ld == 56, ISP_ERR_BAD_SHAPE, "jbu_filters: out_ld must be 49 or 56 (got %d)", out_ld);
   ISP_REQUIRE(aligned16(proj) && aligned16(g), ISP_ERR_MISALIGNED, "jbu_filters: pointers must be 16-byte aligned");
+  ISP_REQUIRE(out_ld != 56 || aligned16(filters), ISP_ERR_MISALIGNED, "jbu_filters: padded filters must be 16-byte aligned");
   ISP_REQUIRE(B <= 65535 && cdiv(H, jf2::A_TH) <= 65535, ISP_ERR_UNSUPPORTED, "jbu_filters: grid too large");
   const int smemA = (int)sizeof(jf2::SmemA), smemB = (int)sizeof(jf2::SmemB);
-  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_range_kernel, smemA)) return e;
+  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_range_kernel<49>, smemA)) return e;
+  if (int e = ensure_dynamic_smem((const void*)jf2::jbu_range_kernel<56>, smemA)) return e;
   if (int e = ensure_dynamic_smem((const void*)jf2::jbu_fixup_kernel<49>, smemB)) return e;
   if (int e = ensure_dynamic_smem((const void*)jf2::jbu_fixup_kernel<56>, smemB)) return e;
   const float inv2s2 = 1.f / (2.f * sigma_spatial * sigma_spatial);
   dim3 gridA(cdiv(W, jf2::A_TW), cdiv(H, jf2::A_TH), B);
-  jf2::jbu_range_kernel<<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2, out_ld);
+  if (out_ld == 56)
+    jf2::jbu_range_kernel<56><<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2);
+  else
+    jf2::jbu_range_kernel<49><<<gridA, jf2::A_THREADS, smemA, as_stream(stream)>>>(proj, filters, H, W, temp, inv2s2);
   ISP_CHECK_LAUNCH("jbu_range_kernel");
   const long long npix = (long long)B * H * W;
   if (out_ld == 56 && !simt) {
