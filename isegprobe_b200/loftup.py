@@ -95,7 +95,10 @@ class LoftUpUpsampler(BaseUpsampler):
     always torch.load()s (loftup.py:155), benchmarks here use random-init weights."""
 
     HEADS = 4
-    chunk_images = 4  # images per internal pass (bounds the [B*HW, 416] intermediates)
+    # images per internal pass (bounds the [B*HW, 416] bf16 intermediates: 1.34 GB each at 8).  8 instead of 4: the
+    # persistent kernels lose less to their last, partly filled wave (attention: 21 -> 42 waves of 256-query tiles per launch),
+    # +1.3 % on the headline step (tools/ab_loftup_chunk.py)
+    chunk_images = 8
     # LayerNorms of the query stream (norm_q, FeedForward's, the transformer's final one) are applied inside the
     # epilogue of the GEMM that consumes them, from row statistics the producing GEMM / conv wrote (tc.gemm ln_stats=)
     fuse_layernorm = True
