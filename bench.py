@@ -642,11 +642,21 @@ def main():
     ctx = Ctx()
     try:
         if args.workload == "all":
+            def done(name):  # progress on stderr, after a device sync: a kernel fault is then attributed to its workload
+                torch.cuda.synchronize()
+                if ctx.rank == 0:
+                    print(f"[bench] workload {name} done", file=sys.stderr, flush=True)
+
             line = run_forward("loftup", args, ctx, args.steps, args.warmup, headline=True)
+            done("loftup")
             sub = args.sub_steps or min(args.steps, 5)
-            subs = {"jbu": run_forward("jbu", args, ctx, args.steps, args.warmup, headline=False),
-                    "train": run_train(args, ctx, sub, 3),
-                    "eval": run_eval(args, ctx, min(sub, 4), 3)}
+            subs = {}
+            subs["jbu"] = run_forward("jbu", args, ctx, args.steps, args.warmup, headline=False)
+            done("jbu")
+            subs["train"] = run_train(args, ctx, sub, 3)
+            done("train")
+            subs["eval"] = run_eval(args, ctx, min(sub, 4), 3)
+            done("eval")
             if line is not None:
                 line["workloads"] = subs
         elif args.workload == "train":

@@ -95,10 +95,11 @@ class LoftUpUpsampler(BaseUpsampler):
     always torch.load()s (loftup.py:155), benchmarks here use random-init weights."""
 
     HEADS = 4
-    # images per internal pass (bounds the [B*HW, 416] bf16 intermediates: 1.34 GB each at 8).  8 instead of 4: the
-    # persistent kernels lose less to their last, partly filled wave (attention: 21 -> 42 waves of 256-query tiles per launch),
-    # +1.3 % on the headline step (tools/ab_loftup_chunk.py)
-    chunk_images = 8
+    # images per internal pass (bounds the [B*HW, 416] bf16 intermediates: 0.67 GB each).  8 was measured 1.3 % faster on the
+    # headline step (fuller last waves of the persistent kernels: tools/ab_loftup_chunk.py), but one of four 2-GPU bench runs
+    # with it ended in a launch failure that was never seen at 4 and could not be reproduced or attributed in the time left:
+    # kept at the value every other measurement of the round was taken with
+    chunk_images = 4
     # LayerNorms of the query stream (norm_q, FeedForward's, the transformer's final one) are applied inside the
     # epilogue of the GEMM that consumes them, from row statistics the producing GEMM / conv wrote (tc.gemm ln_stats=)
     fuse_layernorm = True
