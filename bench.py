@@ -651,12 +651,22 @@ def main():
             done("loftup")
             sub = args.sub_steps or min(args.steps, 5)
             subs = {}
-            subs["jbu"] = run_forward("jbu", args, ctx, args.steps, args.warmup, headline=False)
-            done("jbu")
-            subs["train"] = run_train(args, ctx, sub, 3)
-            done("train")
-            subs["eval"] = run_eval(args, ctx, min(sub, 4), 3)
-            done("eval")
+
+            def sub_record(name, fn):
+                # one GPU: a failing sub-workload must not cost the headline line (several ranks: let it propagate, the
+                # other ranks would otherwise wait at the next barrier)
+                try:
+                    subs[name] = fn()
+                    done(name)
+                except Exception as e:  # noqa: BLE001
+                    if ctx.world > 1:
+                        raise
+                    subs[name] = {"error": repr(e)[:300]}
+                    print(f"[bench] workload {name} FAILED: {e!r}", file=sys.stderr, flush=True)
+
+            sub_record("jbu", lambda: run_forward("jbu", args, ctx, args.steps, args.warmup, headline=False))
+            sub_record("train", lambda: run_train(args, ctx, sub, 3))
+            sub_record("eval", lambda: run_eval(args, ctx, min(sub, 4), 3))
             if line is not None:
                 line["workloads"] = subs
         elif args.workload == "train":
